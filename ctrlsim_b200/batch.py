@@ -1,0 +1,113 @@
+"""GPU-resident scenario batch (struct of arrays in HBM) backing struct CtrlSimBatch of include/ctrlsim_b200.h."""
+from __future__ import annotations
+
+import ctypes as C
+import random
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .scenario import parse_scenario, road_arrays
+
+_DT = {"int64": torch.int64, "int32": torch.int32, "int16": torch.int16, "int8": torch.int8, "uint8": torch.uint8,
+       "float32": torch.float32, "float64": torch.float64}
+MAX_VEH = 64
+
+
+class SceneBatch:
+    """S scenes padded to common (N vehicles, Pm polylines, E edge segments).
+
+    ``scenes``: list of dicts with ``json`` (Nocturne schema) and ``preproc`` (road_points / road_types), e.g. from
+    ctrlsim_b200.synth.make_scene or read from the reference's files.  ``scene_ids`` are the global indices used by the
+    sampler (so sharding scenes over ranks does not change any draw).  ``rng`` reproduces the evaluator's
+    ``random.sample`` of evaluated vehicles (evaluators/policy_evaluator.py:450-454); pass the same ``random.Random``
+    across shards in scene order.
+    """
+
+    def __init__(self, cfg, scenes, scene_ids=None, device="cuda:0", eval_threshold=None, rng=None, parsed=None,
+                 evaluated_sets=None):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        steps = cfg.nocturne.steps
+        self.steps = steps
+        thr = cfg.eval.multi_agent_eval_threshold if eval_threshold is None else eval_threshold
+        rng = rng or random.Random(cfg.eval.seed)
+        sc_cfg = cfg.nocturne["scenario"]
+        if parsed is None:
+            parsed = [parse_scenario(s["json"], steps, sc_cfg["moving_threshold"], sc_cfg["speed_threshold"]) for s in scenes]
+        roads = [road_arrays(s["preproc"]) for s in scenes]
+        S = len(scenes)
+        N = max(1, max(p["n"] for p in parsed))
+        if N > MAX_VEH:
+            raise ValueError(f"at most {MAX_VEH} vehicles per scene are supported (got {N})")
+        Pm = max(1, max(r[0].shape[0] for r in roads))
+        E = max(1, max(p["segs"].shape[0] for p in parsed))
+        T1 = steps + 1
+        dims = {"S": S, "N": N, "Pm": Pm, "E": E, "T": steps, "T1": T1}
+        self.S, self.N, self.Pm, self.E = S, N, Pm, E
+        host = {}
+        for name, dt, shp in _lib.BATCH_FIELDS:
+            shape = [eval(tok, {}, dims) for tok in shp.split(",")]
+            host[name] = np.zeros(shape, dtype=dt)
+        host["eval_order"][:] = -1
+        host["road_type"][:] = -1
+        host["hist_rtg"][..., 1:] = 35  # un-sampled RTG (0,0,0) re-normalises to bins (0,35,35)
+        host["tr_rtg_idx"][:] = -1
+        host["tr_act_idx"][:] = -1
+        self.evaluated_ids = []
+        ids = list(range(S)) if scene_ids is None else list(scene_ids)
+        for s, (p, (rxy, rvalid, rtype)) in enumerate(zip(parsed, roads)):
+            n = p["n"]
+            host["scene_id"][s] = ids[s]
+            host["n_veh"][s] = n
+            host["veh_len"][s, :n], host["veh_wid"][s, :n] = p["size"][:, 0], p["size"][:, 1]
+            host["gt"][s, :n], host["gt_valid"][s, :n] = p["gt"], p["gt_valid"]
+            host["goal"][s, :n], host["goal_norm"][s, :n] = p["goal"], p["goal_norm"]
+            moving = [i for i in range(n) if p["moving"][i]]
+            if evaluated_sets is not None:
+                ev = list(evaluated_sets[s])
+            else:
+                ev = rng.sample(moving, thr) if len(moving) > thr else moving
+            self.evaluated_ids.append(sorted(ev))
+            host["evaluated"][s, ev] = 1
+            if ev:  # descending GT length, exactly the reference's np.argsort(...)[::-1] (autoregressive_policy.py:88-94)
+                lengths = [int(p["gt_valid"][v].astype(np.float64).sum()) for v in ev]
+                order = np.argsort(np.array(lengths))[::-1]
+                host["eval_order"][s, :len(ev)] = np.array(ev)[order]
+            np_ = rxy.shape[0]
+            host["n_poly"][s] = np_
+            host["road_xy"][s, :np_], host["road_valid"][s, :np_], host["road_type"][s, :np_] = rxy, rvalid, rtype
+            ns = p["segs"].shape[0]
+            host["n_seg"][s] = ns
+            host["segs"][s, :ns] = p["segs"]
+        self.t = {k: torch.from_numpy(v).to(self.device) for k, v in host.items()}
+        self._init_dynamic = {k: host[k] for k in ("hist_rtg", "tr_rtg_idx", "tr_act_idx")}
+        self.struct = _lib.CtrlSimBatch(n_scenes=S, max_veh=N, max_poly=Pm, max_seg=E,
+                                        **{k: self.t[k].data_ptr() for k, _, _ in _lib.BATCH_FIELDS})
+        self.n_total = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    @property
+    def ptr(self):
+        return C.byref(self.struct)
+
+    def reset_dynamic(self):
+        """Policy.reset (policies/policy.py:45-59): clear history, trace and group state for a new episode."""
+        static = {"scene_id", "n_veh", "veh_len", "veh_wid", "gt", "gt_valid", "goal", "goal_norm", "evaluated",
+                  "eval_order", "road_xy", "road_valid", "road_type", "n_poly", "segs", "n_seg"}
+        for k, v in self.t.items():
+            if k in static:
+                continue
+            if k in self._init_dynamic:
+                v.copy_(torch.from_numpy(self._init_dynamic[k]))
+            else:
+                v.zero_()
+
+    def n_evaluated(self) -> int:
+        return sum(len(e) for e in self.evaluated_ids)
+
+    def trace(self) -> dict:
+        """Device -> host copy of everything the reference keeps in vehicle_data_dict (for parity dumps)."""
+        keys = ("tr_pos", "tr_vel", "tr_heading", "tr_exist", "tr_action", "tr_reward", "tr_nearest", "tr_rtg_idx",
+                "tr_act_idx", "n_veh")
+        return {k: self.t[k].cpu().numpy() for k in keys}

@@ -1,0 +1,62 @@
+"""In-tree build of the CUDA extension: nvcc -> ctrlsim_b200/lib/libctrlsim_b200.so (sm_100a only).
+
+    python -m ctrlsim_b200.build            # rebuild what is stale
+
+No GPU is needed to build (nvcc cross-compiles).  sim.cu is compiled with -fmad=false (bit-faithful simulator
+arithmetic); everything else with the default contraction.  -lineinfo keeps ncu's source page mapped to our code.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "lib")
+LIB = os.path.join(OUT, "libctrlsim_b200.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+          "--extended-lambda", "-I", os.path.join(os.path.dirname(HERE), "include")]
+UNITS = {"gemm.cu": [], "attention.cu": [], "tokens.cu": [], "sample.cu": [], "model.cu": [], "api.cu": [],
+         "sim.cu": ["-fmad=false"]}
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    tm = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > tm for d in deps)
+
+
+def build(verbose: bool = False, force: bool = False) -> str:
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    os.makedirs(OUT, exist_ok=True)
+    headers = [os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "ctrlsim_b200.h"))
+    objs, procs = [], []
+    for unit, extra in UNITS.items():
+        src = os.path.join(SRC, unit)
+        obj = os.path.join(OUT, unit.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _stale(obj, [src] + headers):
+            cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", src, "-o", obj]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd), flush=True)
+            procs.append((unit, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for unit, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            print(f"--- {unit} ---\n{out}", flush=True)
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    if force or procs or _stale(LIB, objs):
+        subprocess.check_call([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

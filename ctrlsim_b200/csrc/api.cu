@@ -1,0 +1,285 @@
+// extern "C" boundary (include/ctrlsim_b200.h): handle management, weight registry, and the per-step orchestration
+// of the rollout hot path.  No torch types cross this file.
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "model.h"
+#include "model_ws.h"
+
+namespace ctrlsim {
+thread_local std::string g_last_error;
+int set_error(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+}  // namespace ctrlsim
+
+using namespace ctrlsim;
+
+struct CtrlSim {
+  ModelCfg mc;
+  ModelWeights w;
+  bool finalized = false;
+  int n_sm = 148;
+  std::unordered_map<std::string, std::pair<const float*, int64_t>> reg;
+  std::vector<int> h_group_off;
+};
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* ctrlsim_last_error(void) { return g_last_error.c_str(); }
+int ctrlsim_abi_version(void) { return CTRLSIM_ABI_VERSION; }
+
+int ctrlsim_create(const CtrlSimConfig* c, CtrlSim** out) {
+  if (!c || !out) return set_error(-1, "ctrlsim_create: null argument");
+  if (c->abi_version != CTRLSIM_ABI_VERSION) return set_error(-1, "ABI version mismatch: %d vs %d", c->abi_version, CTRLSIM_ABI_VERSION);
+  if (c->hidden_dim != H || c->num_heads != NH || c->dim_feedforward != FF || c->enc_layers != N_ENC ||
+      c->dec_layers != N_DEC || c->max_agents != A || c->context_len != T || c->max_polylines != P ||
+      c->pts_per_polyline != NP || c->n_action_bins != N_ACT || c->n_rtg_bins != N_RTG)
+    return set_error(-2, "ctrlsim_create: kernels are specialised to the reference default model geometry "
+                         "(H=256, heads=8, FF=1024, 2+4 layers, 24 agents, 32 steps, 200x100 map, 1000/350 bins)");
+  int dev = 0, cc_major = 0, n_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_error(-5, "no CUDA device: the product path has no CPU fallback");
+  cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (cc_major < 10) return set_error(-5, "ctrlsim_b200 is built for sm_100a only (device reports sm_%d)", cc_major * 10);
+  CtrlSim* h = new CtrlSim();
+  h->n_sm = n_sm;
+  h->mc.steps = c->steps; h->mc.hist_steps = c->history_steps; h->mc.n_steer = c->n_steer_bins; h->mc.dt = c->dt;
+  h->mc.dt_d = (double)((int)(c->dt * 1000.0f + 0.5f)) / 1000.0;  // 0.1f -> 0.1
+  h->mc.agent_dist = c->agent_dist_threshold;
+  h->mc.min_accel = c->min_accel; h->mc.max_accel = c->max_accel; h->mc.min_steer = c->min_steer; h->mc.max_steer = c->max_steer;
+  h->mc.pos_tol = c->pos_tol; h->mc.heading_tol = c->heading_tol; h->mc.speed_tol = c->speed_tol;
+  h->mc.goal_dist_scaling = c->goal_dist_scaling; h->mc.reward_scaling = c->reward_scaling;
+  *out = h;
+  return 0;
+}
+
+void ctrlsim_destroy(CtrlSim* h) { delete h; }
+
+int ctrlsim_load_weights(CtrlSim* h, const char* name, const float* ptr, int64_t count) {
+  if (!h || !name || !ptr) return set_error(-1, "ctrlsim_load_weights: null argument");
+  h->reg[name] = {ptr, count};
+  h->finalized = false;
+  return 0;
+}
+
+static int need(CtrlSim* h, const std::string& name, int64_t count, const float** out) {
+  auto it = h->reg.find(name);
+  if (it == h->reg.end()) return set_error(-3, "missing weight '%s'", name.c_str());
+  if (it->second.second != count)
+    return set_error(-3, "weight '%s' has %lld elements, expected %lld", name.c_str(), (long long)it->second.second, (long long)count);
+  *out = it->second.first;
+  return 0;
+}
+#define NEED(name, count, dst)                               \
+  do {                                                       \
+    int rc__ = need(h, name, count, &(dst));                 \
+    if (rc__) return rc__;                                   \
+  } while (0)
+
+static int need_mlp(CtrlSim* h, const std::string& p, int din, int dout, MlpW& m) {
+  NEED(p + ".mlp.0.weight", (int64_t)H * din, m.w0);
+  NEED(p + ".mlp.0.bias", H, m.b0);
+  NEED(p + ".mlp.1.weight", H, m.lnw);
+  NEED(p + ".mlp.1.bias", H, m.lnb);
+  NEED(p + ".mlp.3.weight", (int64_t)dout * H, m.w3);
+  NEED(p + ".mlp.3.bias", dout, m.b3);
+  return 0;
+}
+static int need_ln(CtrlSim* h, const std::string& p, LnW& l) {
+  NEED(p + ".weight", H, l.w);
+  NEED(p + ".bias", H, l.b);
+  return 0;
+}
+static int need_mha(CtrlSim* h, const std::string& p, MhaW& m) {
+  NEED(p + ".in_proj_weight", 3 * H * H, m.in_w);
+  NEED(p + ".in_proj_bias", 3 * H, m.in_b);
+  NEED(p + ".out_proj.weight", H * H, m.out_w);
+  NEED(p + ".out_proj.bias", H, m.out_b);
+  return 0;
+}
+
+int ctrlsim_finalize_weights(CtrlSim* h) {
+  if (!h) return set_error(-1, "null handle");
+  ModelWeights& w = h->w;
+  int rc;
+  const std::string me = "encoder.map_encoder";
+  if ((rc = need_mlp(h, me + ".road_pts_encoder", 3, H, w.road_pts))) return rc;
+  NEED("derived.pool_U", NH * H, w.pool_U);
+  NEED("derived.pool_W", (int64_t)H * NH * H, w.pool_W);
+  NEED("derived.pool_b", H, w.pool_b);
+  if ((rc = need_ln(h, me + ".norm1", w.map_n1))) return rc;
+  if ((rc = need_ln(h, me + ".norm2", w.map_n2))) return rc;
+  if ((rc = need_mlp(h, me + ".map_feats", H, H, w.map_feats))) return rc;
+  NEED("derived.type_tab2", 9 * H, w.type_tab2);
+  if ((rc = need_mlp(h, me + ".road_road_type_encoder", 2 * H, H, w.rr))) return rc;
+  if ((rc = need_mlp(h, "encoder.embed_state", 12, H, w.embed_state))) return rc;
+  if ((rc = need_mlp(h, "encoder.embed_goal", 5, H, w.embed_goal))) return rc;
+  NEED("encoder.embed_state_goal.weight", 2 * H * H, w.sg_w);
+  NEED("encoder.embed_state_goal.bias", H, w.sg_b);
+  NEED("encoder.embed_timestep.weight", 90 * H, w.emb.ts);
+  NEED("encoder.embed_agent_id.weight", A * H, w.emb.id);
+  NEED("encoder.embed_action.weight", N_ACT * H, w.emb.act);
+  NEED("derived.rtg_tab_goal", N_RTG * H, w.emb.rtg_goal);
+  NEED("derived.rtg_tab_veh", N_RTG * H, w.emb.rtg_veh);
+  NEED("derived.rtg_tab_road", N_RTG * H, w.emb.rtg_road);
+  NEED("encoder.embed_rtg.bias", H, w.emb.rtg_bias);
+  NEED("encoder.embed_ln.weight", H, w.emb.ln_w);
+  NEED("encoder.embed_ln.bias", H, w.emb.ln_b);
+  for (int l = 0; l < N_ENC; ++l) {
+    const std::string p = "encoder.transformer_encoder.layers." + std::to_string(l);
+    EncLayerW& e = w.enc[l];
+    if ((rc = need_mha(h, p + ".self_attn", e.sa))) return rc;
+    NEED(p + ".linear1.weight", FF * H, e.l1w); NEED(p + ".linear1.bias", FF, e.l1b);
+    NEED(p + ".linear2.weight", H * FF, e.l2w); NEED(p + ".linear2.bias", H, e.l2b);
+    if ((rc = need_ln(h, p + ".norm1", e.n1))) return rc;
+    if ((rc = need_ln(h, p + ".norm2", e.n2))) return rc;
+  }
+  for (int l = 0; l < N_DEC; ++l) {
+    const std::string p = "decoder.transformer_decoder.layers." + std::to_string(l);
+    DecLayerW& d = w.dec[l];
+    if ((rc = need_mha(h, p + ".self_attn", d.sa))) return rc;
+    if ((rc = need_mha(h, p + ".multihead_attn", d.ca))) return rc;
+    NEED(p + ".linear1.weight", FF * H, d.l1w); NEED(p + ".linear1.bias", FF, d.l1b);
+    NEED(p + ".linear2.weight", H * FF, d.l2w); NEED(p + ".linear2.bias", H, d.l2b);
+    if ((rc = need_ln(h, p + ".norm1", d.n1))) return rc;
+    if ((rc = need_ln(h, p + ".norm2", d.n2))) return rc;
+    if ((rc = need_ln(h, p + ".norm3", d.n3))) return rc;
+  }
+  if ((rc = need_mlp(h, "decoder.predict_action", H, N_ACT, w.head_action))) return rc;
+  if ((rc = need_mlp(h, "decoder.predict_rtg", H, N_RTG * 3, w.head_rtg))) return rc;
+  h->finalized = true;
+  return 0;
+}
+
+int64_t ctrlsim_workspace_bytes(const CtrlSim* h, int32_t max_groups) {
+  (void)h;
+  Workspace ws;
+  return (int64_t)ws.carve(nullptr, 0, max_groups);
+}
+
+int ctrlsim_sim_reset(CtrlSim* h, CtrlSimBatch* b, void* stream) { return launch_sim_reset(*b, h->mc, S(stream)); }
+int ctrlsim_observe(CtrlSim* h, CtrlSimBatch* b, int32_t t, void* stream) { return launch_observe(*b, t, h->mc, S(stream)); }
+int ctrlsim_plan_groups(CtrlSim* h, CtrlSimBatch* b, int32_t t, int32_t* n_groups_total, void* stream) {
+  return launch_plan_groups(*b, t, h->mc, n_groups_total, S(stream));
+}
+int ctrlsim_sim_step(CtrlSim* h, CtrlSimBatch* b, int32_t t, void* stream) { return launch_sim_step(*b, t, h->mc, S(stream)); }
+int ctrlsim_metrics(CtrlSim* h, const CtrlSimBatch* b, double* out_scene, int64_t* out_hist, void* stream) {
+  return launch_metrics(*b, h->mc, out_scene, reinterpret_cast<long long*>(out_hist), S(stream));
+}
+
+int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* p, int32_t t, int32_t n_groups_total,
+                        void* workspace, int64_t workspace_bytes, int32_t chunk_groups, void* stream) {
+  if (!h || !h->finalized) return set_error(-3, "ctrlsim_policy_step: weights not finalized");
+  if (n_groups_total <= 0) return 0;
+  cudaStream_t st = S(stream);
+  const int Sn = b->n_scenes;
+  h->h_group_off.resize(Sn + 1);
+  cudaError_t e = cudaMemcpyAsync(h->h_group_off.data(), b->group_off, sizeof(int) * (Sn + 1), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return set_error(-5, "policy_step: reading group offsets: %s", cudaGetErrorString(e));
+  const std::vector<int>& off = h->h_group_off;
+  if (off[Sn] != n_groups_total) return set_error(-4, "policy_step: n_groups_total=%d but the plan holds %d", n_groups_total, off[Sn]);
+  Workspace ws;
+  const size_t need_bytes = ws.carve(nullptr, 0, chunk_groups);
+  if ((int64_t)need_bytes > workspace_bytes)
+    return set_error(-4, "policy_step: workspace of %lld bytes is too small for chunks of %d groups (%lld needed)",
+                     (long long)workspace_bytes, chunk_groups, (long long)need_bytes);
+  ws.carve(workspace, need_bytes, chunk_groups);
+  const int n_t = t < T ? t + 1 : T;
+  int s0 = 0;
+  while (s0 < Sn) {
+    int s1 = s0;
+    while (s1 < Sn && off[s1 + 1] - off[s0] <= chunk_groups) ++s1;
+    if (s1 == s0) return set_error(-4, "policy_step: scene %d has %d groups, more than chunk_groups=%d", s0, off[s0 + 1] - off[s0], chunk_groups);
+    const int g0 = off[s0], ng = off[s1] - off[s0];
+    if (ng > 0) {
+      int rc;
+      if ((rc = launch_tokenize(*b, g0, ng, t, n_t, ws.tk, h->mc, st))) return rc;
+      if ((rc = forward_pass1(h->w, ws, ng, n_t, h->n_sm, st))) return rc;
+      if ((rc = launch_resolve_rtg_range(*b, *p, t, s0, s1, g0, h->mc.steps, ws.rtg_logits, st))) return rc;
+      if ((rc = launch_gather_rtg_steps(*b, g0, ng, t, h->mc.steps, ws.rtg_new, st))) return rc;
+      if ((rc = forward_pass2(h->w, ws, ng, n_t, st))) return rc;
+      if ((rc = launch_sample_actions(*b, *p, g0, ng, t, ws.act_logits, h->mc, st))) return rc;
+    } else {
+      int rc;  // scenes without any group still owe their vehicles the "(0,0,0) RTG appended" bookkeeping
+      if ((rc = launch_resolve_rtg_range(*b, *p, t, s0, s1, g0, h->mc.steps, ws.rtg_logits, st))) return rc;
+    }
+    s0 = s1;
+  }
+  return 0;
+}
+
+int ctrlsim_linear(const float* Ain, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                   int32_t relu, void* stream) {
+  GemmArgs g;
+  g.A = Ain; g.W = W; g.bias = bias; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldc = N; g.relu = relu != 0;
+  return launch_gemm(g, S(stream));
+}
+int ctrlsim_layernorm(const float* X, const float* R, const float* gamma, const float* beta, float* Y, int32_t M,
+                      int32_t relu, void* stream) {
+  return launch_layernorm(X, R, gamma, beta, Y, M, H, H, H, relu != 0, S(stream));
+}
+int ctrlsim_attn_padded(const float* Q, int32_t ldq, const float* K, const float* V, int32_t ldkv,
+                        const uint8_t* key_pad, float* O, int32_t G, int32_t Lq, int32_t Lk, void* stream) {
+  return launch_attn_padded(Q, ldq, K, V, ldkv, key_pad, O, H, G, Lq, Lk, S(stream));
+}
+int ctrlsim_attn_causal(const float* QKV, float* O, int32_t G, int32_t n_t, void* stream) {
+  return launch_attn_causal(QKV, O, G, n_t, S(stream));
+}
+int ctrlsim_map_pool(const float* feats, const uint8_t* pt_valid, const uint8_t* poly_valid, const float* U,
+                     float* pooled, int32_t n_poly, void* stream) {
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  return launch_map_pool(feats, pt_valid, poly_valid, U, pooled, n_poly, n_sm, S(stream));
+}
+int ctrlsim_sample_rows(const float* x, int32_t rows, int32_t n, int32_t ld, int32_t stride, uint64_t seed,
+                        const uint32_t* counters, int32_t* out_idx, void* stream) {
+  return launch_sample_rows(x, rows, n, ld, stride, seed, counters, out_idx, S(stream));
+}
+
+int ctrlsim_forward_tokens(CtrlSim* h, int32_t G, int32_t n_t, int32_t ti, const float* agent_states,
+                           const float* agent_types, const float* goals, const int32_t* actions, const int32_t* rtgs,
+                           const int32_t* timesteps, const float* road_points, const int32_t* road_types,
+                           const int32_t* rtg_idx_pass2, float* rtg_logits, float* action_logits, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  if (!h || !h->finalized) return set_error(-3, "ctrlsim_forward_tokens: weights not finalized");
+  if (n_t < 1 || n_t > T || ti != n_t - 1) return set_error(-2, "forward_tokens: need 1 <= n_t <= 32 and ti == n_t - 1");
+  cudaStream_t st = S(stream);
+  Workspace ws;
+  const size_t need_bytes = ws.carve(nullptr, 0, G);
+  if ((int64_t)need_bytes > workspace_bytes)
+    return set_error(-4, "forward_tokens: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need_bytes);
+  ws.carve(workspace, need_bytes, G);
+  int rc;
+  if ((rc = launch_convert_tokens(G, n_t, agent_states, agent_types, goals, actions, rtgs, timesteps, road_points, road_types, ws.tk, st))) return rc;
+  if ((rc = forward_pass1(h->w, ws, G, n_t, h->n_sm, st))) return rc;
+  cudaMemcpyAsync(rtg_logits, ws.rtg_logits, sizeof(float) * (size_t)G * A * N_RTG * 3, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(ws.rtg_new, rtg_idx_pass2, sizeof(int) * (size_t)G * A * 3, cudaMemcpyDeviceToDevice, st);
+  if ((rc = forward_pass2(h->w, ws, G, n_t, st))) return rc;
+  cudaMemcpyAsync(action_logits, ws.act_logits, sizeof(float) * (size_t)G * A * N_ACT, cudaMemcpyDeviceToDevice, st);
+  return 0;
+}
+
+int ctrlsim_geom_poly_poly(const float* xy1, int32_t n1, const float* xy2, int32_t n2, int32_t* out, void* stream) {
+  return launch_geom_poly_poly(xy1, n1, xy2, n2, out, S(stream));
+}
+int ctrlsim_geom_poly_seg(const float* xy, int32_t n, const float* seg, int32_t* out, void* stream) {
+  return launch_geom_poly_seg(xy, n, seg, out, S(stream));
+}
+
+}  // extern "C"

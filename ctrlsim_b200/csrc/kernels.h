@@ -1,0 +1,33 @@
+// Internal launcher declarations (host side). Every launcher returns 0 or a negative status and records a message
+// retrievable through ctrlsim_last_error().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ctrlsim {
+
+struct GemmArgs {
+  const float* A = nullptr;   // [M,K] row-major, leading dim lda (row gather through agather if set)
+  const float* W = nullptr;   // [N,K] row-major (nn.Linear weight), leading dim ldw
+  const float* bias = nullptr;
+  const float* table = nullptr;  // optional additive rows: C[m] += table[tidx[m]]
+  const int* tidx = nullptr;
+  const int* agather = nullptr;
+  float* C = nullptr;
+  int M = 0, N = 0, K = 0, lda = 0, ldw = 0, ldc = 0, ldt = 0;
+  bool relu = false;
+};
+int launch_gemm(const GemmArgs& g, cudaStream_t st);
+int launch_layernorm(const float* X, const float* R, const float* gamma, const float* beta, float* Y, int M, int ldx,
+                     int ldr, int ldy, bool relu, cudaStream_t st);
+
+// attention.cu
+int launch_attn_padded(const float* Q, int ldq, const float* Kp, const float* Vp, int ldkv, const uint8_t* key_pad,
+                       float* O, int ldo, int G, int Lq, int Lk, cudaStream_t st);
+int launch_attn_causal(const float* QKV, float* O, int G, int n_t, cudaStream_t st);
+int launch_attn_step(const float* QKV_full, const float* qkv_rows, float* O, int G, int n_t_full, int ti,
+                     cudaStream_t st);
+int launch_map_pool(const float* feats, const uint8_t* pt_valid, const uint8_t* poly_valid, const float* U,
+                    float* pooled, int n_poly, int n_sm, cudaStream_t st);
+
+}  // namespace ctrlsim

@@ -1,0 +1,189 @@
+// Forward pass of the CtRL-Sim policy network for a chunk of focal groups (M2-M9), as a sequence of kernel launches
+// on one stream.  Reference: models/ctrl_sim.py:41-45 -> modules/encoder.py:50-178, modules/map_encoder.py:34-54,
+// modules/decoder.py:39-78; the reference runs the whole 2304-token network twice per group per step
+// (policies/autoregressive_policy.py:190,210).  Here:
+//   pass 1  runs the network over the n_t = min(t+1, 32) window steps that exist (later steps are invisible to the
+//           current one under mask rule M1), keeps every decoder layer's K/V rows and the cross-attention K/V of the
+//           memory tokens, and evaluates the RTG head on the 24 state rows of the current step only;
+//   pass 2  recomputes only the 24 rtg-token rows of the current step (the only rows whose inputs changed after the
+//           RTGs were sampled and that the action head reads), attending to the cached K/V.
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "model.h"
+#include "model_ws.h"
+
+namespace ctrlsim {
+
+#define CS_TRY(x)            \
+  do {                       \
+    int rc__ = (x);          \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+static int gemm(const float* Ain, const float* W, const float* bias, float* C, int M, int N, int K, int lda, int ldw,
+                int ldc, bool relu, cudaStream_t st, const float* table = nullptr, const int* tidx = nullptr,
+                int ldt = 0, const int* agather = nullptr) {
+  GemmArgs g;
+  g.A = Ain; g.W = W; g.bias = bias; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldc = ldc;
+  g.relu = relu; g.table = table; g.tidx = tidx; g.ldt = ldt; g.agather = agather;
+  return launch_gemm(g, st);
+}
+static int ln(const float* X, const float* R, const LnW& w, float* Y, int M, bool relu, cudaStream_t st) {
+  return launch_layernorm(X, R, w.w, w.b, Y, M, H, H, H, relu, st);
+}
+
+size_t Workspace::carve(void* base, size_t bytes, int Gc) {
+  char* p = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t n) -> void* {
+    off = (off + 255) & ~size_t(255);
+    void* r = p ? p + off : nullptr;
+    off += n;
+    return r;
+  };
+  const size_t G = (size_t)Gc;
+  const size_t R = G * L, Rm = G * MEM, Rp = G * P, Rpt = Rp * NP, Ra = G * A, Rta = G * T * A;
+  tk.feat_state = (float*)take(Rta * 12 * 4);
+  tk.exist = (uint8_t*)take(Rta);
+  tk.goal_feat = (float*)take(Ra * 5 * 4);
+  tk.act_idx = (int*)take(Rta * 4);
+  tk.rtg_idx = (int*)take(Rta * 3 * 4);
+  tk.ts = (int*)take(G * T * 4);
+  tk.map_pts = (float*)take(Rpt * 3 * 4);
+  tk.map_type = (int*)take(Rp * 4);
+  tk.frame = (double*)take(G * 4 * 8);
+  h1 = (float*)take(Rpt * H * 4);
+  feats = (float*)take(Rpt * H * 4);
+  pt_valid = (uint8_t*)take(Rpt);
+  poly_valid = (uint8_t*)take(Rp);
+  pooled = (float*)take(Rp * NH * H * 4);
+  pe_a = (float*)take(Rp * H * 4);
+  pe_b = (float*)take(Rp * H * 4);
+  pe_c = (float*)take(Rp * H * 4);
+  type_idx = (int*)take(Rp * 4);
+  s1 = (float*)take(Rta * H * 4);
+  s2 = (float*)take(Rta * H * 4);
+  sg = (float*)take(Rta * H * 4);
+  g1 = (float*)take(Ra * H * 4);
+  g2 = (float*)take(Ra * H * 4);
+  gpart = (float*)take(Ra * H * 4);
+  goal_idx = (int*)take(Rta * 4);
+  mem = (float*)take(Rm * H * 4);
+  pad = (uint8_t*)take(Rm);
+  qkv_m = (float*)take(Rm * 3 * H * 4);
+  att_m = (float*)take(Rm * H * 4);
+  tmp_m = (float*)take(Rm * H * 4);
+  ff_m = (float*)take(Rm * FF * 4);
+  X = (float*)take(R * H * 4);
+  for (int l = 0; l < N_DEC; ++l) QKV[l] = (float*)take(R * 3 * H * 4);
+  for (int l = 0; l < N_DEC; ++l) kv_c[l] = (float*)take(Rm * 2 * H * 4);
+  att = (float*)take(R * H * 4);
+  tmp = (float*)take(R * H * 4);
+  q_c = (float*)take(R * H * 4);
+  ff = (float*)take(R * FF * 4);
+  row_idx = (int*)take(Ra * 4);
+  hd1 = (float*)take(Ra * H * 4);
+  rtg_logits = (float*)take(Ra * N_RTG * 3 * 4);
+  act_logits = (float*)take(Ra * N_ACT * 4);
+  rtg_new = (int*)take(Ra * 3 * 4);
+  xr = (float*)take(Ra * H * 4);
+  qkv_r = (float*)take(Ra * 3 * H * 4);
+  att_r = (float*)take(Ra * H * 4);
+  tmp_r = (float*)take(Ra * H * 4);
+  qc_r = (float*)take(Ra * H * 4);
+  ff_r = (float*)take(Ra * FF * 4);
+  off = (off + 255) & ~size_t(255);
+  (void)bytes;
+  return off;
+}
+
+int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm, cudaStream_t st) {
+  const int Rp = G * P, Rpt = Rp * NP, Ra = G * A, Rta = G * n_t * A, Rm = G * MEM;
+  const int Lcur = n_t * TOK_T, R = G * Lcur, ti = n_t - 1;
+  // ---- M2 polyline encoder --------------------------------------------------------------------------------------
+  CS_TRY(launch_map_flags(ws.tk.map_pts, ws.pt_valid, ws.poly_valid, Rp, st));
+  CS_TRY(launch_small_mlp1(3, ws.tk.map_pts, w.road_pts, ws.h1, (size_t)Rpt, st));
+  CS_TRY(gemm(ws.h1, w.road_pts.w3, w.road_pts.b3, ws.feats, Rpt, H, H, H, H, H, false, st));
+  CS_TRY(launch_map_pool(ws.feats, ws.pt_valid, ws.poly_valid, w.pool_U, ws.pooled, Rp, n_sm, st));
+  CS_TRY(gemm(ws.pooled, w.pool_W, w.pool_b, ws.pe_a, Rp, H, NH * H, NH * H, NH * H, H, false, st));
+  CS_TRY(ln(ws.pe_a, nullptr, w.map_n1, ws.pe_b, Rp, false, st));
+  CS_TRY(gemm(ws.pe_b, w.map_feats.w0, w.map_feats.b0, ws.pe_a, Rp, H, H, H, H, H, false, st));
+  CS_TRY(launch_layernorm(ws.pe_a, nullptr, w.map_feats.lnw, w.map_feats.lnb, ws.pe_a, Rp, H, H, H, true, st));
+  CS_TRY(gemm(ws.pe_a, w.map_feats.w3, w.map_feats.b3, ws.pe_c, Rp, H, H, H, H, H, false, st));
+  CS_TRY(ln(ws.pe_b, ws.pe_c, w.map_n2, ws.pe_a, Rp, false, st));
+  CS_TRY(launch_clamp_type_index(Rp, ws.tk.map_type, ws.type_idx, st));
+  CS_TRY(gemm(ws.pe_a, w.rr.w0, nullptr, ws.pe_b, Rp, H, H, H, 2 * H, H, false, st, w.type_tab2, ws.type_idx, H));
+  CS_TRY(launch_layernorm(ws.pe_b, nullptr, w.rr.lnw, w.rr.lnb, ws.pe_b, Rp, H, H, H, true, st));
+  CS_TRY(gemm(ws.pe_b, w.rr.w3, w.rr.b3, ws.pe_c, Rp, H, H, H, H, H, false, st));
+  // ---- M3 token embeddings --------------------------------------------------------------------------------------
+  CS_TRY(launch_small_mlp1(12, ws.tk.feat_state, w.embed_state, ws.s1, (size_t)Rta, st));
+  CS_TRY(gemm(ws.s1, w.embed_state.w3, w.embed_state.b3, ws.s2, Rta, H, H, H, H, H, false, st));
+  CS_TRY(launch_small_mlp1(5, ws.tk.goal_feat, w.embed_goal, ws.g1, (size_t)Ra, st));
+  CS_TRY(gemm(ws.g1, w.embed_goal.w3, w.embed_goal.b3, ws.g2, Ra, H, H, H, H, H, false, st));
+  CS_TRY(gemm(ws.g2, w.sg_w + H, w.sg_b, ws.gpart, Ra, H, H, H, 2 * H, H, false, st));
+  CS_TRY(launch_make_goal_index(G, n_t, ws.goal_idx, st));
+  CS_TRY(gemm(ws.s2, w.sg_w, nullptr, ws.sg, Rta, H, H, H, 2 * H, H, false, st, ws.gpart, ws.goal_idx, H));
+  CS_TRY(launch_assemble_tokens(G, n_t, ws.sg, ws.tk, w.emb, ws.X, ws.mem, st));
+  CS_TRY(launch_build_memory(G, ws.pe_c, ws.poly_valid, ws.tk, n_t, ws.mem, ws.pad, st));
+  // ---- M4 scene encoder -----------------------------------------------------------------------------------------
+  for (int l = 0; l < N_ENC; ++l) {
+    const EncLayerW& e = w.enc[l];
+    CS_TRY(gemm(ws.mem, e.sa.in_w, e.sa.in_b, ws.qkv_m, Rm, 3 * H, H, H, H, 3 * H, false, st));
+    CS_TRY(launch_attn_padded(ws.qkv_m, 3 * H, ws.qkv_m + H, ws.qkv_m + 2 * H, 3 * H, ws.pad, ws.att_m, H, G, MEM, MEM, st));
+    CS_TRY(gemm(ws.att_m, e.sa.out_w, e.sa.out_b, ws.tmp_m, Rm, H, H, H, H, H, false, st));
+    CS_TRY(ln(ws.mem, ws.tmp_m, e.n1, ws.mem, Rm, false, st));
+    CS_TRY(gemm(ws.mem, e.l1w, e.l1b, ws.ff_m, Rm, FF, H, H, H, FF, true, st));
+    CS_TRY(gemm(ws.ff_m, e.l2w, e.l2b, ws.tmp_m, Rm, H, FF, FF, FF, H, false, st));
+    CS_TRY(ln(ws.mem, ws.tmp_m, e.n2, ws.mem, Rm, false, st));
+  }
+  // ---- M5-M7 decoder --------------------------------------------------------------------------------------------
+  for (int l = 0; l < N_DEC; ++l) {
+    const DecLayerW& d = w.dec[l];
+    CS_TRY(gemm(ws.X, d.sa.in_w, d.sa.in_b, ws.QKV[l], R, 3 * H, H, H, H, 3 * H, false, st));
+    CS_TRY(launch_attn_causal(ws.QKV[l], ws.att, G, n_t, st));
+    CS_TRY(gemm(ws.att, d.sa.out_w, d.sa.out_b, ws.tmp, R, H, H, H, H, H, false, st));
+    CS_TRY(ln(ws.X, ws.tmp, d.n1, ws.X, R, false, st));
+    CS_TRY(gemm(ws.X, d.ca.in_w, d.ca.in_b, ws.q_c, R, H, H, H, H, H, false, st));
+    CS_TRY(gemm(ws.mem, d.ca.in_w + (size_t)H * H, d.ca.in_b + H, ws.kv_c[l], Rm, 2 * H, H, H, H, 2 * H, false, st));
+    CS_TRY(launch_attn_padded(ws.q_c, H, ws.kv_c[l], ws.kv_c[l] + H, 2 * H, ws.pad, ws.att, H, G, Lcur, MEM, st));
+    CS_TRY(gemm(ws.att, d.ca.out_w, d.ca.out_b, ws.tmp, R, H, H, H, H, H, false, st));
+    CS_TRY(ln(ws.X, ws.tmp, d.n2, ws.X, R, false, st));
+    CS_TRY(gemm(ws.X, d.l1w, d.l1b, ws.ff, R, FF, H, H, H, FF, true, st));
+    CS_TRY(gemm(ws.ff, d.l2w, d.l2b, ws.tmp, R, H, FF, FF, FF, H, false, st));
+    CS_TRY(ln(ws.X, ws.tmp, d.n3, ws.X, R, false, st));
+  }
+  // ---- M8 RTG head on the state rows of the current step ----------------------------------------------------------
+  CS_TRY(launch_make_row_index(G, n_t, ti, 0, ws.row_idx, st));
+  CS_TRY(gemm(ws.X, w.head_rtg.w0, w.head_rtg.b0, ws.hd1, Ra, H, H, H, H, H, false, st, nullptr, nullptr, 0, ws.row_idx));
+  CS_TRY(launch_layernorm(ws.hd1, nullptr, w.head_rtg.lnw, w.head_rtg.lnb, ws.hd1, Ra, H, H, H, true, st));
+  CS_TRY(gemm(ws.hd1, w.head_rtg.w3, w.head_rtg.b3, ws.rtg_logits, Ra, N_RTG * 3, H, H, H, N_RTG * 3, false, st));
+  return 0;
+}
+
+int forward_pass2(const ModelWeights& w, Workspace& ws, int G, int n_t, cudaStream_t st) {
+  const int Ra = G * A, ti = n_t - 1;
+  CS_TRY(launch_assemble_rtg_rows(G, n_t, ti, ws.rtg_new, ws.tk, w.emb, ws.xr, st));
+  for (int l = 0; l < N_DEC; ++l) {
+    const DecLayerW& d = w.dec[l];
+    CS_TRY(gemm(ws.xr, d.sa.in_w, d.sa.in_b, ws.qkv_r, Ra, 3 * H, H, H, H, 3 * H, false, st));
+    CS_TRY(launch_attn_step(ws.QKV[l], ws.qkv_r, ws.att_r, G, n_t, ti, st));
+    CS_TRY(gemm(ws.att_r, d.sa.out_w, d.sa.out_b, ws.tmp_r, Ra, H, H, H, H, H, false, st));
+    CS_TRY(ln(ws.xr, ws.tmp_r, d.n1, ws.xr, Ra, false, st));
+    CS_TRY(gemm(ws.xr, d.ca.in_w, d.ca.in_b, ws.qc_r, Ra, H, H, H, H, H, false, st));
+    CS_TRY(launch_attn_padded(ws.qc_r, H, ws.kv_c[l], ws.kv_c[l] + H, 2 * H, ws.pad, ws.att_r, H, G, A, MEM, st));
+    CS_TRY(gemm(ws.att_r, d.ca.out_w, d.ca.out_b, ws.tmp_r, Ra, H, H, H, H, H, false, st));
+    CS_TRY(ln(ws.xr, ws.tmp_r, d.n2, ws.xr, Ra, false, st));
+    CS_TRY(gemm(ws.xr, d.l1w, d.l1b, ws.ff_r, Ra, FF, H, H, H, FF, true, st));
+    CS_TRY(gemm(ws.ff_r, d.l2w, d.l2b, ws.tmp_r, Ra, H, FF, FF, FF, H, false, st));
+    CS_TRY(ln(ws.xr, ws.tmp_r, d.n3, ws.xr, Ra, false, st));
+  }
+  // ---- M9 action head on the rtg rows ---------------------------------------------------------------------------
+  CS_TRY(gemm(ws.xr, w.head_action.w0, w.head_action.b0, ws.hd1, Ra, H, H, H, H, H, false, st));
+  CS_TRY(launch_layernorm(ws.hd1, nullptr, w.head_action.lnw, w.head_action.lnb, ws.hd1, Ra, H, H, H, true, st));
+  CS_TRY(gemm(ws.hd1, w.head_action.w3, w.head_action.b3, ws.act_logits, Ra, N_ACT, H, H, H, N_ACT, false, st));
+  return 0;
+}
+
+}  // namespace ctrlsim

@@ -1,0 +1,217 @@
+"""Drop-in policy / evaluator pair for the closed-loop rollout, batched over scenes on one B200.
+
+Mirrors the reference's plugin API for this path:
+
+  B200Policy          <-> policies.AutoregressivePolicy   (policies/policy.py:8-154, autoregressive_policy.py:10-274)
+      same constructor arguments, same attribute names the evaluator reads, and the same four verbs
+      reset / update_state / predict / act - operating on a whole SceneBatch instead of one vehicle_data_dict.
+  B200PolicyEvaluator <-> evaluators.PolicyEvaluator      (evaluators/policy_evaluator.py:27-44,426-595)
+      ``B200PolicyEvaluator(cfg, policy).evaluate_policy() -> (metrics_dict, [str])`` with the reference's keys:
+      goal, collision_rate, offroad_rate, fde, ade, lin_speed_jsd, ang_speed_jsd, accel_jsd, nearest_dist_jsd.
+
+Host code is Python; every per-step operation is a CUDA kernel behind the C-ABI (ctrlsim_b200/lib.py).  Scenes shard
+over ranks (one process per GPU); the only collective is one all-reduce of the summary buffer per evaluation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import pickle
+import random
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .batch import SceneBatch
+from .model import DeviceModel
+
+
+class B200Policy:
+    def __init__(self, cfg, model_path, model, use_rtg=True, predict_rtgs=True, discretize_rtgs=True,
+                 real_time_rewards=False, privileged_return=False, max_return=False, min_return=False, key_dict=None,
+                 tilt_dict=None, name="ctrl_sim", action_temperature=1.0, nucleus_sampling=False,
+                 nucleus_threshold=0.8, seed=0, chunk_groups=128):
+        if not isinstance(model, DeviceModel):
+            raise TypeError("B200Policy needs a ctrlsim_b200.model.DeviceModel (weights resident on the GPU)")
+        if not (use_rtg and predict_rtgs and discretize_rtgs) or real_time_rewards or max_return or min_return:
+            raise NotImplementedError("only the ctrl_sim policy mode (cfgs/policy/ctrl_sim.yaml) is implemented; "
+                                      "real_time_rewards / dt modes are SURVEY 8(f) N1")
+        if nucleus_sampling:
+            raise NotImplementedError("nucleus sampling (cfgs/policy/ctrl_sim.yaml:10) is not implemented yet")
+        self.cfg = cfg.copy()
+        self.model_path, self.model, self.name = model_path, model, name
+        self.model.eval()
+        self.cfg_model, self.cfg_rl_waymo = cfg.model, cfg.dataset.waymo
+        self.steps = self.cfg.nocturne.steps
+        self.use_rtg, self.predict_rtgs, self.discretize_rtgs = use_rtg, predict_rtgs, discretize_rtgs
+        self.real_time_rewards, self.privileged_return = real_time_rewards, privileged_return
+        self.max_return, self.min_return = max_return, min_return
+        self.key_dict = key_dict or {"next_acceleration": "next_acceleration", "next_steering": "next_steering",
+                                     "rtgs": "rtgs"}
+        self.tilt_dict = tilt_dict or {"tilt": True, "goal_tilt": 0, "veh_veh_tilt": 0, "veh_edge_tilt": 0}
+        self.action_temperature, self.nucleus_sampling, self.nucleus_threshold = action_temperature, False, nucleus_threshold
+        if self.tilt_dict["tilt"]:
+            self.goal_tilt, self.veh_veh_tilt = self.tilt_dict["goal_tilt"], self.tilt_dict["veh_veh_tilt"]
+            self.veh_edge_tilt = self.tilt_dict["veh_edge_tilt"]
+        self.seed = seed
+        self.chunk_groups = chunk_groups
+        self.lib = model.lib
+        self.groups_last_step = 0
+        self.launch_count = 0
+
+    def _params(self):
+        td = self.tilt_dict
+        tilt = (C.c_double * 3)(float(td["goal_tilt"] or 0), float(td["veh_veh_tilt"] or 0), float(td["veh_edge_tilt"] or 0))
+        return _lib.CtrlSimPolicyParams(seed=self.seed, tilt=tilt, temperature=float(self.action_temperature),
+                                        tilt_enabled=1 if td["tilt"] else 0)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.model.device).cuda_stream
+
+    # ---- the reference's four verbs, batched -----------------------------------------------------------------------
+    def reset(self, batch: SceneBatch):
+        batch.reset_dynamic()
+        _lib.check(self.lib.ctrlsim_sim_reset(self.model.handle, batch.ptr, self._stream()), "ctrlsim_sim_reset")
+
+    def update_state(self, batch: SceneBatch, t: int):
+        """update_vehicle_data_dict + Policy.update_state for step t (observation, reward, history append)."""
+        _lib.check(self.lib.ctrlsim_observe(self.model.handle, batch.ptr, t, self._stream()), "ctrlsim_observe")
+
+    def predict(self, batch: SceneBatch, t: int):
+        """Focal grouping, tokenisation, two-pass network, RTG + action sampling; leaves next_action on the device."""
+        st = self._stream()
+        _lib.check(self.lib.ctrlsim_plan_groups(self.model.handle, batch.ptr, t, batch.n_total.data_ptr(), st),
+                   "ctrlsim_plan_groups")
+        n_total = int(batch.n_total.item())
+        self.groups_last_step = n_total
+        chunk = max(self.chunk_groups, batch.N)  # a scene's groups are processed together (RTG resolution)
+        ws = self.model.workspace(chunk)
+        p = self._params()
+        _lib.check(self.lib.ctrlsim_policy_step(self.model.handle, batch.ptr, C.byref(p), t, n_total, ws.data_ptr(),
+                                                ws.numel(), chunk, st), "ctrlsim_policy_step")
+        return n_total
+
+    def act(self, batch: SceneBatch, t: int):
+        """policy.act / apply_gt_action for every vehicle, then Simulation.step(dt)."""
+        _lib.check(self.lib.ctrlsim_sim_step(self.model.handle, batch.ptr, t, self._stream()), "ctrlsim_sim_step")
+
+
+def _jsd(p, q):
+    """scipy.spatial.distance.jensenshannon with the natural log (evaluators/policy_evaluator.py:269)."""
+    p = np.asarray(p, np.float64)
+    q = np.asarray(q, np.float64)
+    p, q = p / p.sum(), q / q.sum()
+    m = (p + q) / 2.0
+    left = np.where(p > 0, p * np.log(np.where(p > 0, p, 1.0) / np.where(m > 0, m, 1.0)), 0.0)
+    right = np.where(q > 0, q * np.log(np.where(q > 0, q, 1.0) / np.where(m > 0, m, 1.0)), 0.0)
+    return float(np.sqrt((left.sum() + right.sum()) / 2.0))
+
+
+class B200PolicyEvaluator:
+    def __init__(self, cfg, policy: B200Policy, scenes=None, scene_ids=None):
+        """``scenes`` (optional): in-memory list of {'json', 'preproc'} dicts; otherwise the reference's files are read:
+        <dataset_root>/test_filenames.pkl, <nocturne_waymo_val_folder>/<name>.json and
+        <dataset_root>/preprocess/test/<name>_physics.pkl (evaluators/policy_evaluator.py:33-41, evaluator.py:44-57)."""
+        self.cfg, self.policy = cfg, policy
+        self.cfg_rl_waymo = cfg.dataset.waymo
+        self.steps, self.dt, self.history_steps = cfg.nocturne.steps, cfg.nocturne.dt, cfg.nocturne.history_steps
+        self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        if scenes is None:
+            scenes, scene_ids = self._load_files()
+        self.scenes = scenes
+        self.scene_ids = list(range(len(scenes))) if scene_ids is None else list(scene_ids)
+        self.batch = None
+        self.last_summary = None
+
+    def _load_files(self):
+        with open(os.path.join(self.cfg.dataset_root, "test_filenames.pkl"), "rb") as f:
+            names = pickle.load(f)["test_filenames"]
+        scenes, ids = [], []
+        limit = self.cfg.eval.num_files_to_evaluate // self.cfg.eval.partitions
+        for i, name in enumerate(names):
+            if len(scenes) == limit:
+                break
+            pkl = os.path.join(self.cfg.dataset_root, "preprocess/test", f"{name[:-5]}_physics.pkl")
+            if not os.path.exists(pkl):
+                continue  # the reference silently skips scenes without preprocessed data (policy_evaluator.py:445-446)
+            with open(os.path.join(self.cfg.nocturne_waymo_val_folder, name)) as f:
+                js = json.load(f)
+            with open(pkl, "rb") as f:
+                pre = pickle.load(f)
+            scenes.append({"name": name, "json": js, "preproc": pre})
+            ids.append(i)
+        return scenes, ids
+
+    def build_batch(self, eval_threshold=None):
+        """Shard scenes over ranks (scene i -> rank i mod world) keeping the evaluated-vehicle draw of the
+        single-process evaluator: every rank walks all scenes in order with the same seeded generator."""
+        from .scenario import parse_scenario
+        cfg = self.cfg
+        rng = random.Random(cfg.eval.seed)
+        thr = cfg.eval.multi_agent_eval_threshold if eval_threshold is None else eval_threshold
+        sc = cfg.nocturne["scenario"]
+        mine, mine_ids, mine_parsed, mine_rng = [], [], [], []
+        for k, s in enumerate(self.scenes):
+            own = k % self.world == self.rank
+            p = parse_scenario(s["json"], self.steps, sc["moving_threshold"], sc["speed_threshold"])
+            moving = [i for i in range(p["n"]) if p["moving"][i]]
+            ev = rng.sample(moving, thr) if len(moving) > thr else moving
+            if not ev:
+                continue  # no candidate agent: scene skipped (policy_evaluator.py:461-464)
+            if own:
+                mine.append(s)
+                mine_ids.append(self.scene_ids[k])
+                mine_parsed.append(p)
+                mine_rng.append(ev)
+        self.batch = SceneBatch(cfg, mine, mine_ids, self.policy.model.device, thr, parsed=mine_parsed,
+                                evaluated_sets=mine_rng)
+        return self.batch
+
+    def rollout(self, batch=None, max_steps=None):
+        """The 90-step closed loop of evaluate_policy (policy_evaluator.py:514-557) for the whole batch."""
+        b = batch or self.batch
+        pol = self.policy
+        pol.reset(b)
+        steps = self.steps if max_steps is None else max_steps
+        for t in range(steps):
+            pol.update_state(b, t)
+            pol.predict(b, t)
+            pol.act(b, t)
+        if steps == self.steps:
+            pol.update_state(b, self.steps)
+        return b
+
+    def summarize(self, batch=None):
+        b = batch or self.batch
+        dev = self.policy.model.device
+        out_scene = torch.zeros(b.S, 8, dtype=torch.float64, device=dev)
+        out_hist = torch.zeros(8, 200, dtype=torch.int64, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self.policy.lib.ctrlsim_metrics(self.policy.model.handle, b.ptr, out_scene.data_ptr(),
+                                                   out_hist.data_ptr(), st), "ctrlsim_metrics")
+        # flat summary: [goal_sum, n_agents, sum_scene_coll, sum_scene_off, n_scenes_with_agents, ade_sum, fde_sum, 0]
+        summ = torch.cat([out_scene.sum(0), out_hist.to(torch.float64).flatten()])
+        if self.world > 1:
+            torch.distributed.all_reduce(summ)  # the one collective of an evaluation
+        self.last_summary = summ.cpu().numpy()
+        return self.last_summary
+
+    @staticmethod
+    def metrics_from_summary(s):
+        goal_sum, n_ag, coll_sum, off_sum, n_sc, ade_sum, fde_sum = s[:7]
+        h = s[8:].reshape(8, 200)
+        m = {"goal": goal_sum / n_ag, "collision_rate": coll_sum / n_sc, "offroad_rate": off_sum / n_sc,
+             "fde": fde_sum / n_ag, "ade": ade_sum / n_ag,
+             "lin_speed_jsd": _jsd(h[0], h[1]), "ang_speed_jsd": _jsd(h[2], h[3]),
+             "accel_jsd": _jsd(h[4][:20], h[5][:20]), "nearest_dist_jsd": _jsd(h[6], h[7])}
+        return {k: float(v) for k, v in m.items()}
+
+    def evaluate_policy(self):
+        if self.batch is None:
+            self.build_batch()
+        self.rollout()
+        m = self.metrics_from_summary(self.summarize())
+        return m, ["{}: {:.6f}".format(k, v) for k, v in m.items()]

@@ -1,0 +1,139 @@
+"""ctypes binding of include/ctrlsim_b200.h (the C-ABI of the CUDA extension).
+
+The product path has no CPU fallback: if the shared library is missing it is built (nvcc must be present); if it
+cannot be loaded, importing a GPU entry point raises.  PyTorch only provides device memory and streams; all pointers
+handed over are ``tensor.data_ptr()`` values.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libctrlsim_b200.so")
+ABI_VERSION = 1
+
+
+class CtrlSimConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("hidden_dim", C.c_int32), ("num_heads", C.c_int32), ("dim_feedforward", C.c_int32),
+        ("enc_layers", C.c_int32), ("dec_layers", C.c_int32),
+        ("max_agents", C.c_int32), ("context_len", C.c_int32), ("max_polylines", C.c_int32),
+        ("pts_per_polyline", C.c_int32),
+        ("n_action_bins", C.c_int32), ("n_steer_bins", C.c_int32), ("n_rtg_bins", C.c_int32),
+        ("steps", C.c_int32), ("history_steps", C.c_int32),
+        ("dt", C.c_float),
+        ("agent_dist_threshold", C.c_double),
+        ("min_accel", C.c_double), ("max_accel", C.c_double), ("min_steer", C.c_double), ("max_steer", C.c_double),
+        ("pos_tol", C.c_double), ("heading_tol", C.c_double), ("speed_tol", C.c_double),
+        ("goal_dist_scaling", C.c_double), ("reward_scaling", C.c_double),
+    ]
+
+
+# (field name, torch dtype name, shape expression) in the exact order of struct CtrlSimBatch
+BATCH_FIELDS = [
+    ("scene_id", "int64", "S"), ("n_veh", "int32", "S"), ("veh_len", "float32", "S,N"), ("veh_wid", "float32", "S,N"),
+    ("gt", "float32", "S,N,T1,4"), ("gt_valid", "uint8", "S,N,T1"), ("goal", "float64", "S,N,4"),
+    ("goal_norm", "float64", "S,N"), ("evaluated", "uint8", "S,N"), ("eval_order", "int32", "S,N"),
+    ("road_xy", "float64", "S,Pm,100,2"), ("road_valid", "uint8", "S,Pm,100"), ("road_type", "int8", "S,Pm"),
+    ("n_poly", "int32", "S"), ("segs", "float32", "S,E,4"), ("n_seg", "int32", "S"),
+    ("body", "float32", "S,16,N"), ("obj", "float32", "S,4,N"), ("coll", "uint8", "S,2,N"),
+    ("hist_state", "float64", "S,N,T,8"), ("hist_action", "float64", "S,N,T,2"), ("hist_rtg", "int16", "S,N,T,3"),
+    ("relevant", "int64", "S,N"), ("next_action", "float64", "S,N,2"),
+    ("tr_pos", "float32", "S,N,T1,2"), ("tr_vel", "float32", "S,N,T1,2"), ("tr_heading", "float32", "S,N,T1"),
+    ("tr_exist", "uint8", "S,N,T1"), ("tr_action", "float64", "S,N,T1,2"), ("tr_reward", "float32", "S,N,T1,8"),
+    ("tr_nearest", "float64", "S,N,T1,2"), ("tr_rtg_idx", "int16", "S,N,T,3"), ("tr_act_idx", "int16", "S,N,T"),
+    ("n_groups", "int32", "S"), ("group_off", "int32", "S+1"), ("group_focal", "int32", "S,N"),
+    ("group_members", "int32", "S,N,24"), ("group_served", "int32", "S,N"), ("group_scene", "int32", "S*N"),
+    ("group_local", "int32", "S*N"),
+]
+
+
+class CtrlSimBatch(C.Structure):
+    _fields_ = ([("n_scenes", C.c_int32), ("max_veh", C.c_int32), ("max_poly", C.c_int32), ("max_seg", C.c_int32)]
+                + [(name, C.c_void_p) for name, _, _ in BATCH_FIELDS])
+
+
+class CtrlSimPolicyParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("tilt", C.c_double * 3), ("temperature", C.c_float),
+                ("tilt_enabled", C.c_int32)]
+
+
+class CtrlSimError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_SIGS = {
+    "ctrlsim_last_error": (C.c_char_p, []),
+    "ctrlsim_abi_version": (C.c_int, []),
+    "ctrlsim_create": (C.c_int, [C.POINTER(CtrlSimConfig), C.POINTER(C.c_void_p)]),
+    "ctrlsim_destroy": (None, [C.c_void_p]),
+    "ctrlsim_load_weights": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "ctrlsim_finalize_weights": (C.c_int, [C.c_void_p]),
+    "ctrlsim_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32]),
+    "ctrlsim_sim_reset": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_void_p]),
+    "ctrlsim_observe": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_int32, C.c_void_p]),
+    "ctrlsim_plan_groups": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_int32, C.c_void_p, C.c_void_p]),
+    "ctrlsim_policy_step": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.POINTER(CtrlSimPolicyParams), C.c_int32,
+                                      C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "ctrlsim_sim_step": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_int32, C.c_void_p]),
+    "ctrlsim_metrics": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ctrlsim_linear": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p]),
+    "ctrlsim_layernorm": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 2 + [C.c_void_p]),
+    "ctrlsim_attn_padded": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "ctrlsim_attn_causal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "ctrlsim_map_pool": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
+    "ctrlsim_sample_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "ctrlsim_forward_tokens": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 11
+                               + [C.c_void_p, C.c_int64, C.c_void_p]),
+    "ctrlsim_geom_poly_poly": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ctrlsim_geom_poly_seg": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+EXPORTS = tuple(_SIGS)
+
+
+def load(build_if_missing: bool = True):
+    """Load libctrlsim_b200.so and declare every prototype of include/ctrlsim_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise CtrlSimError(f"{LIB_PATH} is missing; run `python -m ctrlsim_b200.build`")
+        from .build import build
+        build()
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.ctrlsim_abi_version() != ABI_VERSION:
+        raise CtrlSimError("libctrlsim_b200.so ABI version mismatch; rebuild with `python -m ctrlsim_b200.build -f`")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().ctrlsim_last_error()
+        raise CtrlSimError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def make_config(cfg) -> CtrlSimConfig:
+    w, m, n = cfg.dataset.waymo, cfg.model, cfg.nocturne
+    rc = n["rew_cfg"]
+    return CtrlSimConfig(
+        abi_version=ABI_VERSION, hidden_dim=m.hidden_dim, num_heads=m.num_heads, dim_feedforward=m.dim_feedforward,
+        enc_layers=m.num_transformer_encoder_layers, dec_layers=m.num_decoder_layers,
+        max_agents=w.max_num_agents, context_len=w.train_context_length, max_polylines=w.max_num_road_polylines,
+        pts_per_polyline=w.max_num_road_pts_per_polyline,
+        n_action_bins=w.accel_discretization * w.steer_discretization, n_steer_bins=w.steer_discretization,
+        n_rtg_bins=w.rtg_discretization, steps=n.steps, history_steps=n.history_steps, dt=n.dt,
+        agent_dist_threshold=w.agent_dist_threshold, min_accel=w.min_accel, max_accel=w.max_accel,
+        min_steer=w.min_steer, max_steer=w.max_steer, pos_tol=rc["position_target_tolerance"],
+        heading_tol=rc["heading_target_tolerance"], speed_tol=rc["speed_target_tolerance"],
+        goal_dist_scaling=rc.get("shaped_goal_distance_scaling", 1.0), reward_scaling=rc["reward_scaling"])

@@ -34,7 +34,7 @@ ROAD_TYPES = {"none": 0, "lane": 1, "road_line": 2, "road_edge": 3, "stop_sign":
 def make_scene(scene_id: int, n_vehicles: int = 64, n_roads: int = 4, n_chunks: int = 8, steps: int = 91,
                frac_short: float = 0.1, frac_parked: float = 0.0, road_spacing: float = 25.0,
                pts_spacing: float = 0.5, seed: int = 1234, world_offset: bool = True,
-               speed_range=(3.0, 15.0)):
+               speed_range=(3.0, 15.0), lane_ids=None):
     """Returns a dict with keys ``json`` (Nocturne schema) and ``preproc`` (pkl schema)."""
     rng = np.random.default_rng(seed + scene_id)
     ox, oy = (rng.uniform(-5000.0, 5000.0, size=2) if world_offset else (0.0, 0.0))
@@ -52,7 +52,8 @@ def make_scene(scene_id: int, n_vehicles: int = 64, n_roads: int = 4, n_chunks: 
         for li in range(5):
             yl = yc + (li - 2) * LANE_W
             lines.append(("lane", yl))
-            lane_specs.append((yl, 0.0 if li >= 3 else math.pi))
+            if lane_ids is None or li in lane_ids:  # lanes that may carry vehicles
+                lane_specs.append((yl, 0.0 if li >= 3 else math.pi))
         # NB: lanes 0..2 (below the road_line) drive -x, lanes 3..4 drive +x
         for typ, y in lines:
             for c in range(n_chunks):

@@ -1,0 +1,160 @@
+/* ctrlsim_b200 - C ABI of the B200-native CtRL-Sim closed-loop rollout hot path.
+ *
+ * The reference exposes this path through Python objects only: the pybind11 simulator binding
+ * (nocturne/pybind11/src/{simulation,scenario,object,vehicle}.cc) and the Policy / PolicyEvaluator classes
+ * (policies/policy.py:8-154, policies/autoregressive_policy.py:10-274, evaluators/policy_evaluator.py:27-44,426-595).
+ * This header is the flat boundary a maintainer binds instead (ctypes stub in INTEGRATION.md): plain pointers and
+ * sizes, no torch types.  Unless a parameter says "host", every pointer is a DEVICE pointer owned by the caller and
+ * every call is asynchronous on the given cudaStream_t (passed as void*).  Calls return 0 or a negative status;
+ * ctrlsim_last_error() gives the message of the last failure on the calling thread.  A handle is bound to one GPU
+ * and may be used from one host thread at a time.
+ */
+#ifndef CTRLSIM_B200_H
+#define CTRLSIM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTRLSIM_ABI_VERSION 1
+#define CTRLSIM_MAX_VEH 64 /* vehicles per scene supported by the grouping kernel (bitmask width) */
+
+/* Model / episode geometry. The kernels are specialised to the reference defaults (cfgs/model/base.yaml:1-9,
+ * cfgs/dataset/waymo/base.yaml:4,38-43, cfgs/config.yaml:44-46); ctrlsim_create rejects anything else. */
+typedef struct CtrlSimConfig {
+  int32_t abi_version;
+  int32_t hidden_dim, num_heads, dim_feedforward, enc_layers, dec_layers;       /* 256, 8, 1024, 2, 4 */
+  int32_t max_agents, context_len, max_polylines, pts_per_polyline;              /* 24, 32, 200, 100 */
+  int32_t n_action_bins, n_steer_bins, n_rtg_bins;                               /* 1000, 50, 350 */
+  int32_t steps, history_steps;                                                  /* 90, 10 */
+  float dt;                                                                      /* 0.1 */
+  double agent_dist_threshold;                                                   /* 60.0 */
+  double min_accel, max_accel, min_steer, max_steer;                             /* -10, 10, -0.7, 0.7 */
+  double pos_tol, heading_tol, speed_tol, goal_dist_scaling, reward_scaling;     /* rew_cfg, cfgs/config.yaml:72-90 */
+} CtrlSimConfig;
+
+/* A batch of S scenes resident in HBM (struct of arrays; N = max_veh, Pm = max_poly, E = max_seg, T1 = steps+1).
+ * "static" arrays are written once by the host loader; "state" arrays are owned by the library between calls. */
+typedef struct CtrlSimBatch {
+  int32_t n_scenes, max_veh, max_poly, max_seg;
+  /* ---- static scene data (replaces Scenario::LoadScenario, nocturne/cpp/src/scenario.cc:207-264,893-1057) ---- */
+  const int64_t* scene_id;    /* [S] global scene index (sampler counter word 0)                                  */
+  const int32_t* n_veh;       /* [S]                                                                               */
+  const float* veh_len;       /* [S,N]                                                                             */
+  const float* veh_wid;       /* [S,N]                                                                             */
+  const float* gt;            /* [S,N,T1,4] expert x, y, heading, speed (utils/sim.py:20-65)                       */
+  const uint8_t* gt_valid;    /* [S,N,T1]                                                                          */
+  const double* goal;         /* [S,N,4] goal x, y, heading, speed (evaluators/evaluator.py:60-76)                 */
+  const double* goal_norm;    /* [S,N] initial distance to goal (evaluator.py:79-84)                               */
+  const uint8_t* evaluated;   /* [S,N] 1 = policy-controlled                                                       */
+  const int32_t* eval_order;  /* [S,N] evaluated vehicle ids by descending GT length, -1 padded                    */
+  const double* road_xy;      /* [S,Pm,100,2] polyline points, world frame                                         */
+  const uint8_t* road_valid;  /* [S,Pm,100]                                                                        */
+  const int8_t* road_type;    /* [S,Pm] index of the one-hot road type, -1 = padding                               */
+  const int32_t* n_poly;      /* [S]                                                                               */
+  const float* segs;          /* [S,E,4] road_edge segments x0,y0,x1,y1 (scenario.cc:1037-1042)                    */
+  const int32_t* n_seg;       /* [S]                                                                               */
+  /* ---- simulator state (replaces the Box2D bodies + Nocturne objects) --------------------------------------- */
+  float* body;                /* [S,16,N] px,py,cx,cy,lcx,lcy,ang,vx,vy,om,sleep_t,thr,brk,steer,awake,pad         */
+  float* obj;                 /* [S,4,N]  x, y, heading, speed as reported by Vehicle::Step                        */
+  uint8_t* coll;              /* [S,2,N]  collision_type_veh / collision_type_edge flags of the current step       */
+  /* ---- policy state (replaces Policy.reset/update_state buffers, policies/policy.py:45-105) ------------------- */
+  double* hist_state;         /* [S,N,steps,8] x,y,vx,vy,yaw,len,wid,exist                                         */
+  double* hist_action;        /* [S,N,steps,2] applied accel, steer                                                */
+  int16_t* hist_rtg;          /* [S,N,steps,3] RTG bin indices ((0,35,35) where nothing was sampled)               */
+  uint64_t* relevant;         /* [S,N] sticky context membership bitmask (relevant_agent_idxs)                     */
+  double* next_action;        /* [S,N,2] next_acceleration / next_steering                                         */
+  /* ---- trace: everything vehicle_data_dict records (evaluators/policy_evaluator.py:69-96) --------------------- */
+  float* tr_pos;              /* [S,N,T1,2] */
+  float* tr_vel;              /* [S,N,T1,2] */
+  float* tr_heading;          /* [S,N,T1]   */
+  uint8_t* tr_exist;          /* [S,N,T1]   */
+  double* tr_action;          /* [S,N,T1,2] */
+  float* tr_reward;           /* [S,N,T1,8] */
+  double* tr_nearest;         /* [S,N,T1,2] simulated / ground-truth nearest-vehicle distance */
+  int16_t* tr_rtg_idx;        /* [S,N,steps,3] sampled RTG bins, -1 = not sampled this step */
+  int16_t* tr_act_idx;        /* [S,N,steps]   sampled action bin, -1 = none */
+  /* ---- per-step focal groups (autoregressive_policy.py:96-138), rebuilt by ctrlsim_plan_groups --------------- */
+  int32_t* n_groups;          /* [S]                                   */
+  int32_t* group_off;         /* [S+1] exclusive scan of n_groups      */
+  int32_t* group_focal;       /* [S,N]      scene-local group -> focal vehicle */
+  int32_t* group_members;     /* [S,N,24]   vehicle ids ascending, -1 padded   */
+  uint32_t* group_served;     /* [S,N]      bit k = member slot k is served by this group */
+  int32_t* group_scene;       /* [S*N] compact group -> scene          */
+  int32_t* group_local;       /* [S*N] compact group -> scene-local id */
+} CtrlSimBatch;
+
+/* Sampling / control knobs of AutoregressivePolicy (cfgs/policy/ctrl_sim.yaml:6-11). */
+typedef struct CtrlSimPolicyParams {
+  uint64_t seed;
+  double tilt[3];        /* goal, veh_veh, veh_edge */
+  float temperature;
+  int32_t tilt_enabled;
+} CtrlSimPolicyParams;
+
+typedef struct CtrlSim CtrlSim;
+
+const char* ctrlsim_last_error(void);
+int ctrlsim_abi_version(void);
+int ctrlsim_create(const CtrlSimConfig* cfg, CtrlSim** out);
+void ctrlsim_destroy(CtrlSim* h);
+
+/* Register one weight tensor (fp32, device) under its reference state-dict name (ctrlsim_b200/weights.py) or a
+ * "derived.*" name (host-side folding done by ctrlsim_b200/model.py). The handle keeps the pointer, not a copy. */
+int ctrlsim_load_weights(CtrlSim* h, const char* name, const float* ptr, int64_t count);
+int ctrlsim_finalize_weights(CtrlSim* h);
+
+/* Bytes of scratch ctrlsim_policy_step needs for `max_groups` focal groups processed together. */
+int64_t ctrlsim_workspace_bytes(const CtrlSim* h, int32_t max_groups);
+
+/* ---- simulator: replaces nocturne_cpp Simulation/Scenario/Vehicle for the evaluator loop ------------------- */
+/* S3: Vehicle::CreatePhysicsBody for every vehicle + the load-time UpdateCollision (vehicle.cc:137-179, scenario.cc:263) */
+int ctrlsim_sim_reset(CtrlSim* h, CtrlSimBatch* b, void* stream);
+/* S5 + T1: update_vehicle_data_dict + Policy.update_state at step t (policy_evaluator.py:99-159, policy.py:68-105) */
+int ctrlsim_observe(CtrlSim* h, CtrlSimBatch* b, int32_t t, void* stream);
+/* T2: greedy focal grouping of AutoregressivePolicy.get_data; writes group tables and *n_groups_total (device int32) */
+int ctrlsim_plan_groups(CtrlSim* h, CtrlSimBatch* b, int32_t t, int32_t* n_groups_total, void* stream);
+/* T3 + M2-M9 for compact groups [g0, g0+ng): tokenise, encode map + scene, decode, sample RTGs, second pass, sample
+ * actions -> next_action (AutoregressivePolicy.predict, autoregressive_policy.py:168-253). Two-phase because RTG
+ * resolution needs pass 1 of every group of a scene: phase 0 = pass 1 (logits), phase 1 = resolve RTGs (whole batch),
+ * phase 2 = pass 2 + action sampling. ctrlsim_policy_step runs all phases over all groups in chunks. */
+int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* p, int32_t t, int32_t n_groups_total,
+                        void* workspace, int64_t workspace_bytes, int32_t chunk_groups, void* stream);
+/* S6 + S1-S4: policy.act / apply_gt_action (inverse bicycle) then Scenario::Step (scenario.cc:266-292) */
+int ctrlsim_sim_step(CtrlSim* h, CtrlSimBatch* b, int32_t t, void* stream);
+/* S7: per-scene partial metrics + histograms (policy_evaluator.py:162-305). out_scene [S,8] double:
+ * goal_sum, n_agents, coll_mean, off_mean, has_agents, ade_sum, fde_sum, pad; out_hist [8,200] int64 (sim/gt x 4). */
+int ctrlsim_metrics(CtrlSim* h, const CtrlSimBatch* b, double* out_scene, int64_t* out_hist, void* stream);
+
+/* ---- building blocks exported for parity tests and for callers that schedule the model themselves ---------- */
+int ctrlsim_linear(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                   int32_t relu, void* stream);
+int ctrlsim_layernorm(const float* X, const float* R, const float* gamma, const float* beta, float* Y, int32_t M,
+                      int32_t relu, void* stream);
+int ctrlsim_attn_padded(const float* Q, int32_t ldq, const float* K, const float* V, int32_t ldkv,
+                        const uint8_t* key_pad, float* O, int32_t G, int32_t Lq, int32_t Lk, void* stream);
+int ctrlsim_attn_causal(const float* QKV, float* O, int32_t G, int32_t n_t, void* stream);
+int ctrlsim_map_pool(const float* feats, const uint8_t* pt_valid, const uint8_t* poly_valid, const float* U,
+                     float* pooled, int32_t n_poly, void* stream);
+/* one categorical draw per row with the explicit sampler: x [rows, n] fp32 (already tilted / tempered) */
+int ctrlsim_sample_rows(const float* x, int32_t rows, int32_t n, int32_t ld, int32_t stride, uint64_t seed,
+                        const uint32_t* counters /* [rows,4] */, int32_t* out_idx, void* stream);
+/* full first-pass forward on caller-provided tokens of G groups (parity tests against the reference modules):
+ * writes rtg logits [G,24,1050] and, after overwriting the rtg tokens at `ti` with rtg_idx [G,24,3], action logits
+ * [G,24,1000]. Token arrays follow the reference MotionData layout (float32 / int32). */
+int ctrlsim_forward_tokens(CtrlSim* h, int32_t G, int32_t n_t, int32_t ti, const float* agent_states /*[G,24,32,8]*/,
+                           const float* agent_types /*[G,24,5]*/, const float* goals /*[G,24,5]*/,
+                           const int32_t* actions /*[G,24,32]*/, const int32_t* rtgs /*[G,24,32,3]*/,
+                           const int32_t* timesteps /*[G,32]*/, const float* road_points /*[G,200,100,3]*/,
+                           const int32_t* road_types /*[G,200]*/, const int32_t* rtg_idx_pass2 /*[G,24,3]*/,
+                           float* rtg_logits, float* action_logits, void* workspace, int64_t workspace_bytes,
+                           void* stream);
+/* geometry known-answer entry points (nocturne/cpp/tests/src/geometry/{polygon,intersection}_test.cc) */
+int ctrlsim_geom_poly_poly(const float* xy1, int32_t n1, const float* xy2, int32_t n2, int32_t* out, void* stream);
+int ctrlsim_geom_poly_seg(const float* xy, int32_t n, const float* seg, int32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

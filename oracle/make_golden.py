@@ -1,0 +1,91 @@
+"""ORACLE (test infrastructure only): generate the committed fixtures under tests/golden/ from the REFERENCE itself.
+
+    python -m oracle.make_golden [--only NAME]
+
+Runs in the build container only (needs /root/reference and oracle/_ref built by `make -C oracle ref`).  Each fixture
+is a compressed npz holding what the unmodified reference evaluator produced on a synthetic scene (trajectories,
+applied actions, rewards, sampled indices, focal groups, logits at a few steps, final metrics) plus the generator
+arguments needed to rebuild the identical scene and weights anywhere.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+FIXTURES = {
+    # BASELINE config 1 ("plumbing"): 1 scene, 8 vehicles, 32 polylines (8 road_edge). The reference cannot run fewer
+    # than 32 steps (its causal mask is built for 2304 tokens), so the full 90-step episode is recorded and the
+    # 10-step prefix is what the config-1 test checks.
+    "plumbing": dict(scene=dict(scene_id=0, n_vehicles=8, n_roads=1, n_chunks=4), weights=dict(seed=0),
+                     tilts=(0, 0, 0), logit_steps=(0, 9, 31, 32, 60)),
+    # crowded: more than 24 vehicles inside 60 m and more than 200 polylines -> agent cap, polyline trimming, several
+    # focal groups with shared members, tilted RTG sampling, low-entropy actions (still_bias) for long contact-free runs.
+    "crowded": dict(scene=dict(scene_id=7, n_vehicles=30, n_roads=4, n_chunks=8, road_spacing=14.0),
+                    weights=dict(seed=1, still_bias=9.0), tilts=(10, -10, 25), logit_steps=(0, 10, 33)),
+    # sparse: one vehicle per road, all driving +x, near-deterministic coasting -> no Box2D contact for the whole
+    # episode, so the free-running comparison covers the sliding-window phase (t >= 32) and the end-of-episode metrics.
+    "sparse": dict(scene=dict(scene_id=3, n_vehicles=6, n_roads=6, n_chunks=4, lane_ids=[3], frac_short=0.34,
+                              speed_range=(5.0, 12.0)),
+                   weights=dict(seed=2, still_bias=12.0), tilts=(0, 0, 0), logit_steps=(9, 31, 32, 33, 89)),
+}
+
+
+def pack(rec, metrics, spec):
+    out = {k: v for k, v in rec.items() if isinstance(v, np.ndarray)}
+    G = max(len(g) for g in rec["groups"])
+    steps = len(rec["groups"])
+    focal = -np.ones((steps, G), np.int32)
+    members = -np.ones((steps, G, 24), np.int32)
+    served = -np.ones((steps, G, 24), np.int32)
+    for t, gs in enumerate(rec["groups"]):
+        for g, d in enumerate(gs):
+            focal[t, g] = d["focal"]
+            members[t, g] = d["members"]
+            served[t, g, : len(d["served"])] = d["served"]
+    out.update(group_focal=focal, group_members=members, group_served=served)
+    for (t, g), ent in rec["logits"].items():
+        out[f"rtg_logits_{t}_{g}"] = ent["rtg_logits"]
+        out[f"action_logits_{t}_{g}"] = ent["action_logits"]
+        if "inputs" in ent and g == 0:
+            for k, v in ent["inputs"].items():
+                out[f"in_{t}_{k}"] = v.astype(np.float32) if v.dtype == np.float64 else v
+            out[f"in_{t}_rtgs_pass2"] = ent["rtgs_pass2"]
+    out["metrics_json"] = np.frombuffer(json.dumps(metrics).encode(), dtype=np.uint8)
+    out["spec_json"] = np.frombuffer(json.dumps(spec).encode(), dtype=np.uint8)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    sys.path.insert(0, ROOT)
+    from ctrlsim_b200.config import default_config
+    from ctrlsim_b200.synth import make_scene
+    from ctrlsim_b200.weights import make_weights
+    from oracle.ref_harness import run_reference
+
+    os.makedirs(GOLDEN, exist_ok=True)
+    for name, spec in FIXTURES.items():
+        if args.only and name != args.only:
+            continue
+        t0 = time.time()
+        sc = make_scene(**spec["scene"])
+        weights = make_weights(default_config(), **spec["weights"])
+        metrics, recs = run_reference([sc], weights=weights, seed=0, tilts=spec["tilts"],
+                                      logit_steps=spec["logit_steps"])
+        np.savez_compressed(os.path.join(GOLDEN, f"rollout_{name}.npz"), **pack(recs[0], metrics, spec))
+        print(f"[golden] {name}: {time.time() - t0:.1f}s metrics={metrics}", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,280 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Everything goes through the C-ABI of libctrlsim_b200.so.
+
+Checkers: torch fp32 for the floating-point building blocks, the oracle (oracle/*.py, CPU) and the committed
+reference fixtures (tests/golden/, produced by the unmodified reference - oracle/make_golden.py)."""
+import ctypes as C
+import json
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-4   # |logit_gpu - logit_reference_fp32|, logits are O(1..10)
+POS_TOL = 1e-3     # metres, BASELINE.json north_star
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ctrlsim_b200 import lib as L
+    return L.load()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(rc, lib):
+    assert rc == 0, lib.ctrlsim_last_error()
+
+
+# ---------------------------------------------------------------------------------------------- building blocks
+@pytest.mark.parametrize("M,N,K,relu", [(1, 256, 256, False), (200, 768, 256, True), (333, 1050, 256, False),
+                                        (129, 256, 1024, False), (1000, 1000, 256, False), (77, 256, 2048, True)])
+def test_linear_matches_torch(lib, dev, M, N, K, relu):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(dev)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    Cc = torch.empty(M, N, device=dev)
+    _chk(lib.ctrlsim_linear(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cc.data_ptr(), M, N, K, int(relu), _stream()), lib)
+    ref = torch.nn.functional.linear(A.double(), W.double(), b.double())
+    ref = torch.relu(ref) if relu else ref
+    assert (Cc.double() - ref).abs().max().item() < 2e-5 * math.sqrt(K / 256)
+
+
+@pytest.mark.parametrize("M,res,relu", [(1, False, False), (1000, True, False), (257, True, True)])
+def test_layernorm_matches_torch(lib, dev, M, res, relu):
+    g = torch.Generator(device="cpu").manual_seed(M)
+    X = torch.randn(M, 256, generator=g).to(dev) * 3
+    R = torch.randn(M, 256, generator=g).to(dev) if res else None
+    gamma, beta = torch.randn(256, generator=g).to(dev), torch.randn(256, generator=g).to(dev)
+    Y = torch.empty_like(X)
+    _chk(lib.ctrlsim_layernorm(X.data_ptr(), R.data_ptr() if res else None, gamma.data_ptr(), beta.data_ptr(),
+                               Y.data_ptr(), M, int(relu), _stream()), lib)
+    ref = torch.nn.functional.layer_norm((X + R) if res else X, (256,), gamma, beta, 1e-5)
+    ref = torch.relu(ref) if relu else ref
+    assert (Y - ref).abs().max().item() < 2e-5
+
+
+def test_attn_padded_matches_torch(lib, dev):
+    G, Lq, Lk = 3, 150, 224
+    g = torch.Generator(device="cpu").manual_seed(1)
+    q = torch.randn(G, Lq, 256, generator=g).to(dev)
+    kv = torch.randn(G, Lk, 512, generator=g).to(dev)
+    pad = (torch.rand(G, Lk, generator=g) < 0.3).to(dev)
+    pad[:, 0] = False
+    O = torch.empty(G, Lq, 256, device=dev)
+    padu8 = pad.to(torch.uint8).contiguous()
+    _chk(lib.ctrlsim_attn_padded(q.data_ptr(), 256, kv.data_ptr(), kv.data_ptr() + 256 * 4, 512, padu8.data_ptr(),
+                                 O.data_ptr(), G, Lq, Lk, _stream()), lib)
+    qh = q.view(G, Lq, 8, 32).transpose(1, 2)
+    kh = kv[..., :256].reshape(G, Lk, 8, 32).transpose(1, 2)
+    vh = kv[..., 256:].reshape(G, Lk, 8, 32).transpose(1, 2)
+    s = (qh / math.sqrt(32)) @ kh.transpose(-1, -2)
+    s = s.masked_fill(pad[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(G, Lq, 256)
+    assert (O - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("n_t", [1, 2, 7, 32])
+def test_attn_causal_matches_mask_rule(lib, dev, n_t):
+    """Rule M1 evaluated arithmetically == the dense additive mask of utils/train_utils.py:82-130 (pinned against the
+    reference's get_causal_mask in tests/test_oracle.py)."""
+    from oracle.model_port import causal_mask_rule
+    G, L = 2, n_t * 72
+    g = torch.Generator(device="cpu").manual_seed(n_t)
+    qkv = torch.randn(G, L, 768, generator=g).to(dev)
+    O = torch.empty(G, L, 256, device=dev)
+    _chk(lib.ctrlsim_attn_causal(qkv.data_ptr(), O.data_ptr(), G, n_t, _stream()), lib)
+    allowed = causal_mask_rule(24, n_t, 3).to(dev)
+    qh = qkv[..., :256].reshape(G, L, 8, 32).transpose(1, 2)
+    kh = qkv[..., 256:512].reshape(G, L, 8, 32).transpose(1, 2)
+    vh = qkv[..., 512:].reshape(G, L, 8, 32).transpose(1, 2)
+    s = ((qh / math.sqrt(32)) @ kh.transpose(-1, -2)).masked_fill(~allowed, float("-inf"))
+    ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(G, L, 256)
+    assert (O - ref).abs().max().item() < 3e-5
+
+
+def test_map_pool_matches_torch(lib, dev):
+    n_poly = 301  # more polylines than SMs: exercises the 2-stage TMA ring and the phase bookkeeping
+    g = torch.Generator(device="cpu").manual_seed(5)
+    feats = torch.randn(n_poly, 100, 256, generator=g).to(dev)
+    U = (torch.randn(8, 256, generator=g) * 0.1).to(dev)
+    valid = (torch.rand(n_poly, 100, generator=g) < 0.8)
+    valid[3] = False          # all points masked -> point 0 is un-masked (map_encoder.py:31)
+    valid[4, 1:] = False
+    poly_valid = torch.ones(n_poly, dtype=torch.uint8)
+    poly_valid[7] = 0
+    pooled = torch.full((n_poly, 8, 256), float("nan"), device=dev)
+    v8 = valid.to(torch.uint8).to(dev)
+    pv = poly_valid.to(dev)
+    _chk(lib.ctrlsim_map_pool(feats.data_ptr(), v8.data_ptr(), pv.data_ptr(), U.data_ptr(), pooled.data_ptr(), n_poly,
+                              _stream()), lib)
+    torch.cuda.synchronize()
+    mask = ~valid.to(dev)
+    mask[mask.all(-1), 0] = False
+    s = torch.einsum("npd,hd->nhp", feats, U).masked_fill(mask[:, None, :], float("-inf"))
+    ref = torch.einsum("nhp,npd->nhd", torch.softmax(s, -1), feats)
+    ref[7] = 0
+    assert torch.isfinite(pooled).all()
+    assert (pooled - ref).abs().max().item() < 2e-5
+
+
+def test_sampler_bit_exact_vs_oracle(lib, dev):
+    """Given identical fp32 inputs the device sampler returns exactly the oracle's index (integer CDF, explicit exp)."""
+    from oracle import sampler
+    rng = np.random.default_rng(0)
+    for n, stride in ((1000, 1), (350, 3)):
+        rows = 64
+        x = (rng.standard_normal((rows, n * stride)) * rng.uniform(0.5, 8.0, (rows, 1))).astype(np.float32)
+        ctr = rng.integers(0, 2 ** 31, (rows, 4)).astype(np.uint32)
+        xd = torch.from_numpy(x).to(dev)
+        cd = torch.from_numpy(ctr.view(np.int32)).to(dev)
+        out = torch.empty(rows, dtype=torch.int32, device=dev)
+        seed = 0x1234_5678_9ABC
+        _chk(lib.ctrlsim_sample_rows(xd.data_ptr(), rows, n, n * stride, stride, seed, cd.data_ptr(), out.data_ptr(),
+                                     _stream()), lib)
+        got = out.cpu().numpy()
+        want = np.array([sampler.sample_from_x(x[r, ::stride][:n], seed, *[int(c) for c in ctr[r]]) for r in range(rows)])
+        assert (got == want).all(), (got, want)
+
+
+def test_geometry_known_answers(lib, dev):
+    """Reference KATs: nocturne/cpp/tests/src/geometry/polygon_test.cc:60-86, intersection_test.cc:52-76."""
+    eps = 1e-5
+
+    def pp(a, b):
+        A, B = torch.tensor(a, dtype=torch.float32, device=dev), torch.tensor(b, dtype=torch.float32, device=dev)
+        o = torch.zeros(1, dtype=torch.int32, device=dev)
+        _chk(lib.ctrlsim_geom_poly_poly(A.data_ptr(), len(a), B.data_ptr(), len(b), o.data_ptr(), _stream()), lib)
+        return bool(o.item())
+
+    def ps(a, s0, s1):
+        A = torch.tensor(a, dtype=torch.float32, device=dev)
+        Sg = torch.tensor([*s0, *s1], dtype=torch.float32, device=dev)
+        o = torch.zeros(1, dtype=torch.int32, device=dev)
+        _chk(lib.ctrlsim_geom_poly_seg(A.data_ptr(), len(a), Sg.data_ptr(), o.data_ptr(), _stream()), lib)
+        return bool(o.item())
+    sq = [(0, 0), (1, 0), (1, 1), (0, 1)]
+    assert not pp(sq, [(1, 2), (2, 1), (2, 2)]) and not pp([(1, 2), (2, 1), (2, 2)], sq)
+    assert pp(sq, [(1 - eps, 1 - eps), (2, 0), (2, 2)]) and pp([(1 - eps, 1 - eps), (2, 0), (2, 2)], sq)
+    assert pp(sq, [(1, 1), (2, 0), (2, 2)]) and pp([(1, 1), (2, 0), (2, 2)], sq)   # touching vertex = intersects
+    dia = [(1, 0), (0, 1), (-1, 0), (0, -1)]
+    assert ps(dia, (0, 0.5), (0, -0.5)) and ps(dia, (-0.5, -0.5), (-0.5, -1.0))
+    assert ps(dia, (-1, 0.5), (1, 1)) and ps(dia, (1, 1), (-1, -1))
+    assert not ps(dia, (-1, -1 - eps), (1, -1 - eps)) and not ps(dia, (-3, 0.5), (-2, 1))
+
+
+# ---------------------------------------------------------------------------------------------- network vs reference
+def _model(cfg, spec, dev):
+    from ctrlsim_b200.model import DeviceModel
+    from ctrlsim_b200.weights import make_weights
+    return DeviceModel(cfg, make_weights(cfg, **spec["weights"]), dev)
+
+
+@pytest.mark.parametrize("name", ["plumbing", "crowded", "sparse"])
+def test_forward_matches_reference_logits(cfg, dev, name):
+    """Same tokens in -> RTG logits (pass 1) and action logits (pass 2, incremental) of the reference CtRLSim.forward."""
+    g, spec, _ = load_golden(name)
+    model = _model(cfg, spec, dev)
+    for t in spec["logit_steps"]:
+        n_t = min(t + 1, 32)
+        ti = n_t - 1
+        data = {k: g[f"in_{t}_{k}"][None] for k in ("agent_states", "agent_types", "goals", "actions", "road_points",
+                                                    "road_types")}
+        data["rtgs"] = g[f"in_{t}_rtgs_pass1"][None]
+        data["timesteps"] = g[f"in_{t}_timesteps"][None][:, 0, :, 0]
+        r2 = g[f"in_{t}_rtgs_pass2"][None][:, :, ti, :]
+        rtg_logits, act_logits = model.forward_tokens(data, n_t, r2)
+        n_real = int((g[f"in_{t}_agent_types"].sum(-1) > 0).sum())
+        d_rtg = np.abs(rtg_logits[0, :n_real] - g[f"rtg_logits_{t}_0"][:n_real]).max()
+        d_act = np.abs(act_logits[0, :n_real] - g[f"action_logits_{t}_0"][:n_real]).max()
+        assert d_rtg < LOGIT_TOL and d_act < LOGIT_TOL, (name, t, d_rtg, d_act)
+
+
+# ---------------------------------------------------------------------------------------------- closed loop vs reference
+def _rollout(cfg, spec, dev, max_steps=None):
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    sc = make_scene(**spec["scene"])
+    model = _model(cfg, spec, dev)
+    tl = spec["tilts"]
+    pol = B200Policy(cfg, "synthetic", model, tilt_dict={"tilt": True, "goal_tilt": tl[0], "veh_veh_tilt": tl[1],
+                                                         "veh_edge_tilt": tl[2]}, seed=0)
+    ev = B200PolicyEvaluator(cfg, pol, scenes=[sc])
+    b = ev.build_batch(eval_threshold=64)
+    ev.rollout(b, max_steps=max_steps)
+    torch.cuda.synchronize()
+    return ev, b, b.trace()
+
+
+def _first_contact(g):
+    cv = (g["reward"][:, :, 6] * g["existence"]).any(0)
+    idx = np.where(cv)[0]
+    return int(idx[0]) if len(idx) else 91
+
+
+@pytest.mark.parametrize("name", ["plumbing", "crowded", "sparse"])
+def test_rollout_matches_reference(cfg, dev, name):
+    """Free-running closed loop vs the unmodified reference evaluator on the same scene JSON, weights and sampler seed.
+    Compared up to the first vehicle-vehicle contact (Box2D's contact response is not modelled)."""
+    g, spec, ref_metrics = load_golden(name)
+    n = g["pos"].shape[0]
+    tc = _first_contact(g)
+    ev, b, tr = _rollout(cfg, spec, dev, max_steps=None if tc > 90 else tc)
+    T = min(tc, 90)
+    ex = g["existence"][:, :T].astype(bool)
+    assert (tr["tr_exist"][0, :n, :T] == g["existence"][:, :T]).all()
+    # sampled indices: bit-exact under the shared explicit sampler
+    assert (tr["tr_rtg_idx"][0, :n, :T].transpose(1, 0, 2) == g["rtg_idx"][:T]).all()
+    assert (tr["tr_act_idx"][0, :n, :T].T == g["act_idx"][:T]).all()
+    dpos = np.abs(tr["tr_pos"][0, :n, :T].astype(np.float64) - g["pos"][:, :T])[ex].max()
+    dhead = np.abs(tr["tr_heading"][0, :n, :T].astype(np.float64) - g["heading"][:, :T])[ex].max()
+    dvel = np.abs(tr["tr_vel"][0, :n, :T].astype(np.float64) - g["vel"][:, :T])[ex].max()
+    assert dpos < POS_TOL and dhead < 1e-5 and dvel < 1e-4, (dpos, dhead, dvel)
+    dacc = np.abs(tr["tr_action"][0, :n, :T] - np.stack([g["accel"], g["steer"]], -1)[:, :T])[ex].max()
+    assert dacc < 1e-4, dacc
+    drew = np.abs(tr["tr_reward"][0, :n, :T].astype(np.float64) - g["reward"][:, :T])[ex].max()
+    assert drew < 1e-5, drew
+    dnd = np.abs(tr["tr_nearest"][0, :n, :T, 0] - g["nearest_dist"][:, :T])[ex].max()
+    assert dnd < 1e-3, dnd
+    if tc > 90:  # whole episode contact-free: the summary metrics must match the reference's compute_metrics
+        m = ev.metrics_from_summary(ev.summarize(b))
+        for k, v in ref_metrics.items():
+            assert abs(m[k] - v) < 1e-4 * max(1.0, abs(v)), (k, m[k], v)
+
+
+def test_rollout_matches_oracle_port_multi_scene(cfg, dev):
+    """Batched rollout of several scenes == oracle port run scene by scene (first 6 steps; covers batching/compaction)."""
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    from ctrlsim_b200.weights import make_weights
+    from ctrlsim_b200.model import DeviceModel
+    from oracle.model_port import ModelPort
+    from oracle.policy_port import RolloutPort
+    weights = make_weights(cfg, seed=3, still_bias=6.0)
+    scenes = [make_scene(20 + i, n_vehicles=5 + 3 * i, n_roads=2, n_chunks=3) for i in range(3)]
+    steps = 6
+    pol = B200Policy(cfg, "synthetic", DeviceModel(cfg, weights, dev), seed=7)
+    ev = B200PolicyEvaluator(cfg, pol, scenes=scenes)
+    b = ev.build_batch(eval_threshold=64)
+    ev.rollout(b, max_steps=steps)
+    tr = b.trace()
+    port = RolloutPort(cfg, ModelPort(cfg, weights), seed=7, eval_threshold=64)
+    for s, sc in enumerate(scenes):
+        rec = port.run_scene(s, sc["json"], sc["preproc"], max_steps=steps)
+        n = rec["n"]
+        assert (tr["tr_act_idx"][s, :n, :steps].T == rec["act_idx"][:steps]).all()
+        assert (tr["tr_rtg_idx"][s, :n, :steps].transpose(1, 0, 2) == rec["rtg_idx"][:steps]).all()
+        assert np.abs(tr["tr_pos"][s, :n, :steps] - rec["pos"][:, :steps]).max() < POS_TOL
