@@ -12,6 +12,7 @@
 #include "model_ws.h"
 
 namespace ctrlsim {
+long long g_launch_count = 0;
 thread_local std::string g_last_error;
 int set_error(int code, const char* fmt, ...) {
   char buf[512];
@@ -220,7 +221,18 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
     }
     s0 = s1;
   }
+  g_prof.flush(st);
   return 0;
+}
+
+long long ctrlsim_launch_count(void) { return g_launch_count; }
+void ctrlsim_profile_enable(int32_t on) {
+  g_prof.on = on != 0;
+  if (on) for (int c = 0; c < PROF_NCAT; ++c) { g_prof.tot_ms[c] = 0; g_prof.tot_work[c] = 0; g_prof.count[c] = 0; }
+}
+/* out[cat*3 + {0,1,2}] = total ms, total work (flops or bytes), launches; cat: 0 gemm, 1 map_pool, 2 attn_causal, 3 attn_cross */
+void ctrlsim_profile_read(double* out) {
+  for (int c = 0; c < PROF_NCAT; ++c) { out[c * 3] = g_prof.tot_ms[c]; out[c * 3 + 1] = g_prof.tot_work[c]; out[c * 3 + 2] = (double)g_prof.count[c]; }
 }
 
 int ctrlsim_linear(const float* Ain, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,

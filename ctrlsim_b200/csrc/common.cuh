@@ -31,8 +31,11 @@ constexpr float LN_EPS = 1e-5f;
 extern thread_local std::string g_last_error;
 int set_error(int code, const char* fmt, ...);
 
+extern long long g_launch_count;  // kernels launched by this library (bench.py reports it as gpu_launches)
+
 #define CS_CHECK_LAUNCH(name)                                                          \
   do {                                                                                 \
+    ++::ctrlsim::g_launch_count;                                                       \
     cudaError_t e__ = cudaGetLastError();                                              \
     if (e__ != cudaSuccess) return ::ctrlsim::set_error(-5, "%s: %s", name, cudaGetErrorString(e__)); \
   } while (0)

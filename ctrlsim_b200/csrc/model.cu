@@ -22,13 +22,44 @@ namespace ctrlsim {
     if (rc__ != 0) return rc__; \
   } while (0)
 
+// ---- optional per-category CUDA-event timing (bench.py roofline figures) ---------------------------------------------
+Prof g_prof;
+void Prof::begin(int cat, double work, cudaStream_t st) {
+  if (!on) return;
+  Rec r;
+  r.cat = cat; r.work = work;
+  if (pool.size() < 2) { for (int i = 0; i < 256; ++i) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); } }
+  r.a = pool.back(); pool.pop_back();
+  r.b = pool.back(); pool.pop_back();
+  cudaEventRecord(r.a, st);
+  recs.push_back(r);
+}
+void Prof::end(cudaStream_t st) {
+  if (!on) return;
+  cudaEventRecord(recs.back().b, st);
+}
+void Prof::flush(cudaStream_t st) {
+  if (!on || recs.empty()) return;
+  cudaStreamSynchronize(st);
+  for (auto& r : recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    tot_ms[r.cat] += ms; tot_work[r.cat] += r.work; ++count[r.cat];
+    pool.push_back(r.a); pool.push_back(r.b);
+  }
+  recs.clear();
+}
+
 static int gemm(const float* Ain, const float* W, const float* bias, float* C, int M, int N, int K, int lda, int ldw,
                 int ldc, bool relu, cudaStream_t st, const float* table = nullptr, const int* tidx = nullptr,
                 int ldt = 0, const int* agather = nullptr) {
   GemmArgs g;
   g.A = Ain; g.W = W; g.bias = bias; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldc = ldc;
   g.relu = relu; g.table = table; g.tidx = tidx; g.ldt = ldt; g.agather = agather;
-  return launch_gemm(g, st);
+  g_prof.begin(PROF_GEMM, 2.0 * M * (double)N * K, st);
+  const int rc = launch_gemm(g, st);
+  g_prof.end(st);
+  return rc;
 }
 static int ln(const float* X, const float* R, const LnW& w, float* Y, int M, bool relu, cudaStream_t st) {
   return launch_layernorm(X, R, w.w, w.b, Y, M, H, H, H, relu, st);
@@ -106,7 +137,10 @@ int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm
   CS_TRY(launch_map_flags(ws.tk.map_pts, ws.pt_valid, ws.poly_valid, Rp, st));
   CS_TRY(launch_small_mlp1(3, ws.tk.map_pts, w.road_pts, ws.h1, (size_t)Rpt, st));
   CS_TRY(gemm(ws.h1, w.road_pts.w3, w.road_pts.b3, ws.feats, Rpt, H, H, H, H, H, false, st));
+  // algorithmic bytes per polyline: the 100x256 fp32 feature tile + 100 validity bytes in, 8x256 fp32 pooled out
+  g_prof.begin(PROF_MAP_POOL, (double)Rp * (NP * H * 4.0 + NP + NH * H * 4.0), st);
   CS_TRY(launch_map_pool(ws.feats, ws.pt_valid, ws.poly_valid, w.pool_U, ws.pooled, Rp, n_sm, st));
+  g_prof.end(st);
   CS_TRY(gemm(ws.pooled, w.pool_W, w.pool_b, ws.pe_a, Rp, H, NH * H, NH * H, NH * H, H, false, st));
   CS_TRY(ln(ws.pe_a, nullptr, w.map_n1, ws.pe_b, Rp, false, st));
   CS_TRY(gemm(ws.pe_b, w.map_feats.w0, w.map_feats.b0, ws.pe_a, Rp, H, H, H, H, H, false, st));
@@ -142,12 +176,20 @@ int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm
   for (int l = 0; l < N_DEC; ++l) {
     const DecLayerW& d = w.dec[l];
     CS_TRY(gemm(ws.X, d.sa.in_w, d.sa.in_b, ws.QKV[l], R, 3 * H, H, H, H, 3 * H, false, st));
+    {  // useful flops: 4 * d_h per (row, head, visible key); visible keys per step tw: 72*tw + 24 (+0/1/2 own tokens)
+      double vis = 0;
+      for (int tw = 0; tw < n_t; ++tw) vis += (double)TOK_T * (TOK_T * tw + A) + 3.0 * A;
+      g_prof.begin(PROF_ATTN_CAUSAL, (double)G * NH * vis * 4.0 * DH, st);
+    }
     CS_TRY(launch_attn_causal(ws.QKV[l], ws.att, G, n_t, st));
+    g_prof.end(st);
     CS_TRY(gemm(ws.att, d.sa.out_w, d.sa.out_b, ws.tmp, R, H, H, H, H, H, false, st));
     CS_TRY(ln(ws.X, ws.tmp, d.n1, ws.X, R, false, st));
     CS_TRY(gemm(ws.X, d.ca.in_w, d.ca.in_b, ws.q_c, R, H, H, H, H, H, false, st));
     CS_TRY(gemm(ws.mem, d.ca.in_w + (size_t)H * H, d.ca.in_b + H, ws.kv_c[l], Rm, 2 * H, H, H, H, 2 * H, false, st));
+    g_prof.begin(PROF_ATTN_CROSS, (double)G * NH * Lcur * MEM * 4.0 * DH, st);
     CS_TRY(launch_attn_padded(ws.q_c, H, ws.kv_c[l], ws.kv_c[l] + H, 2 * H, ws.pad, ws.att, H, G, Lcur, MEM, st));
+    g_prof.end(st);
     CS_TRY(gemm(ws.att, d.ca.out_w, d.ca.out_b, ws.tmp, R, H, H, H, H, H, false, st));
     CS_TRY(ln(ws.X, ws.tmp, d.n2, ws.X, R, false, st));
     CS_TRY(gemm(ws.X, d.l1w, d.l1b, ws.ff, R, FF, H, H, H, FF, true, st));

@@ -1,5 +1,7 @@
 // Scratch layout of one chunk of focal groups (all device memory, carved from the caller's workspace).
 #pragma once
+#include <vector>
+
 #include "model.h"
 
 namespace ctrlsim {
@@ -25,6 +27,20 @@ struct Workspace {
   // Assign pointers for Gc groups inside [base, base+bytes); base == nullptr only measures. Returns bytes needed.
   size_t carve(void* base, size_t bytes, int Gc);
 };
+
+enum { PROF_GEMM, PROF_MAP_POOL, PROF_ATTN_CAUSAL, PROF_ATTN_CROSS, PROF_NCAT };
+struct Prof {
+  struct Rec { int cat; double work; cudaEvent_t a, b; };
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  std::vector<Rec> recs;
+  double tot_ms[PROF_NCAT] = {0, 0, 0, 0}, tot_work[PROF_NCAT] = {0, 0, 0, 0};
+  long long count[PROF_NCAT] = {0, 0, 0, 0};
+  void begin(int cat, double work, cudaStream_t st);
+  void end(cudaStream_t st);
+  void flush(cudaStream_t st);
+};
+extern Prof g_prof;
 
 int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm, cudaStream_t st);
 int forward_pass2(const ModelWeights& w, Workspace& ws, int G, int n_t, cudaStream_t st);

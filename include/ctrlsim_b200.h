@@ -127,6 +127,14 @@ int ctrlsim_sim_step(CtrlSim* h, CtrlSimBatch* b, int32_t t, void* stream);
  * goal_sum, n_agents, coll_mean, off_mean, has_agents, ade_sum, fde_sum, pad; out_hist [8,200] int64 (sim/gt x 4). */
 int ctrlsim_metrics(CtrlSim* h, const CtrlSimBatch* b, double* out_scene, int64_t* out_hist, void* stream);
 
+/* ---- instrumentation (bench.py): kernels launched so far by this library in this process, and optional CUDA-event
+ * timing of the hot kernel classes inside ctrlsim_policy_step. out has 12 doubles: for category c in (0 linear GEMM,
+ * 1 map_pool, 2 decoder self-attention, 3 decoder cross-attention): total ms, total work (flops; bytes for map_pool),
+ * number of launches. */
+long long ctrlsim_launch_count(void);
+void ctrlsim_profile_enable(int32_t on);
+void ctrlsim_profile_read(double* out);
+
 /* ---- building blocks exported for parity tests and for callers that schedule the model themselves ---------- */
 int ctrlsim_linear(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
                    int32_t relu, void* stream);
