@@ -1,0 +1,273 @@
+"""CPU tests (no GPU): the oracle is pinned against the reference's own known answers and against fixtures produced by
+the unmodified reference (tests/golden/, oracle/make_golden.py); plus host logic and the C-ABI surface."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+# ------------------------------------------------------------------------------------------------ sampler / RNG
+def test_philox_known_answer_vectors():
+    """Random123 KAT for philox4x32-10."""
+    from ctrlsim_b200.philox import philox4x32
+    z = philox4x32(np.zeros(4, np.uint32), np.zeros(2, np.uint32))
+    assert [hex(int(v)) for v in z] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    f = philox4x32(np.full(4, 0xFFFFFFFF, np.uint32), np.full(2, 0xFFFFFFFF, np.uint32))
+    assert [hex(int(v)) for v in f] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+
+
+def test_sampler_is_a_faithful_multinomial():
+    from oracle import sampler
+    x = np.array([0.0, 1.0, 2.0, -1.0, 0.5], np.float32)
+    w = sampler.weights_from_x(x).astype(np.float64)
+    p = np.exp(x.astype(np.float64) - 2.0)
+    assert np.abs(w / w.sum() - p / p.sum()).max() < 1e-6
+    d = np.linspace(-80, 0, 4001).astype(np.float32)
+    assert np.abs(sampler.exp_spec(d) / np.exp(d.astype(np.float64)) - 1).max() < 3e-7
+    draws = np.array([sampler.sample_from_x(x, 3, 0, a, 0, 3) for a in range(4000)])
+    freq = np.bincount(draws, minlength=5) / 4000.0
+    assert np.abs(freq - p / p.sum()).max() < 0.03
+    # tilt: the reference adds tilt * linspace(0,1,350) in float64 (dataset.py:342-348)
+    lg = np.zeros(350, np.float32)
+    assert sampler.rtg_x(lg, 10.0)[-1] == np.float32(10.0) and sampler.rtg_x(lg, 10.0)[0] == 0
+
+
+# ------------------------------------------------------------------------------------------------ simulator oracle
+def test_geometry_known_answers_c_oracle():
+    """nocturne/cpp/tests/src/geometry/polygon_test.cc:60-86 and intersection_test.cc:52-76 on the C restatement."""
+    from oracle import sim_port as sp
+    eps = 1e-5
+    sq = [(0, 0), (1, 0), (1, 1), (0, 1)]
+    tri = [(1, 2), (2, 1), (2, 2)]
+    assert not sp.poly_intersects(sq, tri) and not sp.poly_intersects(tri, sq)
+    tri = [(1 - eps, 1 - eps), (2, 0), (2, 2)]
+    assert sp.poly_intersects(sq, tri) and sp.poly_intersects(tri, sq)
+    tri = [(1, 1), (2, 0), (2, 2)]
+    assert sp.poly_intersects(sq, tri) and sp.poly_intersects(tri, sq)
+    dia = [(1, 0), (0, 1), (-1, 0), (0, -1)]
+    for s0, s1, want in [((0, 0.5), (0, -0.5), True), ((-0.5, -0.5), (-0.5, -1.0), True), ((-1, 0.5), (1, 1), True),
+                         ((1, 1), (-1, -1), True), ((-1, -1 - eps), (1, -1 - eps), False), ((-3, 0.5), (-2, 1), False)]:
+        assert sp.poly_segment_intersects(dia, s0, s1) is want
+
+
+def test_sim_oracle_known_answer_from_reference():
+    """output of the real nocturne_cpp on a 2-vehicle scene (recorded from the reference)."""
+    from oracle import sim_port as sp
+    T = 91
+
+    def obj(x, y, hdeg, speed):
+        vx, vy = speed * math.cos(math.radians(hdeg)), speed * math.sin(math.radians(hdeg))
+        return {"type": "vehicle", "length": 4.5, "width": 2.0, "position": [{"x": x, "y": y}] * T, "heading": [hdeg] * T,
+                "velocity": [{"x": vx, "y": vy}] * T, "valid": [True] * T, "goalPosition": {"x": x, "y": y}}
+    scen = {"objects": [obj(1000.0, 2000.0, 0.0, 10.0), obj(1030.0, 2000.0, 180.0, 5.0)],
+            "roads": [{"type": "road_edge", "geometry": [{"x": 990.0 + i, "y": 2005.0} for i in range(100)]}]}
+    sim = sp.ScenePort(sp.parse_scenario(scen))
+    want = {0: (1001.0175, 2000.0510, 0.02269, 10.1874, 0), 9: (1010.9034, 2001.7715, 0.24659, 11.9577, 0),
+            14: (1016.7851, 2003.9357, 0.38627, 12.9344, 1), 19: (1022.7221, 2007.1527, 0.53677, 13.9050, 0)}
+    for k in range(20):
+        sim.set_action(0, 2.0, 0.1)
+        sim.set_action(1, -1.0, 0.0)
+        sim.step(0.1)
+        if k in want:
+            x, y, h, s, edge = want[k]
+            assert abs(sim.position()[0, 0] - x) < 2e-4 and abs(sim.position()[0, 1] - y) < 2e-4
+            assert abs(sim.heading()[0] - h) < 1e-5 and abs(sim.speed()[0] - s) < 1e-4
+            assert bool(sim.collisions()[1][0]) == bool(edge)
+    assert abs(sim.speed()[1] - 3.0) < 1e-5 and abs(sim.heading()[1] + np.pi) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref")) or not os.path.isdir("/root/reference"),
+                    reason="needs the reference build (build container only)")
+def test_sim_oracle_bit_exact_vs_reference_nocturne(tmp_path, cfg):
+    """Random actions on a contact-free scene: the C restatement is bit-identical to the real nocturne_cpp."""
+    import json
+    from ctrlsim_b200.synth import make_scene
+    from oracle import ref_shims, sim_port
+    ref_shims.install()
+    import nocturne
+    sc = make_scene(5, n_vehicles=6, n_roads=6, n_chunks=4, lane_ids=[3])
+    path = tmp_path / "s.json"
+    path.write_text(json.dumps(sc["json"]))
+    sim = nocturne.Simulation(scenario_path=str(path), config=cfg.nocturne["scenario"])
+    vehs = sim.getScenario().vehicles()
+    for v in vehs:
+        v.expert_control = False
+        v.physics_simulated = True
+    port = sim_port.ScenePort(sim_port.parse_scenario(sc["json"]))
+    rng = np.random.default_rng(0)
+    for t in range(60):
+        p = np.array([[v.getPosition().x, v.getPosition().y] for v in vehs])
+        assert (p == port.position()).all() and (np.array([v.getHeading() for v in vehs]) == port.heading()).all()
+        assert (np.array([v.getSpeed() for v in vehs]) == port.speed()).all()
+        assert (np.array([int(v.collision_type_edge) == 2 for v in vehs]) == port.collisions()[1]).all()
+        for i, v in enumerate(vehs):
+            a, s = rng.uniform(-3, 3), rng.uniform(-0.3, 0.3)
+            if t % 7 == 3:
+                a = 0.0
+            if a > 0:
+                v.acceleration = a
+            else:
+                v.brake(abs(a))
+            v.steering = s
+            port.set_action(i, a, s)
+        sim.step(0.1)
+        port.step(0.1)
+
+
+# ------------------------------------------------------------------------------------------------ model oracle
+def test_mask_rule_matches_its_definition():
+    from oracle.model_port import causal_mask_rule
+    A = 3
+    m = causal_mask_rule(A, 2, 3).numpy()
+
+    def idx(t, a, k):
+        return (t * A + a) * 3 + k
+    assert m[idx(1, 0, 0), idx(0, 2, 2)]          # everything in the past is visible
+    assert m[idx(1, 0, 0), idx(1, 2, 0)]          # all current states are visible, even of later agents
+    assert not m[idx(1, 0, 0), idx(1, 0, 1)]      # a state token does not see its own rtg
+    assert m[idx(1, 0, 1), idx(1, 0, 1)] and not m[idx(1, 0, 1), idx(1, 0, 2)]
+    assert m[idx(1, 0, 2), idx(1, 0, 1)] and not m[idx(1, 0, 2), idx(1, 1, 1)]
+    assert not m[idx(0, 1, 2), idx(1, 0, 0)]      # never the future
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference tree (build container only)")
+def test_mask_rule_equals_reference_get_causal_mask(cfg):
+    import sys
+    import types
+    from oracle.model_port import causal_mask_rule
+    if "utils" not in sys.modules:
+        mod = types.ModuleType("utils")
+        mod.__path__ = ["/root/reference/utils"]
+        sys.modules["utils"] = mod
+    from utils.train_utils import get_causal_mask
+    small = cfg.copy()
+    small.dataset.waymo.max_num_agents = 4
+    ref = get_causal_mask(small, 5, 3)
+    assert ((ref == 0).numpy() == causal_mask_rule(4, 5, 3).numpy()).all()
+
+
+@pytest.mark.parametrize("name,step", [("plumbing", 9), ("crowded", 33), ("sparse", 89)])
+def test_model_port_matches_reference_logits(cfg, name, step):
+    """oracle/model_port.py vs logits the reference CtRLSim.forward produced on the same tokens (fixtures)."""
+    from ctrlsim_b200.weights import make_weights
+    from oracle.model_port import ModelPort
+    g, spec, _ = load_golden(name)
+    model = ModelPort(cfg, make_weights(cfg, **spec["weights"]))
+    t = step
+    ti = t if t < 32 else 31
+    data = {k: torch.from_numpy(g[f"in_{t}_{k}"][None]) for k in ("agent_states", "agent_types", "goals", "actions",
+                                                                   "timesteps", "road_points", "road_types")}
+    data["rtgs"] = torch.from_numpy(g[f"in_{t}_rtgs_pass1"][None])
+    out = model.forward(data)
+    assert np.abs(out["rtg_preds"][0, :, ti].numpy() - g[f"rtg_logits_{t}_0"]).max() < 5e-5
+    data["rtgs"] = torch.from_numpy(g[f"in_{t}_rtgs_pass2"][None])
+    out = model.forward(data)
+    assert np.abs(out["action_preds"][0, :, ti].numpy() - g[f"action_logits_{t}_0"]).max() < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ rollout oracle
+def test_rollout_port_matches_reference_prefix(cfg):
+    """BASELINE config 1 (1 scene, 8 vehicles, 32 polylines, 10 steps): oracle port vs the unmodified reference
+    evaluator - sampled bins identical, trajectories identical, groups identical."""
+    from ctrlsim_b200.synth import make_scene
+    from ctrlsim_b200.weights import make_weights
+    from oracle.model_port import ModelPort
+    from oracle.policy_port import RolloutPort
+    g, spec, _ = load_golden("plumbing")
+    steps = 10
+    port = RolloutPort(cfg, ModelPort(cfg, make_weights(cfg, **spec["weights"])), seed=0, tilts=tuple(spec["tilts"]),
+                       eval_threshold=64)
+    sc = make_scene(**spec["scene"])
+    rec = port.run_scene(0, sc["json"], sc["preproc"], max_steps=steps)
+    assert (rec["rtg_idx"][:steps] == g["rtg_idx"][:steps]).all()
+    assert (rec["act_idx"][:steps] == g["act_idx"][:steps]).all()
+    for k in ("pos", "vel", "heading", "existence", "accel", "steer", "reward", "nearest_dist", "gt_nearest_dist"):
+        assert np.abs(rec[k][:, :steps] - g[k][:, :steps]).max() < 1e-9, k
+    for t in range(steps):
+        for gi, d in enumerate(rec["groups"][t]):
+            assert d["focal"] == g["group_focal"][t, gi] and (d["members"] == g["group_members"][t, gi]).all()
+            assert d["served"] == [int(v) for v in g["group_served"][t, gi] if v >= 0]
+
+
+def test_metrics_port_matches_reference_metrics(cfg):
+    """S7: feeding the reference's own recorded trajectories through the oracle metrics reproduces its metrics dict."""
+    from oracle.policy_port import MetricsPort
+    for name in ("plumbing", "crowded", "sparse"):
+        g, spec, ref = load_golden(name)
+        mp = MetricsPort(cfg)
+        rec = {k: g[k] for k in ("existence", "reward", "pos", "gt_pos", "vel", "gt_speed", "heading", "gt_heading",
+                                 "gt_accel", "accel", "gt_nearest_dist", "nearest_dist")}
+        mp.add_scene(rec, [int(v) for v in g["evaluated"]])
+        got = mp.compute()
+        for k, v in ref.items():
+            assert abs(got[k] - v) < 1e-9, (name, k, got[k], v)
+
+
+def test_tokenizer_port_matches_reference_inputs(cfg):
+    """T2/T3 teacher-forced on the reference's recorded history: the port's group tokens at sliding-window steps equal
+    the tensors the reference fed its model (fixture in_<t>_*)."""
+    from ctrlsim_b200.synth import make_scene
+    from oracle.policy_port import RolloutPort
+    g, spec, _ = load_golden("sparse")
+    sc = make_scene(**spec["scene"])
+    n = g["pos"].shape[0]
+    port = RolloutPort(cfg, model=None, eval_threshold=64)
+    for t in (9, 33, 89):
+        ep = {"states": np.zeros((n, 90, 8)), "actions": np.zeros((n, 90, 2)), "rtgs": np.zeros((n, 90, 3)),
+              "goals": np.zeros((n, 90, 5)), "timesteps": np.zeros((n, 90, 1)), "types": np.tile(np.eye(5)[1], (n, 1)),
+              "road_points": sc["preproc"]["road_points"], "road_types": sc["preproc"]["road_types"]}
+        ep["states"][:, :t + 1, :2], ep["states"][:, :t + 1, 2:4] = g["pos"][:, :t + 1], g["vel"][:, :t + 1]
+        ep["states"][:, :t + 1, 4], ep["states"][:, :t + 1, 7] = g["heading"][:, :t + 1], g["existence"][:, :t + 1]
+        ep["states"][:, :t + 1, 5:7] = g["size"][:, None]
+        ep["actions"][:, :t, 0], ep["actions"][:, :t, 1] = g["accel"][:, :t], g["steer"][:, :t]
+        ep["rtgs"][:, :t] = g["rtgs"][:, :t]
+        ep["timesteps"][:, :t + 1, 0] = np.arange(t + 1)
+        gl = g["goal"]
+        ep["goals"][:] = np.stack([gl[:, 0], gl[:, 1], gl[:, 3] * np.cos(gl[:, 2]), gl[:, 3] * np.sin(gl[:, 2]),
+                                   gl[:, 2]], -1)[:, None]
+        focal = int(g["group_focal"][t, 0])
+        closest = np.array([v for v in g["group_members"][t, 0] if v >= 0])
+        tok = port.tokenize(ep, t, focal, closest)
+        for k in ("agent_states", "agent_types", "goals", "actions", "road_points", "road_types"):
+            assert np.abs(tok[k].astype(np.float32) - g[f"in_{t}_{k}"].astype(np.float32)).max() < 1e-5, (t, k)
+        assert (tok["rtgs"] == g[f"in_{t}_rtgs_pass1"]).all()
+        assert (tok["timesteps"] == g[f"in_{t}_timesteps"]).all()
+
+
+# ------------------------------------------------------------------------------------------------ C-ABI surface
+def test_library_loads_and_exports_every_declared_symbol():
+    from ctrlsim_b200 import lib
+    from ctrlsim_b200.build import build
+    path = build()
+    so = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "ctrlsim_b200.h")).read()
+    declared = set(re.findall(r"\b(ctrlsim_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no prototypes parsed from the header"
+    for name in declared:
+        assert hasattr(so, name), f"{name} declared in include/ctrlsim_b200.h but not exported"
+    assert set(lib.EXPORTS) == declared
+    so.ctrlsim_abi_version.restype = ctypes.c_int
+    assert so.ctrlsim_abi_version() == lib.ABI_VERSION
+
+
+def test_batch_struct_matches_header_field_order():
+    from ctrlsim_b200 import lib
+    header = open(os.path.join(ROOT, "include", "ctrlsim_b200.h")).read()
+    body = header[header.index("typedef struct CtrlSimBatch {"):header.index("} CtrlSimBatch;")]
+    fields = re.findall(r"\*\s*([a-z_0-9]+);", body)
+    assert fields == [n for n, _, _ in lib.BATCH_FIELDS]
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ctrlsim_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
