@@ -6,8 +6,9 @@
 //                keys get -inf, softmax, P.V  (torch.nn.functional.multi_head_attention_forward).
 //  attn_causal   decoder self-attention over (timestep, agent, {state,rtg,action}) tokens with the structured mask
 //                of utils/train_utils.py:82-130 evaluated arithmetically (rule M1) instead of reading the 21 MB mask.
-//  attn_step     the same rule for the 24 rtg-token rows of the current timestep only (second pass after the RTGs
-//                were sampled), streaming the layer's K/V rows written by the first pass.
+//  attn_step     the same rule for 24 rows of the current timestep only, streaming the layer's K/V rows written by the
+//                first pass: the rtg-token rows of the second pass (after the RTGs were sampled; own new key appended)
+//                and the state-token rows of the last first-pass layer (the only rows the RTG head reads).
 //  map_pool      the polyline encoder's single learned-query attention over the 100 points of a polyline
 //                (modules/map_encoder.py:41-45) in its algebraically reduced form: scores = feats . U_h with
 //                U_h = W_k,h^T q_h (the key bias shifts every score of a head equally and cancels in the softmax),
@@ -204,7 +205,7 @@ int launch_attn_causal(const float* QKV, float* O, int G, int n_t, cudaStream_t 
 // row's own (new) rtg key/value.  QKV_full: first-pass [G*Lfull, 768]; qkv_rows: [G*A, 768]; O: [G*A, 256].
 __global__ void __launch_bounds__(32)
 attn_step_kernel(const float* __restrict__ QKV_full, const float* __restrict__ qkv_rows, float* __restrict__ O,
-                 int Lfull, int ti) {
+                 int Lfull, int ti, int own_row) {
   __shared__ __align__(16) KVTile<CCH> sm;
   const int g = blockIdx.y, h = blockIdx.x;
   const int a = threadIdx.x;
@@ -240,6 +241,10 @@ attn_step_kernel(const float* __restrict__ QKV_full, const float* __restrict__ q
     }
   }
   __syncwarp();
+  if (!own_row) {  // state rows of the last first-pass layer: their own key is already among the state tokens above
+    if (active) store_o(O + ((size_t)g * A + a) * H + h * DH, acc, l);
+    return;
+  }
   // own rtg key/value: stage the A new rows as one more tile, each thread uses only its own row
   for (int i = threadIdx.x; i < A * (DH / 4); i += 32) {
     const int r = i >> 3, c = (i & 7) << 2;
@@ -259,10 +264,10 @@ attn_step_kernel(const float* __restrict__ QKV_full, const float* __restrict__ q
 }
 
 int launch_attn_step(const float* QKV_full, const float* qkv_rows, float* O, int G, int n_t_full, int ti,
-                     cudaStream_t st) {
+                     bool own_row, cudaStream_t st) {
   if (G <= 0) return 0;
   dim3 grid(NH, G);
-  attn_step_kernel<<<grid, 32, 0, st>>>(QKV_full, qkv_rows, O, n_t_full * TOK_T, ti);
+  attn_step_kernel<<<grid, 32, 0, st>>>(QKV_full, qkv_rows, O, n_t_full * TOK_T, ti, own_row ? 1 : 0);
   CS_CHECK_LAUNCH("attn_step");
   return 0;
 }
@@ -333,13 +338,14 @@ map_pool_kernel(const float* __restrict__ feats, const uint8_t* __restrict__ pt_
     }
     // scores: one warp per point, lane owns 8 consecutive feature dims, 8 head dot-products reduced by butterfly
     for (int p = warp; p < NP; p += POOL_THREADS / 32) {
-      const float4 f0 = *reinterpret_cast<const float4*>(&sm.feats[s][p][lane * 8]);
-      const float4 f1 = *reinterpret_cast<const float4*>(&sm.feats[s][p][lane * 8 + 4]);
+      // lane owns dims [4 lane, 4 lane + 4) and [128 + 4 lane, ...): consecutive lanes read consecutive 16-byte chunks
+      const float4 f0 = *reinterpret_cast<const float4*>(&sm.feats[s][p][lane * 4]);
+      const float4 f1 = *reinterpret_cast<const float4*>(&sm.feats[s][p][128 + lane * 4]);
       float d[NH];
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh) {
-        const float4 u0 = *reinterpret_cast<const float4*>(&sm.U[hh][lane * 8]);
-        const float4 u1 = *reinterpret_cast<const float4*>(&sm.U[hh][lane * 8 + 4]);
+        const float4 u0 = *reinterpret_cast<const float4*>(&sm.U[hh][lane * 4]);
+        const float4 u1 = *reinterpret_cast<const float4*>(&sm.U[hh][128 + lane * 4]);
         float x = f0.x * u0.x;
         x = fmaf(f0.y, u0.y, x); x = fmaf(f0.z, u0.z, x); x = fmaf(f0.w, u0.w, x);
         x = fmaf(f1.x, u1.x, x); x = fmaf(f1.y, u1.y, x); x = fmaf(f1.z, u1.z, x); x = fmaf(f1.w, u1.w, x);

@@ -5,6 +5,8 @@
 // register micro-tile read as float4 from k-major shared tiles, register-staged double buffering of the global loads.
 // Both operands are K-contiguous ("TN" layout: activations row-major, nn.Linear weights [out,in]).
 // DESIGN.md lists the tcgen05 (kind::tf32, 3-pass split) replacement as the next step for this kernel.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -116,8 +118,19 @@ gemm_tn_kernel(const float* __restrict__ Aa, const float* __restrict__ W, const 
   }
 }
 
+// CTRLSIM_GEMM=simt forces the FP32 FFMA kernel (A/B testing); the default is the tcgen05 3xTF32 kernel.
+static bool use_tc() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("CTRLSIM_GEMM");
+    mode = (e && std::string(e) == "simt") ? 0 : 1;
+  }
+  return mode == 1;
+}
+
 int launch_gemm(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0) return 0;
+  if (use_tc() && g.K % 32 == 0) return launch_gemm_tc(g, st);
   if (g.K % BK != 0 || (g.lda & 3) || (g.ldw & 3))
     return set_error(-2, "gemm: K=%d must be a multiple of %d and lda/ldw multiples of 4", g.K, BK);
   dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN);

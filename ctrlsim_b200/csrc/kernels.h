@@ -17,7 +17,8 @@ struct GemmArgs {
   int M = 0, N = 0, K = 0, lda = 0, ldw = 0, ldc = 0, ldt = 0;
   bool relu = false;
 };
-int launch_gemm(const GemmArgs& g, cudaStream_t st);
+int launch_gemm(const GemmArgs& g, cudaStream_t st);     // dispatches to the tcgen05 kernel unless CTRLSIM_GEMM=simt
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);  // gemm_tc.cu
 int launch_layernorm(const float* X, const float* R, const float* gamma, const float* beta, float* Y, int M, int ldx,
                      int ldr, int ldy, bool relu, cudaStream_t st);
 
@@ -26,7 +27,7 @@ int launch_attn_padded(const float* Q, int ldq, const float* Kp, const float* Vp
                        float* O, int ldo, int G, int Lq, int Lk, cudaStream_t st);
 int launch_attn_causal(const float* QKV, float* O, int G, int n_t, cudaStream_t st);
 int launch_attn_step(const float* QKV_full, const float* qkv_rows, float* O, int G, int n_t_full, int ti,
-                     cudaStream_t st);
+                     bool own_row, cudaStream_t st);
 int launch_map_pool(const float* feats, const uint8_t* pt_valid, const uint8_t* poly_valid, const float* U,
                     float* pooled, int n_poly, int n_sm, cudaStream_t st);
 

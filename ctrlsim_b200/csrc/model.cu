@@ -173,7 +173,10 @@ int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm
     CS_TRY(ln(ws.mem, ws.tmp_m, e.n2, ws.mem, Rm, false, st));
   }
   // ---- M5-M7 decoder --------------------------------------------------------------------------------------------
-  for (int l = 0; l < N_DEC; ++l) {
+  // Layers 0..2 run on every row (their outputs are the next layer's keys/values).  Of the last layer's output only
+  // the 24 state rows of the current step are read (RTG head), so it computes K/V for every row (the second pass
+  // needs them) but queries / attention / cross-attention / FFN for those 24 rows only.
+  for (int l = 0; l < N_DEC - 1; ++l) {
     const DecLayerW& d = w.dec[l];
     CS_TRY(gemm(ws.X, d.sa.in_w, d.sa.in_b, ws.QKV[l], R, 3 * H, H, H, H, 3 * H, false, st));
     {  // useful flops: 4 * d_h per (row, head, visible key); visible keys per step tw: 72*tw + 24 (+0/1/2 own tokens)
@@ -196,9 +199,28 @@ int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm
     CS_TRY(gemm(ws.ff, d.l2w, d.l2b, ws.tmp, R, H, FF, FF, FF, H, false, st));
     CS_TRY(ln(ws.X, ws.tmp, d.n3, ws.X, R, false, st));
   }
+  {
+    const int l = N_DEC - 1;
+    const DecLayerW& d = w.dec[l];
+    // K | V of every row into columns [256, 768) of QKV[l]
+    CS_TRY(gemm(ws.X, d.sa.in_w + (size_t)H * H, d.sa.in_b + H, ws.QKV[l] + H, R, 2 * H, H, H, H, 3 * H, false, st));
+    CS_TRY(gemm(ws.mem, d.ca.in_w + (size_t)H * H, d.ca.in_b + H, ws.kv_c[l], Rm, 2 * H, H, H, H, 2 * H, false, st));
+    CS_TRY(launch_make_row_index(G, n_t, ti, 0, ws.row_idx, st));
+    CS_TRY(launch_gather_rows(Ra, ws.X, ws.row_idx, ws.xr, st));
+    CS_TRY(gemm(ws.xr, d.sa.in_w, d.sa.in_b, ws.qkv_r, Ra, H, H, H, H, 3 * H, false, st));
+    CS_TRY(launch_attn_step(ws.QKV[l], ws.qkv_r, ws.att_r, G, n_t, ti, false, st));
+    CS_TRY(gemm(ws.att_r, d.sa.out_w, d.sa.out_b, ws.tmp_r, Ra, H, H, H, H, H, false, st));
+    CS_TRY(ln(ws.xr, ws.tmp_r, d.n1, ws.xr, Ra, false, st));
+    CS_TRY(gemm(ws.xr, d.ca.in_w, d.ca.in_b, ws.qc_r, Ra, H, H, H, H, H, false, st));
+    CS_TRY(launch_attn_padded(ws.qc_r, H, ws.kv_c[l], ws.kv_c[l] + H, 2 * H, ws.pad, ws.att_r, H, G, A, MEM, st));
+    CS_TRY(gemm(ws.att_r, d.ca.out_w, d.ca.out_b, ws.tmp_r, Ra, H, H, H, H, H, false, st));
+    CS_TRY(ln(ws.xr, ws.tmp_r, d.n2, ws.xr, Ra, false, st));
+    CS_TRY(gemm(ws.xr, d.l1w, d.l1b, ws.ff_r, Ra, FF, H, H, H, FF, true, st));
+    CS_TRY(gemm(ws.ff_r, d.l2w, d.l2b, ws.tmp_r, Ra, H, FF, FF, FF, H, false, st));
+    CS_TRY(ln(ws.xr, ws.tmp_r, d.n3, ws.xr, Ra, false, st));
+  }
   // ---- M8 RTG head on the state rows of the current step ----------------------------------------------------------
-  CS_TRY(launch_make_row_index(G, n_t, ti, 0, ws.row_idx, st));
-  CS_TRY(gemm(ws.X, w.head_rtg.w0, w.head_rtg.b0, ws.hd1, Ra, H, H, H, H, H, false, st, nullptr, nullptr, 0, ws.row_idx));
+  CS_TRY(gemm(ws.xr, w.head_rtg.w0, w.head_rtg.b0, ws.hd1, Ra, H, H, H, H, H, false, st));
   CS_TRY(launch_layernorm(ws.hd1, nullptr, w.head_rtg.lnw, w.head_rtg.lnb, ws.hd1, Ra, H, H, H, true, st));
   CS_TRY(gemm(ws.hd1, w.head_rtg.w3, w.head_rtg.b3, ws.rtg_logits, Ra, N_RTG * 3, H, H, H, N_RTG * 3, false, st));
   return 0;
@@ -210,7 +232,7 @@ int forward_pass2(const ModelWeights& w, Workspace& ws, int G, int n_t, cudaStre
   for (int l = 0; l < N_DEC; ++l) {
     const DecLayerW& d = w.dec[l];
     CS_TRY(gemm(ws.xr, d.sa.in_w, d.sa.in_b, ws.qkv_r, Ra, 3 * H, H, H, H, 3 * H, false, st));
-    CS_TRY(launch_attn_step(ws.QKV[l], ws.qkv_r, ws.att_r, G, n_t, ti, st));
+    CS_TRY(launch_attn_step(ws.QKV[l], ws.qkv_r, ws.att_r, G, n_t, ti, true, st));
     CS_TRY(gemm(ws.att_r, d.sa.out_w, d.sa.out_b, ws.tmp_r, Ra, H, H, H, H, H, false, st));
     CS_TRY(ln(ws.xr, ws.tmp_r, d.n1, ws.xr, Ra, false, st));
     CS_TRY(gemm(ws.xr, d.ca.in_w, d.ca.in_b, ws.qc_r, Ra, H, H, H, H, H, false, st));

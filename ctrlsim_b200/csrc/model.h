@@ -75,6 +75,7 @@ int launch_build_memory(int G, const float* poly_emb, const uint8_t* poly_valid,
                         float* mem, uint8_t* pad, cudaStream_t st);
 int launch_make_row_index(int G, int n_t, int ti, int k, int* out, cudaStream_t st);
 int launch_make_goal_index(int G, int n_t, int* out, cudaStream_t st);
+int launch_gather_rows(int n, const float* X, const int* idx, float* Y, cudaStream_t st);
 int launch_clamp_type_index(int n, const int* in, int* out, cudaStream_t st);
 
 // sim.cu

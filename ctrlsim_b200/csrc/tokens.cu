@@ -435,6 +435,20 @@ int launch_make_row_index(int G, int n_t, int ti, int k, int* out, cudaStream_t 
   return 0;
 }
 
+// Y[i] = X[idx[i]] for H-wide rows (state rows of the current step for the pruned last decoder layer)
+__global__ void gather_rows_kernel(int n, const float* __restrict__ X, const int* __restrict__ idx, float* __restrict__ Y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * (H / 4)) return;
+  const int r = i / (H / 4), c = (i % (H / 4)) * 4;
+  *reinterpret_cast<float4*>(Y + (size_t)r * H + c) = *reinterpret_cast<const float4*>(X + (size_t)idx[r] * H + c);
+}
+int launch_gather_rows(int n, const float* X, const int* idx, float* Y, cudaStream_t st) {
+  if (n <= 0) return 0;
+  gather_rows_kernel<<<(n * (H / 4) + 255) / 256, 256, 0, st>>>(n, X, idx, Y);
+  CS_CHECK_LAUNCH("gather_rows");
+  return 0;
+}
+
 // tidx for the goal-part table add of embed_state_goal: row (g, tw, a) -> g*A + a ; and polyline type rows.
 __global__ void make_goal_index_kernel(int n, int n_t, int* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

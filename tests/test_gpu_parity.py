@@ -50,7 +50,8 @@ def test_linear_matches_torch(lib, dev, M, N, K, relu):
     _chk(lib.ctrlsim_linear(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cc.data_ptr(), M, N, K, int(relu), _stream()), lib)
     ref = torch.nn.functional.linear(A.double(), W.double(), b.double())
     ref = torch.relu(ref) if relu else ref
-    assert (Cc.double() - ref).abs().max().item() < 2e-5 * math.sqrt(K / 256)
+    # tcgen05 accumulates with truncation: the error grows ~linearly with K/8 chained MMAs (gemm_tc.cu header)
+    assert (Cc.double() - ref).abs().max().item() < 1e-5 * max(1.0, K / 256)
 
 
 @pytest.mark.parametrize("M,res,relu", [(1, False, False), (1000, True, False), (257, True, True)])
