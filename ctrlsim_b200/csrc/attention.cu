@@ -16,6 +16,8 @@
 //                pooled vectors by one GEMM.  This is the HBM-bound "encoder-attn" kernel of BASELINE.json: each
 //                polyline's 100x256 fp32 feature tile (102,400 B) is fetched by one TMA bulk copy
 //                (cp.async.bulk + mbarrier) into a 2-stage shared-memory ring by a persistent CTA per SM.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -121,9 +123,20 @@ attn_padded_kernel(const float* __restrict__ Q, int ldq, const float* __restrict
   if (active) store_o(O + ((size_t)g * Lq + row) * ldo + h * DH, acc, l);
 }
 
+// CTRLSIM_ATTN=simt selects the FP32 FFMA kernels of this file (A/B testing); the default is attention_mma.cu.
+static bool use_mma_attn() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("CTRLSIM_ATTN");
+    mode = (e && std::string(e) == "simt") ? 0 : 1;
+  }
+  return mode == 1;
+}
+
 int launch_attn_padded(const float* Q, int ldq, const float* Kp, const float* Vp, int ldkv, const uint8_t* key_pad,
                        float* O, int ldo, int G, int Lq, int Lk, cudaStream_t st) {
   if (G <= 0 || Lq <= 0) return 0;
+  if (use_mma_attn()) return launch_attn_padded_mma(Q, ldq, Kp, Vp, ldkv, key_pad, O, ldo, G, Lq, Lk, st);
   if (Lk % 8 != 0) return set_error(-2, "attn_padded: Lk=%d must be a multiple of 8", Lk);
   dim3 grid((Lq + 127) / 128, NH, G);
   attn_padded_kernel<<<grid, 128, 0, st>>>(Q, ldq, Kp, Vp, ldkv, key_pad, O, ldo, Lq, Lk);
@@ -192,6 +205,7 @@ attn_causal_kernel(const float* __restrict__ QKV, float* __restrict__ O, int Lcu
 
 int launch_attn_causal(const float* QKV, float* O, int G, int n_t, cudaStream_t st) {
   if (G <= 0 || n_t <= 0) return 0;
+  if (use_mma_attn()) return launch_attn_causal_mma(QKV, O, G, n_t, st);
   const int Lcur = n_t * TOK_T;
   dim3 grid((Lcur + 127) / 128, NH, G);
   attn_causal_kernel<<<grid, 128, 0, st>>>(QKV, O, Lcur);
