@@ -19,6 +19,10 @@
 //              (4 k-steps of 8 x 3 split products, M=128, N=256) and tcgen05.commit's to empty[stage]; the last commit
 //              signals the epilogue.
 // 2 stages x 96 KB (A_hi, A_lo 16 KB each; B_hi, B_lo 32 KB each) of dynamic shared memory.
+#include <cuda.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -109,6 +113,50 @@ __device__ __forceinline__ void tc_split_store(float* hi, float* lo, int off, fl
   *reinterpret_cast<float4*>(lo + off) = l;
 }
 
+// Epilogue of one 32-column chunk held by this thread (row m, columns nc0 .. nc0+31): main + cross accumulators, bias,
+// optional table row, ReLU, store.  The bias is fetched with ONE coalesced load per chunk and broadcast by shuffles
+// (a per-element __ldg serialises ~200 cycles of latency per output); must be called by all 32 lanes of the warp.
+template <bool RELU>
+__device__ __forceinline__ void tc_epilogue_chunk(const uint32_t (&r)[32], const uint32_t (&rx)[32], int m, int M, int nc0,
+                                                  int N, const float* __restrict__ bias, const float* __restrict__ trow,
+                                                  float* __restrict__ C, int ldc, bool vec_ok, int lane) {
+  const float bl = (bias && nc0 + lane < N) ? __ldg(bias + nc0 + lane) : 0.f;
+  float t[32];
+  if (trow) {
+#pragma unroll
+    for (int q = 0; q < 32; q += 4) {
+      if (nc0 + q + 3 < N) {
+        const float4 tv = __ldg(reinterpret_cast<const float4*>(trow + nc0 + q));
+        t[q] = tv.x; t[q + 1] = tv.y; t[q + 2] = tv.z; t[q + 3] = tv.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) t[q + e] = (nc0 + q + e < N) ? __ldg(trow + nc0 + q + e) : 0.f;
+      }
+    }
+  }
+  float* dst = C + (size_t)m * ldc + nc0;
+#pragma unroll
+  for (int q = 0; q < 32; q += 4) {
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float x = __uint_as_float(r[q + e]) + __uint_as_float(rx[q + e]);
+      x += __shfl_sync(0xffffffffu, bl, q + e);
+      if (trow) x += t[q + e];
+      v[e] = RELU ? fmaxf(x, 0.f) : x;
+    }
+    if (m < M) {
+      if (vec_ok && nc0 + q + 3 < N) {
+        *reinterpret_cast<float4*>(dst + q) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (nc0 + q + e < N) dst[q + e] = v[e];
+      }
+    }
+  }
+}
+
 template <bool RELU>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const float* __restrict__ Aa, const float* __restrict__ W, const float* __restrict__ bias,
@@ -181,31 +229,7 @@ gemm_tc_kernel(const float* __restrict__ Aa, const float* __restrict__ W, const 
       uint32_t r[32], rx[32];
       tc_ld32(tmem + ((uint32_t)(32 * lg) << 16) + (uint32_t)col0, r);
       tc_ld32(tmem + ((uint32_t)(32 * lg) << 16) + (uint32_t)(TC_BN + col0), rx);
-      if (m < M) {
-        float* dst = C + (size_t)m * ldc + n0 + col0;
-#pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int n = n0 + col0 + q + e;
-            float x = __uint_as_float(r[q + e]) + __uint_as_float(rx[q + e]);
-            if (n < N) {
-              if (bias) x += __ldg(bias + n);
-              if (trow) x += __ldg(trow + n);
-            }
-            v[e] = RELU ? fmaxf(x, 0.f) : x;
-          }
-          const int n = n0 + col0 + q;
-          if (vec_ok && n + 3 < N) {
-            *reinterpret_cast<float4*>(dst + q) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (n + e < N) dst[q + e] = v[e];
-          }
-        }
-      }
+      tc_epilogue_chunk<RELU>(r, rx, m, M, n0 + col0, N, bias, trow, C, ldc, vec_ok, lane);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else {
@@ -241,10 +265,426 @@ gemm_tc_kernel(const float* __restrict__ Aa, const float* __restrict__ W, const 
   }
 }
 
+
+// =====================================================================================================================
+// v2: persistent, warp-specialised (one CTA per SM loops over 128 x 128 output tiles).
+//   warps 0-7   producers only: global -> (register prefetch of the next k-slab) -> hi/lo split -> swizzled smem,
+//               3 stages x 64 KB (A_hi, A_lo, B_hi, B_lo of 128 x 32 floats each)
+//   warp  8     MMA issuer: 12 tcgen05.mma (M=128, N=128, K=8) per k-slab into TMEM buffer b = tile & 1
+//               (columns b*256 + [0,128): hi*hi, + [128,256): cross terms); commits free the smem stage / publish the tile
+//   warps 9-12  epilogue: tcgen05.ld of buffer b while the MMA warp already works on buffer b^1 for the next tile
+constexpr int P_BM = 128, P_BN = 128, P_BK = 32, P_STAGES = 3;
+constexpr int P_PRODUCERS = 256, P_EPI = 128, P_THREADS = P_PRODUCERS + 32 + P_EPI;
+
+struct alignas(1024) PStage {
+  float a_hi[P_BM * P_BK];
+  float a_lo[P_BM * P_BK];
+  float b_hi[P_BN * P_BK];
+  float b_lo[P_BN * P_BK];
+};
+struct PSmem {
+  PStage stage[P_STAGES];
+  uint64_t full[P_STAGES];
+  uint64_t empty[P_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+template <bool RELU>
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_tc_persistent_kernel(const float* __restrict__ Aa, const float* __restrict__ W, const float* __restrict__ bias,
+                          const float* __restrict__ table, const int* __restrict__ tidx,
+                          const int* __restrict__ agather, float* __restrict__ C, int M, int N, int K, int lda, int ldw,
+                          int ldc, int ldt, int n_tiles_n, int n_tiles) {
+  extern __shared__ unsigned char tc_raw[];
+  PSmem& sm = *reinterpret_cast<PSmem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk = K / P_BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < P_STAGES; ++s) { tc_mbar_init(&sm.full[s], P_PRODUCERS); tc_mbar_init(&sm.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { tc_mbar_init(&sm.tmem_full[b], 1); tc_mbar_init(&sm.tmem_empty[b], P_EPI); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ producers
+    const int c = tid & 7, rbase = tid >> 3;
+    const int sc = (c ^ (rbase & 7)) << 2;
+    uint32_t it = 0;  // global k-slab counter (stage ring position)
+    float4 va[4], vb[4];
+    const float* ap[4];
+    const float* wp[4];
+    auto set_tile = [&](int tile) {
+      const int m0 = (tile / n_tiles_n) * P_BM, n0 = (tile % n_tiles_n) * P_BN;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + rbase + 32 * i, n = n0 + rbase + 32 * i;
+        ap[i] = m < M ? Aa + (size_t)(agather ? agather[m] : m) * lda + c * 4 : nullptr;
+        wp[i] = n < N ? W + (size_t)n * ldw + c * 4 : nullptr;
+      }
+    };
+    auto gload = [&](int k0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        va[i] = ap[i] ? *reinterpret_cast<const float4*>(ap[i] + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[i] = wp[i] ? __ldg(reinterpret_cast<const float4*>(wp[i] + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    int tile = blockIdx.x;
+    if (tile < n_tiles) { set_tile(tile); gload(0); }
+    while (tile < n_tiles) {
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int s = it % P_STAGES;
+        tc_mbar_wait(&sm.empty[s], ((it / P_STAGES) & 1) ^ 1);
+        PStage& st = sm.stage[s];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          tc_split_store(st.a_hi, st.a_lo, (rbase + 32 * i) * P_BK + sc, va[i]);
+          tc_split_store(st.b_hi, st.b_lo, (rbase + 32 * i) * P_BK + sc, vb[i]);
+        }
+        // prefetch the next k-slab (possibly of the next tile) into registers before publishing this one
+        if (kc + 1 < nk) {
+          gload((kc + 1) * P_BK);
+        } else {
+          const int nt = tile + gridDim.x;
+          if (nt < n_tiles) { set_tile(nt); gload(0); }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_mbar_arrive(&sm.full[s]);
+      }
+      tile += gridDim.x;
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = tc_make_idesc(P_BM, P_BN);
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1;
+      tc_mbar_wait(&sm.tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_main = tmem + buf * 256, d_cross = d_main + 128;
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int s = it % P_STAGES;
+        tc_mbar_wait(&sm.full[s], (it / P_STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          PStage& st = sm.stage[s];
+          const uint64_t dah = tc_make_desc(tc_smem_u32(st.a_hi)), dal = tc_make_desc(tc_smem_u32(st.a_lo));
+          const uint64_t dbh = tc_make_desc(tc_smem_u32(st.b_hi)), dbl = tc_make_desc(tc_smem_u32(st.b_lo));
+#pragma unroll
+          for (int ks = 0; ks < P_BK / 8; ++ks) {
+            const uint64_t o = (uint64_t)(2 * ks);
+            const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
+            tc_mma(d_cross, dal + o, dbh + o, idesc, acc);
+            tc_mma(d_cross, dah + o, dbl + o, idesc, 1u);
+            tc_mma(d_main, dah + o, dbh + o, idesc, acc);
+          }
+          tc_commit(&sm.empty[s]);
+          if (kc == nk - 1) tc_commit(&sm.tmem_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 9..12)
+    const int lg = warp & 3;  // TMEM lane group this warp may access
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1;
+      const int m0 = (tile / n_tiles_n) * P_BM, n0 = (tile % n_tiles_n) * P_BN;
+      tc_mbar_wait(&sm.tmem_full[buf], (ti >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = m0 + 32 * lg + lane;
+      const float* trow = (table && m < M) ? table + (size_t)tidx[m] * ldt : nullptr;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int col0 = j * 32;
+        uint32_t r[32], rx[32];
+        const uint32_t ta = tmem + ((uint32_t)(32 * lg) << 16) + buf * 256 + (uint32_t)col0;
+        tc_ld32(ta, r);
+        tc_ld32(ta + 128, rx);
+        tc_epilogue_chunk<RELU>(r, rx, m, M, n0 + col0, N, bias, trow, C, ldc, vec_ok, lane);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      tc_mbar_arrive(&sm.tmem_empty[buf]);
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+static int launch_gemm_tc_persistent(const GemmArgs& g, cudaStream_t st) {
+  static int n_sm = 0;
+  const int smem = (int)sizeof(PSmem) + 1024;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { n_sm = 0; return set_error(-5, "gemm_tc_persistent smem attr: %s", cudaGetErrorString(e)); }
+  }
+  const int tn = (g.N + P_BN - 1) / P_BN, tm = (g.M + P_BM - 1) / P_BM;
+  const long long tiles = (long long)tn * tm;
+  if (tiles > 0x7fffffffLL) return set_error(-2, "gemm_tc: too many tiles");
+  const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+  if (g.relu)
+    gemm_tc_persistent_kernel<true><<<grid, P_THREADS, smem, st>>>(g.A, g.W, g.bias, g.table, g.tidx, g.agather, g.C, g.M, g.N,
+                                                                   g.K, g.lda, g.ldw, g.ldc, g.ldt, tn, (int)tiles);
+  else
+    gemm_tc_persistent_kernel<false><<<grid, P_THREADS, smem, st>>>(g.A, g.W, g.bias, g.table, g.tidx, g.agather, g.C, g.M, g.N,
+                                                                    g.K, g.lda, g.ldw, g.ldc, g.ldt, tn, (int)tiles);
+  CS_CHECK_LAUNCH("gemm_tc_persistent");
+  return 0;
+}
+
+
+// =====================================================================================================================
+// v3: v2's persistent structure, but the operand tiles are fetched by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor
+// maps) so that no warp ever waits on a global load: the raw fp32 tile lands in shared memory already in the canonical
+// K-major layout and is used DIRECTLY as the "hi" operand - kind::tf32 ignores the 13 low mantissa bits of its 32-bit
+// inputs, i.e. it sees trunc13(x) - while the 8 producer warps only derive the lo = x - trunc13(x) tiles from it.
+//   warp 9      TMA issuer (one lane): expect_tx + 2 tensor copies (A box 32 x 128, W box 32 x 128) per k-slab
+//   warps 0-7   lo producers; warp 8 MMA issuer; warps 10-13 epilogue (as v2)
+// Rows beyond M / N are zero-filled by the TMA unit.  Row gather (agather) is not expressible: those two small GEMMs
+// use the v1 kernel.
+struct alignas(1024) P3Stage {
+  float a_raw[P_BM * P_BK];
+  float a_lo[P_BM * P_BK];
+  float b_raw[P_BN * P_BK];
+  float b_lo[P_BN * P_BK];
+};
+struct P3Smem {
+  P3Stage stage[P_STAGES];
+  uint64_t tma_full[P_STAGES];
+  uint64_t full[P_STAGES];
+  uint64_t empty[P_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+constexpr int P3_THREADS = 256 + 32 + 32 + 128;
+
+__device__ __forceinline__ void tc_tma_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(tc_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float4 tc_lo4(float4 v) {
+  float4 l;
+  l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+  l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+  l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+  l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+  return l;
+}
+
+template <bool RELU>
+__global__ void __launch_bounds__(P3_THREADS, 1)
+gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                   const float* __restrict__ bias, const float* __restrict__ table, const int* __restrict__ tidx,
+                   float* __restrict__ C, int M, int N, int K, int ldc, int ldt, int n_tiles_n, int n_tiles) {
+  extern __shared__ unsigned char tc_raw[];
+  P3Smem& sm = *reinterpret_cast<P3Smem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk = K / P_BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < P_STAGES; ++s) {
+      tc_mbar_init(&sm.tma_full[s], 1); tc_mbar_init(&sm.full[s], 8); tc_mbar_init(&sm.empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) { tc_mbar_init(&sm.tmem_full[b], 1); tc_mbar_init(&sm.tmem_empty[b], P_EPI); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ lo producers
+    const int c = tid & 7, rbase = tid >> 3;
+    const int sc = (c ^ (rbase & 7)) << 2;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int s = it % P_STAGES;
+        tc_mbar_wait(&sm.tma_full[s], (it / P_STAGES) & 1);
+        P3Stage& st = sm.stage[s];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int off = (rbase + 32 * i) * P_BK + sc;
+          *reinterpret_cast<float4*>(st.a_lo + off) = tc_lo4(*reinterpret_cast<const float4*>(st.a_raw + off));
+          *reinterpret_cast<float4*>(st.b_lo + off) = tc_lo4(*reinterpret_cast<const float4*>(st.b_raw + off));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(&sm.full[s]);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = tc_make_idesc(P_BM, P_BN);
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1;
+      tc_mbar_wait(&sm.tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_main = tmem + buf * 256, d_cross = d_main + 128;
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int s = it % P_STAGES;
+        tc_mbar_wait(&sm.full[s], (it / P_STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          P3Stage& st = sm.stage[s];
+          const uint64_t dah = tc_make_desc(tc_smem_u32(st.a_raw)), dal = tc_make_desc(tc_smem_u32(st.a_lo));
+          const uint64_t dbh = tc_make_desc(tc_smem_u32(st.b_raw)), dbl = tc_make_desc(tc_smem_u32(st.b_lo));
+#pragma unroll
+          for (int ks = 0; ks < P_BK / 8; ++ks) {
+            const uint64_t o = (uint64_t)(2 * ks);
+            const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
+            tc_mma(d_cross, dal + o, dbh + o, idesc, acc);
+            tc_mma(d_cross, dah + o, dbl + o, idesc, 1u);
+            tc_mma(d_main, dah + o, dbh + o, idesc, acc);
+          }
+          tc_commit(&sm.empty[s]);
+          if (kc == nk - 1) tc_commit(&sm.tmem_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ TMA issuer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles_n) * P_BM, n0 = (tile % n_tiles_n) * P_BN;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % P_STAGES;
+          tc_mbar_wait(&sm.empty[s], ((it / P_STAGES) & 1) ^ 1);
+          P3Stage& st = sm.stage[s];
+          tc_expect_tx(&sm.tma_full[s], (P_BM + P_BN) * P_BK * 4);
+          tc_tma_2d(st.a_raw, &tmA, kc * P_BK, m0, &sm.tma_full[s]);
+          tc_tma_2d(st.b_raw, &tmW, kc * P_BK, n0, &sm.tma_full[s]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 10..13)
+    const int lg = warp & 3;
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1;
+      const int m0 = (tile / n_tiles_n) * P_BM, n0 = (tile % n_tiles_n) * P_BN;
+      tc_mbar_wait(&sm.tmem_full[buf], (ti >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = m0 + 32 * lg + lane;
+      const float* trow = (table && m < M) ? table + (size_t)tidx[m] * ldt : nullptr;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int col0 = j * 32;
+        uint32_t r[32], rx[32];
+        const uint32_t ta = tmem + ((uint32_t)(32 * lg) << 16) + buf * 256 + (uint32_t)col0;
+        tc_ld32(ta, r);
+        tc_ld32(ta + 128, rx);
+        tc_epilogue_chunk<RELU>(r, rx, m, M, n0 + col0, N, bias, trow, C, ldc, vec_ok, lane);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      tc_mbar_arrive(&sm.tmem_empty[buf]);
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(EncodeTiledFn enc, CUtensorMap* map, const float* base, int rows, int K, int ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)P_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(-5, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld);
+  return 0;
+}
+
+static int launch_gemm_tc_tma(const GemmArgs& g, cudaStream_t st) {
+  static int n_sm = 0;
+  static EncodeTiledFn enc = nullptr;
+  const int smem = (int)sizeof(P3Smem) + 1024;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) { n_sm = 0; return set_error(-5, "cuTensorMapEncodeTiled entry point unavailable"); }
+    enc = reinterpret_cast<EncodeTiledFn>(fn);
+    e = cudaFuncSetAttribute(gemm_tc_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { n_sm = 0; return set_error(-5, "gemm_tc_tma smem attr: %s", cudaGetErrorString(e)); }
+  }
+  CUtensorMap tmA, tmW;
+  int rc;
+  if ((rc = make_map(enc, &tmA, g.A, g.M, g.K, g.lda, P_BM))) return rc;
+  if ((rc = make_map(enc, &tmW, g.W, g.N, g.K, g.ldw, P_BN))) return rc;
+  const int tn = (g.N + P_BN - 1) / P_BN, tm = (g.M + P_BM - 1) / P_BM;
+  const long long tiles = (long long)tn * tm;
+  const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+  if (g.relu)
+    gemm_tc_tma_kernel<true><<<grid, P3_THREADS, smem, st>>>(tmA, tmW, g.bias, g.table, g.tidx, g.C, g.M, g.N, g.K, g.ldc, g.ldt, tn, (int)tiles);
+  else
+    gemm_tc_tma_kernel<false><<<grid, P3_THREADS, smem, st>>>(tmA, tmW, g.bias, g.table, g.tidx, g.C, g.M, g.N, g.K, g.ldc, g.ldt, tn, (int)tiles);
+  CS_CHECK_LAUNCH("gemm_tc_tma");
+  return 0;
+}
+
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0) return 0;
   if (g.K % TC_BK != 0 || (g.lda & 3) || (g.ldw & 3))
     return set_error(-2, "gemm_tc: K=%d must be a multiple of %d and lda/ldw multiples of 4", g.K, TC_BK);
+  {  // CTRLSIM_GEMM=tc1 keeps the one-tile-per-CTA kernel above for A/B runs
+    static int v1 = -1;
+    if (v1 < 0) { const char* e = getenv("CTRLSIM_GEMM"); v1 = (e && std::string(e) == "tc1") ? 1 : 0; }
+    static int v2 = -1;
+    if (v2 < 0) { const char* e = getenv("CTRLSIM_GEMM"); v2 = (e && std::string(e) == "tc2") ? 1 : 0; }
+    const bool tma_ok = !g.agather && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.W) & 15) == 0);
+    if (!v1 && !v2 && tma_ok) return launch_gemm_tc_tma(g, st);
+    if (!v1 && v2) return launch_gemm_tc_persistent(g, st);
+  }
   static bool attr_set = false;
   const int smem = (int)sizeof(TcSmem) + 1024;
   if (!attr_set) {
