@@ -25,6 +25,7 @@ int set_error(int code, const char* fmt, ...) {
 }
 }  // namespace ctrlsim
 
+namespace ctrlsim { void set_attn_debug(int v); }
 using namespace ctrlsim;
 
 struct CtrlSim {
@@ -225,6 +226,7 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
   return 0;
 }
 
+void ctrlsim_debug_attn(int32_t v) { ctrlsim::set_attn_debug(v); }
 long long ctrlsim_launch_count(void) { return g_launch_count; }
 void ctrlsim_profile_enable(int32_t on) {
   g_prof.on = on != 0;

@@ -124,18 +124,21 @@ attn_padded_kernel(const float* __restrict__ Q, int ldq, const float* __restrict
 }
 
 // CTRLSIM_ATTN=simt selects the FP32 FFMA kernels of this file (A/B testing); the default is attention_mma.cu.
-static bool use_mma_attn() {
+static int attn_mode() {  // 0 = simt, 1 = mma.sync, 2 = tcgen05 (default; falls back to mma.sync for tiny query counts)
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("CTRLSIM_ATTN");
-    mode = (e && std::string(e) == "simt") ? 0 : 1;
+    mode = (e && std::string(e) == "simt") ? 0 : (e && std::string(e) == "mma") ? 1 : 2;
   }
-  return mode == 1;
+  return mode;
 }
+static bool use_mma_attn() { return attn_mode() >= 1; }
 
 int launch_attn_padded(const float* Q, int ldq, const float* Kp, const float* Vp, int ldkv, const uint8_t* key_pad,
                        float* O, int ldo, int G, int Lq, int Lk, cudaStream_t st) {
   if (G <= 0 || Lq <= 0) return 0;
+  if (attn_mode() == 2 && Lq >= 128 && Lk <= 256 && Vp > Kp && ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(Kp)) & 15) == 0)
+    return launch_attn_tc(false, Q, ldq, H, 0, Kp, ldkv, (int)(Vp - Kp) + H, 0, (int)(Vp - Kp), key_pad, O, ldo, G, Lq, Lk, st);
   if (use_mma_attn()) return launch_attn_padded_mma(Q, ldq, Kp, Vp, ldkv, key_pad, O, ldo, G, Lq, Lk, st);
   if (Lk % 8 != 0) return set_error(-2, "attn_padded: Lk=%d must be a multiple of 8", Lk);
   dim3 grid((Lq + 127) / 128, NH, G);
@@ -205,6 +208,8 @@ attn_causal_kernel(const float* __restrict__ QKV, float* __restrict__ O, int Lcu
 
 int launch_attn_causal(const float* QKV, float* O, int G, int n_t, cudaStream_t st) {
   if (G <= 0 || n_t <= 0) return 0;
+  if (attn_mode() == 2 && n_t * TOK_T >= 128 && (reinterpret_cast<uintptr_t>(QKV) & 15) == 0)
+    return launch_attn_tc(true, QKV, 3 * H, 3 * H, 0, QKV, 3 * H, 3 * H, H, 2 * H, nullptr, O, H, G, n_t * TOK_T, n_t * TOK_T, st);
   if (use_mma_attn()) return launch_attn_causal_mma(QKV, O, G, n_t, st);
   const int Lcur = n_t * TOK_T;
   dim3 grid((Lcur + 127) / 128, NH, G);

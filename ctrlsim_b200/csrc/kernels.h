@@ -29,6 +29,9 @@ int launch_attn_causal(const float* QKV, float* O, int G, int n_t, cudaStream_t 
 int launch_attn_padded_mma(const float* Q, int ldq, const float* Kp, const float* Vp, int ldkv, const uint8_t* key_pad,
                            float* O, int ldo, int G, int Lq, int Lk, cudaStream_t st);  // attention_mma.cu
 int launch_attn_causal_mma(const float* QKV, float* O, int G, int n_t, cudaStream_t st);
+int launch_attn_tc(bool causal, const float* Qbase, int ldq, int q_cols, int q_col0, const float* KVbase, int ldkv,
+                   int kv_cols, int k_col0, int v_col0, const uint8_t* key_pad, float* O, int ldo, int G, int Lq, int Lk,
+                   cudaStream_t st);  // attention_tc.cu
 int launch_attn_step(const float* QKV_full, const float* qkv_rows, float* O, int G, int n_t_full, int ti,
                      bool own_row, cudaStream_t st);
 int launch_map_pool(const float* feats, const uint8_t* pt_valid, const uint8_t* poly_valid, const float* U,

@@ -132,6 +132,7 @@ int ctrlsim_metrics(CtrlSim* h, const CtrlSimBatch* b, double* out_scene, int64_
  * 1 map_pool, 2 decoder self-attention, 3 decoder cross-attention): total ms, total work (flops; bytes for map_pool),
  * number of launches. */
 long long ctrlsim_launch_count(void);
+void ctrlsim_debug_attn(int32_t mode); /* bring-up aid for attention_tc.cu; 0 = normal */
 void ctrlsim_profile_enable(int32_t on);
 void ctrlsim_profile_read(double* out);
 
