@@ -222,12 +222,17 @@ int launch_attn_causal(const float* QKV, float* O, int G, int n_t, cudaStream_t 
 // Second pass: queries are the A rtg-token rows (ti, a, 1) of each group, recomputed after RTG sampling.
 // Visible keys: every first-pass token of timesteps < ti, the A state tokens of timestep ti (first pass), and the
 // row's own (new) rtg key/value.  QKV_full: first-pass [G*Lfull, 768]; qkv_rows: [G*A, 768]; O: [G*A, 256].
-__global__ void __launch_bounds__(32)
+constexpr int SCH = 32;  // keys per per-warp tile in attn_step
+
+// 4 warps per (group, head): warp w streams key tiles w, w+4, ... for all 24 query rows (thread = query), then the
+// partial online-softmax states are merged through shared memory.
+__global__ void __launch_bounds__(128)
 attn_step_kernel(const float* __restrict__ QKV_full, const float* __restrict__ qkv_rows, float* __restrict__ O,
                  int Lfull, int ti, int own_row) {
-  __shared__ __align__(16) KVTile<CCH> sm;
+  __shared__ __align__(16) KVTile<SCH> sm[4];
+  __shared__ float part[4][A][DH + 2];
   const int g = blockIdx.y, h = blockIdx.x;
-  const int a = threadIdx.x;
+  const int warp = threadIdx.x >> 5, a = threadIdx.x & 31;
   const bool active = a < A;
   float q[DH], acc[DH];
   float m = -INFINITY, l = 0.f;
@@ -238,16 +243,17 @@ attn_step_kernel(const float* __restrict__ QKV_full, const float* __restrict__ q
   const float* base = QKV_full + (size_t)g * Lfull * (3 * H);
   const int n_hist = ti * TOK_T;          // all tokens of earlier timesteps
   const int n_keys = n_hist + A;          // + state tokens of timestep ti
-  for (int k0 = 0; k0 < n_keys; k0 += CCH) {
-    const int nk = min(CCH, n_keys - k0);
+  KVTile<SCH>& t = sm[warp];
+  for (int k0 = warp * SCH; k0 < n_keys; k0 += 4 * SCH) {
+    const int nk = min(SCH, n_keys - k0);
     __syncwarp();
-    for (int i = threadIdx.x; i < nk * (DH / 4); i += 32) {
+    for (int i = a; i < nk * (DH / 4); i += 32) {
       const int r = i >> 3, c = (i & 7) << 2;
       const int key = k0 + r;
       const int tok = key < n_hist ? key : n_hist + (key - n_hist) * KT;  // state token of agent (key - n_hist)
       const float* src = base + (size_t)tok * (3 * H) + h * DH + c;
-      *reinterpret_cast<float4*>(&sm.k[r][c]) = *reinterpret_cast<const float4*>(src + H);
-      *reinterpret_cast<float4*>(&sm.v[r][c]) = *reinterpret_cast<const float4*>(src + 2 * H);
+      *reinterpret_cast<float4*>(&t.k[r][c]) = *reinterpret_cast<const float4*>(src + H);
+      *reinterpret_cast<float4*>(&t.v[r][c]) = *reinterpret_cast<const float4*>(src + 2 * H);
     }
     __syncwarp();
     if (active) {
@@ -255,30 +261,50 @@ attn_step_kernel(const float* __restrict__ QKV_full, const float* __restrict__ q
         bool ok[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) ok[j] = b + j < nk;
-        online_block8(q, sm.k, sm.v, b, ok, m, l, acc);
+        online_block8(q, t.k, t.v, b, ok, m, l, acc);
       }
     }
   }
-  __syncwarp();
-  if (!own_row) {  // state rows of the last first-pass layer: their own key is already among the state tokens above
-    if (active) store_o(O + ((size_t)g * A + a) * H + h * DH, acc, l);
-    return;
-  }
-  // own rtg key/value: stage the A new rows as one more tile, each thread uses only its own row
-  for (int i = threadIdx.x; i < A * (DH / 4); i += 32) {
-    const int r = i >> 3, c = (i & 7) << 2;
-    const float* src = qkv_rows + ((size_t)g * A + r) * (3 * H) + h * DH + c;
-    *reinterpret_cast<float4*>(&sm.k[r][c]) = *reinterpret_cast<const float4*>(src + H);
-    *reinterpret_cast<float4*>(&sm.v[r][c]) = *reinterpret_cast<const float4*>(src + 2 * H);
-  }
-  __syncwarp();
-  if (active) {
-    const int b = (a >> 3) << 3;
-    bool ok[8];
+  if (own_row && warp == 3) {  // own (new) rtg key/value of the second pass: each thread uses only its own row
+    __syncwarp();
+    for (int i = a; i < A * (DH / 4); i += 32) {
+      const int r = i >> 3, c = (i & 7) << 2;
+      const float* src = qkv_rows + ((size_t)g * A + r) * (3 * H) + h * DH + c;
+      *reinterpret_cast<float4*>(&t.k[r][c]) = *reinterpret_cast<const float4*>(src + H);
+      *reinterpret_cast<float4*>(&t.v[r][c]) = *reinterpret_cast<const float4*>(src + 2 * H);
+    }
+    __syncwarp();
+    if (active) {
+      const int b = (a >> 3) << 3;
+      bool ok[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ok[j] = (b + j) == a;
-    online_block8(q, sm.k, sm.v, b, ok, m, l, acc);
-    store_o(O + ((size_t)g * A + a) * H + h * DH, acc, l);
+      for (int j = 0; j < 8; ++j) ok[j] = (b + j) == a;
+      online_block8(q, t.k, t.v, b, ok, m, l, acc);
+    }
+  }
+  if (active) {
+    part[warp][a][DH] = m;
+    part[warp][a][DH + 1] = l;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) part[warp][a][c] = acc[c];
+  }
+  __syncthreads();
+  if (warp == 0 && active) {
+    float ms = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) ms = fmaxf(ms, part[w][a][DH]);
+    float lt = 0.f;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = part[w][a][DH];
+      const float f = mw == -INFINITY ? 0.f : exp2f(mw - ms);
+      lt = fmaf(part[w][a][DH + 1], f, lt);
+#pragma unroll
+      for (int c = 0; c < DH; ++c) acc[c] = fmaf(part[w][a][c], f, acc[c]);
+    }
+    store_o(O + ((size_t)g * A + a) * H + h * DH, acc, lt);
   }
 }
 
@@ -286,7 +312,7 @@ int launch_attn_step(const float* QKV_full, const float* qkv_rows, float* O, int
                      bool own_row, cudaStream_t st) {
   if (G <= 0) return 0;
   dim3 grid(NH, G);
-  attn_step_kernel<<<grid, 32, 0, st>>>(QKV_full, qkv_rows, O, n_t_full * TOK_T, ti, own_row ? 1 : 0);
+  attn_step_kernel<<<grid, 128, 0, st>>>(QKV_full, qkv_rows, O, n_t_full * TOK_T, ti, own_row ? 1 : 0);
   CS_CHECK_LAUNCH("attn_step");
   return 0;
 }

@@ -219,40 +219,51 @@ template <int DIN>
 __global__ void __launch_bounds__(256)
 small_mlp1_kernel(const float* __restrict__ X, const float* __restrict__ W1, const float* __restrict__ b1,
                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ Y, size_t M) {
-  const size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  float x[DIN];
-#pragma unroll
-  for (int k = 0; k < DIN; ++k) x[k] = X[row * DIN + k];
-  float v[8];
-  float s = 0.f;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  // this lane's 8 output channels: weights, bias and LN affine live in registers for all rows the warp processes
+  float w[8][DIN], bb[8], gm[8], bt[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int o = lane * 8 + i;
-    float acc = __ldg(b1 + o);
+    bb[i] = __ldg(b1 + o); gm[i] = __ldg(gamma + o); bt[i] = __ldg(beta + o);
 #pragma unroll
-    for (int k = 0; k < DIN; ++k) acc = fmaf(__ldg(W1 + o * DIN + k), x[k], acc);
-    v[i] = acc;
-    s += acc;
+    for (int k = 0; k < DIN; ++k) w[i][k] = __ldg(W1 + o * DIN + k);
   }
-  const float mean = warp_sum(s) * (1.0f / H);
-  float q = 0.f;
+  for (size_t row = warp0; row < M; row += nwarps) {
+    float x[DIN];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + LN_EPS);
-  float o8[8];
+    for (int k = 0; k < DIN; ++k) x[k] = X[row * DIN + k];
+    float v[8];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    o8[i] = fmaxf((v[i] - mean) * rstd * __ldg(gamma + lane * 8 + i) + __ldg(beta + lane * 8 + i), 0.f);
-  float* y = Y + row * H + lane * 8;
-  *reinterpret_cast<float4*>(y) = make_float4(o8[0], o8[1], o8[2], o8[3]);
-  *reinterpret_cast<float4*>(y + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+    for (int i = 0; i < 8; ++i) {
+      float acc = bb[i];
+#pragma unroll
+      for (int k = 0; k < DIN; ++k) acc = fmaf(w[i][k], x[k], acc);
+      v[i] = acc;
+      s += acc;
+    }
+    const float mean = warp_sum(s) * (1.0f / H);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + LN_EPS);
+    float o8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o8[i] = fmaxf((v[i] - mean) * rstd * gm[i] + bt[i], 0.f);
+    float* y = Y + row * H + lane * 8;
+    *reinterpret_cast<float4*>(y) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+    *reinterpret_cast<float4*>(y + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+  }
 }
 
 int launch_small_mlp1(int din, const float* X, const MlpW& w, float* Y, size_t M, cudaStream_t st) {
   if (M == 0) return 0;
-  const unsigned blocks = (unsigned)((M + 7) / 8);
+  // persistent-ish grid: each warp keeps its weight slice in registers and strides over rows
+  size_t want = (M + 7) / 8;
+  const unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
   if (din == 3) small_mlp1_kernel<3><<<blocks, 256, 0, st>>>(X, w.w0, w.b0, w.lnw, w.lnb, Y, M);
   else if (din == 5) small_mlp1_kernel<5><<<blocks, 256, 0, st>>>(X, w.w0, w.b0, w.lnw, w.lnb, Y, M);
   else if (din == 12) small_mlp1_kernel<12><<<blocks, 256, 0, st>>>(X, w.w0, w.b0, w.lnw, w.lnb, Y, M);
