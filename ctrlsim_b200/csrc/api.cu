@@ -25,7 +25,7 @@ int set_error(int code, const char* fmt, ...) {
 }
 }  // namespace ctrlsim
 
-namespace ctrlsim { void set_attn_debug(int v); }
+namespace ctrlsim { void set_attn_debug(int v); void read_attn_trace(long long* out); }
 using namespace ctrlsim;
 
 struct CtrlSim {
@@ -227,6 +227,7 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
 }
 
 void ctrlsim_debug_attn(int32_t v) { ctrlsim::set_attn_debug(v); }
+void ctrlsim_debug_attn_trace(int64_t* out) { ctrlsim::read_attn_trace(reinterpret_cast<long long*>(out)); }
 long long ctrlsim_launch_count(void) { return g_launch_count; }
 void ctrlsim_profile_enable(int32_t on) {
   g_prof.on = on != 0;

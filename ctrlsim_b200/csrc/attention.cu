@@ -341,9 +341,8 @@ constexpr int POOL_THREADS = 256;
 constexpr uint32_t TILE_BYTES = NP * H * sizeof(float);  // 102,400
 
 struct PoolSmem {
-  float feats[2][NP][H];   // 2 x 100 KB
-  float U[NH][H];          // 8 KB
-  float prob[NH][NP + 4];  // softmax weights of the current polyline
+  float feats[2][NP][H];  // 2 x 100 KB
+  float prob[NP][NH];     // scores, then softmax weights, of the current polyline (point-major: float4 reads)
   uint64_t full[2];
 };
 
@@ -354,11 +353,17 @@ map_pool_kernel(const float* __restrict__ feats, const uint8_t* __restrict__ pt_
   extern __shared__ __align__(128) unsigned char smraw[];
   PoolSmem& sm = *reinterpret_cast<PoolSmem*>(smraw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < NH * H; i += POOL_THREADS) (&sm.U[0][0])[i] = U[i];
   if (tid == 0) {
     mbar_init(&sm.full[0], 1);
     mbar_init(&sm.full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // the folded query/key matrix U lives in registers: lane owns dims [4 lane, 4 lane + 4) and [128 + 4 lane, ...)
+  float4 u0[NH], u1[NH];
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh) {
+    u0[hh] = __ldg(reinterpret_cast<const float4*>(U + hh * H + lane * 4));
+    u1[hh] = __ldg(reinterpret_cast<const float4*>(U + hh * H + 128 + lane * 4));
   }
   __syncthreads();
   const int stride = gridDim.x;
@@ -381,27 +386,35 @@ map_pool_kernel(const float* __restrict__ feats, const uint8_t* __restrict__ pt_
       __syncthreads();
       continue;
     }
-    // scores: one warp per point, lane owns 8 consecutive feature dims, 8 head dot-products reduced by butterfly
+    // scores: one warp per point; the 8 per-head partial dot products are reduced with a transposing butterfly
+    // (4 + 2 + 1 + 2 shuffles instead of 8 x 5)
     for (int p = warp; p < NP; p += POOL_THREADS / 32) {
-      // lane owns dims [4 lane, 4 lane + 4) and [128 + 4 lane, ...): consecutive lanes read consecutive 16-byte chunks
       const float4 f0 = *reinterpret_cast<const float4*>(&sm.feats[s][p][lane * 4]);
       const float4 f1 = *reinterpret_cast<const float4*>(&sm.feats[s][p][128 + lane * 4]);
       float d[NH];
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh) {
-        const float4 u0 = *reinterpret_cast<const float4*>(&sm.U[hh][lane * 4]);
-        const float4 u1 = *reinterpret_cast<const float4*>(&sm.U[hh][128 + lane * 4]);
-        float x = f0.x * u0.x;
-        x = fmaf(f0.y, u0.y, x); x = fmaf(f0.z, u0.z, x); x = fmaf(f0.w, u0.w, x);
-        x = fmaf(f1.x, u1.x, x); x = fmaf(f1.y, u1.y, x); x = fmaf(f1.z, u1.z, x); x = fmaf(f1.w, u1.w, x);
-        d[hh] = warp_sum(x);
+        float x = f0.x * u0[hh].x;
+        x = fmaf(f0.y, u0[hh].y, x); x = fmaf(f0.z, u0[hh].z, x); x = fmaf(f0.w, u0[hh].w, x);
+        x = fmaf(f1.x, u1[hh].x, x); x = fmaf(f1.y, u1[hh].y, x); x = fmaf(f1.z, u1[hh].z, x);
+        d[hh] = fmaf(f1.w, u1[hh].w, x);
       }
-      if (lane < NH) {
-        float v = d[0];
+      const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+      float e[4], g2[2];
 #pragma unroll
-        for (int hh = 1; hh < NH; ++hh) v = (lane == hh) ? d[hh] : v;
-        sm.prob[lane][p] = v;
+      for (int i = 0; i < 4; ++i) {
+        const float keep = b16 ? d[i + 4] : d[i], send = b16 ? d[i] : d[i + 4];
+        e[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
       }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float keep = b8 ? e[i + 2] : e[i], send = b8 ? e[i] : e[i + 2];
+        g2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      float r = (b4 ? g2[1] : g2[0]) + __shfl_xor_sync(0xffffffffu, b4 ? g2[0] : g2[1], 4);
+      r += __shfl_xor_sync(0xffffffffu, r, 2);
+      r += __shfl_xor_sync(0xffffffffu, r, 1);
+      if ((lane & 3) == 0) sm.prob[p][lane >> 2] = r;  // head index = lane bits 4..2
     }
     __syncthreads();
     // masked softmax over the 100 points, one warp per head (all-masked rows un-mask point 0, map_encoder.py:31)
@@ -423,7 +436,7 @@ map_pool_kernel(const float* __restrict__ feats, const uint8_t* __restrict__ pt_
       for (int j = 0; j < 4; ++j) {
         const int p = lane + 32 * j;
         if (!any && p == 0) ok[j] = true;
-        sc[j] = ok[j] ? sm.prob[hh][p] * kLog2e : -INFINITY;
+        sc[j] = ok[j] ? sm.prob[p][hh] * kLog2e : -INFINITY;
         mx = fmaxf(mx, sc[j]);
       }
       mx = warp_max(mx);
@@ -435,19 +448,24 @@ map_pool_kernel(const float* __restrict__ feats, const uint8_t* __restrict__ pt_
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int p = lane + 32 * j;
-        if (p < NP) sm.prob[hh][p] = sc[j] * inv;
+        if (p < NP) sm.prob[p][hh] = sc[j] * inv;
       }
     }
     __syncthreads();
-    // pooled[h][d] = sum_p prob[h][p] * feats[p][d]; thread owns column d
+    // pooled[h][d] = sum_p prob[p][h] * feats[p][d]; thread owns column d
     {
       float accp[NH];
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh) accp[hh] = 0.f;
+#pragma unroll 4
       for (int p = 0; p < NP; ++p) {
         const float f = sm.feats[s][p][tid];
-#pragma unroll
-        for (int hh = 0; hh < NH; ++hh) accp[hh] = fmaf(sm.prob[hh][p], f, accp[hh]);
+        const float4 pa = *reinterpret_cast<const float4*>(&sm.prob[p][0]);
+        const float4 pb = *reinterpret_cast<const float4*>(&sm.prob[p][4]);
+        accp[0] = fmaf(pa.x, f, accp[0]); accp[1] = fmaf(pa.y, f, accp[1]);
+        accp[2] = fmaf(pa.z, f, accp[2]); accp[3] = fmaf(pa.w, f, accp[3]);
+        accp[4] = fmaf(pb.x, f, accp[4]); accp[5] = fmaf(pb.y, f, accp[5]);
+        accp[6] = fmaf(pb.z, f, accp[6]); accp[7] = fmaf(pb.w, f, accp[7]);
       }
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh) out[hh * H + tid] = accp[hh];

@@ -136,7 +136,9 @@ __device__ __forceinline__ bool at_m1_allowed(int tq, int aq, int kq, int key) {
   return kk == 0 || (ak == aq && kk <= kq);
 }
 
-__device__ int g_attn_debug = 0;  // bring-up aid: 1 dump S, 2 dump raw PV, 3 dump P_hi read back after PV
+__device__ int g_attn_debug = 0;  // bring-up aid: 2 dump raw PV, 3 dump P_hi read back after PV, 4 record a timeline
+__device__ long long g_attn_trace[8 * 64];  // mode 4: clock64() at 8 events x up to 64 key tiles of CTA (0, 0, 0)
+#define AT_TRACE(slot) do { if (trace_on && j < 64) g_attn_trace[j * 8 + (slot)] = clock64(); } while (0)
 
 template <bool CAUSAL>
 __global__ void __launch_bounds__(AT_THREADS, 2)
@@ -175,6 +177,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
+  const bool trace_on = g_attn_debug == 4 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
+                        (warp == 0 || warp == 4 || warp == 6);
 
   if (warp < 4) {
     // ------------------------------------------------------------------ softmax + output (thread = query row)
@@ -211,8 +215,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         okm = sm.pad_mask[j];
       }
       const bool fast = __all_sync(0xffffffffu, okm == ~0ull);
+      AT_TRACE(7);
       at_wait(&sm.s_full, j & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      AT_TRACE(0);
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
@@ -235,6 +241,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const float mn = fmaxf(m, mx);
       const float ref = mn == -INFINITY ? 0.f : mn;
       const float corr = exp2f(m - ref);
+      AT_TRACE(1);
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
@@ -261,8 +268,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       at_arrive(&sm.p_ready);
+      AT_TRACE(2);
       at_wait(&sm.o_full, j & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      AT_TRACE(3);
       if (g_attn_debug == 3 && j == 0) {
         uint32_t r[32];
         at_ld32(lane_addr + AT_S_MAIN, r);
@@ -275,7 +284,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         uint32_t r[32], rx[32];
         at_ld32(lane_addr + AT_O_MAIN, r);
         at_ld32(lane_addr + AT_O_CROSS, rx);
-        if (g_attn_debug >= 2 && g_attn_debug != 3 && j == 0) {
+        if (g_attn_debug == 2 && j == 0) {
 #pragma unroll
           for (int i = 0; i < DH; ++i) o[i] = __uint_as_float(r[i]);
           l = 1.f;
@@ -284,6 +293,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < DH; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(r[i]) + __uint_as_float(rx[i]));
       }
+      AT_TRACE(4);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     if (row_ok) {
@@ -328,6 +338,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) at_arrive(&sm.lo_ready[s]);
+      AT_TRACE(5);
     }
   } else if (warp == 6) {
     // ------------------------------------------------------------------ MMA issuer
@@ -353,6 +364,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       __syncwarp();
       at_wait(&sm.p_ready, j & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      AT_TRACE(6);
       if (lane == 0) {
         const uint64_t dvh = at_desc(at_u32(sm.kv[s].vt_hi)), dvl = at_desc(at_u32(sm.kv[s].vt_lo));
 #pragma unroll
@@ -391,6 +403,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 void set_attn_debug(int v) { cudaMemcpyToSymbol(g_attn_debug, &v, sizeof(int)); }
+void read_attn_trace(long long* out) { cudaMemcpyFromSymbol(out, g_attn_trace, sizeof(long long) * 8 * 64); }
 
 typedef CUresult (*AtEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -83,6 +83,7 @@ _SIGS = {
     "ctrlsim_metrics": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_void_p, C.c_void_p, C.c_void_p]),
     "ctrlsim_launch_count": (C.c_longlong, []),
     "ctrlsim_debug_attn": (None, [C.c_int32]),
+    "ctrlsim_debug_attn_trace": (None, [C.c_void_p]),
     "ctrlsim_profile_enable": (None, [C.c_int32]),
     "ctrlsim_profile_read": (None, [C.POINTER(C.c_double)]),
     "ctrlsim_linear": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p]),
