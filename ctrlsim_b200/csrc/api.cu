@@ -1,6 +1,7 @@
 // extern "C" boundary (include/ctrlsim_b200.h): handle management, weight registry, and the per-step orchestration
 // of the rollout hot path.  No torch types cross this file.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -34,7 +35,18 @@ struct CtrlSim {
   bool finalized = false;
   int n_sm = 148;
   std::unordered_map<std::string, std::pair<const float*, int64_t>> reg;
-  std::vector<int> h_group_off;
+  float* w_lo = nullptr;  // lo parts of all registered weights (see ctrlsim_finalize_weights)
+  std::vector<int> h_group_off, h_group_focal;
+  // per-focal polyline-encoder cache for the steps whose window still starts at t = 0 (see MapPlan, model_ws.h)
+  float* mc_emb = nullptr;
+  uint8_t* mc_valid = nullptr;
+  int64_t mc_blocks = 0;
+  std::vector<uint8_t> mc_dir;     // host directory: block (scene * max_veh + focal) holds a valid encoding
+  const void* mc_owner = nullptr;  // batch the directory describes (its hist_state pointer)
+  int mc_last_t = -1;
+  int* h_idx = nullptr;            // pinned staging for the per-chunk index lists
+  size_t h_idx_cap = 0;
+  long long mc_hits = 0, mc_misses = 0;
 };
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -69,7 +81,9 @@ int ctrlsim_create(const CtrlSimConfig* c, CtrlSim** out) {
   return 0;
 }
 
-void ctrlsim_destroy(CtrlSim* h) { delete h; }
+void ctrlsim_destroy(CtrlSim* h) {
+  if (h) { gemm_clear_weight_lo(h); if (h->w_lo) cudaFree(h->w_lo); }
+  if (h && h->h_idx) cudaFreeHost(h->h_idx); delete h; }
 
 int ctrlsim_load_weights(CtrlSim* h, const char* name, const float* ptr, int64_t count) {
   if (!h || !name || !ptr) return set_error(-1, "ctrlsim_load_weights: null argument");
@@ -163,6 +177,23 @@ int ctrlsim_finalize_weights(CtrlSim* h) {
   }
   if ((rc = need_mlp(h, "decoder.predict_action", H, N_ACT, w.head_action))) return rc;
   if ((rc = need_mlp(h, "decoder.predict_rtg", H, N_RTG * 3, w.head_rtg))) return rc;
+  // lo-part copies (x - trunc13(x)) of every registered tensor, in one allocation owned by the handle: the GEMM's TMA
+  // fetches them as the W_lo operand of the 3xTF32 split. Call ctrlsim_finalize_weights again after changing weights.
+  gemm_clear_weight_lo(h);
+  if (h->w_lo) { cudaFree(h->w_lo); h->w_lo = nullptr; }
+  if (getenv("CTRLSIM_WLO") == nullptr || std::string(getenv("CTRLSIM_WLO")) != "0") {
+    size_t total = 0;
+    for (auto& kv : h->reg) total += ((size_t)kv.second.second + 63) & ~size_t(63);
+    if (cudaMalloc(&h->w_lo, total * sizeof(float)) != cudaSuccess) return set_error(-5, "finalize_weights: cudaMalloc of %zu bytes failed", total * sizeof(float));
+    size_t off = 0;
+    for (auto& kv : h->reg) {
+      const size_t n = (size_t)kv.second.second;
+      if ((rc = launch_weight_lo(kv.second.first, h->w_lo + off, n, 0))) return rc;
+      gemm_register_weight_lo(h, kv.second.first, n, h->w_lo + off);
+      off += (n + 63) & ~size_t(63);
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) return set_error(-5, "finalize_weights: lo-part kernel failed");
+  }
   h->finalized = true;
   return 0;
 }
@@ -171,6 +202,26 @@ int64_t ctrlsim_workspace_bytes(const CtrlSim* h, int32_t max_groups) {
   (void)h;
   Workspace ws;
   return (int64_t)ws.carve(nullptr, 0, max_groups);
+}
+
+int64_t ctrlsim_map_cache_bytes(int32_t n_scenes, int32_t max_veh) {
+  return (int64_t)n_scenes * max_veh * ((int64_t)P * H * sizeof(float) + P) + 256;
+}
+int ctrlsim_attach_map_cache(CtrlSim* h, void* mem, int64_t bytes) {
+  if (!h) return set_error(-1, "ctrlsim_attach_map_cache: null handle");
+  h->mc_dir.clear(); h->mc_owner = nullptr; h->mc_last_t = -1;
+  if (!mem || bytes <= 0) { h->mc_emb = nullptr; h->mc_valid = nullptr; h->mc_blocks = 0; return 0; }
+  if (reinterpret_cast<uintptr_t>(mem) & 15) return set_error(-2, "ctrlsim_attach_map_cache: memory must be 16-byte aligned");
+  const int64_t per = (int64_t)P * H * sizeof(float) + P;
+  h->mc_blocks = (bytes - 256) / per;
+  if (h->mc_blocks <= 0) return set_error(-4, "ctrlsim_attach_map_cache: %lld bytes hold no block", (long long)bytes);
+  h->mc_emb = reinterpret_cast<float*>(mem);
+  h->mc_valid = reinterpret_cast<uint8_t*>(mem) + h->mc_blocks * (int64_t)P * H * sizeof(float);
+  return 0;
+}
+void ctrlsim_map_cache_stats(const CtrlSim* h, int64_t* hits, int64_t* misses) {
+  if (hits) *hits = h ? h->mc_hits : 0;
+  if (misses) *misses = h ? h->mc_misses : 0;
 }
 
 int ctrlsim_sim_reset(CtrlSim* h, CtrlSimBatch* b, void* stream) { return launch_sim_reset(*b, h->mc, S(stream)); }
@@ -190,7 +241,14 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
   cudaStream_t st = S(stream);
   const int Sn = b->n_scenes;
   h->h_group_off.resize(Sn + 1);
+  const int Nv = b->max_veh;
+  // the map cache applies while the window starts at t = 0 and the batch fits the attached memory
+  const bool use_mc = t < T && h->mc_emb && (int64_t)Sn * Nv <= h->mc_blocks;
   cudaError_t e = cudaMemcpyAsync(h->h_group_off.data(), b->group_off, sizeof(int) * (Sn + 1), cudaMemcpyDeviceToHost, st);
+  if (use_mc && e == cudaSuccess) {
+    h->h_group_focal.resize((size_t)Sn * Nv);
+    e = cudaMemcpyAsync(h->h_group_focal.data(), b->group_focal, sizeof(int) * (size_t)Sn * Nv, cudaMemcpyDeviceToHost, st);
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return set_error(-5, "policy_step: reading group offsets: %s", cudaGetErrorString(e));
   const std::vector<int>& off = h->h_group_off;
@@ -202,6 +260,23 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
                      (long long)workspace_bytes, chunk_groups, (long long)need_bytes);
   ws.carve(workspace, need_bytes, chunk_groups);
   const int n_t = t < T ? t + 1 : T;
+  if (use_mc) {
+    // a directory entry stays valid for one episode of one batch, stepped in order
+    if (t == 0 || h->mc_owner != (const void*)b->hist_state || t != h->mc_last_t + 1 || h->mc_dir.size() != (size_t)Sn * Nv) {
+      h->mc_dir.assign((size_t)Sn * Nv, 0);
+      h->mc_owner = (const void*)b->hist_state;
+    }
+    h->mc_last_t = t;
+    const size_t need_idx = 3 * (size_t)n_groups_total;
+    if (need_idx > h->h_idx_cap) {
+      if (h->h_idx) cudaFreeHost(h->h_idx);
+      h->h_idx = nullptr; h->h_idx_cap = 0;
+      if (cudaMallocHost(&h->h_idx, need_idx * 2 * sizeof(int)) != cudaSuccess) return set_error(-5, "policy_step: pinned staging allocation failed");
+      h->h_idx_cap = need_idx * 2;
+    }
+  } else {
+    h->mc_last_t = -1;
+  }
   int s0 = 0;
   while (s0 < Sn) {
     int s1 = s0;
@@ -210,8 +285,29 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
     const int g0 = off[s0], ng = off[s1] - off[s0];
     if (ng > 0) {
       int rc;
-      if ((rc = launch_tokenize(*b, g0, ng, t, n_t, ws.tk, h->mc, st))) return rc;
-      if ((rc = forward_pass1(h->w, ws, ng, n_t, h->n_sm, st))) return rc;
+      MapPlan mp;
+      if (use_mc) {
+        int* slot = h->h_idx + 3 * (size_t)g0;  // [ng] slot | [ng] sel | [ng] dst, staged per chunk
+        int* sel = slot + ng;
+        int* dst = sel + ng;
+        int n_miss = 0, gl = 0;
+        for (int sc = s0; sc < s1; ++sc)
+          for (int lg = 0; lg < off[sc + 1] - off[sc]; ++lg, ++gl) {
+            const int blk = sc * Nv + h->h_group_focal[(size_t)sc * Nv + lg];
+            slot[gl] = blk;
+            if (!h->mc_dir[blk]) { h->mc_dir[blk] = 1; sel[n_miss] = gl; dst[n_miss] = blk; ++n_miss; }
+          }
+        h->mc_misses += n_miss; h->mc_hits += ng - n_miss;
+        cudaError_t ce = cudaMemcpyAsync(ws.map_slot, slot, sizeof(int) * ng, cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess && n_miss) ce = cudaMemcpyAsync(ws.map_sel, sel, sizeof(int) * n_miss, cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess && n_miss) ce = cudaMemcpyAsync(ws.map_dst, dst, sizeof(int) * n_miss, cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) return set_error(-5, "policy_step: uploading map-cache lists: %s", cudaGetErrorString(ce));
+        mp.n_map = n_miss; mp.slot = ws.map_slot; mp.dst = ws.map_dst; mp.cache_emb = h->mc_emb; mp.cache_valid = h->mc_valid;
+        if ((rc = launch_tokenize(*b, g0, ng, t, n_t, ws.tk, h->mc, st, ws.map_sel, n_miss))) return rc;
+      } else {
+        if ((rc = launch_tokenize(*b, g0, ng, t, n_t, ws.tk, h->mc, st))) return rc;
+      }
+      if ((rc = forward_pass1(h->w, ws, ng, n_t, h->n_sm, st, mp))) return rc;
       if ((rc = launch_resolve_rtg_range(*b, *p, t, s0, s1, g0, h->mc.steps, ws.rtg_logits, st))) return rc;
       if ((rc = launch_gather_rtg_steps(*b, g0, ng, t, h->mc.steps, ws.rtg_new, st))) return rc;
       if ((rc = forward_pass2(h->w, ws, ng, n_t, st))) return rc;

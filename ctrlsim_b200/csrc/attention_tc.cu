@@ -7,16 +7,20 @@
 //               used directly as the "hi" operands (kind::tf32 ignores the 13 low mantissa bits).
 //   warps 4-5   derive the lo = x - trunc13(x) tiles (Q once, K per tile) and stage V^T hi / lo from global memory
 //   warp 6      MMA issuer.  S = Q K^T: A = Q (smem, K-major), B = K tile (smem, K-major), M=128 N=64, 4 k-steps x 3
-//               split products into two TMEM accumulators (hi*hi and cross terms).  O_tile = P V: A = P read FROM TMEM
-//               (the softmax warps overwrite S in place with P_hi / P_lo, FlashAttention-4 style, so P never touches
-//               shared memory), B = V^T tile (K-major; the producer warps transpose V while splitting it - an MN-major
-//               tf32 B operand needs the SWIZZLE_128B_BASE32B layout, which this kernel avoids), M=128 N=32,
-//               8 k-steps x 3, fresh accumulators per tile (the tensor core adds with truncation; short chains only).
-//   warps 0-3   softmax: thread = query row = TMEM lane.  Two sweeps over S (max, then exp2 / row sum / hi-lo split /
-//               tcgen05.st of P); after the PV commit the tile's output is added to the register-resident running
-//               output with a rounded fp32 FMA together with the online-softmax rescale.
-// TMEM (256 columns per CTA, two CTAs per SM): [0,64) S_main -> P_hi, [64,128) S_cross -> P_lo, [128,160) O_main,
-// [160,192) O_cross.
+//               split products into ONE TMEM accumulator.  The tensor core adds into its fp32 accumulator with
+//               truncation, so the order matters: the 8 small cross products (Q_lo K_hi, Q_hi K_lo; 2^-11 of the
+//               result) are issued first and the 4 main products last - only 4 truncations happen at full magnitude,
+//               the same error as a separate cross accumulator but half the TMEM traffic.  O_tile = P V: A = P read
+//               FROM TMEM (FlashAttention-4 style, P never touches shared memory), B = V^T tile (K-major; the producer
+//               warps transpose V while splitting it - an MN-major tf32 B operand needs the SWIZZLE_128B_BASE32B
+//               layout, which this kernel avoids), M=128 N=32, 8 k-steps x 3 (16 cross products first), a fresh
+//               accumulator per key tile.
+//   warps 0-3   softmax: thread = query row = TMEM lane.  ONE sweep over S per tile: p = ex2(s * scale - ref) against a
+//               lazily updated reference exponent (FlashAttention-4's conditional rescale): ref only moves when a
+//               score exceeds it by more than 2^16, in which case the tile is redone from the still intact S (P_hi /
+//               P_lo live in their own TMEM columns).  The tile's P V product is added to the register-resident
+//               running output with a rounded fp32 add.
+// TMEM (256 columns per CTA, two CTAs per SM): [0,64) S, [64,128) P_hi, [128,192) P_lo, [192,224) O_tile.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -28,7 +32,8 @@ namespace ctrlsim {
 
 constexpr int AT_QT = 128, AT_KT = 64, AT_STAGES = 2, AT_THREADS = 256;
 constexpr uint32_t AT_TMEM_COLS = 256;
-constexpr uint32_t AT_S_MAIN = 0, AT_S_CROSS = 64, AT_O_MAIN = 128, AT_O_CROSS = 160;
+constexpr uint32_t AT_S0 = 0, AT_PLO = 128, AT_O = 192;  // S1 = AT_S0 + 64
+constexpr float AT_LAZY = 16.f;  // log2 head-room before the softmax reference is moved
 
 struct alignas(1024) AtKV {
   float k_raw[AT_KT * DH];   // [64 keys][32 dims], K-major (TMA, SWIZZLE_128B)
@@ -40,7 +45,8 @@ struct AtSmem {
   float q_raw[AT_QT * DH];
   float q_lo[AT_QT * DH];
   AtKV kv[AT_STAGES];
-  uint64_t q_full, q_lo_ready, kv_full[AT_STAGES], lo_ready[AT_STAGES], kv_empty[AT_STAGES], s_full, p_ready, o_full;
+  uint64_t q_full, q_lo_ready, k_full[AT_STAGES], k_ready[AT_STAGES], k_empty[AT_STAGES], v_ready[AT_STAGES],
+      v_empty[AT_STAGES], s_full[2], p_ready, o_full;
   uint32_t tmem_base;
   unsigned long long pad_mask[4];  // padded mode: bit c of word j = key 64 j + c is valid and inside Lk
 };
@@ -127,16 +133,12 @@ __device__ __forceinline__ void at_lo_tile(float* lo, const float* raw, int n_fl
     reinterpret_cast<float4*>(lo)[i] = l;
   }
 }
-__device__ __forceinline__ bool at_m1_allowed(int tq, int aq, int kq, int key) {
-  const int tk = key / TOK_T;
-  if (tk < tq) return true;
-  if (tk > tq) return false;
-  const int rem = key - tk * TOK_T;
-  const int ak = rem / KT, kk = rem - ak * KT;
-  return kk == 0 || (ak == aq && kk <= kq);
+__device__ __forceinline__ float at_ex2(float x) {  // 2^x, flush-to-zero; ex2(-inf) = +0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-
-__device__ int g_attn_debug = 0;  // bring-up aid: 2 dump raw PV, 3 dump P_hi read back after PV, 4 record a timeline
+__device__ int g_attn_debug = 0;  // 4: record a timeline of CTA (0, 0, 0)
 __device__ long long g_attn_trace[8 * 64];  // mode 4: clock64() at 8 events x up to 64 key tiles of CTA (0, 0, 0)
 #define AT_TRACE(slot) do { if (trace_on && j < 64) g_attn_trace[j * 8 + (slot)] = clock64(); } while (0)
 
@@ -157,8 +159,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   if (tid == 0) {
     at_mbar_init(&sm.q_full, 1); at_mbar_init(&sm.q_lo_ready, 2);
-    for (int s = 0; s < AT_STAGES; ++s) { at_mbar_init(&sm.kv_full[s], 1); at_mbar_init(&sm.lo_ready[s], 2); at_mbar_init(&sm.kv_empty[s], 1); }
-    at_mbar_init(&sm.s_full, 1); at_mbar_init(&sm.p_ready, 128); at_mbar_init(&sm.o_full, 1);
+    for (int s = 0; s < AT_STAGES; ++s) {
+      at_mbar_init(&sm.k_full[s], 1); at_mbar_init(&sm.k_ready[s], 2); at_mbar_init(&sm.k_empty[s], 1);
+      at_mbar_init(&sm.v_ready[s], 2); at_mbar_init(&sm.v_empty[s], 1); at_mbar_init(&sm.s_full[s], 1);
+    }
+    at_mbar_init(&sm.p_ready, 128); at_mbar_init(&sm.o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (!CAUSAL && tid < 4) {
@@ -184,87 +189,98 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // ------------------------------------------------------------------ softmax + output (thread = query row)
     const int row = r0 + 32 * warp + lane;
     const bool row_ok = row < Lq;
-    int tq = 0, aq = 0, kq = 0;
-    if (CAUSAL) { tq = row / TOK_T; const int rem = row - tq * TOK_T; aq = rem / KT; kq = rem - aq * KT; }
+    int tq = 0;
+    // visibility pattern of the 72 keys of the row's own timestep (rule M1): every state token, plus the row's own
+    // rtg / action token if the row is at or past it.  Bit b <-> key tq * 72 + b; bits 64..71 live in pat_hi.
+    unsigned long long pat_lo = 0x9249249249249249ull, pat_hi = 0x24ull;
+    if (CAUSAL) {
+      tq = row / TOK_T;
+      const int rem = row - tq * TOK_T;
+      const int aq = rem / KT, kq = rem - aq * KT;
+      for (int kk = 1; kk <= kq; ++kk) {
+        const int bpos = 3 * aq + kk;
+        if (bpos < 64) pat_lo |= 1ull << bpos; else pat_hi |= 1ull << (bpos - 64);
+      }
+    }
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16);
     const float scale = 0.17677669529663687f * 1.4426950408889634f;  // d_h^-0.5 * log2(e)
-    float m = -INFINITY, l = 0.f, o[DH];
+    // ref: reference exponent (log2 domain, always an INTEGER so that moving it rescales by an exact power of two) of
+    // every p, l and o accumulated so far
+    float ref = -INFINITY, l = 0.f, o[DH];
 #pragma unroll
     for (int i = 0; i < DH; ++i) o[i] = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       const int k0 = j * AT_KT;
+      const uint32_t s_addr = lane_addr + AT_S0 + (uint32_t)(j & 1) * AT_KT;  // S of this tile, overwritten by P_hi
       // visibility of the 64 keys of this tile for this row, as a bit mask (bit c <-> key k0 + c)
       unsigned long long okm;
       if (CAUSAL) {
+        const int base = tq * TOK_T - k0;  // position of the row's own timestep relative to the tile
         if (!row_ok) okm = 0ull;
-        else if (k0 + AT_KT <= tq * TOK_T) okm = ~0ull;
-        else {
-          okm = 0ull;
-#pragma unroll 4
-          for (int c = 0; c < AT_KT; ++c) {
-            const int key = k0 + c;
-            const int tk = key / TOK_T;
-            const int rem = key - tk * TOK_T;
-            const int ak = rem / KT;
-            const int kk = rem - ak * KT;
-            const bool ok = (key < kend) & ((tk < tq) | ((tk == tq) & ((kk == 0) | ((ak == aq) & (kk <= kq)))));
-            okm |= (unsigned long long)ok << c;
-          }
-        }
+        else if (base >= AT_KT) okm = ~0ull;
+        else if (base >= 0) okm = ((1ull << base) - 1ull) | (pat_lo << base);
+        else if (base > -64) okm = (pat_lo >> (-base)) | (pat_hi << (64 + base));
+        else if (base > -TOK_T) okm = pat_hi >> (-base - 64);
+        else okm = 0ull;
       } else {
         okm = sm.pad_mask[j];
       }
       const bool fast = __all_sync(0xffffffffu, okm == ~0ull);
       AT_TRACE(7);
-      at_wait(&sm.s_full, j & 1);
+      at_wait(&sm.s_full[j & 1], (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       AT_TRACE(0);
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
-        uint32_t r[32], rx[32];
-        at_ld32(lane_addr + AT_S_MAIN + 32 * c, r);
-        at_ld32(lane_addr + AT_S_CROSS + 32 * c, rx);
-        if (fast) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]) + __uint_as_float(rx[i]));
-        } else {
+        uint32_t r[32], rl[32];
+        at_ld32(s_addr + 32 * c, r);
+        if (!fast) {
           const unsigned bits = (unsigned)(okm >> (32 * c));
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float s = __uint_as_float(r[i]) + __uint_as_float(rx[i]);
-            mx4[i & 3] = fmaxf(mx4[i & 3], ((bits >> i) & 1u) ? s : -INFINITY);
+          for (int i = 0; i < 32; ++i) r[i] = ((bits >> i) & 1u) ? r[i] : 0xff800000u;  // -inf: p = 0, ignored by max
+        }
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+        const float cmx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale;
+        // lazy reference update: only when a score exceeds the reference by more than 2^AT_LAZY (or none exists yet)
+        const bool bump = cmx > ref + AT_LAZY || (ref == -INFINITY && cmx > -INFINITY);
+        if (__any_sync(0xffffffffu, bump)) {
+          const float nref = bump ? ceilf(cmx) : ref;
+          const float f = (nref == ref) ? 1.f : at_ex2(ref - nref);  // exact power of two (0 when ref was -inf)
+          l *= f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) s4[i] *= f;
+#pragma unroll
+          for (int i = 0; i < DH; ++i) o[i] *= f;
+          ref = nref;
+          if (c == 1) {  // the first half of this tile's P was written against the old reference: rescale it in place
+            uint32_t t[32];
+            at_ld32(s_addr, t);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * f);
+            at_st32(s_addr, t);
+            at_ld32(lane_addr + AT_PLO, t);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * f);
+            at_st32(lane_addr + AT_PLO, t);
           }
         }
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * scale;  // scale > 0 commutes with max
-      const float mn = fmaxf(m, mx);
-      const float ref = mn == -INFINITY ? 0.f : mn;
-      const float corr = exp2f(m - ref);
-      AT_TRACE(1);
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32], rx[32];
-        at_ld32(lane_addr + AT_S_MAIN + 32 * c, r);
-        at_ld32(lane_addr + AT_S_CROSS + 32 * c, rx);
-        const unsigned bits = fast ? 0xffffffffu : (unsigned)(okm >> (32 * c));
+        const float rr = ref == -INFINITY ? 0.f : ref;  // no visible key yet: every p below is ex2(-inf) = 0
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(r[i]) + __uint_as_float(rx[i]);
-          float p = exp2f(fmaf(s, scale, -ref));
-          p = ((bits >> i) & 1u) ? p : 0.f;
-          sum4[i & 3] += p;
+          const float p = at_ex2(fmaf(__uint_as_float(r[i]), scale, -rr));
+          s4[i & 3] += p;
           const uint32_t hi = __float_as_uint(p) & 0xFFFFE000u;
           r[i] = hi;
-          rx[i] = __float_as_uint(p - __uint_as_float(hi));
+          rl[i] = __float_as_uint(p - __uint_as_float(hi));
         }
-        at_st32(lane_addr + AT_S_MAIN + 32 * c, r);   // P_hi over S_main
-        at_st32(lane_addr + AT_S_CROSS + 32 * c, rx); // P_lo over S_cross
+        at_st32(s_addr + 32 * c, r);
+        at_st32(lane_addr + AT_PLO + 32 * c, rl);
       }
-      const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      l = l * corr + sum;
-      m = mn;
+      l += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      AT_TRACE(1);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       at_arrive(&sm.p_ready);
@@ -272,26 +288,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       at_wait(&sm.o_full, j & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       AT_TRACE(3);
-      if (g_attn_debug == 3 && j == 0) {
-        uint32_t r[32];
-        at_ld32(lane_addr + AT_S_MAIN, r);
-#pragma unroll
-        for (int i = 0; i < DH; ++i) o[i] = __uint_as_float(r[i]);
-        l = 1.f;
-        break;
-      }
       {
-        uint32_t r[32], rx[32];
-        at_ld32(lane_addr + AT_O_MAIN, r);
-        at_ld32(lane_addr + AT_O_CROSS, rx);
-        if (g_attn_debug == 2 && j == 0) {
+        uint32_t r[32];
+        at_ld32(lane_addr + AT_O, r);
 #pragma unroll
-          for (int i = 0; i < DH; ++i) o[i] = __uint_as_float(r[i]);
-          l = 1.f;
-          break;
-        }
-#pragma unroll
-        for (int i = 0; i < DH; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(r[i]) + __uint_as_float(rx[i]));
+        for (int i = 0; i < DH; ++i) o[i] += __uint_as_float(r[i]);
       }
       AT_TRACE(4);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -311,72 +312,99 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) at_arrive(&sm.q_lo_ready);
-    const float* vsrc = Vbase + (size_t)g * Lk * ldkv + h * DH + (pt & 7) * 4;
+    const int u = pt & 7, hrot = u >> 1;  // this thread's 4 dims 4u..4u+3 of V; store order rotated by hrot (bank spread)
+    const float* vsrc = Vbase + (size_t)g * Lk * ldkv + h * DH + u * 4;
     for (int j = 0; j < n_tiles; ++j) {
       const int s = j % AT_STAGES;
       float4 vv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {  // V rows of this tile: key = j*64 + pt/8 + 8 i, dims 4*(pt&7) .. +3
+      for (int i = 0; i < 8; ++i) {  // V rows of this tile: key = j*64 + pt/8 + 8 i, dims 4u .. 4u+3
         const int key = j * AT_KT + (pt >> 3) + 8 * i;
         vv[i] = key < Lk ? *reinterpret_cast<const float4*>(vsrc + (size_t)key * ldkv) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      at_wait(&sm.kv_full[s], (j / AT_STAGES) & 1);
+      at_wait(&sm.k_full[s], (j / AT_STAGES) & 1);
       at_lo_tile(sm.kv[s].k_lo, sm.kv[s].k_raw, AT_KT * DH / 4, pt, 64);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) at_arrive(&sm.k_ready[s]);
+      at_wait(&sm.v_empty[s], ((j / AT_STAGES) & 1) ^ 1);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int kl = (pt >> 3) + 8 * i;                 // key within the tile
         const int cb = kl >> 5, kk = kl & 31;
-        const float x[4] = {vv[i].x, vv[i].y, vv[i].z, vv[i].w};
+        // rotate the four values by hrot so that in every store instruction the 8 threads sharing a key hit 8
+        // different (d & 7) classes: with the 128-byte swizzle below the warp's 32 stores land in 32 distinct banks
+        float x0 = vv[i].x, x1 = vv[i].y, x2 = vv[i].z, x3 = vv[i].w;
+        if (hrot & 1) { const float t0 = x0; x0 = x1; x1 = x2; x2 = x3; x3 = t0; }
+        if (hrot & 2) { const float t0 = x0, t1 = x1; x0 = x2; x1 = x3; x2 = t0; x3 = t1; }
+        const float x[4] = {x0, x1, x2, x3};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int d = (pt & 7) * 4 + e;
+        for (int n = 0; n < 4; ++n) {
+          const int d = u * 4 + ((n + hrot) & 3);
           const int off = cb * (DH * 32) + d * 32 + ((((kk >> 2) ^ (d & 7)) << 2) | (kk & 3));
-          sm.kv[s].vt_hi[off] = x[e];
-          sm.kv[s].vt_lo[off] = x[e] - __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u);
+          sm.kv[s].vt_hi[off] = x[n];
+          sm.kv[s].vt_lo[off] = x[n] - __uint_as_float(__float_as_uint(x[n]) & 0xFFFFE000u);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) at_arrive(&sm.lo_ready[s]);
+      if (lane == 0) at_arrive(&sm.v_ready[s]);
       AT_TRACE(5);
     }
   } else if (warp == 6) {
     // ------------------------------------------------------------------ MMA issuer
+    // Issue order QK(0), QK(1), PV(0), QK(2), PV(1), ...: S is double-buffered, so the scores of tile j+1 are computed
+    // while the softmax warps work on tile j.
     const uint32_t id_qk = at_idesc(AT_QT, AT_KT, false), id_pv = at_idesc(AT_QT, DH, false);
     at_wait(&sm.q_lo_ready, 0);
     const uint64_t dqh = at_desc(at_u32(sm.q_raw)), dql = at_desc(at_u32(sm.q_lo));
-    for (int j = 0; j < n_tiles; ++j) {
-      const int s = j % AT_STAGES;
-      at_wait(&sm.lo_ready[s], (j / AT_STAGES) & 1);
+    auto issue_qk = [&](int i) {
+      const int s = i % AT_STAGES;
+      at_wait(&sm.k_ready[s], (i / AT_STAGES) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
+        const uint32_t d_s = tmem + AT_S0 + (uint32_t)(i & 1) * AT_KT;
         const uint64_t dkh = at_desc(at_u32(sm.kv[s].k_raw)), dkl = at_desc(at_u32(sm.kv[s].k_lo));
+#pragma unroll
+        for (int ks = 0; ks < DH / 8; ++ks) {  // small cross products first (see the header comment)
+          const uint64_t o2 = (uint64_t)(2 * ks);
+          at_mma_ss(d_s, dql + o2, dkh + o2, id_qk, ks > 0 ? 1u : 0u);
+          at_mma_ss(d_s, dqh + o2, dkl + o2, id_qk, 1u);
+        }
 #pragma unroll
         for (int ks = 0; ks < DH / 8; ++ks) {
           const uint64_t o2 = (uint64_t)(2 * ks);
-          const uint32_t acc = ks > 0 ? 1u : 0u;
-          at_mma_ss(tmem + AT_S_CROSS, dql + o2, dkh + o2, id_qk, acc);
-          at_mma_ss(tmem + AT_S_CROSS, dqh + o2, dkl + o2, id_qk, 1u);
-          at_mma_ss(tmem + AT_S_MAIN, dqh + o2, dkh + o2, id_qk, acc);
+          at_mma_ss(d_s, dqh + o2, dkh + o2, id_qk, 1u);
         }
-        at_commit(&sm.s_full);
+        at_commit(&sm.k_empty[s]);
+        at_commit(&sm.s_full[i & 1]);
       }
       __syncwarp();
+    };
+    issue_qk(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j % AT_STAGES;
+      if (j + 1 < n_tiles) issue_qk(j + 1);
+      at_wait(&sm.v_ready[s], (j / AT_STAGES) & 1);
       at_wait(&sm.p_ready, j & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       AT_TRACE(6);
       if (lane == 0) {
+        const uint32_t a_hi = tmem + AT_S0 + (uint32_t)(j & 1) * AT_KT, a_lo = tmem + AT_PLO;
         const uint64_t dvh = at_desc(at_u32(sm.kv[s].vt_hi)), dvl = at_desc(at_u32(sm.kv[s].vt_lo));
+        // V^T is [32 dims][64 keys] K-major: 8 keys = 32 bytes inside a 128-byte atom row, 32 keys per 4 KB column block
 #pragma unroll
         for (int ks = 0; ks < AT_KT / 8; ++ks) {
-          // V^T is [32 dims][64 keys] K-major: 8 keys = 32 bytes inside a 128-byte atom row, 32 keys per 4 KB column block
           const uint64_t ob = (uint64_t)((ks >> 2) * ((DH * 128) >> 4) + (ks & 3) * 2);
-          const uint32_t acc = ks > 0 ? 1u : 0u;
-          at_mma_ts(tmem + AT_O_CROSS, tmem + AT_S_CROSS + 8 * ks, dvh + ob, id_pv, acc);
-          at_mma_ts(tmem + AT_O_CROSS, tmem + AT_S_MAIN + 8 * ks, dvl + ob, id_pv, 1u);
-          at_mma_ts(tmem + AT_O_MAIN, tmem + AT_S_MAIN + 8 * ks, dvh + ob, id_pv, acc);
+          at_mma_ts(tmem + AT_O, a_lo + 8 * ks, dvh + ob, id_pv, ks > 0 ? 1u : 0u);
+          at_mma_ts(tmem + AT_O, a_hi + 8 * ks, dvl + ob, id_pv, 1u);
         }
-        at_commit(&sm.kv_empty[s]);
+#pragma unroll
+        for (int ks = 0; ks < AT_KT / 8; ++ks) {
+          const uint64_t ob = (uint64_t)((ks >> 2) * ((DH * 128) >> 4) + (ks & 3) * 2);
+          at_mma_ts(tmem + AT_O, a_hi + 8 * ks, dvh + ob, id_pv, 1u);
+        }
+        at_commit(&sm.v_empty[s]);
         at_commit(&sm.o_full);
       }
       __syncwarp();
@@ -389,9 +417,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       at_tma_2d(sm.q_raw, &tmQ, q_col0 + h * DH, g * Lq + r0, &sm.q_full);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % AT_STAGES;
-        at_wait(&sm.kv_empty[s], ((j / AT_STAGES) & 1) ^ 1);
-        at_expect_tx(&sm.kv_full[s], AT_KT * DH * 4);
-        at_tma_2d(sm.kv[s].k_raw, &tmKV, k_col0 + h * DH, g * Lk + j * AT_KT, &sm.kv_full[s]);
+        at_wait(&sm.k_empty[s], ((j / AT_STAGES) & 1) ^ 1);
+        at_expect_tx(&sm.k_full[s], AT_KT * DH * 4);
+        at_tma_2d(sm.kv[s].k_raw, &tmKV, k_col0 + h * DH, g * Lk + j * AT_KT, &sm.k_full[s]);
       }
     }
   }

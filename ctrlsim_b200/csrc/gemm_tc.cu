@@ -22,6 +22,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -497,10 +498,10 @@ __device__ __forceinline__ float4 tc_lo4(float4 v) {
   return l;
 }
 
-template <bool RELU>
+template <bool RELU, bool WLO>
 __global__ void __launch_bounds__(P3_THREADS, 1)
 gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                   const float* __restrict__ bias, const float* __restrict__ table, const int* __restrict__ tidx,
+                   const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* __restrict__ table, const int* __restrict__ tidx,
                    float* __restrict__ C, int M, int N, int K, int ldc, int ldt, int n_tiles_n, int n_tiles) {
   extern __shared__ unsigned char tc_raw[];
   P3Smem& sm = *reinterpret_cast<P3Smem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
@@ -537,7 +538,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int i = 0; i < 4; ++i) {
           const int off = (rbase + 32 * i) * P_BK + sc;
           *reinterpret_cast<float4*>(st.a_lo + off) = tc_lo4(*reinterpret_cast<const float4*>(st.a_raw + off));
-          *reinterpret_cast<float4*>(st.b_lo + off) = tc_lo4(*reinterpret_cast<const float4*>(st.b_raw + off));
+          if (!WLO) *reinterpret_cast<float4*>(st.b_lo + off) = tc_lo4(*reinterpret_cast<const float4*>(st.b_raw + off));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -546,7 +547,10 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = tc_make_idesc(P_BM, P_BN);
+    // Per k-step TWO instructions: A_hi x [B_hi ; B_lo] with N = 256 (b_raw and b_lo are adjacent in shared memory and
+    // the main / cross accumulators adjacent in TMEM, so one MMA yields main += A_hi B_hi and cross += A_hi B_lo while
+    // reading A_hi once), then cross += A_lo x B_hi with N = 128.
+    const uint32_t idesc2 = tc_make_idesc(P_BM, 2 * P_BN), idesc1 = tc_make_idesc(P_BM, P_BN);
     uint32_t it = 0, ti = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const uint32_t buf = ti & 1;
@@ -560,14 +564,12 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) {
           P3Stage& st = sm.stage[s];
           const uint64_t dah = tc_make_desc(tc_smem_u32(st.a_raw)), dal = tc_make_desc(tc_smem_u32(st.a_lo));
-          const uint64_t dbh = tc_make_desc(tc_smem_u32(st.b_raw)), dbl = tc_make_desc(tc_smem_u32(st.b_lo));
+          const uint64_t dbh = tc_make_desc(tc_smem_u32(st.b_raw));
 #pragma unroll
           for (int ks = 0; ks < P_BK / 8; ++ks) {
             const uint64_t o = (uint64_t)(2 * ks);
-            const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
-            tc_mma(d_cross, dal + o, dbh + o, idesc, acc);
-            tc_mma(d_cross, dah + o, dbl + o, idesc, 1u);
-            tc_mma(d_main, dah + o, dbh + o, idesc, acc);
+            tc_mma(d_main, dah + o, dbh + o, idesc2, (kc > 0 || ks > 0) ? 1u : 0u);
+            tc_mma(d_cross, dal + o, dbh + o, idesc1, 1u);
           }
           tc_commit(&sm.empty[s]);
           if (kc == nk - 1) tc_commit(&sm.tmem_full[buf]);
@@ -586,9 +588,10 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int s = it % P_STAGES;
           tc_mbar_wait(&sm.empty[s], ((it / P_STAGES) & 1) ^ 1);
           P3Stage& st = sm.stage[s];
-          tc_expect_tx(&sm.tma_full[s], (P_BM + P_BN) * P_BK * 4);
+          tc_expect_tx(&sm.tma_full[s], (P_BM + (WLO ? 2 : 1) * P_BN) * P_BK * 4);
           tc_tma_2d(st.a_raw, &tmA, kc * P_BK, m0, &sm.tma_full[s]);
           tc_tma_2d(st.b_raw, &tmW, kc * P_BK, n0, &sm.tma_full[s]);
+          if (WLO) tc_tma_2d(st.b_lo, &tmWlo, kc * P_BK, n0, &sm.tma_full[s]);
         }
       }
     }
@@ -640,6 +643,37 @@ static int make_map(EncodeTiledFn enc, CUtensorMap* map, const float* base, int 
   return 0;
 }
 
+// lo = x - trunc13(x) copies of the registered weights (ctrlsim_finalize_weights): when the W operand of a GEMM lies
+// inside a registered tensor its lo tile is fetched by TMA instead of being derived in shared memory by the producers.
+struct LoRange { const void* owner; const float* base; size_t count; const float* lo; };
+static std::vector<LoRange> g_lo_ranges;
+void gemm_clear_weight_lo(const void* owner) {
+  for (size_t i = 0; i < g_lo_ranges.size();)
+    if (g_lo_ranges[i].owner == owner) g_lo_ranges.erase(g_lo_ranges.begin() + i); else ++i;
+}
+void gemm_register_weight_lo(const void* owner, const float* base, size_t count, const float* lo) {
+  for (size_t i = 0; i < g_lo_ranges.size();) {  // a range overlapping the new one describes memory that was re-used
+    const LoRange& r = g_lo_ranges[i];
+    if (base < r.base + r.count && r.base < base + count) g_lo_ranges.erase(g_lo_ranges.begin() + i); else ++i;
+  }
+  g_lo_ranges.push_back({owner, base, count, lo});
+}
+static const float* find_weight_lo(const float* W, size_t span) {
+  for (const LoRange& r : g_lo_ranges)
+    if (W >= r.base && W + span <= r.base + r.count) return r.lo + (W - r.base);
+  return nullptr;
+}
+__global__ void weight_lo_kernel(const float* __restrict__ w, float* __restrict__ lo, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float x = w[i]; lo[i] = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+}
+int launch_weight_lo(const float* w, float* lo, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  weight_lo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, lo, n);
+  CS_CHECK_LAUNCH("weight_lo");
+  return 0;
+}
+
 static int launch_gemm_tc_tma(const GemmArgs& g, cudaStream_t st) {
   static int n_sm = 0;
   static EncodeTiledFn enc = nullptr;
@@ -653,21 +687,27 @@ static int launch_gemm_tc_tma(const GemmArgs& g, cudaStream_t st) {
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) { n_sm = 0; return set_error(-5, "cuTensorMapEncodeTiled entry point unavailable"); }
     enc = reinterpret_cast<EncodeTiledFn>(fn);
-    e = cudaFuncSetAttribute(gemm_tc_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(gemm_tc_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { n_sm = 0; return set_error(-5, "gemm_tc_tma smem attr: %s", cudaGetErrorString(e)); }
   }
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmWlo;
   int rc;
   if ((rc = make_map(enc, &tmA, g.A, g.M, g.K, g.lda, P_BM))) return rc;
   if ((rc = make_map(enc, &tmW, g.W, g.N, g.K, g.ldw, P_BN))) return rc;
+  const float* wlo = find_weight_lo(g.W, (size_t)(g.N - 1) * g.ldw + g.K);
+  if (wlo && (reinterpret_cast<uintptr_t>(wlo) & 15)) wlo = nullptr;
+  if (wlo) { if ((rc = make_map(enc, &tmWlo, wlo, g.N, g.K, g.ldw, P_BN))) return rc; }
+  else tmWlo = tmW;
   const int tn = (g.N + P_BN - 1) / P_BN, tm = (g.M + P_BM - 1) / P_BM;
   const long long tiles = (long long)tn * tm;
   const int grid = (int)(tiles < n_sm ? tiles : n_sm);
-  if (g.relu)
-    gemm_tc_tma_kernel<true><<<grid, P3_THREADS, smem, st>>>(tmA, tmW, g.bias, g.table, g.tidx, g.C, g.M, g.N, g.K, g.ldc, g.ldt, tn, (int)tiles);
-  else
-    gemm_tc_tma_kernel<false><<<grid, P3_THREADS, smem, st>>>(tmA, tmW, g.bias, g.table, g.tidx, g.C, g.M, g.N, g.K, g.ldc, g.ldt, tn, (int)tiles);
+#define CS_LAUNCH_TMA(R, L) gemm_tc_tma_kernel<R, L><<<grid, P3_THREADS, smem, st>>>(tmA, tmW, tmWlo, g.bias, g.table, g.tidx, g.C, g.M, g.N, g.K, g.ldc, g.ldt, tn, (int)tiles)
+  if (g.relu) { if (wlo) CS_LAUNCH_TMA(true, true); else CS_LAUNCH_TMA(true, false); }
+  else { if (wlo) CS_LAUNCH_TMA(false, true); else CS_LAUNCH_TMA(false, false); }
+#undef CS_LAUNCH_TMA
   CS_CHECK_LAUNCH("gemm_tc_tma");
   return 0;
 }

@@ -2,6 +2,7 @@
 // retrievable through ctrlsim_last_error().
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace ctrlsim {
@@ -19,6 +20,10 @@ struct GemmArgs {
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t st);     // dispatches to the tcgen05 kernel unless CTRLSIM_GEMM=simt
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);  // gemm_tc.cu
+// gemm_tc.cu: lo-part copies of registered weights (fetched by TMA instead of being derived per tile)
+void gemm_register_weight_lo(const void* owner, const float* base, size_t count, const float* lo);
+void gemm_clear_weight_lo(const void* owner);
+int launch_weight_lo(const float* w, float* lo, size_t n, cudaStream_t st);
 int launch_layernorm(const float* X, const float* R, const float* gamma, const float* beta, float* Y, int M, int ldx,
                      int ldr, int ldy, bool relu, cudaStream_t st);
 

@@ -94,6 +94,9 @@ size_t Workspace::carve(void* base, size_t bytes, int Gc) {
   pe_b = (float*)take(Rp * H * 4);
   pe_c = (float*)take(Rp * H * 4);
   type_idx = (int*)take(Rp * 4);
+  map_slot = (int*)take(G * 4);
+  map_sel = (int*)take(G * 4);
+  map_dst = (int*)take(G * 4);
   s1 = (float*)take(Rta * H * 4);
   s2 = (float*)take(Rta * H * 4);
   sg = (float*)take(Rta * H * 4);
@@ -130,10 +133,12 @@ size_t Workspace::carve(void* base, size_t bytes, int Gc) {
   return off;
 }
 
-int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm, cudaStream_t st) {
-  const int Rp = G * P, Rpt = Rp * NP, Ra = G * A, Rta = G * n_t * A, Rm = G * MEM;
+int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm, cudaStream_t st, const MapPlan& mp) {
+  const int Gm = mp.n_map < 0 ? G : mp.n_map;  // groups whose polylines are encoded this step
+  const int Rp = Gm * P, Rpt = Rp * NP, Ra = G * A, Rta = G * n_t * A, Rm = G * MEM;
   const int Lcur = n_t * TOK_T, R = G * Lcur, ti = n_t - 1;
   // ---- M2 polyline encoder --------------------------------------------------------------------------------------
+  if (Gm > 0) {
   CS_TRY(launch_map_flags(ws.tk.map_pts, ws.pt_valid, ws.poly_valid, Rp, st));
   CS_TRY(launch_small_mlp1(3, ws.tk.map_pts, w.road_pts, ws.h1, (size_t)Rpt, st));
   CS_TRY(gemm(ws.h1, w.road_pts.w3, w.road_pts.b3, ws.feats, Rpt, H, H, H, H, H, false, st));
@@ -151,6 +156,8 @@ int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm
   CS_TRY(gemm(ws.pe_a, w.rr.w0, nullptr, ws.pe_b, Rp, H, H, H, 2 * H, H, false, st, w.type_tab2, ws.type_idx, H));
   CS_TRY(launch_layernorm(ws.pe_b, nullptr, w.rr.lnw, w.rr.lnb, ws.pe_b, Rp, H, H, H, true, st));
   CS_TRY(gemm(ws.pe_b, w.rr.w3, w.rr.b3, ws.pe_c, Rp, H, H, H, H, H, false, st));
+  if (mp.cache_emb) CS_TRY(launch_scatter_map(Gm, ws.pe_c, ws.poly_valid, mp.dst, mp.cache_emb, mp.cache_valid, st));
+  }
   // ---- M3 token embeddings --------------------------------------------------------------------------------------
   CS_TRY(launch_small_mlp1(12, ws.tk.feat_state, w.embed_state, ws.s1, (size_t)Rta, st));
   CS_TRY(gemm(ws.s1, w.embed_state.w3, w.embed_state.b3, ws.s2, Rta, H, H, H, H, H, false, st));
@@ -160,7 +167,8 @@ int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm
   CS_TRY(launch_make_goal_index(G, n_t, ws.goal_idx, st));
   CS_TRY(gemm(ws.s2, w.sg_w, nullptr, ws.sg, Rta, H, H, H, 2 * H, H, false, st, ws.gpart, ws.goal_idx, H));
   CS_TRY(launch_assemble_tokens(G, n_t, ws.sg, ws.tk, w.emb, ws.X, ws.mem, st));
-  CS_TRY(launch_build_memory(G, ws.pe_c, ws.poly_valid, ws.tk, n_t, ws.mem, ws.pad, st));
+  if (mp.cache_emb) CS_TRY(launch_build_memory(G, mp.cache_emb, mp.cache_valid, mp.slot, ws.tk, n_t, ws.mem, ws.pad, st));
+  else CS_TRY(launch_build_memory(G, ws.pe_c, ws.poly_valid, nullptr, ws.tk, n_t, ws.mem, ws.pad, st));
   // ---- M4 scene encoder -----------------------------------------------------------------------------------------
   for (int l = 0; l < N_ENC; ++l) {
     const EncLayerW& e = w.enc[l];

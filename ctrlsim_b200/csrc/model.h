@@ -60,8 +60,10 @@ struct TokenBufs {  // internal token representation of a chunk of groups (time-
 };
 
 // launchers (tokens.cu)
+// map_sel (optional, device): chunk-local groups whose polyline tokens are rebuilt (n_map of them, into map slots
+// 0..n_map-1); nullptr = every group.
 int launch_tokenize(const CtrlSimBatch& b, int g0, int ng, int t, int n_t, const TokenBufs& tk, const ModelCfg& mc,
-                    cudaStream_t st);
+                    cudaStream_t st, const int* map_sel = nullptr, int n_map = 0);
 int launch_convert_tokens(int G, int n_t, const float* agent_states, const float* agent_types, const float* goals,
                           const int* actions, const int* rtgs, const int* timesteps, const float* road_points,
                           const int* road_types, const TokenBufs& tk, cudaStream_t st);
@@ -71,8 +73,10 @@ int launch_assemble_tokens(int G, int n_t, const float* sg, const TokenBufs& tk,
                            cudaStream_t st);
 int launch_assemble_rtg_rows(int G, int n_t, int ti, const int* rtg_new, const TokenBufs& tk, const EmbedW& ew,
                              float* Xr, cudaStream_t st);
-int launch_build_memory(int G, const float* poly_emb, const uint8_t* poly_valid, const TokenBufs& tk, int n_t,
-                        float* mem, uint8_t* pad, cudaStream_t st);
+int launch_build_memory(int G, const float* poly_emb, const uint8_t* poly_valid, const int* slot, const TokenBufs& tk,
+                        int n_t, float* mem, uint8_t* pad, cudaStream_t st);
+int launch_scatter_map(int n, const float* emb, const uint8_t* valid, const int* dst, float* cache_emb,
+                       uint8_t* cache_valid, cudaStream_t st);
 int launch_make_row_index(int G, int n_t, int ti, int k, int* out, cudaStream_t st);
 int launch_make_goal_index(int G, int n_t, int* out, cudaStream_t st);
 int launch_gather_rows(int n, const float* X, const int* idx, float* Y, cudaStream_t st);

@@ -12,6 +12,7 @@ struct Workspace {
   float *h1, *feats, *pooled, *pe_a, *pe_b, *pe_c;
   uint8_t *pt_valid, *poly_valid;
   int* type_idx;
+  int *map_slot, *map_sel, *map_dst;  // map-cache index lists of the chunk (api.cu)
   // embeddings
   float *s1, *s2, *sg, *g1, *g2, *gpart;
   int* goal_idx;
@@ -42,7 +43,19 @@ struct Prof {
 };
 extern Prof g_prof;
 
-int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm, cudaStream_t st);
+// Which polyline-encoder outputs a chunk uses.  While the window still starts at t = 0 (t < 32) the normalisation
+// frame of a focal group is the focal agent's pose at t = 0, so the polyline encoder's output is the same at every
+// step; it is computed once per (scene, focal) and kept in a caller-provided cache (ctrlsim_attach_map_cache).
+struct MapPlan {
+  int n_map = -1;                 // groups to encode this step (their tokens sit in map slots 0..n_map-1); -1 = all G
+  const int* slot = nullptr;      // [G] cache block of every group of the chunk; nullptr = group g uses ws block g
+  const int* dst = nullptr;       // [n_map] cache block each freshly encoded map is stored to
+  float* cache_emb = nullptr;     // [n_blocks, P, H]
+  uint8_t* cache_valid = nullptr; // [n_blocks, P]
+};
+
+int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm, cudaStream_t st,
+                  const MapPlan& mp = MapPlan());
 int forward_pass2(const ModelWeights& w, Workspace& ws, int G, int n_t, cudaStream_t st);
 
 int launch_resolve_rtg_range(const CtrlSimBatch& b, const CtrlSimPolicyParams& p, int t, int s0, int s1, int g_base,

@@ -99,14 +99,16 @@ tokenize_agents_kernel(CtrlSimBatch b, int g0, int t, int n_t, int steps, TokenB
 
 // tokenize_map: one block per group. Keeps the max_polylines polylines whose farthest valid point is nearest to the
 // focal agent, in ascending order of that distance (dataset.py:417-421), else pads (dataset.py:423-427).
+// `sel` (optional) lists the chunk-local groups whose map must be (re)built; block i writes map slot i.
 __global__ void __launch_bounds__(256)
-tokenize_map_kernel(CtrlSimBatch b, int g0, TokenBufs tk) {
+tokenize_map_kernel(CtrlSimBatch b, int g0, TokenBufs tk, const int* __restrict__ sel) {
   __shared__ double key[1024];
   __shared__ int idx[1024];
-  const int gl = blockIdx.x, g = g0 + gl;
+  const int gsrc = sel ? sel[blockIdx.x] : blockIdx.x;  // chunk-local group whose frame is used
+  const int gl = blockIdx.x, g = g0 + gsrc;             // gl: output map slot
   const int s = b.group_scene[g];
   const int Pm = b.max_poly, np_s = b.n_poly[s];
-  const double tx = tk.frame[gl * 4 + 0], ty = tk.frame[gl * 4 + 1], rot = tk.frame[gl * 4 + 2];
+  const double tx = tk.frame[gsrc * 4 + 0], ty = tk.frame[gsrc * 4 + 1], rot = tk.frame[gsrc * 4 + 2];
   const double cr = cos(rot), sr = sin(rot);
   const double* rxy = b.road_xy + (size_t)s * Pm * NP * 2;
   const uint8_t* rv = b.road_valid + (size_t)s * Pm * NP;
@@ -167,14 +169,17 @@ tokenize_map_kernel(CtrlSimBatch b, int g0, TokenBufs tk) {
 }
 
 int launch_tokenize(const CtrlSimBatch& b, int g0, int ng, int t, int n_t, const TokenBufs& tk, const ModelCfg& mc,
-                    cudaStream_t st) {
+                    cudaStream_t st, const int* map_sel, int n_map) {
   if (ng <= 0) return 0;
   if (b.max_poly > 1024) return set_error(-2, "tokenize: at most 1024 polylines per scene (got %d)", b.max_poly);
   tokenize_agents_kernel<<<ng, 256, 0, st>>>(b, g0, t, n_t, mc.steps, tk, mc.min_accel, mc.max_accel, mc.min_steer,
                                              mc.max_steer, mc.n_steer);
   CS_CHECK_LAUNCH("tokenize_agents");
-  tokenize_map_kernel<<<ng, 256, 0, st>>>(b, g0, tk);
-  CS_CHECK_LAUNCH("tokenize_map");
+  const int nm = map_sel ? n_map : ng;
+  if (nm > 0) {
+    tokenize_map_kernel<<<nm, 256, 0, st>>>(b, g0, tk, map_sel);
+    CS_CHECK_LAUNCH("tokenize_map");
+  }
   return 0;
 }
 
@@ -407,28 +412,55 @@ int launch_assemble_rtg_rows(int G, int n_t, int ti, const int* rtg_new, const T
 }
 
 // Memory tokens: rows [g, 0..P) <- polyline embeddings, key padding mask = !valid (encoder.py:155-166).
+// `slot` (optional): group gl reads block slot[gl] of poly_emb / poly_valid (the per-focal map cache) instead of gl.
 __global__ void build_memory_kernel(int G, const float* __restrict__ poly_emb, const uint8_t* __restrict__ poly_valid,
-                                    TokenBufs tk, int n_t, float* __restrict__ mem, uint8_t* __restrict__ pad) {
+                                    const int* __restrict__ slot, TokenBufs tk, int n_t, float* __restrict__ mem,
+                                    uint8_t* __restrict__ pad) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t n4 = (size_t)G * P * (H / 4);
   if (i < n4) {
     const size_t row = i / (H / 4);
     const int c = (int)(i % (H / 4)) * 4;
     const size_t gl = row / P, j = row % P;
-    *reinterpret_cast<float4*>(mem + (gl * MEM + j) * H + c) = *reinterpret_cast<const float4*>(poly_emb + row * H + c);
+    const size_t src = slot ? (size_t)slot[gl] : gl;
+    *reinterpret_cast<float4*>(mem + (gl * MEM + j) * H + c) =
+        *reinterpret_cast<const float4*>(poly_emb + (src * P + j) * H + c);
   }
   if (i < (size_t)G * MEM) {
     const int gl = (int)(i / MEM), j = (int)(i % MEM);
-    pad[i] = j < P ? !poly_valid[gl * P + j] : !tk.exist[((size_t)gl * n_t + 0) * A + (j - P)];
+    const size_t src = slot ? (size_t)slot[gl] : (size_t)gl;
+    pad[i] = j < P ? !poly_valid[src * P + j] : !tk.exist[((size_t)gl * n_t + 0) * A + (j - P)];
   }
 }
 
-int launch_build_memory(int G, const float* poly_emb, const uint8_t* poly_valid, const TokenBufs& tk, int n_t,
-                        float* mem, uint8_t* pad, cudaStream_t st) {
+int launch_build_memory(int G, const float* poly_emb, const uint8_t* poly_valid, const int* slot, const TokenBufs& tk,
+                        int n_t, float* mem, uint8_t* pad, cudaStream_t st) {
   if (G <= 0) return 0;
   const size_t n = (size_t)G * P * (H / 4);
-  build_memory_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(G, poly_emb, poly_valid, tk, n_t, mem, pad);
+  build_memory_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(G, poly_emb, poly_valid, slot, tk, n_t, mem, pad);
   CS_CHECK_LAUNCH("build_memory");
+  return 0;
+}
+
+// Map cache fill: block i of the freshly encoded polyline embeddings -> cache block dst[i].
+__global__ void scatter_map_kernel(int n, const float* __restrict__ emb, const uint8_t* __restrict__ valid,
+                                   const int* __restrict__ dst, float* __restrict__ cache_emb,
+                                   uint8_t* __restrict__ cache_valid) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per = (size_t)P * (H / 4);
+  if (i >= (size_t)n * per) return;
+  const size_t blk = i / per, r = i % per;
+  const size_t d = (size_t)dst[blk];
+  reinterpret_cast<float4*>(cache_emb)[d * per + r] = reinterpret_cast<const float4*>(emb)[i];
+  if (r < P) cache_valid[d * P + r] = valid[blk * P + r];
+}
+
+int launch_scatter_map(int n, const float* emb, const uint8_t* valid, const int* dst, float* cache_emb,
+                       uint8_t* cache_valid, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const size_t tot = (size_t)n * P * (H / 4);
+  scatter_map_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n, emb, valid, dst, cache_emb, cache_valid);
+  CS_CHECK_LAUNCH("scatter_map");
   return 0;
 }
 

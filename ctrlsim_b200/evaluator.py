@@ -60,6 +60,8 @@ class B200Policy:
         self.lib = model.lib
         self.groups_last_step = 0
         self.launch_count = 0
+        self._map_cache = None  # device memory of the per-focal polyline-encoder cache (steps 0..31)
+        self.use_map_cache = os.environ.get("CTRLSIM_MAP_CACHE", "1") != "0"
 
     def _params(self):
         td = self.tilt_dict
@@ -73,6 +75,14 @@ class B200Policy:
     # ---- the reference's four verbs, batched -----------------------------------------------------------------------
     def reset(self, batch: SceneBatch):
         batch.reset_dynamic()
+        if self.use_map_cache:
+            need = int(self.lib.ctrlsim_map_cache_bytes(batch.S, batch.N))
+            if self._map_cache is None or self._map_cache.numel() < need:
+                self._map_cache = torch.empty(need, dtype=torch.uint8, device=self.model.device)
+            _lib.check(self.lib.ctrlsim_attach_map_cache(self.model.handle, self._map_cache.data_ptr(),
+                                                         self._map_cache.numel()), "ctrlsim_attach_map_cache")
+        else:
+            _lib.check(self.lib.ctrlsim_attach_map_cache(self.model.handle, None, 0), "ctrlsim_attach_map_cache")
         _lib.check(self.lib.ctrlsim_sim_reset(self.model.handle, batch.ptr, self._stream()), "ctrlsim_sim_reset")
 
     def update_state(self, batch: SceneBatch, t: int):

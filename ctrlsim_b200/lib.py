@@ -74,6 +74,9 @@ _SIGS = {
     "ctrlsim_load_weights": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "ctrlsim_finalize_weights": (C.c_int, [C.c_void_p]),
     "ctrlsim_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32]),
+    "ctrlsim_map_cache_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "ctrlsim_attach_map_cache": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "ctrlsim_map_cache_stats": (None, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ctrlsim_sim_reset": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_void_p]),
     "ctrlsim_observe": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_int32, C.c_void_p]),
     "ctrlsim_plan_groups": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_int32, C.c_void_p, C.c_void_p]),

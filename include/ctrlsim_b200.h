@@ -108,6 +108,16 @@ int ctrlsim_finalize_weights(CtrlSim* h);
 /* Bytes of scratch ctrlsim_policy_step needs for `max_groups` focal groups processed together. */
 int64_t ctrlsim_workspace_bytes(const CtrlSim* h, int32_t max_groups);
 
+/* Optional per-focal cache of the polyline encoder's output (M2). While a group's 32-step window still starts at
+ * t = 0 (steps 0..31) its normalisation frame - the focal agent's pose at window index 0, dataset.py:390-428 - does not
+ * move, so the encoder output is identical at every step; with a cache attached ctrlsim_policy_step computes it once
+ * per (scene, focal) and episode and re-reads it afterwards (results are bit-identical to recomputing). The memory is
+ * caller-owned device memory of at least ctrlsim_map_cache_bytes(n_scenes, max_veh); pass NULL to detach. The
+ * directory is reset at t = 0, when another batch is stepped, or when steps are not consecutive. */
+int64_t ctrlsim_map_cache_bytes(int32_t n_scenes, int32_t max_veh);
+int ctrlsim_attach_map_cache(CtrlSim* h, void* mem, int64_t bytes);
+void ctrlsim_map_cache_stats(const CtrlSim* h, int64_t* hits, int64_t* misses);
+
 /* ---- simulator: replaces nocturne_cpp Simulation/Scenario/Vehicle for the evaluator loop ------------------- */
 /* S3: Vehicle::CreatePhysicsBody for every vehicle + the load-time UpdateCollision (vehicle.cc:137-179, scenario.cc:263) */
 int ctrlsim_sim_reset(CtrlSim* h, CtrlSimBatch* b, void* stream);
