@@ -255,10 +255,11 @@ def main():
         "config": {"workload": WORKLOAD, "scenes_per_gpu": args.scenes, "controlled_agents_rank0": n_agents,
                    "focal_groups_per_step_avg": groups_all / args.steps / world, "chunk_groups": args.chunk,
                    "l2": "per-step working set (>10 GB of activations per chunk) far exceeds the 126 MB L2; no explicit flush",
-                   "weights": "random-init (deterministic generator), reference architecture"},
+                   "weights": "random-init (deterministic generator), reference architecture",
+                   "map_cache": "per-focal polyline-encoder cache for steps 0..31 (ctrlsim_attach_map_cache): " + ("on" if pol.use_map_cache else "off")},
         "gpu_launches": int(launches_all),
         "clocks": clk,
-        "roofline": {"kernel": "gemm_tn_kernel (all linear layers, fp32 FFMA)", "bound": "tensor", "achieved": gemm_tf,
+        "roofline": {"kernel": "gemm_tc_tma_kernel (every nn.Linear: tcgen05 kind::tf32, 3-product hi/lo split = fp32-accurate, 3 tensor flops per counted flop)", "bound": "tensor", "achieved": gemm_tf,
                      "peak": pk["tf"] / 1.0, "unit": "TFLOP/s", "frac": gemm_tf / pk["tf"], "traffic": None,
                      "peak_source": pk["tf_src"], "share_of_step": gemm_ms / ms, "launches": int(gemm_n),
                      "avg_launch_ms": gemm_ms / max(gemm_n, 1)},

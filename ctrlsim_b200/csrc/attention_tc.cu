@@ -6,21 +6,24 @@
 //   warp 7      TMA: Q tile once, then raw K tiles (cp.async.bulk.tensor.2d, SWIZZLE_128B).  The raw fp32 tiles are
 //               used directly as the "hi" operands (kind::tf32 ignores the 13 low mantissa bits).
 //   warps 4-5   derive the lo = x - trunc13(x) tiles (Q once, K per tile) and stage V^T hi / lo from global memory
+//               (bank-conflict-free: the four values a thread holds are stored in a rotated order)
 //   warp 6      MMA issuer.  S = Q K^T: A = Q (smem, K-major), B = K tile (smem, K-major), M=128 N=64, 4 k-steps x 3
 //               split products into ONE TMEM accumulator.  The tensor core adds into its fp32 accumulator with
 //               truncation, so the order matters: the 8 small cross products (Q_lo K_hi, Q_hi K_lo; 2^-11 of the
 //               result) are issued first and the 4 main products last - only 4 truncations happen at full magnitude,
-//               the same error as a separate cross accumulator but half the TMEM traffic.  O_tile = P V: A = P read
+//               the same error as a separate cross accumulator at half the TMEM traffic.  O_tile = P V: A = P read
 //               FROM TMEM (FlashAttention-4 style, P never touches shared memory), B = V^T tile (K-major; the producer
 //               warps transpose V while splitting it - an MN-major tf32 B operand needs the SWIZZLE_128B_BASE32B
 //               layout, which this kernel avoids), M=128 N=32, 8 k-steps x 3 (16 cross products first), a fresh
-//               accumulator per key tile.
+//               accumulator per key tile.  S is double-buffered and the issue order is QK(0) QK(1) PV(0) QK(2) PV(1)
+//               ..., so the scores of tile j+1 are ready while the softmax warps still work on tile j; K tiles and V^T
+//               tiles are released separately (K right after its QK).
 //   warps 0-3   softmax: thread = query row = TMEM lane.  ONE sweep over S per tile: p = ex2(s * scale - ref) against a
-//               lazily updated reference exponent (FlashAttention-4's conditional rescale): ref only moves when a
-//               score exceeds it by more than 2^16, in which case the tile is redone from the still intact S (P_hi /
-//               P_lo live in their own TMEM columns).  The tile's P V product is added to the register-resident
-//               running output with a rounded fp32 add.
-// TMEM (256 columns per CTA, two CTAs per SM): [0,64) S, [64,128) P_hi, [128,192) P_lo, [192,224) O_tile.
+//               lazily updated INTEGER reference exponent (FlashAttention-4's conditional rescale): ref only moves when
+//               a score exceeds it by more than 2^16; moving it multiplies l, o and the part of P already written by an
+//               exact power of two.  P_hi overwrites S in place, P_lo has its own columns.  The tile's P V product is
+//               added to the register-resident running output with a rounded fp32 add.
+// TMEM (256 columns per CTA, two CTAs per SM): [0,64) S0 / P_hi, [64,128) S1 / P_hi, [128,192) P_lo, [192,224) O_tile.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -121,6 +124,27 @@ __device__ __forceinline__ void at_st32(uint32_t taddr, const uint32_t (&r)[32])
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
         "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void at_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void at_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// multiply 32 TMEM columns of this thread's lane by f (rare softmax-reference move; small pieces keep registers free)
+__device__ __noinline__ void at_scale32(uint32_t taddr, float f) {
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    uint32_t t[8];
+    at_ld8(taddr + 8 * q, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * f);
+    at_st8(taddr + 8 * q, t);
+  }
 }
 __device__ __forceinline__ void at_lo_tile(float* lo, const float* raw, int n_float4, int tid, int nthreads) {
   for (int i = tid; i < n_float4; i += nthreads) {
@@ -248,7 +272,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const bool bump = cmx > ref + AT_LAZY || (ref == -INFINITY && cmx > -INFINITY);
         if (__any_sync(0xffffffffu, bump)) {
           const float nref = bump ? ceilf(cmx) : ref;
-          const float f = (nref == ref) ? 1.f : at_ex2(ref - nref);  // exact power of two (0 when ref was -inf)
+          const float dref = ref - nref;  // 0, a negative integer, or -inf (no reference before)
+          const float f = dref == 0.f ? 1.f : (dref < -126.f ? 0.f : __int_as_float((127 + (int)dref) << 23));  // 2^dref, exact
           l *= f;
 #pragma unroll
           for (int i = 0; i < 4; ++i) s4[i] *= f;
@@ -256,15 +281,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int i = 0; i < DH; ++i) o[i] *= f;
           ref = nref;
           if (c == 1) {  // the first half of this tile's P was written against the old reference: rescale it in place
-            uint32_t t[32];
-            at_ld32(s_addr, t);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * f);
-            at_st32(s_addr, t);
-            at_ld32(lane_addr + AT_PLO, t);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * f);
-            at_st32(lane_addr + AT_PLO, t);
+            at_scale32(s_addr, f);
+            at_scale32(lane_addr + AT_PLO, f);
           }
         }
         const float rr = ref == -INFINITY ? 0.f : ref;  // no visible key yet: every p below is ex2(-inf) = 0
