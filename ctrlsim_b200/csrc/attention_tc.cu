@@ -14,8 +14,9 @@
 //               the same error as a separate cross accumulator at half the TMEM traffic.  O_tile = P V: A = P read
 //               FROM TMEM (FlashAttention-4 style, P never touches shared memory), B = V^T tile (K-major; the producer
 //               warps transpose V while splitting it - an MN-major tf32 B operand needs the SWIZZLE_128B_BASE32B
-//               layout, which this kernel avoids), M=128 N=32, 8 k-steps x 3 (16 cross products first), a fresh
-//               accumulator per key tile.  S is double-buffered and the issue order is QK(0) QK(1) PV(0) QK(2) PV(1)
+//               layout, which this kernel avoids), 8 k-steps of two instructions: [O_a | O_b] += P_hi [V_hi ; V_lo]
+//               (N=64) and O_b += P_lo V_hi (N=32) - P_hi is read from TMEM once instead of twice and the cross products
+//               have their own accumulator; fresh accumulators per key tile.  S is double-buffered and the issue order is QK(0) QK(1) PV(0) QK(2) PV(1)
 //               ..., so the scores of tile j+1 are ready while the softmax warps still work on tile j; K tiles and V^T
 //               tiles are released separately (K right after its QK).
 //   warps 0-3   softmax: thread = query row = TMEM lane.  ONE sweep over S per tile: p = ex2(s * scale - ref) against a
@@ -23,7 +24,8 @@
 //               a score exceeds it by more than 2^16; moving it multiplies l, o and the part of P already written by an
 //               exact power of two.  P_hi overwrites S in place, P_lo has its own columns.  The tile's P V product is
 //               added to the register-resident running output with a rounded fp32 add.
-// TMEM (256 columns per CTA, two CTAs per SM): [0,64) S0 / P_hi, [64,128) S1 / P_hi, [128,192) P_lo, [192,224) O_tile.
+// TMEM (256 columns per CTA, two CTAs per SM): [0,64) S0 / P_hi, [64,128) S1 / P_hi, [128,192) P_lo, [192,224) O_a (main
+// products), [224,256) O_b (cross products).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -41,8 +43,9 @@ constexpr float AT_LAZY = 16.f;  // log2 head-room before the softmax reference 
 struct alignas(1024) AtKV {
   float k_raw[AT_KT * DH];   // [64 keys][32 dims], K-major (TMA, SWIZZLE_128B)
   float k_lo[AT_KT * DH];
-  float vt_hi[DH * AT_KT];   // V^T: [32 dims][64 keys], K-major: two 4 KB column blocks of 32 keys (written by warps 4-5)
-  float vt_lo[DH * AT_KT];
+  // V^T, K-major, written by warps 4-5: two 8 KB blocks of 32 keys each; block cb = [hi: 32 dims x 32 keys (4 KB)]
+  // [lo: 32 dims x 32 keys (4 KB)], so one N = 64 B-operand descriptor spans [V_hi ; V_lo] of a key block
+  float vt[2 * DH * AT_KT];
 };
 struct AtSmem {
   float q_raw[AT_QT * DH];
@@ -113,6 +116,28 @@ __device__ __forceinline__ void at_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// two 32-column loads in flight before one wait (a tcgen05.ld round trip is ~115 cycles)
+__device__ __forceinline__ void at_ld32x2(uint32_t ta, uint32_t (&r)[32], uint32_t tb, uint32_t (&q)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(ta));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
+        "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
+        "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+      : "r"(tb));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void at_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -190,13 +215,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     at_mbar_init(&sm.p_ready, 128); at_mbar_init(&sm.o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (!CAUSAL && tid < 4) {
-    unsigned long long mk = 0ull;
-    for (int c = 0; c < 64; ++c) {
-      const int key = tid * 64 + c;
-      if (key < Lk && !key_pad[(size_t)g * Lk + key]) mk |= 1ull << c;
-    }
-    sm.pad_mask[tid] = mk;
+  if (!CAUSAL) {  // key-padding bits: thread = key (Lk <= 256), one ballot per warp = one 32-bit half of a tile's mask
+    const bool ok = tid < Lk && !key_pad[(size_t)g * Lk + tid];
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) reinterpret_cast<unsigned*>(sm.pad_mask)[warp] = bal;
   }
   if (warp == 6) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(at_u32(&sm.tmem_base)), "r"(AT_TMEM_COLS) : "memory");
@@ -307,10 +329,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       AT_TRACE(3);
       {
-        uint32_t r[32];
-        at_ld32(lane_addr + AT_O, r);
+        uint32_t r[32], rb[32];
+        at_ld32x2(lane_addr + AT_O, r, lane_addr + AT_O + DH, rb);
 #pragma unroll
-        for (int i = 0; i < DH; ++i) o[i] += __uint_as_float(r[i]);
+        for (int i = 0; i < DH; ++i) o[i] += __uint_as_float(r[i]) + __uint_as_float(rb[i]);
       }
       AT_TRACE(4);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -359,9 +381,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
           const int d = u * 4 + ((n + hrot) & 3);
-          const int off = cb * (DH * 32) + d * 32 + ((((kk >> 2) ^ (d & 7)) << 2) | (kk & 3));
-          sm.kv[s].vt_hi[off] = x[n];
-          sm.kv[s].vt_lo[off] = x[n] - __uint_as_float(__float_as_uint(x[n]) & 0xFFFFE000u);
+          const int off = cb * (2 * DH * 32) + d * 32 + ((((kk >> 2) ^ (d & 7)) << 2) | (kk & 3));
+          sm.kv[s].vt[off] = x[n];
+          sm.kv[s].vt[off + DH * 32] = x[n] - __uint_as_float(__float_as_uint(x[n]) & 0xFFFFE000u);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -373,7 +395,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // ------------------------------------------------------------------ MMA issuer
     // Issue order QK(0), QK(1), PV(0), QK(2), PV(1), ...: S is double-buffered, so the scores of tile j+1 are computed
     // while the softmax warps work on tile j.
-    const uint32_t id_qk = at_idesc(AT_QT, AT_KT, false), id_pv = at_idesc(AT_QT, DH, false);
+    const uint32_t id_qk = at_idesc(AT_QT, AT_KT, false), id_pv = at_idesc(AT_QT, DH, false), id_pv2 = at_idesc(AT_QT, 2 * DH, false);
     at_wait(&sm.q_lo_ready, 0);
     const uint64_t dqh = at_desc(at_u32(sm.q_raw)), dql = at_desc(at_u32(sm.q_lo));
     auto issue_qk = [&](int i) {
@@ -409,18 +431,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       AT_TRACE(6);
       if (lane == 0) {
         const uint32_t a_hi = tmem + AT_S0 + (uint32_t)(j & 1) * AT_KT, a_lo = tmem + AT_PLO;
-        const uint64_t dvh = at_desc(at_u32(sm.kv[s].vt_hi)), dvl = at_desc(at_u32(sm.kv[s].vt_lo));
-        // V^T is [32 dims][64 keys] K-major: 8 keys = 32 bytes inside a 128-byte atom row, 32 keys per 4 KB column block
+        const uint64_t dv = at_desc(at_u32(sm.kv[s].vt));
+        // V^T is K-major: 8 keys = 32 bytes inside a 128-byte atom row; key block cb (32 keys) = 8 KB [V_hi ; V_lo].
+        // Per k-step two instructions: [O_a | O_b] += P_hi x [V_hi ; V_lo] (N = 64, P_hi read once) and O_b += P_lo x V_hi
+        // (N = 32): O_a collects the 8 main products, O_b the 16 small cross products; they are added in registers.
 #pragma unroll
         for (int ks = 0; ks < AT_KT / 8; ++ks) {
-          const uint64_t ob = (uint64_t)((ks >> 2) * ((DH * 128) >> 4) + (ks & 3) * 2);
-          at_mma_ts(tmem + AT_O, a_lo + 8 * ks, dvh + ob, id_pv, ks > 0 ? 1u : 0u);
-          at_mma_ts(tmem + AT_O, a_hi + 8 * ks, dvl + ob, id_pv, 1u);
-        }
-#pragma unroll
-        for (int ks = 0; ks < AT_KT / 8; ++ks) {
-          const uint64_t ob = (uint64_t)((ks >> 2) * ((DH * 128) >> 4) + (ks & 3) * 2);
-          at_mma_ts(tmem + AT_O, a_hi + 8 * ks, dvh + ob, id_pv, 1u);
+          const uint64_t ob = (uint64_t)((ks >> 2) * ((2 * DH * 128) >> 4) + (ks & 3) * 2);
+          at_mma_ts(tmem + AT_O, a_hi + 8 * ks, dv + ob, id_pv2, ks > 0 ? 1u : 0u);
+          at_mma_ts(tmem + AT_O + DH, a_lo + 8 * ks, dv + ob, id_pv, 1u);
         }
         at_commit(&sm.v_empty[s]);
         at_commit(&sm.o_full);
