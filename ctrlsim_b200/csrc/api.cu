@@ -47,7 +47,31 @@ struct CtrlSim {
   int* h_idx = nullptr;            // pinned staging for the per-chunk index lists
   size_t h_idx_cap = 0;
   long long mc_hits = 0, mc_misses = 0;
+  // prefix cache (see PrefixSlot, model_ws.h): one slot per chunk of a step, validated by the chunk's group signature
+  char* pc_mem = nullptr;
+  int64_t pc_slots = 0;
+  int pc_chunk = 0;
+  struct PcDir { std::vector<int> sig; int last_t = -1; };
+  std::vector<PcDir> pc_dir;
+  const void* pc_owner = nullptr;
+  int pc_last_t = -1;
+  std::vector<int> h_members;
+  long long pc_hits = 0, pc_misses = 0;
 };
+
+static size_t pc_align(size_t n) { return (n + 255) & ~size_t(255); }
+static size_t pc_slot_bytes(int Gc) {
+  return N_DEC * pc_align((size_t)Gc * L * 2 * H * sizeof(float)) + N_DEC * pc_align((size_t)Gc * MEM * 2 * H * sizeof(float)) +
+         pc_align((size_t)Gc * MEM);
+}
+static PrefixSlot pc_slot(char* mem, int Gc, int64_t slot) {
+  PrefixSlot p;
+  char* q = mem + (size_t)slot * pc_slot_bytes(Gc);
+  for (int l = 0; l < N_DEC; ++l) { p.KV[l] = reinterpret_cast<float*>(q); q += pc_align((size_t)Gc * L * 2 * H * sizeof(float)); }
+  for (int l = 0; l < N_DEC; ++l) { p.KVC[l] = reinterpret_cast<float*>(q); q += pc_align((size_t)Gc * MEM * 2 * H * sizeof(float)); }
+  p.PAD = reinterpret_cast<uint8_t*>(q);
+  return p;
+}
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -224,6 +248,30 @@ void ctrlsim_map_cache_stats(const CtrlSim* h, int64_t* hits, int64_t* misses) {
   if (misses) *misses = h ? h->mc_misses : 0;
 }
 
+int64_t ctrlsim_prefix_cache_bytes(int32_t chunk_groups, int32_t n_slots) {
+  return (int64_t)pc_slot_bytes(chunk_groups) * n_slots;
+}
+int ctrlsim_attach_prefix_cache(CtrlSim* h, void* mem, int64_t bytes, int32_t chunk_groups) {
+  if (!h) return set_error(-1, "ctrlsim_attach_prefix_cache: null handle");
+  h->pc_dir.clear(); h->pc_owner = nullptr; h->pc_last_t = -1;
+  h->pc_mem = nullptr; h->pc_slots = 0; h->pc_chunk = 0;
+  if (!mem || bytes <= 0) return 0;
+  if (chunk_groups <= 0) return set_error(-2, "ctrlsim_attach_prefix_cache: chunk_groups must be positive");
+  if (reinterpret_cast<uintptr_t>(mem) & 255) return set_error(-2, "ctrlsim_attach_prefix_cache: memory must be 256-byte aligned");
+  const int64_t slots = bytes / (int64_t)pc_slot_bytes(chunk_groups);
+  if (slots <= 0) return set_error(-4, "ctrlsim_attach_prefix_cache: %lld bytes hold no slot of %d groups (%lld needed)",
+                                   (long long)bytes, chunk_groups, (long long)pc_slot_bytes(chunk_groups));
+  // key rows past a group's current length are masked, but they are still multiplied: keep them finite
+  if (cudaMemset(mem, 0, (size_t)slots * pc_slot_bytes(chunk_groups)) != cudaSuccess) return set_error(-5, "ctrlsim_attach_prefix_cache: cudaMemset failed");
+  h->pc_mem = reinterpret_cast<char*>(mem); h->pc_slots = slots; h->pc_chunk = chunk_groups;
+  h->pc_dir.assign((size_t)slots, CtrlSim::PcDir());
+  return 0;
+}
+void ctrlsim_prefix_cache_stats(const CtrlSim* h, int64_t* incremental_chunks, int64_t* full_chunks) {
+  if (incremental_chunks) *incremental_chunks = h ? h->pc_hits : 0;
+  if (full_chunks) *full_chunks = h ? h->pc_misses : 0;
+}
+
 int ctrlsim_sim_reset(CtrlSim* h, CtrlSimBatch* b, void* stream) { return launch_sim_reset(*b, h->mc, S(stream)); }
 int ctrlsim_observe(CtrlSim* h, CtrlSimBatch* b, int32_t t, void* stream) { return launch_observe(*b, t, h->mc, S(stream)); }
 int ctrlsim_plan_groups(CtrlSim* h, CtrlSimBatch* b, int32_t t, int32_t* n_groups_total, void* stream) {
@@ -245,9 +293,14 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
   // the map cache applies while the window starts at t = 0 and the batch fits the attached memory
   const bool use_mc = t < T && h->mc_emb && (int64_t)Sn * Nv <= h->mc_blocks;
   cudaError_t e = cudaMemcpyAsync(h->h_group_off.data(), b->group_off, sizeof(int) * (Sn + 1), cudaMemcpyDeviceToHost, st);
-  if (use_mc && e == cudaSuccess) {
+  const bool use_pc = t < T && h->pc_mem && h->pc_chunk == chunk_groups;
+  if ((use_mc || use_pc) && e == cudaSuccess) {
     h->h_group_focal.resize((size_t)Sn * Nv);
     e = cudaMemcpyAsync(h->h_group_focal.data(), b->group_focal, sizeof(int) * (size_t)Sn * Nv, cudaMemcpyDeviceToHost, st);
+  }
+  if (use_pc && e == cudaSuccess) {
+    h->h_members.resize((size_t)Sn * Nv * A);
+    e = cudaMemcpyAsync(h->h_members.data(), b->group_members, sizeof(int) * (size_t)Sn * Nv * A, cudaMemcpyDeviceToHost, st);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return set_error(-5, "policy_step: reading group offsets: %s", cudaGetErrorString(e));
@@ -277,7 +330,17 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
   } else {
     h->mc_last_t = -1;
   }
+  if (use_pc) {
+    if (t == 0 || h->pc_owner != (const void*)b->hist_state || t != h->pc_last_t + 1) {
+      for (auto& d : h->pc_dir) d.last_t = -1;
+      h->pc_owner = (const void*)b->hist_state;
+    }
+    h->pc_last_t = t;
+  } else {
+    h->pc_last_t = -1;
+  }
   int s0 = 0;
+  int64_t chunk_idx = 0;
   while (s0 < Sn) {
     int s1 = s0;
     while (s1 < Sn && off[s1 + 1] - off[s0] <= chunk_groups) ++s1;
@@ -285,20 +348,45 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
     const int g0 = off[s0], ng = off[s1] - off[s0];
     if (ng > 0) {
       int rc;
+      // prefix cache: the chunk runs incrementally if its slot was filled at step t-1 by exactly these groups
+      PrefixSlot slot;
+      const PrefixSlot* pc = nullptr;
+      if (use_pc && chunk_idx < h->pc_slots) {
+        CtrlSim::PcDir& d = h->pc_dir[(size_t)chunk_idx];
+        std::vector<int> sig;
+        sig.reserve((size_t)ng * (A + 2));
+        for (int sc = s0; sc < s1; ++sc)
+          for (int lg = 0; lg < off[sc + 1] - off[sc]; ++lg) {
+            sig.push_back(sc);
+            sig.push_back(h->h_group_focal[(size_t)sc * Nv + lg]);
+            const int* m = h->h_members.data() + ((size_t)sc * Nv + lg) * A;
+            sig.insert(sig.end(), m, m + A);
+          }
+        slot = pc_slot(h->pc_mem, h->pc_chunk, chunk_idx);
+        slot.incr = t >= 1 && d.last_t == t - 1 && d.sig == sig;
+        d.sig.swap(sig);
+        d.last_t = t;
+        pc = &slot;
+        if (slot.incr) ++h->pc_hits; else ++h->pc_misses;
+      }
+      ++chunk_idx;
       MapPlan mp;
-      if (use_mc) {
-        int* slot = h->h_idx + 3 * (size_t)g0;  // [ng] slot | [ng] sel | [ng] dst, staged per chunk
-        int* sel = slot + ng;
+      if (pc && pc->incr) {
+        // nothing upstream of the decoder is recomputed; tokenise the last two window steps only
+        if ((rc = launch_tokenize(*b, g0, ng, t, 2, ws.tk, h->mc, st, ws.map_sel, 0, t - 1))) return rc;
+      } else if (use_mc) {
+        int* slot_l = h->h_idx + 3 * (size_t)g0;  // [ng] slot | [ng] sel | [ng] dst, staged per chunk
+        int* sel = slot_l + ng;
         int* dst = sel + ng;
         int n_miss = 0, gl = 0;
         for (int sc = s0; sc < s1; ++sc)
           for (int lg = 0; lg < off[sc + 1] - off[sc]; ++lg, ++gl) {
             const int blk = sc * Nv + h->h_group_focal[(size_t)sc * Nv + lg];
-            slot[gl] = blk;
+            slot_l[gl] = blk;
             if (!h->mc_dir[blk]) { h->mc_dir[blk] = 1; sel[n_miss] = gl; dst[n_miss] = blk; ++n_miss; }
           }
         h->mc_misses += n_miss; h->mc_hits += ng - n_miss;
-        cudaError_t ce = cudaMemcpyAsync(ws.map_slot, slot, sizeof(int) * ng, cudaMemcpyHostToDevice, st);
+        cudaError_t ce = cudaMemcpyAsync(ws.map_slot, slot_l, sizeof(int) * ng, cudaMemcpyHostToDevice, st);
         if (ce == cudaSuccess && n_miss) ce = cudaMemcpyAsync(ws.map_sel, sel, sizeof(int) * n_miss, cudaMemcpyHostToDevice, st);
         if (ce == cudaSuccess && n_miss) ce = cudaMemcpyAsync(ws.map_dst, dst, sizeof(int) * n_miss, cudaMemcpyHostToDevice, st);
         if (ce != cudaSuccess) return set_error(-5, "policy_step: uploading map-cache lists: %s", cudaGetErrorString(ce));
@@ -307,10 +395,10 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
       } else {
         if ((rc = launch_tokenize(*b, g0, ng, t, n_t, ws.tk, h->mc, st))) return rc;
       }
-      if ((rc = forward_pass1(h->w, ws, ng, n_t, h->n_sm, st, mp))) return rc;
+      if ((rc = forward_pass1(h->w, ws, ng, n_t, h->n_sm, st, mp, pc))) return rc;
       if ((rc = launch_resolve_rtg_range(*b, *p, t, s0, s1, g0, h->mc.steps, ws.rtg_logits, st))) return rc;
       if ((rc = launch_gather_rtg_steps(*b, g0, ng, t, h->mc.steps, ws.rtg_new, st))) return rc;
-      if ((rc = forward_pass2(h->w, ws, ng, n_t, st))) return rc;
+      if ((rc = forward_pass2(h->w, ws, ng, n_t, st, pc))) return rc;
       if ((rc = launch_sample_actions(*b, *p, g0, ng, t, ws.act_logits, h->mc, st))) return rc;
     } else {
       int rc;  // scenes without any group still owe their vehicles the "(0,0,0) RTG appended" bookkeeping

@@ -218,6 +218,15 @@ int launch_attn_causal(const float* QKV, float* O, int G, int n_t, cudaStream_t 
   return 0;
 }
 
+// Incremental decode (prefix cache): the last n_q rows of every group attend to the group's first Lk cached keys.
+int launch_attn_causal_tail(const float* Q, int ldq, const KvView& kv, float* O, int G, int n_q, int Lk, cudaStream_t st) {
+  if (G <= 0 || n_q <= 0) return 0;
+  if (n_q < 128 || attn_mode() != 2 || ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(kv.base)) & 15))
+    return set_error(-2, "attn_causal_tail: needs the tcgen05 kernel and at least 128 query rows (got %d)", n_q);
+  return launch_attn_tc(true, Q, ldq, ldq, 0, kv.base, kv.ld, kv.ld, kv.k_off, kv.v_off, nullptr, O, H, G, n_q, Lk, st,
+                        Lk - n_q, kv.group_rows);
+}
+
 // -------------------------------------------------------------------------------------------------------------
 // Second pass: queries are the A rtg-token rows (ti, a, 1) of each group, recomputed after RTG sampling.
 // Visible keys: every first-pass token of timesteps < ti, the A state tokens of timestep ti (first pass), and the
@@ -227,8 +236,8 @@ constexpr int SCH = 32;  // keys per per-warp tile in attn_step
 // 4 warps per (group, head): warp w streams key tiles w, w+4, ... for all 24 query rows (thread = query), then the
 // partial online-softmax states are merged through shared memory.
 __global__ void __launch_bounds__(128)
-attn_step_kernel(const float* __restrict__ QKV_full, const float* __restrict__ qkv_rows, float* __restrict__ O,
-                 int Lfull, int ti, int own_row) {
+attn_step_kernel(const float* __restrict__ KVbuf, int ld, int k_off, int v_off, int group_rows,
+                 const float* __restrict__ qkv_rows, float* __restrict__ O, int ti, int own_row) {
   __shared__ __align__(16) KVTile<SCH> sm[4];
   __shared__ float part[4][A][DH + 2];
   const int g = blockIdx.y, h = blockIdx.x;
@@ -240,7 +249,7 @@ attn_step_kernel(const float* __restrict__ QKV_full, const float* __restrict__ q
   for (int c = 0; c < DH; ++c) acc[c] = 0.f;
   const float* myrow = qkv_rows + ((size_t)g * A + (active ? a : 0)) * (3 * H) + h * DH;
   if (active) load_q(myrow, q);
-  const float* base = QKV_full + (size_t)g * Lfull * (3 * H);
+  const float* base = KVbuf + (size_t)g * group_rows * ld;
   const int n_hist = ti * TOK_T;          // all tokens of earlier timesteps
   const int n_keys = n_hist + A;          // + state tokens of timestep ti
   KVTile<SCH>& t = sm[warp];
@@ -251,9 +260,9 @@ attn_step_kernel(const float* __restrict__ QKV_full, const float* __restrict__ q
       const int r = i >> 3, c = (i & 7) << 2;
       const int key = k0 + r;
       const int tok = key < n_hist ? key : n_hist + (key - n_hist) * KT;  // state token of agent (key - n_hist)
-      const float* src = base + (size_t)tok * (3 * H) + h * DH + c;
-      *reinterpret_cast<float4*>(&t.k[r][c]) = *reinterpret_cast<const float4*>(src + H);
-      *reinterpret_cast<float4*>(&t.v[r][c]) = *reinterpret_cast<const float4*>(src + 2 * H);
+      const float* src = base + (size_t)tok * ld + h * DH + c;
+      *reinterpret_cast<float4*>(&t.k[r][c]) = *reinterpret_cast<const float4*>(src + k_off);
+      *reinterpret_cast<float4*>(&t.v[r][c]) = *reinterpret_cast<const float4*>(src + v_off);
     }
     __syncwarp();
     if (active) {
@@ -308,11 +317,10 @@ attn_step_kernel(const float* __restrict__ QKV_full, const float* __restrict__ q
   }
 }
 
-int launch_attn_step(const float* QKV_full, const float* qkv_rows, float* O, int G, int n_t_full, int ti,
-                     bool own_row, cudaStream_t st) {
+int launch_attn_step(const KvView& kv, const float* qkv_rows, float* O, int G, int ti, bool own_row, cudaStream_t st) {
   if (G <= 0) return 0;
   dim3 grid(NH, G);
-  attn_step_kernel<<<grid, 128, 0, st>>>(QKV_full, qkv_rows, O, n_t_full * TOK_T, ti, own_row ? 1 : 0);
+  attn_step_kernel<<<grid, 128, 0, st>>>(kv.base, kv.ld, kv.k_off, kv.v_off, kv.group_rows, qkv_rows, O, ti, own_row ? 1 : 0);
   CS_CHECK_LAUNCH("attn_step");
   return 0;
 }

@@ -195,7 +195,9 @@ template <bool CAUSAL>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int q_col0, int k_col0,
                const float* __restrict__ Vbase, int ldkv, const uint8_t* __restrict__ key_pad, float* __restrict__ O,
-               int ldo, int Lq, int Lk) {
+               int ldo, int Lq, int Lk, int q_pos0, int kv_group_rows) {
+  // Lq query rows per group (tensor-map rows g * Lq + row); causal mode: row i sits at sequence position q_pos0 + i.
+  // Lk keys are valid; the K / V rows of group g start at row g * kv_group_rows of their buffer.
   extern __shared__ unsigned char at_raw[];
   AtSmem& sm = *reinterpret_cast<AtSmem*>((reinterpret_cast<uintptr_t>(at_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -203,7 +205,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;  // heavy (late) causal tiles first
   const int r0 = qt * AT_QT;
   int kend = Lk;
-  if (CAUSAL) kend = min(Lk, (min(r0 + AT_QT - 1, Lq - 1) / TOK_T + 1) * TOK_T);
+  if (CAUSAL) kend = min(Lk, ((q_pos0 + min(r0 + AT_QT - 1, Lq - 1)) / TOK_T + 1) * TOK_T);
   const int n_tiles = (kend + AT_KT - 1) / AT_KT;
 
   if (tid == 0) {
@@ -240,8 +242,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // rtg / action token if the row is at or past it.  Bit b <-> key tq * 72 + b; bits 64..71 live in pat_hi.
     unsigned long long pat_lo = 0x9249249249249249ull, pat_hi = 0x24ull;
     if (CAUSAL) {
-      tq = row / TOK_T;
-      const int rem = row - tq * TOK_T;
+      tq = (q_pos0 + row) / TOK_T;
+      const int rem = (q_pos0 + row) - tq * TOK_T;
       const int aq = rem / KT, kq = rem - aq * KT;
       for (int kk = 1; kk <= kq; ++kk) {
         const int bpos = 3 * aq + kk;
@@ -353,7 +355,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     __syncwarp();
     if (lane == 0) at_arrive(&sm.q_lo_ready);
     const int u = pt & 7, hrot = u >> 1;  // this thread's 4 dims 4u..4u+3 of V; store order rotated by hrot (bank spread)
-    const float* vsrc = Vbase + (size_t)g * Lk * ldkv + h * DH + u * 4;
+    const float* vsrc = Vbase + (size_t)g * kv_group_rows * ldkv + h * DH + u * 4;
     for (int j = 0; j < n_tiles; ++j) {
       const int s = j % AT_STAGES;
       float4 vv[8];
@@ -456,7 +458,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int s = j % AT_STAGES;
         at_wait(&sm.k_empty[s], ((j / AT_STAGES) & 1) ^ 1);
         at_expect_tx(&sm.k_full[s], AT_KT * DH * 4);
-        at_tma_2d(sm.kv[s].k_raw, &tmKV, k_col0 + h * DH, g * Lk + j * AT_KT, &sm.k_full[s]);
+        at_tma_2d(sm.kv[s].k_raw, &tmKV, k_col0 + h * DH, g * kv_group_rows + j * AT_KT, &sm.k_full[s]);
       }
     }
   }
@@ -489,7 +491,8 @@ static int at_make_map(AtEncodeFn enc, CUtensorMap* map, const float* base, long
 // Q rows: [G*Lq, q_cols] at Qbase (ldq), head h at columns q_col0 + 32h; K / V rows: [G*Lk, kv_cols] at KVbase (ldkv).
 int launch_attn_tc(bool causal, const float* Qbase, int ldq, int q_cols, int q_col0, const float* KVbase, int ldkv,
                    int kv_cols, int k_col0, int v_col0, const uint8_t* key_pad, float* O, int ldo, int G, int Lq, int Lk,
-                   cudaStream_t st) {
+                   cudaStream_t st, int q_pos0, int kv_group_rows) {
+  if (kv_group_rows <= 0) kv_group_rows = Lk;
   static AtEncodeFn enc = nullptr;
   const int smem = (int)sizeof(AtSmem) + 1024;
   if (!enc) {
@@ -506,12 +509,12 @@ int launch_attn_tc(bool causal, const float* Qbase, int ldq, int q_cols, int q_c
   CUtensorMap tmQ, tmKV;
   int rc;
   if ((rc = at_make_map(enc, &tmQ, Qbase, (long long)G * Lq, q_cols, ldq, AT_QT))) return rc;
-  if ((rc = at_make_map(enc, &tmKV, KVbase, (long long)G * Lk, kv_cols, ldkv, AT_KT))) return rc;
+  if ((rc = at_make_map(enc, &tmKV, KVbase, (long long)G * kv_group_rows, kv_cols, ldkv, AT_KT))) return rc;
   dim3 grid((Lq + AT_QT - 1) / AT_QT, NH, G);
   if (causal)
-    attn_tc_kernel<true><<<grid, AT_THREADS, smem, st>>>(tmQ, tmKV, q_col0, k_col0, KVbase + v_col0, ldkv, key_pad, O, ldo, Lq, Lk);
+    attn_tc_kernel<true><<<grid, AT_THREADS, smem, st>>>(tmQ, tmKV, q_col0, k_col0, KVbase + v_col0, ldkv, key_pad, O, ldo, Lq, Lk, q_pos0, kv_group_rows);
   else
-    attn_tc_kernel<false><<<grid, AT_THREADS, smem, st>>>(tmQ, tmKV, q_col0, k_col0, KVbase + v_col0, ldkv, key_pad, O, ldo, Lq, Lk);
+    attn_tc_kernel<false><<<grid, AT_THREADS, smem, st>>>(tmQ, tmKV, q_col0, k_col0, KVbase + v_col0, ldkv, key_pad, O, ldo, Lq, Lk, 0, kv_group_rows);
   CS_CHECK_LAUNCH("attn_tc");
   return 0;
 }

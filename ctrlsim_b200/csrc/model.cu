@@ -133,7 +133,103 @@ size_t Workspace::carve(void* base, size_t bytes, int Gc) {
   return off;
 }
 
-int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm, cudaStream_t st, const MapPlan& mp) {
+// ---- pieces shared by the full forward and the incremental (prefix-cache) forward -----------------------------------
+// M3: embeddings of n_tok token steps per group -> X [G * n_tok * 72, H] (and the initial-state memory rows if asked)
+static int embed_tokens(const ModelWeights& w, Workspace& ws, int G, int n_tok, bool with_mem, cudaStream_t st) {
+  const int Ra = G * A, Rta = G * n_tok * A;
+  CS_TRY(launch_small_mlp1(12, ws.tk.feat_state, w.embed_state, ws.s1, (size_t)Rta, st));
+  CS_TRY(gemm(ws.s1, w.embed_state.w3, w.embed_state.b3, ws.s2, Rta, H, H, H, H, H, false, st));
+  CS_TRY(launch_small_mlp1(5, ws.tk.goal_feat, w.embed_goal, ws.g1, (size_t)Ra, st));
+  CS_TRY(gemm(ws.g1, w.embed_goal.w3, w.embed_goal.b3, ws.g2, Ra, H, H, H, H, H, false, st));
+  CS_TRY(gemm(ws.g2, w.sg_w + H, w.sg_b, ws.gpart, Ra, H, H, H, 2 * H, H, false, st));
+  CS_TRY(launch_make_goal_index(G, n_tok, ws.goal_idx, st));
+  CS_TRY(gemm(ws.s2, w.sg_w, nullptr, ws.sg, Rta, H, H, H, 2 * H, H, false, st, ws.gpart, ws.goal_idx, H));
+  CS_TRY(launch_assemble_tokens(G, n_tok, ws.sg, ws.tk, w.emb, ws.X, with_mem ? ws.mem : nullptr, st));
+  return 0;
+}
+
+// everything of a decoder layer after self-attention, on R rows of ws.X (attention output in ws.att)
+static int decoder_layer_rest(const DecLayerW& d, Workspace& ws, int G, int rows_per_group, const float* kvc,
+                              const uint8_t* pad, cudaStream_t st) {
+  const int R = G * rows_per_group;
+  CS_TRY(gemm(ws.att, d.sa.out_w, d.sa.out_b, ws.tmp, R, H, H, H, H, H, false, st));
+  CS_TRY(ln(ws.X, ws.tmp, d.n1, ws.X, R, false, st));
+  CS_TRY(gemm(ws.X, d.ca.in_w, d.ca.in_b, ws.q_c, R, H, H, H, H, H, false, st));
+  g_prof.begin(PROF_ATTN_CROSS, (double)G * NH * rows_per_group * MEM * 4.0 * DH, st);
+  CS_TRY(launch_attn_padded(ws.q_c, H, kvc, kvc + H, 2 * H, pad, ws.att, H, G, rows_per_group, MEM, st));
+  g_prof.end(st);
+  CS_TRY(gemm(ws.att, d.ca.out_w, d.ca.out_b, ws.tmp, R, H, H, H, H, H, false, st));
+  CS_TRY(ln(ws.X, ws.tmp, d.n2, ws.X, R, false, st));
+  CS_TRY(gemm(ws.X, d.l1w, d.l1b, ws.ff, R, FF, H, H, H, FF, true, st));
+  CS_TRY(gemm(ws.ff, d.l2w, d.l2b, ws.tmp, R, H, FF, FF, FF, H, false, st));
+  CS_TRY(ln(ws.X, ws.tmp, d.n3, ws.X, R, false, st));
+  return 0;
+}
+
+// Last decoder layer + RTG head for the 24 state rows of the current step only (the only rows of the last layer's
+// output that are read): token step ti_tok of the n_tok tokenised steps, window index ti_abs.
+static int last_layer_state_rows(const ModelWeights& w, Workspace& ws, int G, int n_tok, int ti_tok, int ti_abs,
+                                 const KvView& kv, const float* kvc, const uint8_t* pad, cudaStream_t st) {
+  const int Ra = G * A;
+  const DecLayerW& d = w.dec[N_DEC - 1];
+  CS_TRY(launch_make_row_index(G, n_tok, ti_tok, 0, ws.row_idx, st));
+  CS_TRY(launch_gather_rows(Ra, ws.X, ws.row_idx, ws.xr, st));
+  CS_TRY(gemm(ws.xr, d.sa.in_w, d.sa.in_b, ws.qkv_r, Ra, H, H, H, H, 3 * H, false, st));
+  CS_TRY(launch_attn_step(kv, ws.qkv_r, ws.att_r, G, ti_abs, false, st));
+  CS_TRY(gemm(ws.att_r, d.sa.out_w, d.sa.out_b, ws.tmp_r, Ra, H, H, H, H, H, false, st));
+  CS_TRY(ln(ws.xr, ws.tmp_r, d.n1, ws.xr, Ra, false, st));
+  CS_TRY(gemm(ws.xr, d.ca.in_w, d.ca.in_b, ws.qc_r, Ra, H, H, H, H, H, false, st));
+  CS_TRY(launch_attn_padded(ws.qc_r, H, kvc, kvc + H, 2 * H, pad, ws.att_r, H, G, A, MEM, st));
+  CS_TRY(gemm(ws.att_r, d.ca.out_w, d.ca.out_b, ws.tmp_r, Ra, H, H, H, H, H, false, st));
+  CS_TRY(ln(ws.xr, ws.tmp_r, d.n2, ws.xr, Ra, false, st));
+  CS_TRY(gemm(ws.xr, d.l1w, d.l1b, ws.ff_r, Ra, FF, H, H, H, FF, true, st));
+  CS_TRY(gemm(ws.ff_r, d.l2w, d.l2b, ws.tmp_r, Ra, H, FF, FF, FF, H, false, st));
+  CS_TRY(ln(ws.xr, ws.tmp_r, d.n3, ws.xr, Ra, false, st));
+  // ---- M8 RTG head ------------------------------------------------------------------------------------------------
+  CS_TRY(gemm(ws.xr, w.head_rtg.w0, w.head_rtg.b0, ws.hd1, Ra, H, H, H, H, H, false, st));
+  CS_TRY(launch_layernorm(ws.hd1, nullptr, w.head_rtg.lnw, w.head_rtg.lnb, ws.hd1, Ra, H, H, H, true, st));
+  CS_TRY(gemm(ws.hd1, w.head_rtg.w3, w.head_rtg.b3, ws.rtg_logits, Ra, N_RTG * 3, H, H, H, N_RTG * 3, false, st));
+  return 0;
+}
+
+static KvView ws_view(const Workspace& ws, int l, int Lcur) {
+  KvView v; v.base = ws.QKV[l]; v.ld = 3 * H; v.k_off = H; v.v_off = 2 * H; v.group_rows = Lcur; return v;
+}
+static KvView cache_view(const PrefixSlot& pc, int l) {
+  KvView v; v.base = pc.KV[l]; v.ld = 2 * H; v.k_off = 0; v.v_off = H; v.group_rows = L; return v;
+}
+
+// Incremental first pass at step t (1 <= t < 32) of a chunk whose groups are unchanged since step t-1: only the
+// tokens of window steps t-1 (whose rtg / action tokens got their final values after step t-1) and t are embedded and
+// run through the decoder; they attend to the cached keys / values of all earlier tokens.  Nothing upstream of the
+// decoder is recomputed: polyline encoder, scene encoder and cross-attention K/V do not change while the window
+// still starts at t = 0.
+static int forward_incr(const ModelWeights& w, Workspace& ws, int G, int t, cudaStream_t st, const PrefixSlot& pc) {
+  const int n_tok = 2, rows = n_tok * TOK_T, R = G * rows, Lk = (t + 1) * TOK_T, row0 = (t - 1) * TOK_T;
+  CS_TRY(embed_tokens(w, ws, G, n_tok, false, st));
+  for (int l = 0; l < N_DEC - 1; ++l) {
+    const DecLayerW& d = w.dec[l];
+    CS_TRY(gemm(ws.X, d.sa.in_w, d.sa.in_b, ws.QKV[l], R, 3 * H, H, H, H, 3 * H, false, st));
+    CS_TRY(launch_store_kv(ws.QKV[l] + H, 3 * H, G, rows, pc.KV[l], row0, st));
+    {
+      double vis = 0;
+      for (int tw = t - 1; tw <= t; ++tw) vis += (double)TOK_T * (TOK_T * tw + A) + 3.0 * A;
+      g_prof.begin(PROF_ATTN_CAUSAL, (double)G * NH * vis * 4.0 * DH, st);
+    }
+    CS_TRY(launch_attn_causal_tail(ws.QKV[l], 3 * H, cache_view(pc, l), ws.att, G, rows, Lk, st));
+    g_prof.end(st);
+    CS_TRY(decoder_layer_rest(d, ws, G, rows, pc.KVC[l], pc.PAD, st));
+  }
+  const int l = N_DEC - 1;
+  const DecLayerW& d = w.dec[l];
+  CS_TRY(gemm(ws.X, d.sa.in_w + (size_t)H * H, d.sa.in_b + H, ws.QKV[l] + H, R, 2 * H, H, H, H, 3 * H, false, st));
+  CS_TRY(launch_store_kv(ws.QKV[l] + H, 3 * H, G, rows, pc.KV[l], row0, st));
+  return last_layer_state_rows(w, ws, G, n_tok, n_tok - 1, t, cache_view(pc, l), pc.KVC[l], pc.PAD, st);
+}
+
+int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm, cudaStream_t st, const MapPlan& mp,
+                  const PrefixSlot* pc) {
+  if (pc && pc->incr) return forward_incr(w, ws, G, n_t - 1, st, *pc);
   const int Gm = mp.n_map < 0 ? G : mp.n_map;  // groups whose polylines are encoded this step
   const int Rp = Gm * P, Rpt = Rp * NP, Ra = G * A, Rta = G * n_t * A, Rm = G * MEM;
   const int Lcur = n_t * TOK_T, R = G * Lcur, ti = n_t - 1;
@@ -159,16 +255,10 @@ int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm
   if (mp.cache_emb) CS_TRY(launch_scatter_map(Gm, ws.pe_c, ws.poly_valid, mp.dst, mp.cache_emb, mp.cache_valid, st));
   }
   // ---- M3 token embeddings --------------------------------------------------------------------------------------
-  CS_TRY(launch_small_mlp1(12, ws.tk.feat_state, w.embed_state, ws.s1, (size_t)Rta, st));
-  CS_TRY(gemm(ws.s1, w.embed_state.w3, w.embed_state.b3, ws.s2, Rta, H, H, H, H, H, false, st));
-  CS_TRY(launch_small_mlp1(5, ws.tk.goal_feat, w.embed_goal, ws.g1, (size_t)Ra, st));
-  CS_TRY(gemm(ws.g1, w.embed_goal.w3, w.embed_goal.b3, ws.g2, Ra, H, H, H, H, H, false, st));
-  CS_TRY(gemm(ws.g2, w.sg_w + H, w.sg_b, ws.gpart, Ra, H, H, H, 2 * H, H, false, st));
-  CS_TRY(launch_make_goal_index(G, n_t, ws.goal_idx, st));
-  CS_TRY(gemm(ws.s2, w.sg_w, nullptr, ws.sg, Rta, H, H, H, 2 * H, H, false, st, ws.gpart, ws.goal_idx, H));
-  CS_TRY(launch_assemble_tokens(G, n_t, ws.sg, ws.tk, w.emb, ws.X, ws.mem, st));
+  CS_TRY(embed_tokens(w, ws, G, n_t, true, st));
   if (mp.cache_emb) CS_TRY(launch_build_memory(G, mp.cache_emb, mp.cache_valid, mp.slot, ws.tk, n_t, ws.mem, ws.pad, st));
   else CS_TRY(launch_build_memory(G, ws.pe_c, ws.poly_valid, nullptr, ws.tk, n_t, ws.mem, ws.pad, st));
+  if (pc) CS_TRY(launch_copy_bytes(ws.pad, pc->PAD, (size_t)G * MEM, st));
   // ---- M4 scene encoder -----------------------------------------------------------------------------------------
   for (int l = 0; l < N_ENC; ++l) {
     const EncLayerW& e = w.enc[l];
@@ -184,9 +274,19 @@ int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm
   // Layers 0..2 run on every row (their outputs are the next layer's keys/values).  Of the last layer's output only
   // the 24 state rows of the current step are read (RTG head), so it computes K/V for every row (the second pass
   // needs them) but queries / attention / cross-attention / FFN for those 24 rows only.
-  for (int l = 0; l < N_DEC - 1; ++l) {
+  // With a prefix-cache slot the cross-attention K/V go straight into the slot and every layer's K | V rows are
+  // copied into it, so that the next step can run incrementally.
+  for (int l = 0; l < N_DEC; ++l) {
     const DecLayerW& d = w.dec[l];
-    CS_TRY(gemm(ws.X, d.sa.in_w, d.sa.in_b, ws.QKV[l], R, 3 * H, H, H, H, 3 * H, false, st));
+    float* kvc = pc ? pc->KVC[l] : ws.kv_c[l];
+    CS_TRY(gemm(ws.mem, d.ca.in_w + (size_t)H * H, d.ca.in_b + H, kvc, Rm, 2 * H, H, H, H, 2 * H, false, st));
+    if (l < N_DEC - 1) {
+      CS_TRY(gemm(ws.X, d.sa.in_w, d.sa.in_b, ws.QKV[l], R, 3 * H, H, H, H, 3 * H, false, st));
+    } else {  // K | V of every row into columns [256, 768) of QKV[l]
+      CS_TRY(gemm(ws.X, d.sa.in_w + (size_t)H * H, d.sa.in_b + H, ws.QKV[l] + H, R, 2 * H, H, H, H, 3 * H, false, st));
+    }
+    if (pc) CS_TRY(launch_store_kv(ws.QKV[l] + H, 3 * H, G, Lcur, pc->KV[l], 0, st));
+    if (l == N_DEC - 1) break;
     {  // useful flops: 4 * d_h per (row, head, visible key); visible keys per step tw: 72*tw + 24 (+0/1/2 own tokens)
       double vis = 0;
       for (int tw = 0; tw < n_t; ++tw) vis += (double)TOK_T * (TOK_T * tw + A) + 3.0 * A;
@@ -194,57 +294,28 @@ int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm
     }
     CS_TRY(launch_attn_causal(ws.QKV[l], ws.att, G, n_t, st));
     g_prof.end(st);
-    CS_TRY(gemm(ws.att, d.sa.out_w, d.sa.out_b, ws.tmp, R, H, H, H, H, H, false, st));
-    CS_TRY(ln(ws.X, ws.tmp, d.n1, ws.X, R, false, st));
-    CS_TRY(gemm(ws.X, d.ca.in_w, d.ca.in_b, ws.q_c, R, H, H, H, H, H, false, st));
-    CS_TRY(gemm(ws.mem, d.ca.in_w + (size_t)H * H, d.ca.in_b + H, ws.kv_c[l], Rm, 2 * H, H, H, H, 2 * H, false, st));
-    g_prof.begin(PROF_ATTN_CROSS, (double)G * NH * Lcur * MEM * 4.0 * DH, st);
-    CS_TRY(launch_attn_padded(ws.q_c, H, ws.kv_c[l], ws.kv_c[l] + H, 2 * H, ws.pad, ws.att, H, G, Lcur, MEM, st));
-    g_prof.end(st);
-    CS_TRY(gemm(ws.att, d.ca.out_w, d.ca.out_b, ws.tmp, R, H, H, H, H, H, false, st));
-    CS_TRY(ln(ws.X, ws.tmp, d.n2, ws.X, R, false, st));
-    CS_TRY(gemm(ws.X, d.l1w, d.l1b, ws.ff, R, FF, H, H, H, FF, true, st));
-    CS_TRY(gemm(ws.ff, d.l2w, d.l2b, ws.tmp, R, H, FF, FF, FF, H, false, st));
-    CS_TRY(ln(ws.X, ws.tmp, d.n3, ws.X, R, false, st));
+    CS_TRY(decoder_layer_rest(d, ws, G, Lcur, kvc, ws.pad, st));
   }
-  {
-    const int l = N_DEC - 1;
-    const DecLayerW& d = w.dec[l];
-    // K | V of every row into columns [256, 768) of QKV[l]
-    CS_TRY(gemm(ws.X, d.sa.in_w + (size_t)H * H, d.sa.in_b + H, ws.QKV[l] + H, R, 2 * H, H, H, H, 3 * H, false, st));
-    CS_TRY(gemm(ws.mem, d.ca.in_w + (size_t)H * H, d.ca.in_b + H, ws.kv_c[l], Rm, 2 * H, H, H, H, 2 * H, false, st));
-    CS_TRY(launch_make_row_index(G, n_t, ti, 0, ws.row_idx, st));
-    CS_TRY(launch_gather_rows(Ra, ws.X, ws.row_idx, ws.xr, st));
-    CS_TRY(gemm(ws.xr, d.sa.in_w, d.sa.in_b, ws.qkv_r, Ra, H, H, H, H, 3 * H, false, st));
-    CS_TRY(launch_attn_step(ws.QKV[l], ws.qkv_r, ws.att_r, G, n_t, ti, false, st));
-    CS_TRY(gemm(ws.att_r, d.sa.out_w, d.sa.out_b, ws.tmp_r, Ra, H, H, H, H, H, false, st));
-    CS_TRY(ln(ws.xr, ws.tmp_r, d.n1, ws.xr, Ra, false, st));
-    CS_TRY(gemm(ws.xr, d.ca.in_w, d.ca.in_b, ws.qc_r, Ra, H, H, H, H, H, false, st));
-    CS_TRY(launch_attn_padded(ws.qc_r, H, ws.kv_c[l], ws.kv_c[l] + H, 2 * H, ws.pad, ws.att_r, H, G, A, MEM, st));
-    CS_TRY(gemm(ws.att_r, d.ca.out_w, d.ca.out_b, ws.tmp_r, Ra, H, H, H, H, H, false, st));
-    CS_TRY(ln(ws.xr, ws.tmp_r, d.n2, ws.xr, Ra, false, st));
-    CS_TRY(gemm(ws.xr, d.l1w, d.l1b, ws.ff_r, Ra, FF, H, H, H, FF, true, st));
-    CS_TRY(gemm(ws.ff_r, d.l2w, d.l2b, ws.tmp_r, Ra, H, FF, FF, FF, H, false, st));
-    CS_TRY(ln(ws.xr, ws.tmp_r, d.n3, ws.xr, Ra, false, st));
-  }
-  // ---- M8 RTG head on the state rows of the current step ----------------------------------------------------------
-  CS_TRY(gemm(ws.xr, w.head_rtg.w0, w.head_rtg.b0, ws.hd1, Ra, H, H, H, H, H, false, st));
-  CS_TRY(launch_layernorm(ws.hd1, nullptr, w.head_rtg.lnw, w.head_rtg.lnb, ws.hd1, Ra, H, H, H, true, st));
-  CS_TRY(gemm(ws.hd1, w.head_rtg.w3, w.head_rtg.b3, ws.rtg_logits, Ra, N_RTG * 3, H, H, H, N_RTG * 3, false, st));
-  return 0;
+  return last_layer_state_rows(w, ws, G, n_t, ti, ti, ws_view(ws, N_DEC - 1, Lcur),
+                               pc ? pc->KVC[N_DEC - 1] : ws.kv_c[N_DEC - 1], ws.pad, st);
 }
 
-int forward_pass2(const ModelWeights& w, Workspace& ws, int G, int n_t, cudaStream_t st) {
-  const int Ra = G * A, ti = n_t - 1;
-  CS_TRY(launch_assemble_rtg_rows(G, n_t, ti, ws.rtg_new, ws.tk, w.emb, ws.xr, st));
+// Second pass: the 24 rtg rows of the current step with the sampled RTGs, against the first pass' keys / values
+// (workspace or prefix-cache slot).
+int forward_pass2(const ModelWeights& w, Workspace& ws, int G, int n_t, cudaStream_t st, const PrefixSlot* pc) {
+  const bool incr = pc && pc->incr;
+  const int Ra = G * A, ti = n_t - 1, n_tok = incr ? 2 : n_t, Lcur = n_t * TOK_T;
+  CS_TRY(launch_assemble_rtg_rows(G, n_tok, n_tok - 1, ws.rtg_new, ws.tk, w.emb, ws.xr, st));
   for (int l = 0; l < N_DEC; ++l) {
     const DecLayerW& d = w.dec[l];
+    const float* kvc = pc ? pc->KVC[l] : ws.kv_c[l];
+    const uint8_t* pad = incr ? pc->PAD : ws.pad;
     CS_TRY(gemm(ws.xr, d.sa.in_w, d.sa.in_b, ws.qkv_r, Ra, 3 * H, H, H, H, 3 * H, false, st));
-    CS_TRY(launch_attn_step(ws.QKV[l], ws.qkv_r, ws.att_r, G, n_t, ti, true, st));
+    CS_TRY(launch_attn_step(incr ? cache_view(*pc, l) : ws_view(ws, l, Lcur), ws.qkv_r, ws.att_r, G, ti, true, st));
     CS_TRY(gemm(ws.att_r, d.sa.out_w, d.sa.out_b, ws.tmp_r, Ra, H, H, H, H, H, false, st));
     CS_TRY(ln(ws.xr, ws.tmp_r, d.n1, ws.xr, Ra, false, st));
     CS_TRY(gemm(ws.xr, d.ca.in_w, d.ca.in_b, ws.qc_r, Ra, H, H, H, H, H, false, st));
-    CS_TRY(launch_attn_padded(ws.qc_r, H, ws.kv_c[l], ws.kv_c[l] + H, 2 * H, ws.pad, ws.att_r, H, G, A, MEM, st));
+    CS_TRY(launch_attn_padded(ws.qc_r, H, kvc, kvc + H, 2 * H, pad, ws.att_r, H, G, A, MEM, st));
     CS_TRY(gemm(ws.att_r, d.ca.out_w, d.ca.out_b, ws.tmp_r, Ra, H, H, H, H, H, false, st));
     CS_TRY(ln(ws.xr, ws.tmp_r, d.n2, ws.xr, Ra, false, st));
     CS_TRY(gemm(ws.xr, d.l1w, d.l1b, ws.ff_r, Ra, FF, H, H, H, FF, true, st));

@@ -63,7 +63,7 @@ struct TokenBufs {  // internal token representation of a chunk of groups (time-
 // map_sel (optional, device): chunk-local groups whose polyline tokens are rebuilt (n_map of them, into map slots
 // 0..n_map-1); nullptr = every group.
 int launch_tokenize(const CtrlSimBatch& b, int g0, int ng, int t, int n_t, const TokenBufs& tk, const ModelCfg& mc,
-                    cudaStream_t st, const int* map_sel = nullptr, int n_map = 0);
+                    cudaStream_t st, const int* map_sel = nullptr, int n_map = 0, int tok_first = 0);
 int launch_convert_tokens(int G, int n_t, const float* agent_states, const float* agent_types, const float* goals,
                           const int* actions, const int* rtgs, const int* timesteps, const float* road_points,
                           const int* road_types, const TokenBufs& tk, cudaStream_t st);
@@ -77,6 +77,9 @@ int launch_build_memory(int G, const float* poly_emb, const uint8_t* poly_valid,
                         int n_t, float* mem, uint8_t* pad, cudaStream_t st);
 int launch_scatter_map(int n, const float* emb, const uint8_t* valid, const int* dst, float* cache_emb,
                        uint8_t* cache_valid, cudaStream_t st);
+// dst[g, dst_row0 + r, 0..2H) = src[(g * rows + r) * ld_src + 0..2H)   (K | V rows into a prefix-cache slot [G, L, 2H])
+int launch_store_kv(const float* src, int ld_src, int G, int rows, float* dst, int dst_row0, cudaStream_t st);
+int launch_copy_bytes(const uint8_t* src, uint8_t* dst, size_t n, cudaStream_t st);
 int launch_make_row_index(int G, int n_t, int ti, int k, int* out, cudaStream_t st);
 int launch_make_goal_index(int G, int n_t, int* out, cudaStream_t st);
 int launch_gather_rows(int n, const float* X, const int* idx, float* Y, cudaStream_t st);

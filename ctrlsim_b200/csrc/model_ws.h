@@ -54,9 +54,19 @@ struct MapPlan {
   uint8_t* cache_valid = nullptr; // [n_blocks, P]
 };
 
+// One chunk slot of the caller-attached prefix cache (ctrlsim_attach_prefix_cache): decoder keys / values of every
+// token seen so far, cross-attention keys / values of the memory tokens and the memory padding mask of the chunk's
+// groups.  Valid while the 32-step window still starts at t = 0 and the chunk's focal groups do not change.
+struct PrefixSlot {
+  float* KV[N_DEC];    // [Gc, L, 2H]   K | V rows of decoder layer l
+  float* KVC[N_DEC];   // [Gc, MEM, 2H] cross-attention K | V of layer l
+  uint8_t* PAD;        // [Gc, MEM]
+  bool incr = false;   // true: step t reuses the slot (incremental first pass); false: a full forward (re)fills it
+};
+
 int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm, cudaStream_t st,
-                  const MapPlan& mp = MapPlan());
-int forward_pass2(const ModelWeights& w, Workspace& ws, int G, int n_t, cudaStream_t st);
+                  const MapPlan& mp = MapPlan(), const PrefixSlot* pc = nullptr);
+int forward_pass2(const ModelWeights& w, Workspace& ws, int G, int n_t, cudaStream_t st, const PrefixSlot* pc = nullptr);
 
 int launch_resolve_rtg_range(const CtrlSimBatch& b, const CtrlSimPolicyParams& p, int t, int s0, int s1, int g_base,
                              int steps, const float* rtg_logits, cudaStream_t st);

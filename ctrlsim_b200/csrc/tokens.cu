@@ -28,8 +28,10 @@ __device__ __forceinline__ double angle_sub_d(double cur, double tgt) {  // util
 // ---------------------------------------------------------------------------------------------------------------
 // tokenize_agents: one block per compact group, one thread per (window step, slot).
 __global__ void __launch_bounds__(256)
-tokenize_agents_kernel(CtrlSimBatch b, int g0, int t, int n_t, int steps, TokenBufs tk, double min_accel,
+tokenize_agents_kernel(CtrlSimBatch b, int g0, int t, int n_t, int tok_first, int steps, TokenBufs tk, double min_accel,
                        double max_accel, double min_steer, double max_steer, int n_steer) {
+  // n_t token steps starting at window index tok_first (0 = whole window; the incremental decode of the prefix cache
+  // tokenises only the last two window steps); the normalisation frame is always the focal pose at window index 0.
   const int gl = blockIdx.x, g = g0 + gl;
   const int s = b.group_scene[g], lg = b.group_local[g];
   const int N = b.max_veh;
@@ -57,7 +59,7 @@ tokenize_agents_kernel(CtrlSimBatch b, int g0, int t, int n_t, int steps, TokenB
       tk.act_idx[row] = 0;
       tk.rtg_idx[row * 3 + 0] = tk.rtg_idx[row * 3 + 1] = tk.rtg_idx[row * 3 + 2] = 0;
     } else {
-      const double* st = hs + ((size_t)v * steps + t0 + tw) * 8;
+      const double* st = hs + ((size_t)v * steps + t0 + tok_first + tw) * 8;
       const double dx = st[0] - tx, dy = st[1] - ty;
       f[0] = (float)(cr * dx + (-sr) * dy);
       f[1] = (float)(sr * dx + cr * dy);
@@ -68,16 +70,16 @@ tokenize_agents_kernel(CtrlSimBatch b, int g0, int t, int n_t, int steps, TokenB
       f[6] = (float)st[6];
       f[7] = 0.f; f[8] = 1.f; f[9] = 0.f; f[10] = 0.f; f[11] = 0.f;  // one-hot "vehicle" (utils/data.py:326-328)
       tk.exist[row] = st[7] != 0.0;
-      const double* ac = b.hist_action + ((size_t)s * N * steps + (size_t)v * steps + t0 + tw) * 2;
+      const double* ac = b.hist_action + ((size_t)s * N * steps + (size_t)v * steps + t0 + tok_first + tw) * 2;
       const double a0 = (fmin(fmax(ac[0], min_accel), max_accel) - min_accel) / (max_accel - min_accel);
       const double a1 = (fmin(fmax(ac[1], min_steer), max_steer) - min_steer) / (max_steer - min_steer);
       tk.act_idx[row] = (int)(rint(a0 * (N_ACT / n_steer - 1)) * n_steer + rint(a1 * (n_steer - 1)));
-      const int16_t* rt = b.hist_rtg + ((size_t)s * N * steps + (size_t)v * steps + t0 + tw) * 3;
+      const int16_t* rt = b.hist_rtg + ((size_t)s * N * steps + (size_t)v * steps + t0 + tok_first + tw) * 3;
       tk.rtg_idx[row * 3 + 0] = rt[0]; tk.rtg_idx[row * 3 + 1] = rt[1]; tk.rtg_idx[row * 3 + 2] = rt[2];
     }
   }
   for (int tw = threadIdx.x; tw < n_t; tw += blockDim.x)
-    tk.ts[gl * n_t + tw] = (t0 + tw <= t) ? t0 + tw : 0;  // policy.timesteps[0, window] (policy.py:81)
+    tk.ts[gl * n_t + tw] = (t0 + tok_first + tw <= t) ? t0 + tok_first + tw : 0;  // policy.timesteps[0, window] (policy.py:81)
   for (int a = threadIdx.x; a < A; a += blockDim.x) {
     const int v = members[a];
     float* gf = tk.goal_feat + ((size_t)gl * A + a) * 5;
@@ -169,11 +171,11 @@ tokenize_map_kernel(CtrlSimBatch b, int g0, TokenBufs tk, const int* __restrict_
 }
 
 int launch_tokenize(const CtrlSimBatch& b, int g0, int ng, int t, int n_t, const TokenBufs& tk, const ModelCfg& mc,
-                    cudaStream_t st, const int* map_sel, int n_map) {
+                    cudaStream_t st, const int* map_sel, int n_map, int tok_first) {
   if (ng <= 0) return 0;
   if (b.max_poly > 1024) return set_error(-2, "tokenize: at most 1024 polylines per scene (got %d)", b.max_poly);
-  tokenize_agents_kernel<<<ng, 256, 0, st>>>(b, g0, t, n_t, mc.steps, tk, mc.min_accel, mc.max_accel, mc.min_steer,
-                                             mc.max_steer, mc.n_steer);
+  tokenize_agents_kernel<<<ng, 256, 0, st>>>(b, g0, t, n_t, tok_first, mc.steps, tk, mc.min_accel, mc.max_accel,
+                                             mc.min_steer, mc.max_steer, mc.n_steer);
   CS_CHECK_LAUNCH("tokenize_agents");
   const int nm = map_sel ? n_map : ng;
   if (nm > 0) {
@@ -461,6 +463,30 @@ int launch_scatter_map(int n, const float* emb, const uint8_t* valid, const int*
   const size_t tot = (size_t)n * P * (H / 4);
   scatter_map_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n, emb, valid, dst, cache_emb, cache_valid);
   CS_CHECK_LAUNCH("scatter_map");
+  return 0;
+}
+
+__global__ void store_kv_kernel(const float* __restrict__ src, int ld_src, int rows, size_t n4, float* __restrict__ dst,
+                                int dst_row0) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int c = (int)(i % (2 * H / 4)) * 4;
+  const size_t r = i / (2 * H / 4);
+  const size_t g = r / rows, rr = r % rows;
+  *reinterpret_cast<float4*>(dst + (g * L + dst_row0 + rr) * (2 * H) + c) =
+      *reinterpret_cast<const float4*>(src + r * ld_src + c);
+}
+int launch_store_kv(const float* src, int ld_src, int G, int rows, float* dst, int dst_row0, cudaStream_t st) {
+  const size_t n4 = (size_t)G * rows * (2 * H / 4);
+  if (n4 == 0) return 0;
+  store_kv_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(src, ld_src, rows, n4, dst, dst_row0);
+  CS_CHECK_LAUNCH("store_kv");
+  return 0;
+}
+int launch_copy_bytes(const uint8_t* src, uint8_t* dst, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  cudaError_t e = cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return set_error(-5, "copy_bytes: %s", cudaGetErrorString(e));
   return 0;
 }
 

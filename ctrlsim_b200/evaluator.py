@@ -62,6 +62,10 @@ class B200Policy:
         self.launch_count = 0
         self._map_cache = None  # device memory of the per-focal polyline-encoder cache (steps 0..31)
         self.use_map_cache = os.environ.get("CTRLSIM_MAP_CACHE", "1") != "0"
+        self._prefix_cache = None  # device memory of the decoder prefix cache (steps 0..31), one slot per chunk
+        self._prefix_geom = None
+        self.use_prefix_cache = os.environ.get("CTRLSIM_PREFIX_CACHE", "1") != "0"
+        self.prefix_cache_max_bytes = int(float(os.environ.get("CTRLSIM_PREFIX_CACHE_GB", "96")) * 2**30)
 
     def _params(self):
         td = self.tilt_dict
@@ -98,10 +102,39 @@ class B200Policy:
         self.groups_last_step = n_total
         chunk = max(self.chunk_groups, batch.N)  # a scene's groups are processed together (RTG resolution)
         ws = self.model.workspace(chunk)
+        if t == 0:
+            self._attach_prefix_cache(chunk, n_total)
         p = self._params()
         _lib.check(self.lib.ctrlsim_policy_step(self.model.handle, batch.ptr, C.byref(p), t, n_total, ws.data_ptr(),
                                                 ws.numel(), chunk, st), "ctrlsim_policy_step")
         return n_total
+
+    def _attach_prefix_cache(self, chunk: int, n_total: int):
+        """Size the prefix cache for this episode: one slot per chunk (scene runs pack a little worse than
+        n_total / chunk), bounded by prefix_cache_max_bytes and by the free device memory."""
+        if not self.use_prefix_cache or n_total <= 0:
+            if self._prefix_geom is not None:
+                _lib.check(self.lib.ctrlsim_attach_prefix_cache(self.model.handle, None, 0, 0), "ctrlsim_attach_prefix_cache")
+                self._prefix_geom = None
+            return
+        per = int(self.lib.ctrlsim_prefix_cache_bytes(chunk, 1))
+        want = -(-n_total // chunk) + 1 + n_total // (8 * chunk)
+        have = 0 if self._prefix_cache is None else self._prefix_cache.numel()
+        free, _ = torch.cuda.mem_get_info(self.model.device)
+        budget = min(self.prefix_cache_max_bytes, have + max(0, free - (6 << 30)))
+        slots = max(0, min(want, budget // per))
+        if self._prefix_geom == (chunk, slots) and self._prefix_cache is not None:
+            return  # the handle keeps its directory; entries are invalidated at t = 0 anyway
+        if slots == 0:
+            _lib.check(self.lib.ctrlsim_attach_prefix_cache(self.model.handle, None, 0, 0), "ctrlsim_attach_prefix_cache")
+            self._prefix_geom = None
+            return
+        if have < slots * per:
+            self._prefix_cache = None
+            self._prefix_cache = torch.empty(slots * per, dtype=torch.uint8, device=self.model.device)
+        _lib.check(self.lib.ctrlsim_attach_prefix_cache(self.model.handle, self._prefix_cache.data_ptr(), slots * per,
+                                                        chunk), "ctrlsim_attach_prefix_cache")
+        self._prefix_geom = (chunk, slots)
 
     def act(self, batch: SceneBatch, t: int):
         """policy.act / apply_gt_action for every vehicle, then Simulation.step(dt)."""

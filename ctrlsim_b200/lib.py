@@ -77,6 +77,9 @@ _SIGS = {
     "ctrlsim_map_cache_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "ctrlsim_attach_map_cache": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "ctrlsim_map_cache_stats": (None, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ctrlsim_prefix_cache_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "ctrlsim_attach_prefix_cache": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]),
+    "ctrlsim_prefix_cache_stats": (None, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ctrlsim_sim_reset": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_void_p]),
     "ctrlsim_observe": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_int32, C.c_void_p]),
     "ctrlsim_plan_groups": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_int32, C.c_void_p, C.c_void_p]),

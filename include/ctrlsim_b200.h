@@ -118,6 +118,19 @@ int64_t ctrlsim_map_cache_bytes(int32_t n_scenes, int32_t max_veh);
 int ctrlsim_attach_map_cache(CtrlSim* h, void* mem, int64_t bytes);
 void ctrlsim_map_cache_stats(const CtrlSim* h, int64_t* hits, int64_t* misses);
 
+/* Optional prefix cache for the same steps (0..31): decoder keys / values of every token seen so far, cross-attention
+ * keys / values and padding mask of the memory tokens, one slot per chunk of `chunk_groups` focal groups. A chunk
+ * whose focal groups (scene, focal, member slots) are exactly those that filled its slot at step t-1 runs step t
+ * incrementally: only the tokens of window steps t-1 and t (144 rows per group instead of 72 (t+1)) go through the
+ * decoder and attend to the cached keys; polyline encoder, scene encoder and cross-attention K/V are not recomputed.
+ * Any other chunk runs the full forward and refills its slot. Per-row arithmetic is unchanged, so sampled bins are
+ * those of the full forward. Caller-owned, 256-byte aligned device memory of n_slots *
+ * ctrlsim_prefix_cache_bytes(chunk_groups, 1); chunks beyond n_slots are not cached; `chunk_groups` must equal the
+ * value later passed to ctrlsim_policy_step. The memory is zero-filled on attach. NULL detaches. */
+int64_t ctrlsim_prefix_cache_bytes(int32_t chunk_groups, int32_t n_slots);
+int ctrlsim_attach_prefix_cache(CtrlSim* h, void* mem, int64_t bytes, int32_t chunk_groups);
+void ctrlsim_prefix_cache_stats(const CtrlSim* h, int64_t* incremental_chunks, int64_t* full_chunks);
+
 /* ---- simulator: replaces nocturne_cpp Simulation/Scenario/Vehicle for the evaluator loop ------------------- */
 /* S3: Vehicle::CreatePhysicsBody for every vehicle + the load-time UpdateCollision (vehicle.cc:137-179, scenario.cc:263) */
 int ctrlsim_sim_reset(CtrlSim* h, CtrlSimBatch* b, void* stream);

@@ -279,3 +279,40 @@ def test_rollout_matches_oracle_port_multi_scene(cfg, dev):
         assert (tr["tr_act_idx"][s, :n, :steps].T == rec["act_idx"][:steps]).all()
         assert (tr["tr_rtg_idx"][s, :n, :steps].transpose(1, 0, 2) == rec["rtg_idx"][:steps]).all()
         assert np.abs(tr["tr_pos"][s, :n, :steps] - rec["pos"][:, :steps]).max() < POS_TOL
+
+
+@pytest.mark.gpu
+def test_caches_do_not_change_results(cfg, dev, monkeypatch):
+    """Steps 0..31 with the polyline-encoder cache and the decoder prefix cache (incremental decode) == the same steps
+    with every group recomputed from scratch: identical sampled bins, trajectories within float tolerance; and the
+    incremental path is really taken.  Multi-chunk (chunk_groups smaller than the batch) on purpose."""
+    import ctypes as C
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    from ctrlsim_b200.weights import make_weights
+    from ctrlsim_b200.model import DeviceModel
+    weights = make_weights(cfg, seed=5, still_bias=5.0)
+    scenes = [make_scene(40 + i, n_vehicles=20 + 2 * i, n_roads=3, n_chunks=4, frac_short=0.3) for i in range(12)]
+    steps = 36  # crosses t = 32, where both caches stop applying
+    traces = {}
+    for mode in ("cached", "plain"):
+        monkeypatch.setenv("CTRLSIM_MAP_CACHE", "1" if mode == "cached" else "0")
+        monkeypatch.setenv("CTRLSIM_PREFIX_CACHE", "1" if mode == "cached" else "0")
+        model = DeviceModel(cfg, weights, dev)
+        pol = B200Policy(cfg, "synthetic", model, seed=11, chunk_groups=48)
+        ev = B200PolicyEvaluator(cfg, pol, scenes=scenes)
+        b = ev.build_batch(eval_threshold=64)
+        ev.rollout(b, max_steps=steps)
+        traces[mode] = b.trace()
+        if mode == "cached":
+            inc, full = C.c_int64(0), C.c_int64(0)
+            pol.lib.ctrlsim_prefix_cache_stats(model.handle, C.byref(inc), C.byref(full))
+            assert inc.value >= 31 and full.value >= 1, (inc.value, full.value)
+            hit, miss = C.c_int64(0), C.c_int64(0)
+            pol.lib.ctrlsim_map_cache_stats(model.handle, C.byref(hit), C.byref(miss))
+            assert miss.value >= 1
+    a, p = traces["cached"], traces["plain"]
+    assert (a["tr_rtg_idx"][:, :, :steps] == p["tr_rtg_idx"][:, :, :steps]).all()
+    assert (a["tr_act_idx"][:, :, :steps] == p["tr_act_idx"][:, :, :steps]).all()
+    assert (a["tr_exist"] == p["tr_exist"]).all()
+    assert np.abs(a["tr_pos"][:, :, :steps].astype(np.float64) - p["tr_pos"][:, :, :steps]).max() < POS_TOL
