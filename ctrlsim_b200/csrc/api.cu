@@ -410,6 +410,8 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
   return 0;
 }
 
+void ctrlsim_debug_gemm(int32_t v) { ctrlsim::set_gemm_debug(v); }
+void ctrlsim_debug_gemm_trace(int64_t* out) { ctrlsim::read_gemm_trace(reinterpret_cast<long long*>(out)); }
 void ctrlsim_debug_attn(int32_t v) { ctrlsim::set_attn_debug(v); }
 void ctrlsim_debug_attn_trace(int64_t* out) { ctrlsim::read_attn_trace(reinterpret_cast<long long*>(out)); }
 long long ctrlsim_launch_count(void) { return g_launch_count; }

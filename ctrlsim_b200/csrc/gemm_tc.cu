@@ -498,6 +498,10 @@ __device__ __forceinline__ float4 tc_lo4(float4 v) {
   return l;
 }
 
+__device__ int g_gemm_debug = 0;                // 1: record a timeline of CTA 0
+__device__ long long g_gemm_trace[4 * 128];     // [k-slab][event]: 0 TMA issued, 1 data landed, 2 lo tiles published, 3 MMAs issued
+#define GT_TRACE(slot) do { if (gtrace && it < 128) g_gemm_trace[it * 4 + (slot)] = clock64(); } while (0)
+
 template <bool RELU, bool WLO>
 __global__ void __launch_bounds__(P3_THREADS, 1)
 gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -507,6 +511,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   P3Smem& sm = *reinterpret_cast<P3Smem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nk = K / P_BK;
+  const bool gtrace = g_gemm_debug == 1 && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
 
   if (tid == 0) {
     for (int s = 0; s < P_STAGES; ++s) {
@@ -533,6 +538,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int kc = 0; kc < nk; ++kc, ++it) {
         const int s = it % P_STAGES;
         tc_mbar_wait(&sm.tma_full[s], (it / P_STAGES) & 1);
+        if (warp == 0) GT_TRACE(1);
         P3Stage& st = sm.stage[s];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -543,6 +549,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) tc_mbar_arrive(&sm.full[s]);
+        if (warp == 0) GT_TRACE(2);
       }
     }
   } else if (warp == 8) {
@@ -571,6 +578,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             tc_mma(d_main, dah + o, dbh + o, idesc2, (kc > 0 || ks > 0) ? 1u : 0u);
             tc_mma(d_cross, dal + o, dbh + o, idesc1, 1u);
           }
+          GT_TRACE(3);
           tc_commit(&sm.empty[s]);
           if (kc == nk - 1) tc_commit(&sm.tmem_full[buf]);
         }
@@ -588,6 +596,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int s = it % P_STAGES;
           tc_mbar_wait(&sm.empty[s], ((it / P_STAGES) & 1) ^ 1);
           P3Stage& st = sm.stage[s];
+          GT_TRACE(0);
           tc_expect_tx(&sm.tma_full[s], (P_BM + (WLO ? 2 : 1) * P_BN) * P_BK * 4);
           tc_tma_2d(st.a_raw, &tmA, kc * P_BK, m0, &sm.tma_full[s]);
           tc_tma_2d(st.b_raw, &tmW, kc * P_BK, n0, &sm.tma_full[s]);
@@ -711,6 +720,9 @@ static int launch_gemm_tc_tma(const GemmArgs& g, cudaStream_t st) {
   CS_CHECK_LAUNCH("gemm_tc_tma");
   return 0;
 }
+
+void set_gemm_debug(int v) { cudaMemcpyToSymbol(g_gemm_debug, &v, sizeof(int)); }
+void read_gemm_trace(long long* out) { cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(long long) * 4 * 128); }
 
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0) return 0;

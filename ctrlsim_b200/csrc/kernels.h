@@ -24,6 +24,8 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);  // gemm_tc.cu
 void gemm_register_weight_lo(const void* owner, const float* base, size_t count, const float* lo);
 void gemm_clear_weight_lo(const void* owner);
 int launch_weight_lo(const float* w, float* lo, size_t n, cudaStream_t st);
+void set_gemm_debug(int v);
+void read_gemm_trace(long long* out);
 int launch_layernorm(const float* X, const float* R, const float* gamma, const float* beta, float* Y, int M, int ldx,
                      int ldr, int ldy, bool relu, cudaStream_t st);
 

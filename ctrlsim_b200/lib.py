@@ -88,6 +88,8 @@ _SIGS = {
     "ctrlsim_sim_step": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_int32, C.c_void_p]),
     "ctrlsim_metrics": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_void_p, C.c_void_p, C.c_void_p]),
     "ctrlsim_launch_count": (C.c_longlong, []),
+    "ctrlsim_debug_gemm": (None, [C.c_int32]),
+    "ctrlsim_debug_gemm_trace": (None, [C.c_void_p]),
     "ctrlsim_debug_attn": (None, [C.c_int32]),
     "ctrlsim_debug_attn_trace": (None, [C.c_void_p]),
     "ctrlsim_profile_enable": (None, [C.c_int32]),

@@ -155,6 +155,8 @@ int ctrlsim_metrics(CtrlSim* h, const CtrlSimBatch* b, double* out_scene, int64_
  * 1 map_pool, 2 decoder self-attention, 3 decoder cross-attention): total ms, total work (flops; bytes for map_pool),
  * number of launches. */
 long long ctrlsim_launch_count(void);
+void ctrlsim_debug_gemm(int32_t mode); /* 1: record a clock64 timeline of CTA 0 of the linear-layer GEMM */
+void ctrlsim_debug_gemm_trace(int64_t* out_128x4); /* [k-slab][TMA issued, data landed, lo tiles published, MMAs issued] */
 void ctrlsim_debug_attn(int32_t mode); /* bring-up aid for attention_tc.cu; 0 = normal */
 void ctrlsim_debug_attn_trace(int64_t* out_8x64); /* mode 4: clock64 timeline of CTA (0,0,0), [tile][event] */
 void ctrlsim_profile_enable(int32_t on);
