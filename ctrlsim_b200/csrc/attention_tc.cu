@@ -172,14 +172,15 @@ __device__ __noinline__ void at_scale32(uint32_t taddr, float f) {
   }
 }
 __device__ __forceinline__ void at_lo_tile(float* lo, const float* raw, int n_float4, int tid, int nthreads) {
+  const uint32_t lo_a = at_u32(lo), raw_a = at_u32(raw);
   for (int i = tid; i < n_float4; i += nthreads) {
-    const float4 v = reinterpret_cast<const float4*>(raw)[i];
+    const float4 v = lds128(raw_a + 16u * (uint32_t)i);
     float4 l;
     l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
     l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
     l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
     l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-    reinterpret_cast<float4*>(lo)[i] = l;
+    sts128(lo_a + 16u * (uint32_t)i, l);
   }
 }
 __device__ __forceinline__ float at_ex2(float x) {  // 2^x, flush-to-zero; ex2(-inf) = +0
@@ -370,6 +371,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) at_arrive(&sm.k_ready[s]);
       at_wait(&sm.v_empty[s], ((j / AT_STAGES) & 1) ^ 1);
+      const uint32_t vt_a = at_u32(sm.kv[s].vt);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int kl = (pt >> 3) + 8 * i;                 // key within the tile
@@ -384,8 +386,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int n = 0; n < 4; ++n) {
           const int d = u * 4 + ((n + hrot) & 3);
           const int off = cb * (2 * DH * 32) + d * 32 + ((((kk >> 2) ^ (d & 7)) << 2) | (kk & 3));
-          sm.kv[s].vt[off] = x[n];
-          sm.kv[s].vt[off + DH * 32] = x[n] - __uint_as_float(__float_as_uint(x[n]) & 0xFFFFE000u);
+          sts32(vt_a + 4u * (uint32_t)off, x[n]);
+          sts32(vt_a + 4u * (uint32_t)(off + DH * 32), x[n] - __uint_as_float(__float_as_uint(x[n]) & 0xFFFFE000u));
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

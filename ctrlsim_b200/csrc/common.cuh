@@ -40,6 +40,21 @@ extern long long g_launch_count;  // kernels launched by this library (bench.py 
     if (e__ != cudaSuccess) return ::ctrlsim::set_error(-5, "%s: %s", name, cudaGetErrorString(e__)); \
   } while (0)
 
+// Explicit shared-state-space accesses.  The kernels carve dynamic shared memory through an aligned uintptr_t, after
+// which the compiler no longer knows the address space and emits GENERIC loads / stores (LD.E / ST.E) - slower and
+// queued with global traffic.  Hot shared-memory paths use these instead (addr = __cvta_generic_to_shared(ptr)).
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

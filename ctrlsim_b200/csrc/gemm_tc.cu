@@ -104,6 +104,101 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld32x2(uint32_t ta, uint32_t (&r)[32], uint32_t tb, uint32_t (&q)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(ta));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
+        "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
+        "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+      : "r"(tb));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 16 TMEM lanes x 32 columns without waiting: register 4k + 2h + e = (lane (t >> 2) + 8 h, column 8 k + 2 (t & 3) + e)
+// (the m16n8 accumulator-fragment layout, repeated over 4 column blocks)
+__device__ __forceinline__ void tc_ld16x256_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// Epilogue of one 32-row x 32-column chunk of a warp's accumulator rows, coalesced: the accumulators are read in the
+// 16x256b fragment layout (4 lanes share a row), lane pairs swap half of their values so that every lane owns four
+// consecutive columns, and each store instruction writes 8 rows x 64 contiguous bytes (instead of 32 rows x 16 bytes
+// with one row per thread).  m_base: first row of the warp's 32 rows; nc0: first column of the chunk.
+template <bool RELU>
+__device__ __forceinline__ void tc_epilogue_chunk_frag(uint32_t tmem_main, uint32_t tmem_cross, int m_base, int M, int nc0,
+                                                       int N, const float* __restrict__ bias,
+                                                       const float* __restrict__ table, const int* __restrict__ tidx,
+                                                       int ldt, float* __restrict__ C, int ldc, bool vec_ok, int lane,
+                                                       bool skip_store) {
+  const int t0 = lane & 3, t1 = lane >> 2, odd = t0 & 1;
+  // bias of the 8 columns this thread holds before the swap: columns nc0 + 8 k + 2 t0 + e
+  float bz[4][2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = nc0 + 8 * k + 2 * t0;
+    bz[k][0] = (bias && c < N) ? __ldg(bias + c) : 0.f;
+    bz[k][1] = (bias && c + 1 < N) ? __ldg(bias + c + 1) : 0.f;
+  }
+  uint32_t a0[16], x0[16], a1[16], x1[16];  // main / cross of lanes 0..15 and 16..31 of the warp's lane quadrant
+  tc_ld16x256_x4(tmem_main, a0);
+  tc_ld16x256_x4(tmem_cross, x0);
+  tc_ld16x256_x4(tmem_main + (16u << 16), a1);
+  tc_ld16x256_x4(tmem_cross + (16u << 16), x1);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {  // row t1 + 8 h of the warp's 32 rows
+    const int m = m_base + t1 + 8 * h;
+    const float* trow = (table && m < M) ? table + (size_t)tidx[m] * ldt : nullptr;
+    float v[4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ri = 4 * k + 2 * (h & 1) + e;
+        const float acc = h < 2 ? __uint_as_float(a0[ri]) + __uint_as_float(x0[ri]) : __uint_as_float(a1[ri]) + __uint_as_float(x1[ri]);
+        float x = acc + bz[k][e];
+        if (trow) { const int c = nc0 + 8 * k + 2 * t0 + e; if (c < N) x += __ldg(trow + c); }
+        v[k][e] = RELU ? fmaxf(x, 0.f) : x;
+      }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {  // column blocks 2p (kept by even t0) and 2p+1 (kept by odd t0)
+      const float k0 = odd ? v[2 * p + 1][0] : v[2 * p][0], k1 = odd ? v[2 * p + 1][1] : v[2 * p][1];
+      const float s0 = odd ? v[2 * p][0] : v[2 * p + 1][0], s1 = odd ? v[2 * p][1] : v[2 * p + 1][1];
+      const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+      const float4 out = odd ? make_float4(g0, g1, k0, k1) : make_float4(k0, k1, g0, g1);
+      const int c = nc0 + 8 * (2 * p + odd) + 2 * (t0 & 2);  // first of this lane's four consecutive columns
+      if (m < M && !skip_store) {
+        float* dst = C + (size_t)m * ldc + c;
+        if (vec_ok && c + 3 < N) {
+          *reinterpret_cast<float4*>(dst) = out;
+        } else {
+          if (c < N) dst[0] = out.x;
+          if (c + 1 < N) dst[1] = out.y;
+          if (c + 2 < N) dst[2] = out.z;
+          if (c + 3 < N) dst[3] = out.w;
+        }
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void tc_split_store(float* hi, float* lo, int off, float4 v) {
   float4 h, l;
   h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
@@ -119,9 +214,9 @@ __device__ __forceinline__ void tc_split_store(float* hi, float* lo, int off, fl
 // (a per-element __ldg serialises ~200 cycles of latency per output); must be called by all 32 lanes of the warp.
 template <bool RELU>
 __device__ __forceinline__ void tc_epilogue_chunk(const uint32_t (&r)[32], const uint32_t (&rx)[32], int m, int M, int nc0,
-                                                  int N, const float* __restrict__ bias, const float* __restrict__ trow,
-                                                  float* __restrict__ C, int ldc, bool vec_ok, int lane) {
-  const float bl = (bias && nc0 + lane < N) ? __ldg(bias + nc0 + lane) : 0.f;
+                                                  int N, const float bl /* bias[nc0 + lane] or 0 */,
+                                                  const float* __restrict__ trow, float* __restrict__ C, int ldc,
+                                                  bool vec_ok) {
   float t[32];
   if (trow) {
 #pragma unroll
@@ -230,7 +325,8 @@ gemm_tc_kernel(const float* __restrict__ Aa, const float* __restrict__ W, const 
       uint32_t r[32], rx[32];
       tc_ld32(tmem + ((uint32_t)(32 * lg) << 16) + (uint32_t)col0, r);
       tc_ld32(tmem + ((uint32_t)(32 * lg) << 16) + (uint32_t)(TC_BN + col0), rx);
-      tc_epilogue_chunk<RELU>(r, rx, m, M, n0 + col0, N, bias, trow, C, ldc, vec_ok, lane);
+      const float bl = (bias && n0 + col0 + lane < N) ? __ldg(bias + n0 + col0 + lane) : 0.f;
+      tc_epilogue_chunk<RELU>(r, rx, m, M, n0 + col0, N, bl, trow, C, ldc, vec_ok);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else {
@@ -416,7 +512,8 @@ gemm_tc_persistent_kernel(const float* __restrict__ Aa, const float* __restrict_
         const uint32_t ta = tmem + ((uint32_t)(32 * lg) << 16) + buf * 256 + (uint32_t)col0;
         tc_ld32(ta, r);
         tc_ld32(ta + 128, rx);
-        tc_epilogue_chunk<RELU>(r, rx, m, M, n0 + col0, N, bias, trow, C, ldc, vec_ok, lane);
+        const float bl = (bias && n0 + col0 + lane < N) ? __ldg(bias + n0 + col0 + lane) : 0.f;
+        tc_epilogue_chunk<RELU>(r, rx, m, M, n0 + col0, N, bl, trow, C, ldc, vec_ok);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       tc_mbar_arrive(&sm.tmem_empty[buf]);
@@ -500,6 +597,8 @@ __device__ __forceinline__ float4 tc_lo4(float4 v) {
 
 __device__ int g_gemm_debug = 0;                // 1: record a timeline of CTA 0
 __device__ long long g_gemm_trace[4 * 128];     // [k-slab][event]: 0 TMA issued, 1 data landed, 2 lo tiles published, 3 MMAs issued
+__device__ long long g_gemm_epi_trace[4 * 64];  // [tile][event]: 0 accumulators ready, 1 first TMEM loads back, 2 first chunk stored, 3 buffer released
+#define GE_TRACE(slot) do { if (gtrace && ti < 64) g_gemm_epi_trace[ti * 4 + (slot)] = clock64(); } while (0)
 #define GT_TRACE(slot) do { if (gtrace && it < 128) g_gemm_trace[it * 4 + (slot)] = clock64(); } while (0)
 
 template <bool RELU, bool WLO>
@@ -511,7 +610,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   P3Smem& sm = *reinterpret_cast<P3Smem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nk = K / P_BK;
-  const bool gtrace = g_gemm_debug == 1 && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
+  const bool gtrace = g_gemm_debug >= 1 && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
 
   if (tid == 0) {
     for (int s = 0; s < P_STAGES; ++s) {
@@ -540,11 +639,20 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tc_mbar_wait(&sm.tma_full[s], (it / P_STAGES) & 1);
         if (warp == 0) GT_TRACE(1);
         P3Stage& st = sm.stage[s];
+        const uint32_t a_raw = tc_smem_u32(st.a_raw), a_lo = tc_smem_u32(st.a_lo);
+        const uint32_t b_raw = tc_smem_u32(st.b_raw), b_lo = tc_smem_u32(st.b_lo);
+        float4 va[4], vb[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int off = (rbase + 32 * i) * P_BK + sc;
-          *reinterpret_cast<float4*>(st.a_lo + off) = tc_lo4(*reinterpret_cast<const float4*>(st.a_raw + off));
-          if (!WLO) *reinterpret_cast<float4*>(st.b_lo + off) = tc_lo4(*reinterpret_cast<const float4*>(st.b_raw + off));
+          const uint32_t off = (uint32_t)((rbase + 32 * i) * P_BK + sc) * 4u;
+          va[i] = lds128(a_raw + off);
+          if (!WLO) vb[i] = lds128(b_raw + off);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t off = (uint32_t)((rbase + 32 * i) * P_BK + sc) * 4u;
+          sts128(a_lo + off, tc_lo4(va[i]));
+          if (!WLO) sts128(b_lo + off, tc_lo4(vb[i]));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -614,19 +722,17 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int m0 = (tile / n_tiles_n) * P_BM, n0 = (tile % n_tiles_n) * P_BN;
       tc_mbar_wait(&sm.tmem_full[buf], (ti >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int m = m0 + 32 * lg + lane;
-      const float* trow = (table && m < M) ? table + (size_t)tidx[m] * ldt : nullptr;
+      if (warp == 10) GE_TRACE(0);
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
-        const int col0 = j * 32;
-        uint32_t r[32], rx[32];
-        const uint32_t ta = tmem + ((uint32_t)(32 * lg) << 16) + buf * 256 + (uint32_t)col0;
-        tc_ld32(ta, r);
-        tc_ld32(ta + 128, rx);
-        tc_epilogue_chunk<RELU>(r, rx, m, M, n0 + col0, N, bias, trow, C, ldc, vec_ok, lane);
+        const uint32_t ta = tmem + ((uint32_t)(32 * lg) << 16) + buf * 256 + (uint32_t)(32 * j);
+        tc_epilogue_chunk_frag<RELU>(ta, ta + 128, m0 + 32 * lg, M, n0 + 32 * j, N, bias, table, tidx, ldt, C, ldc, vec_ok, lane,
+                                     g_gemm_debug == 2 /* timing experiment: no global stores */);
+        if (warp == 10 && j == 0) GE_TRACE(2);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       tc_mbar_arrive(&sm.tmem_empty[buf]);
+      if (warp == 10) GE_TRACE(3);
     }
   }
   __syncthreads();
@@ -722,7 +828,10 @@ static int launch_gemm_tc_tma(const GemmArgs& g, cudaStream_t st) {
 }
 
 void set_gemm_debug(int v) { cudaMemcpyToSymbol(g_gemm_debug, &v, sizeof(int)); }
-void read_gemm_trace(long long* out) { cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(long long) * 4 * 128); }
+void read_gemm_trace(long long* out) {
+  cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(long long) * 4 * 128);
+  cudaMemcpyFromSymbol(out + 4 * 128, g_gemm_epi_trace, sizeof(long long) * 4 * 64);
+}
 
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0) return 0;

@@ -37,33 +37,40 @@ def parse_scenario(scen: dict, steps: int = 90, moving_threshold: float = 0.2, s
     size = np.zeros((n, 2), np.float32)
     target = np.zeros((n, 4), np.float32)
     moving = np.zeros(n, bool)
+    two_pi = 2.0 * math.pi
     for i, o in enumerate(objs):
-        if len(o["position"]) < T1:
-            raise ValueError(f"object {i}: {len(o['position'])} states, the evaluator needs {T1}")
+        L = len(o["position"])
+        if L < T1:
+            raise ValueError(f"object {i}: {L} states, the evaluator needs {T1}")
         size[i] = (o["length"], o["width"])
         gp = o.get("goalPosition", {"x": 0.0, "y": 0.0})
         target[i, :2] = (gp["x"], gp["y"])
-        for t in range(len(o["position"])):
-            x, y = np.float32(o["position"][t]["x"]), np.float32(o["position"][t]["y"])
-            h = _normalize_angle_f32(o["heading"][t])
-            vx, vy = np.float32(o["velocity"][t]["x"]), np.float32(o["velocity"][t]["y"])
-            sp = np.sqrt(np.float32(vx * vx + vy * vy))
-            if t < T1:
-                gt[i, t] = (x, y, h, sp)
-                gt_valid[i, t] = x != np.float32(-10000.0)  # utils/sim.py:28 existence rule
-            if bool(o["valid"][t]):
-                target[i, 2], target[i, 3] = h, sp
-                dx, dy = x - target[i, 0], y - target[i, 1]
-                dist = np.sqrt(np.float32(dx * dx + dy * dy))
-                if sp > np.float32(speed_threshold) or dist > np.float32(moving_threshold):
-                    moving[i] = True
+        # whole track at once, in the arithmetic of the scalar rules above (float32 simulator values; the angle goes
+        # float32 -> double -> float32 twice exactly like geometry_utils.h:41-58 with T = float)
+        pos = np.array([(q["x"], q["y"]) for q in o["position"]], np.float32).reshape(L, 2)
+        vel = np.array([(q["x"], q["y"]) for q in o["velocity"]], np.float32).reshape(L, 2)
+        deg = np.asarray(o["heading"], np.float32)
+        rad = (deg.astype(np.float64) / 180.0 * math.pi).astype(np.float32)
+        r = np.fmod(rad.astype(np.float64), two_pi).astype(np.float32).astype(np.float64)
+        h = np.where(r > math.pi, r - two_pi, np.where(r < -math.pi, r + two_pi, r)).astype(np.float32)
+        sp = np.sqrt(vel[:, 0] * vel[:, 0] + vel[:, 1] * vel[:, 1])
+        gt[i, :, 0], gt[i, :, 1], gt[i, :, 2], gt[i, :, 3] = pos[:T1, 0], pos[:T1, 1], h[:T1], sp[:T1]
+        gt_valid[i] = pos[:T1, 0] != np.float32(-10000.0)  # utils/sim.py:28 existence rule
+        valid = np.asarray(o["valid"][:L], bool)
+        if valid.any():
+            last = int(np.nonzero(valid)[0][-1])
+            target[i, 2], target[i, 3] = h[last], sp[last]
+            dx, dy = pos[:, 0] - target[i, 0], pos[:, 1] - target[i, 1]
+            dist = np.sqrt(dx * dx + dy * dy)
+            moving[i] = bool(((sp > np.float32(speed_threshold)) | (dist > np.float32(moving_threshold)))[valid].any())
     segs = []
     for road in scen["roads"]:
         g = road["geometry"]
-        if road["type"] != "road_edge" or isinstance(g, dict):
+        if road["type"] != "road_edge" or isinstance(g, dict) or len(g) < 2:
             continue
-        for k in range(len(g) - 1):
-            segs.append((g[k]["x"], g[k]["y"], g[k + 1]["x"], g[k + 1]["y"]))
+        pts = np.array([(q["x"], q["y"]) for q in g], np.float32).reshape(len(g), 2)
+        segs.append(np.concatenate([pts[:-1], pts[1:]], axis=1))
+    segs = np.concatenate(segs, axis=0) if segs else np.zeros((0, 4), np.float32)
     # goals (evaluators/evaluator.py:60-76), float64 views of float32 values
     goal = np.zeros((n, 4), np.float64)
     for i in range(n):
@@ -78,7 +85,7 @@ def parse_scenario(scen: dict, steps: int = 90, moving_threshold: float = 0.2, s
         goal[i] = (gp[0], gp[1], gh, gs)
     goal_norm = np.linalg.norm(gt[:, 0, :2].astype(np.float64) - goal[:, :2], axis=1)
     return dict(n=n, gt=gt, gt_valid=gt_valid, size=size, moving=moving, goal=goal, goal_norm=goal_norm,
-                segs=np.asarray(segs, np.float32).reshape(-1, 4))
+                segs=segs)
 
 
 def road_arrays(preproc: dict):

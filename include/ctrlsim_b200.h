@@ -156,7 +156,7 @@ int ctrlsim_metrics(CtrlSim* h, const CtrlSimBatch* b, double* out_scene, int64_
  * number of launches. */
 long long ctrlsim_launch_count(void);
 void ctrlsim_debug_gemm(int32_t mode); /* 1: record a clock64 timeline of CTA 0 of the linear-layer GEMM */
-void ctrlsim_debug_gemm_trace(int64_t* out_128x4); /* [k-slab][TMA issued, data landed, lo tiles published, MMAs issued] */
+void ctrlsim_debug_gemm_trace(int64_t* out_192x4); /* 128 x [k-slab][TMA issued, data landed, lo tiles published, MMAs issued], then 64 x [tile][epilogue events] */
 void ctrlsim_debug_attn(int32_t mode); /* bring-up aid for attention_tc.cu; 0 = normal */
 void ctrlsim_debug_attn_trace(int64_t* out_8x64); /* mode 4: clock64 timeline of CTA (0,0,0), [tile][event] */
 void ctrlsim_profile_enable(int32_t on);

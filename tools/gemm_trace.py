@@ -18,10 +18,10 @@ if os.environ.get("TRACE_WLO", "1") == "1" and (N, K) in ((768, 256), (1024, 256
 Cm = torch.empty(M, N, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 lib.ctrlsim_linear(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cm.data_ptr(), M, N, K, 0, st)
-lib.ctrlsim_debug_gemm(1)
+lib.ctrlsim_debug_gemm(int(os.environ.get('GEMM_DEBUG', '1')))
 lib.ctrlsim_linear(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cm.data_ptr(), M, N, K, 0, st)
 torch.cuda.synchronize()
-tr = np.zeros((128, 4), dtype=np.int64)
+tr = np.zeros((192, 4), dtype=np.int64)
 lib.ctrlsim_debug_gemm_trace(tr.ctypes.data)
 lib.ctrlsim_debug_gemm(0)
 t0 = tr[0, 0]
@@ -29,5 +29,10 @@ print(f"M={M} N={N} K={K}: slab  tma_issue  landed  lo_done  mma_issued   (clk, 
 for i in range(8, 72):
     r = tr[i] - t0
     print(f"{i:4d} {int(r[0]):9d} {int(r[1]):9d} {int(r[2]):9d} {int(r[3]):9d}   land-issue {int(r[1]-r[0]):5d}  lo {int(r[2]-r[1]):4d}  mma-after-lo {int(r[3]-r[2]):5d}")
+ep = tr[128:]
+print("epilogue of CTA 0: tile  acc_ready  first_ld  first_chunk  released  (relative) | ld latency, chunk, total")
+for i in range(2, 10):
+    r = ep[i] - t0
+    print(f"{i:4d} {int(r[0]):9d} {int(r[1]):9d} {int(r[2]):9d} {int(r[3]):9d} | {int(r[1]-r[0]):5d} {int(r[2]-r[1]):5d} {int(r[3]-r[0]):6d}")
 d = np.diff(tr[16:120, 3])
 print("slab period (clk): median", np.median(d), "mean", d.mean(), " ideal MMA time 813 (12 x 68) -> now 8 instr: 4 x (136 + 68) = 816")

@@ -1,0 +1,6 @@
+set -x
+timeout 300 python tools/gemm_bench.py > gpurun_out/s10_gemm_bench.log 2>&1; cat gpurun_out/s10_gemm_bench.log
+timeout 300 python tools/gemm_trace.py 768 256 > gpurun_out/s10_gemm_trace_768.log 2>&1; tail -12 gpurun_out/s10_gemm_trace_768.log
+timeout 300 python tools/gemm_trace.py 256 1024 > gpurun_out/s10_gemm_trace_k1024.log 2>&1; tail -11 gpurun_out/s10_gemm_trace_k1024.log
+(time timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/s10_pytest.log 2>&1; tail -4 gpurun_out/s10_pytest.log
+timeout 600 python bench.py --scenes 64 --steps 45 --warmup 3 --no-cpu --no-e2e > gpurun_out/s10_bench64.log 2>&1; tail -c 900 gpurun_out/s10_bench64.log
