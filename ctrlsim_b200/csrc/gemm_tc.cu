@@ -141,7 +141,7 @@ __device__ __forceinline__ void tc_ld16x256_x4(uint32_t taddr, uint32_t (&r)[16]
 // 16x256b fragment layout (4 lanes share a row), lane pairs swap half of their values so that every lane owns four
 // consecutive columns, and each store instruction writes 8 rows x 64 contiguous bytes (instead of 32 rows x 16 bytes
 // with one row per thread).  m_base: first row of the warp's 32 rows; nc0: first column of the chunk.
-template <bool RELU>
+template <bool RELU, bool FAST /* tile fully inside C, vector stores, no table: no per-element checks */>
 __device__ __forceinline__ void tc_epilogue_chunk_frag(uint32_t tmem_main, uint32_t tmem_cross, int m_base, int M, int nc0,
                                                        int N, const float* __restrict__ bias,
                                                        const float* __restrict__ table, const int* __restrict__ tidx,
@@ -153,28 +153,34 @@ __device__ __forceinline__ void tc_epilogue_chunk_frag(uint32_t tmem_main, uint3
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int c = nc0 + 8 * k + 2 * t0;
-    bz[k][0] = (bias && c < N) ? __ldg(bias + c) : 0.f;
-    bz[k][1] = (bias && c + 1 < N) ? __ldg(bias + c + 1) : 0.f;
+    if (FAST) {
+      if (bias) { const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + c)); bz[k][0] = b2.x; bz[k][1] = b2.y; }
+      else { bz[k][0] = 0.f; bz[k][1] = 0.f; }
+    } else {
+      bz[k][0] = (bias && c < N) ? __ldg(bias + c) : 0.f;
+      bz[k][1] = (bias && c + 1 < N) ? __ldg(bias + c + 1) : 0.f;
+    }
   }
-  uint32_t a0[16], x0[16], a1[16], x1[16];  // main / cross of lanes 0..15 and 16..31 of the warp's lane quadrant
-  tc_ld16x256_x4(tmem_main, a0);
-  tc_ld16x256_x4(tmem_cross, x0);
-  tc_ld16x256_x4(tmem_main + (16u << 16), a1);
-  tc_ld16x256_x4(tmem_cross + (16u << 16), x1);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {  // lanes 0..15, then 16..31 of the warp's lane quadrant
+  uint32_t a0[16], x0[16];                // main / cross accumulators
+  tc_ld16x256_x4(tmem_main + ((uint32_t)(16 * half) << 16), a0);
+  tc_ld16x256_x4(tmem_cross + ((uint32_t)(16 * half) << 16), x0);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int h = 0; h < 4; ++h) {  // row t1 + 8 h of the warp's 32 rows
+  for (int hh = 0; hh < 2; ++hh) {  // row t1 + 8 h of the warp's 32 rows
+    const int h = 2 * half + hh;
     const int m = m_base + t1 + 8 * h;
-    const float* trow = (table && m < M) ? table + (size_t)tidx[m] * ldt : nullptr;
+    const float* trow = (!FAST && table && m < M) ? table + (size_t)tidx[m] * ldt : nullptr;
     float v[4][2];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int ri = 4 * k + 2 * (h & 1) + e;
-        const float acc = h < 2 ? __uint_as_float(a0[ri]) + __uint_as_float(x0[ri]) : __uint_as_float(a1[ri]) + __uint_as_float(x1[ri]);
+        const int ri = 4 * k + 2 * hh + e;
+        const float acc = __uint_as_float(a0[ri]) + __uint_as_float(x0[ri]);
         float x = acc + bz[k][e];
-        if (trow) { const int c = nc0 + 8 * k + 2 * t0 + e; if (c < N) x += __ldg(trow + c); }
+        if (!FAST && trow) { const int c = nc0 + 8 * k + 2 * t0 + e; if (c < N) x += __ldg(trow + c); }
         v[k][e] = RELU ? fmaxf(x, 0.f) : x;
       }
 #pragma unroll
@@ -184,7 +190,9 @@ __device__ __forceinline__ void tc_epilogue_chunk_frag(uint32_t tmem_main, uint3
       const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
       const float4 out = odd ? make_float4(g0, g1, k0, k1) : make_float4(k0, k1, g0, g1);
       const int c = nc0 + 8 * (2 * p + odd) + 2 * (t0 & 2);  // first of this lane's four consecutive columns
-      if (m < M && !skip_store) {
+      if (FAST) {
+        if (!skip_store) *reinterpret_cast<float4*>(C + (size_t)m * ldc + c) = out;
+      } else if (m < M && !skip_store) {
         float* dst = C + (size_t)m * ldc + c;
         if (vec_ok && c + 3 < N) {
           *reinterpret_cast<float4*>(dst) = out;
@@ -196,6 +204,7 @@ __device__ __forceinline__ void tc_epilogue_chunk_frag(uint32_t tmem_main, uint3
         }
       }
     }
+  }
   }
 }
 
@@ -558,7 +567,8 @@ static int launch_gemm_tc_persistent(const GemmArgs& g, cudaStream_t st) {
 // K-major layout and is used DIRECTLY as the "hi" operand - kind::tf32 ignores the 13 low mantissa bits of its 32-bit
 // inputs, i.e. it sees trunc13(x) - while the 8 producer warps only derive the lo = x - trunc13(x) tiles from it.
 //   warp 9      TMA issuer (one lane): expect_tx + 2 tensor copies (A box 32 x 128, W box 32 x 128) per k-slab
-//   warps 0-7   lo producers; warp 8 MMA issuer; warps 10-13 epilogue (as v2)
+//   warps 0-7   lo producers; warp 8 MMA issuer; warps 10-17 epilogue (two per TMEM lane quadrant: a single warp per
+//               quadrant needs ~2100 dependent instructions per tile and could not keep up with K = 256 tiles)
 // Rows beyond M / N are zero-filled by the TMA unit.  Row gather (agather) is not expressible: those two small GEMMs
 // use the v1 kernel.
 struct alignas(1024) P3Stage {
@@ -576,7 +586,8 @@ struct P3Smem {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
 };
-constexpr int P3_THREADS = 256 + 32 + 32 + 128;
+constexpr int P3_EPI = 256;  // 8 epilogue warps: two per TMEM lane quadrant, each owns one 64-column half of the tile
+constexpr int P3_THREADS = 256 + 32 + 32 + P3_EPI;
 
 __device__ __forceinline__ void tc_tma_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -616,7 +627,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int s = 0; s < P_STAGES; ++s) {
       tc_mbar_init(&sm.tma_full[s], 1); tc_mbar_init(&sm.full[s], 8); tc_mbar_init(&sm.empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) { tc_mbar_init(&sm.tmem_full[b], 1); tc_mbar_init(&sm.tmem_empty[b], P_EPI); }
+    for (int b = 0; b < 2; ++b) { tc_mbar_init(&sm.tmem_full[b], 1); tc_mbar_init(&sm.tmem_empty[b], P3_EPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {
@@ -713,7 +724,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 10..13)
+    // ------------------------------------------------------------------ epilogue (warps 10..17)
     const int lg = warp & 3;
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
     uint32_t ti = 0;
@@ -723,12 +734,17 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_mbar_wait(&sm.tmem_full[buf], (ti >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (warp == 10) GE_TRACE(0);
+      const bool fast = m0 + P_BM <= M && n0 + P_BN <= N && vec_ok && !table && (reinterpret_cast<uintptr_t>(bias) & 7) == 0;
+      const bool nostore = g_gemm_debug == 2;  // timing experiment: no global stores
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = 2 * ((warp - 10) >> 2) + jj;  // this warp's 64-column half of the tile
         const uint32_t ta = tmem + ((uint32_t)(32 * lg) << 16) + buf * 256 + (uint32_t)(32 * j);
-        tc_epilogue_chunk_frag<RELU>(ta, ta + 128, m0 + 32 * lg, M, n0 + 32 * j, N, bias, table, tidx, ldt, C, ldc, vec_ok, lane,
-                                     g_gemm_debug == 2 /* timing experiment: no global stores */);
-        if (warp == 10 && j == 0) GE_TRACE(2);
+        if (fast)
+          tc_epilogue_chunk_frag<RELU, true>(ta, ta + 128, m0 + 32 * lg, M, n0 + 32 * j, N, bias, table, tidx, ldt, C, ldc, vec_ok, lane, nostore);
+        else
+          tc_epilogue_chunk_frag<RELU, false>(ta, ta + 128, m0 + 32 * lg, M, n0 + 32 * j, N, bias, table, tidx, ldt, C, ldc, vec_ok, lane, nostore);
+        if (warp == 10 && jj == 0) GE_TRACE(2);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       tc_mbar_arrive(&sm.tmem_empty[buf]);
