@@ -156,13 +156,14 @@ layernorm_kernel(const float* __restrict__ X, const float* __restrict__ R, const
   if (warp >= M) return;
   const float* x = X + (size_t)warp * ldx;
   float v[8];
-  float4 p0 = *reinterpret_cast<const float4*>(x + lane * 8);
-  float4 p1 = *reinterpret_cast<const float4*>(x + lane * 8 + 4);
+  // lane owns columns 4 lane .. 4 lane + 3 and 128 + 4 lane .. + 3: every warp access is one contiguous 512-byte run
+  float4 p0 = *reinterpret_cast<const float4*>(x + lane * 4);
+  float4 p1 = *reinterpret_cast<const float4*>(x + H / 2 + lane * 4);
   v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
   if (R) {
     const float* r = R + (size_t)warp * ldr;
-    float4 q0 = *reinterpret_cast<const float4*>(r + lane * 8);
-    float4 q1 = *reinterpret_cast<const float4*>(r + lane * 8 + 4);
+    float4 q0 = *reinterpret_cast<const float4*>(r + lane * 4);
+    float4 q1 = *reinterpret_cast<const float4*>(r + H / 2 + lane * 4);
     v[0] += q0.x; v[1] += q0.y; v[2] += q0.z; v[3] += q0.w; v[4] += q1.x; v[5] += q1.y; v[6] += q1.z; v[7] += q1.w;
   }
   float s = 0.f;
@@ -176,12 +177,13 @@ layernorm_kernel(const float* __restrict__ X, const float* __restrict__ R, const
   float o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    float y = (v[i] - mean) * rstd * __ldg(gamma + lane * 8 + i) + __ldg(beta + lane * 8 + i);
+    const int c = (i < 4 ? 0 : H / 2) + lane * 4 + (i & 3);
+    float y = (v[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
     o[i] = RELU ? fmaxf(y, 0.f) : y;
   }
-  float* y = Y + (size_t)warp * ldy + lane * 8;
-  *reinterpret_cast<float4*>(y) = make_float4(o[0], o[1], o[2], o[3]);
-  *reinterpret_cast<float4*>(y + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  float* y = Y + (size_t)warp * ldy;
+  *reinterpret_cast<float4*>(y + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<float4*>(y + H / 2 + lane * 4) = make_float4(o[4], o[5], o[6], o[7]);
 }
 
 int launch_layernorm(const float* X, const float* R, const float* gamma, const float* beta, float* Y, int M, int ldx,
