@@ -85,6 +85,10 @@ def cpu_reference_run(cfg, weights, steps, n_scenes=1):
     import torch
     from oracle.model_port import ModelPort
     from oracle.policy_port import RolloutPort
+    try:  # torchrun exports OMP_NUM_THREADS=1 to its workers: take every host core this process may use
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     scenes, ids = make_scenes(n_scenes, 10_000, 1)
     port = RolloutPort(cfg, ModelPort(cfg, weights), seed=0, eval_threshold=64)
     t0 = time.perf_counter()
@@ -121,14 +125,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        # bounded sample of the same workload: the first min(K, 6) steps of ONE of its scenes (each step = 64 agent-steps
+        # = 2 full forwards for each of the scene's ~12 focal groups); ms_per_step extrapolates to one step of the
+        # whole N-GPU job (256 scenes x 64 agents per GPU) at the measured rate
         steps = max(1, args.steps)
-        for _ in range(0):
-            pass
         v, cores, sample = cpu_reference_run(cfg, weights, steps=min(steps, 6))
         line = {"impl": "reference", "metric": "agent-steps/s", "value": v, "unit": "agent-steps/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * 64 / v, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "note": "bounded sample: one scene of the workload on host cores"},
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.scenes * 64 * args.gpus / v,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "note": "bounded sample: one scene of the workload on this box's host "
+                           "cores (the CPU path does not use the GPUs; value is the same for every N)"},
                 "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
@@ -274,7 +280,7 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # the CPU baseline is reported by the single-GPU run only
         v, cores, sample = cpu_reference_run(cfg, weights, steps=args.cpu_steps)
         line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line), flush=True)
