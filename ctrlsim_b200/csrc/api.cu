@@ -453,6 +453,11 @@ int ctrlsim_sample_rows(const float* x, int32_t rows, int32_t n, int32_t ld, int
   return launch_sample_rows(x, rows, n, ld, stride, seed, counters, out_idx, S(stream));
 }
 
+int ctrlsim_sample_rows_nucleus(const float* x, int32_t rows, int32_t n, int32_t ld, int32_t stride, uint64_t seed,
+                                const uint32_t* counters, double top_p, int32_t* out_idx, void* stream) {
+  return launch_sample_rows(x, rows, n, ld, stride, seed, counters, out_idx, S(stream), true, top_p);
+}
+
 int ctrlsim_forward_tokens(CtrlSim* h, int32_t G, int32_t n_t, int32_t ti, const float* agent_states,
                            const float* agent_types, const float* goals, const int32_t* actions, const int32_t* rtgs,
                            const int32_t* timesteps, const float* road_points, const int32_t* road_types,

@@ -96,7 +96,7 @@ int launch_geom_poly_seg(const float* xy, int n, const float* seg, int* out, cud
 
 // sample.cu
 int launch_sample_rows(const float* x, int rows, int n, int ld, int stride, uint64_t seed, const uint32_t* counters,
-                       int* out_idx, cudaStream_t st);
+                       int* out_idx, cudaStream_t st, bool nucleus = false, double top_p = 1.0);
 int launch_sample_actions(const CtrlSimBatch& b, const CtrlSimPolicyParams& p, int g0, int ng, int t,
                           const float* act_logits, const ModelCfg& mc, cudaStream_t st);
 

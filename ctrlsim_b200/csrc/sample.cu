@@ -13,19 +13,21 @@
 namespace ctrlsim {
 
 __global__ void sample_rows_kernel(const float* __restrict__ x, int rows, int n, int ld, int stride, uint64_t seed,
-                                   const uint32_t* __restrict__ ctr, int* __restrict__ out) {
+                                   const uint32_t* __restrict__ ctr, int* __restrict__ out, int nucleus, double top_p) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= rows) return;
   const float* row = x + (size_t)r * ld;
   const uint64_t bits = sampler_bits(seed, ctr[r * 4], ctr[r * 4 + 1], ctr[r * 4 + 2], ctr[r * 4 + 3]);
-  const int idx = warp_sample(n, [&](int i) { return row[(size_t)i * stride]; }, bits);
+  const auto xf = [&](int i) { return row[(size_t)i * stride]; };
+  const int idx = nucleus ? warp_sample_nucleus(n, xf, bits, top_p) : warp_sample(n, xf, bits);
   if ((threadIdx.x & 31) == 0) out[r] = idx;
 }
 
 int launch_sample_rows(const float* x, int rows, int n, int ld, int stride, uint64_t seed, const uint32_t* counters,
-                       int* out_idx, cudaStream_t st) {
+                       int* out_idx, cudaStream_t st, bool nucleus, double top_p) {
   if (rows <= 0) return 0;
-  sample_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, n, ld, stride, seed, counters, out_idx);
+  if (nucleus && n > 1024) return set_error(-2, "sample_rows: nucleus sampling supports at most 1024 categories (got %d)", n);
+  sample_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, n, ld, stride, seed, counters, out_idx, nucleus ? 1 : 0, top_p);
   CS_CHECK_LAUNCH("sample_rows");
   return 0;
 }
@@ -115,7 +117,8 @@ sample_actions_kernel(CtrlSimBatch b, CtrlSimPolicyParams p, int g0, int ng, int
   const float* row = act_logits + (size_t)w * N_ACT;
   const float temp = p.temperature;
   const uint64_t bits = sampler_bits(p.seed, (uint32_t)b.scene_id[s], (uint32_t)v, (uint32_t)t, 3u);
-  const int idx = warp_sample(N_ACT, [&](int i) { return __fdiv_rn(row[i], temp); }, bits);
+  const auto xf = [&](int i) { return __fdiv_rn(row[i], temp); };
+  const int idx = p.nucleus_sampling ? warp_sample_nucleus(N_ACT, xf, bits, p.nucleus_threshold) : warp_sample(N_ACT, xf, bits);
   if (lane == 0) {
     const int n_acc = N_ACT / n_steer;
     double* na = b.next_action + ((size_t)s * N + v) * 2;

@@ -83,4 +83,81 @@ __device__ __forceinline__ int warp_sample(int n, XF xval, uint64_t bits) {
   return n - 1;  // unreachable: the last inclusive prefix equals tot > target
 }
 
+// Nucleus (top-p) variant for n <= 1024 categories (oracle/sampler.py, "Nucleus"): the kept set is the shortest prefix,
+// in (weight descending, index ascending) order, that reaches p * total.  No sort is needed: with
+// S_gt(v) = sum of the weights > v, the kept weight values are those v with S_gt(v) < thr (monotone in v, found by
+// bisection), and the ties at the smallest kept value are kept in index order while S_gt + v * rank < thr.
+template <class XF>
+__device__ __forceinline__ int warp_sample_nucleus(int n, XF xval, uint64_t bits, double p) {
+  const int lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (int i = lane; i < n; i += 32) mx = fmaxf(mx, xval(i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  uint32_t w[32];  // category 32 q + lane lives in w[q]; weights are at most 2^30
+  uint64_t tot = 0;
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const int i = 32 * q + lane;
+    w[q] = i < n ? (uint32_t)sampler_weight(xval(i), mx) : 0u;
+    tot += w[q];
+  }
+  tot = warp_sum_u64(tot);
+  const double thr = p * (double)tot;
+  // smallest v with S_gt(v) < thr; S_gt(2^30) = 0, so hi always qualifies unless thr <= 0 (then only the arg-max is kept)
+  uint32_t lo = 0, hi = 1u << 30;
+  uint64_t s_gt_hi = 0;
+  if (thr > 0.0) {
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      uint64_t sgt = 0;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) sgt += w[q] > mid ? w[q] : 0u;
+      sgt = warp_sum_u64(sgt);
+      if ((double)sgt < thr) hi = mid; else lo = mid + 1;
+    }
+    uint64_t sgt = 0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) sgt += w[q] > hi ? w[q] : 0u;
+    s_gt_hi = warp_sum_u64(sgt);
+  }
+  const uint32_t vmin = hi;  // weights > vmin are kept entirely; ties at vmin partially, in index order
+  // number of ties kept: ranks r = 0, 1, ... while S_gt + vmin * r < thr (rank 0 always: it is what made vmin qualify;
+  // with thr <= 0, vmin = 2^30 and the first arg-max tie is the single kept category)
+  uint64_t base = 0, kept_total;
+  uint32_t ties_seen = 0;
+  {
+    uint64_t kt = 0;
+    uint32_t seen = 0;
+    for (int q = 0; q < 32; ++q) {
+      const bool tie = w[q] == vmin && vmin > 0u && (32 * q + lane) < n;
+      const unsigned tb = __ballot_sync(0xffffffffu, tie);
+      const uint32_t rank = seen + __popc(tb & ((1u << lane) - 1u));
+      const bool keep = w[q] > vmin || (tie && (rank == 0u || (double)(s_gt_hi + (uint64_t)vmin * rank) < thr));
+      kt += keep ? w[q] : 0u;
+      seen += __popc(tb);
+    }
+    kept_total = warp_sum_u64(kt);
+  }
+  const uint64_t target = __umul64hi(bits, kept_total);
+  for (int q = 0; q < 32; ++q) {
+    const int i = 32 * q + lane;
+    const bool tie = w[q] == vmin && vmin > 0u && i < n;
+    const unsigned tb = __ballot_sync(0xffffffffu, tie);
+    const uint32_t rank = ties_seen + __popc(tb & ((1u << lane) - 1u));
+    const bool keep = w[q] > vmin || (tie && (rank == 0u || (double)(s_gt_hi + (uint64_t)vmin * rank) < thr));
+    ties_seen += __popc(tb);
+    uint64_t inc = keep ? w[q] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, i < n && base + inc > target);
+    if (hit) return 32 * q + __ffs(hit) - 1;
+    base += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  return n - 1;  // unreachable
+}
+
 }  // namespace ctrlsim

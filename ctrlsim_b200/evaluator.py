@@ -38,8 +38,6 @@ class B200Policy:
         if not (use_rtg and predict_rtgs and discretize_rtgs) or real_time_rewards or max_return or min_return:
             raise NotImplementedError("only the ctrl_sim policy mode (cfgs/policy/ctrl_sim.yaml) is implemented; "
                                       "real_time_rewards / dt modes are SURVEY 8(f) N1")
-        if nucleus_sampling:
-            raise NotImplementedError("nucleus sampling (cfgs/policy/ctrl_sim.yaml:10) is not implemented yet")
         self.cfg = cfg.copy()
         self.model_path, self.model, self.name = model_path, model, name
         self.model.eval()
@@ -51,7 +49,8 @@ class B200Policy:
         self.key_dict = key_dict or {"next_acceleration": "next_acceleration", "next_steering": "next_steering",
                                      "rtgs": "rtgs"}
         self.tilt_dict = tilt_dict or {"tilt": True, "goal_tilt": 0, "veh_veh_tilt": 0, "veh_edge_tilt": 0}
-        self.action_temperature, self.nucleus_sampling, self.nucleus_threshold = action_temperature, False, nucleus_threshold
+        self.action_temperature = action_temperature
+        self.nucleus_sampling, self.nucleus_threshold = bool(nucleus_sampling), float(nucleus_threshold)
         if self.tilt_dict["tilt"]:
             self.goal_tilt, self.veh_veh_tilt = self.tilt_dict["goal_tilt"], self.tilt_dict["veh_veh_tilt"]
             self.veh_edge_tilt = self.tilt_dict["veh_edge_tilt"]
@@ -71,7 +70,9 @@ class B200Policy:
         td = self.tilt_dict
         tilt = (C.c_double * 3)(float(td["goal_tilt"] or 0), float(td["veh_veh_tilt"] or 0), float(td["veh_edge_tilt"] or 0))
         return _lib.CtrlSimPolicyParams(seed=self.seed, tilt=tilt, temperature=float(self.action_temperature),
-                                        tilt_enabled=1 if td["tilt"] else 0)
+                                        tilt_enabled=1 if td["tilt"] else 0,
+                                        nucleus_sampling=1 if self.nucleus_sampling else 0,
+                                        nucleus_threshold=self.nucleus_threshold)
 
     def _stream(self):
         return torch.cuda.current_stream(self.model.device).cuda_stream

@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libctrlsim_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class CtrlSimConfig(C.Structure):
@@ -57,7 +57,7 @@ class CtrlSimBatch(C.Structure):
 
 class CtrlSimPolicyParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("tilt", C.c_double * 3), ("temperature", C.c_float),
-                ("tilt_enabled", C.c_int32)]
+                ("tilt_enabled", C.c_int32), ("nucleus_sampling", C.c_int32), ("nucleus_threshold", C.c_double)]
 
 
 class CtrlSimError(RuntimeError):
@@ -102,6 +102,8 @@ _SIGS = {
     "ctrlsim_map_pool": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
     "ctrlsim_sample_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "ctrlsim_sample_rows_nucleus": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p,
+                                              C.c_double, C.c_void_p, C.c_void_p]),
     "ctrlsim_forward_tokens": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 11
                                + [C.c_void_p, C.c_int64, C.c_void_p]),
     "ctrlsim_geom_poly_poly": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define CTRLSIM_ABI_VERSION 1
+#define CTRLSIM_ABI_VERSION 2
 #define CTRLSIM_MAX_VEH 64 /* vehicles per scene supported by the grouping kernel (bitmask width) */
 
 /* Model / episode geometry. The kernels are specialised to the reference defaults (cfgs/model/base.yaml:1-9,
@@ -91,6 +91,8 @@ typedef struct CtrlSimPolicyParams {
   double tilt[3];        /* goal, veh_veh, veh_edge */
   float temperature;
   int32_t tilt_enabled;
+  int32_t nucleus_sampling;   /* 0 / 1: top-p filtering of the action distribution (autoregressive_policy.py:216-230) */
+  double nucleus_threshold;   /* p, cfgs/policy/ctrl_sim.yaml:11 */
 } CtrlSimPolicyParams;
 
 typedef struct CtrlSim CtrlSim;
@@ -175,6 +177,9 @@ int ctrlsim_map_pool(const float* feats, const uint8_t* pt_valid, const uint8_t*
 /* one categorical draw per row with the explicit sampler: x [rows, n] fp32 (already tilted / tempered) */
 int ctrlsim_sample_rows(const float* x, int32_t rows, int32_t n, int32_t ld, int32_t stride, uint64_t seed,
                         const uint32_t* counters /* [rows,4] */, int32_t* out_idx, void* stream);
+/* the same with top-p (nucleus) filtering on the sampler's integer weights (n <= 1024), see oracle/sampler.py */
+int ctrlsim_sample_rows_nucleus(const float* x, int32_t rows, int32_t n, int32_t ld, int32_t stride, uint64_t seed,
+                                const uint32_t* counters /* [rows,4] */, double top_p, int32_t* out_idx, void* stream);
 /* full first-pass forward on caller-provided tokens of G groups (parity tests against the reference modules):
  * writes rtg logits [G,24,1050] and, after overwriting the rtg tokens at `ti` with rtg_idx [G,24,3], action logits
  * [G,24,1000]. Token arrays follow the reference MotionData layout (float32 / int32). */

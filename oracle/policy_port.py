@@ -147,10 +147,11 @@ class MetricsPort:
 
 
 class RolloutPort:
-    def __init__(self, cfg, model, seed=0, tilts=(0, 0, 0), temperature=1.0, eval_threshold=None):
+    def __init__(self, cfg, model, seed=0, tilts=(0, 0, 0), temperature=1.0, eval_threshold=None, nucleus=None):
         self.cfg, self.model = cfg, model
         self.w, self.m = cfg.dataset.waymo, cfg.model
         self.seed, self.tilts, self.temperature = seed, tilts, float(temperature)
+        self.nucleus = nucleus  # None, or the nucleus threshold p (autoregressive_policy.py:216-230)
         self.steps, self.dt, self.hist = cfg.nocturne.steps, cfg.nocturne.dt, cfg.nocturne.history_steps
         self.eval_threshold = eval_threshold if eval_threshold is not None else cfg.eval.multi_agent_eval_threshold
         self.metrics = MetricsPort(cfg)
@@ -365,8 +366,11 @@ class RolloutPort:
                 if t in logit_steps:
                     rec["logits"][(t, g)] = {"rtg_logits": rtg_logits.copy(), "action_logits": act_logits.copy()}
                 for v in served:
-                    idx = sampler.sample_from_x(sampler.action_x(act_logits[slot[v]], self.temperature),
-                                                self.seed, scene_idx, v, t, sampler.COMP_ACTION)
+                    ax = sampler.action_x(act_logits[slot[v]], self.temperature)
+                    if self.nucleus is None:
+                        idx = sampler.sample_from_x(ax, self.seed, scene_idx, v, t, sampler.COMP_ACTION)
+                    else:
+                        idx = sampler.sample_from_x_nucleus(ax, self.nucleus, self.seed, scene_idx, v, t, sampler.COMP_ACTION)
                     rec["act_idx"][t, v] = idx
                     next_act[v, 0] = (idx // w.steer_discretization) / (w.accel_discretization - 1) * (w.max_accel - w.min_accel) + w.min_accel
                     next_act[v, 1] = (idx % w.steer_discretization) / (w.steer_discretization - 1) * (w.max_steer - w.min_steer) + w.min_steer

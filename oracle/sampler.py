@@ -15,6 +15,13 @@ oracle/ref_harness.py); it is a faithful multinomial draw from softmax(x) up to 
   r   = Philox4x32-10(key=seed, counter=(scene, agent, step, component))  -> 64 random bits
   idx = min{ i : w_0 + ... + w_i > mulhi64(r, sum_j w_j) }         (integer prefix sums: any scan order agrees)
 
+Nucleus (top-p) sampling of the action (autoregressive_policy.py:216-230, off in every reference config) is stated on the
+same integer weights: order the categories by (w descending, index ascending); with cum_k the inclusive prefix sums
+in that order keep category k iff k == 0 or float64(cum_{k-1}) < float64(p) * float64(sum_j w_j) - the reference's
+"cum_probs < p shifted right by one" - and draw idx = the first KEPT i, in index order, whose inclusive prefix over
+the kept weights exceeds mulhi64(r, sum_kept w).  (The reference takes the prefix on fp32 probabilities; the two sets
+differ only when a cumulative probability lies within 2^-30 of p.)
+
 component: 0/1/2 = RTG goal / veh / road, 3 = action.  `scene` is the global scene index, `agent` the vehicle's
 index in the scenario, so results do not depend on how scenes are sharded over GPUs.
 """
@@ -61,6 +68,28 @@ def random_bits(seed: int, scene: int, agent: int, step: int, comp: int) -> int:
 
 def sample_from_x(x, seed, scene, agent, step, comp) -> int:
     w = weights_from_x(x)
+    total = int(w.sum())
+    target = (random_bits(seed, scene, agent, step, comp) * total) >> 64
+    return int(np.searchsorted(np.cumsum(w), np.uint64(target), side="right"))
+
+
+def nucleus_keep(w, p: float):
+    """Boolean keep mask of the top-p set on integer weights w (definition above; straightforward sort)."""
+    w = np.asarray(w, dtype=np.uint64)
+    n = len(w)
+    order = np.lexsort((np.arange(n), -w.astype(np.int64)))  # w descending, index ascending
+    cum = np.cumsum(w[order])
+    thr = float(p) * float(int(w.sum()))
+    keep_sorted = np.ones(n, bool)
+    keep_sorted[1:] = cum[:-1].astype(np.float64) < thr
+    keep = np.zeros(n, bool)
+    keep[order] = keep_sorted
+    return keep
+
+
+def sample_from_x_nucleus(x, p, seed, scene, agent, step, comp) -> int:
+    w = weights_from_x(x)
+    w = np.where(nucleus_keep(w, p), w, np.uint64(0))
     total = int(w.sum())
     target = (random_bits(seed, scene, agent, step, comp) * total) >> 64
     return int(np.searchsorted(np.cumsum(w), np.uint64(target), side="right"))

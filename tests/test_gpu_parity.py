@@ -151,6 +151,53 @@ def test_sampler_bit_exact_vs_oracle(lib, dev):
         assert (got == want).all(), (got, want)
 
 
+def test_nucleus_sampler_bit_exact_vs_oracle(lib, dev):
+    """Top-p filtering on the integer weights: the device's sort-free bisection == the oracle's sort-based definition,
+    including heavy ties (quantised logits) and the edge thresholds."""
+    from oracle import sampler
+    rng = np.random.default_rng(1)
+    rows, n = 96, 1000
+    x = (rng.standard_normal((rows, n)) * rng.uniform(0.5, 8.0, (rows, 1))).astype(np.float32)
+    x[rows // 2:] = np.round(x[rows // 2:] * 2) / 2  # many exact ties
+    x[-1] = 0.0                                       # all categories tie
+    ctr = rng.integers(0, 2 ** 31, (rows, 4)).astype(np.uint32)
+    xd = torch.from_numpy(x).to(dev)
+    cd = torch.from_numpy(ctr.view(np.int32)).to(dev)
+    out = torch.empty(rows, dtype=torch.int32, device=dev)
+    seed = 0x0BAD_5EED_1234
+    for p in (0.0, 0.3, 0.8, 0.95, 1.0, 1.5):
+        _chk(lib.ctrlsim_sample_rows_nucleus(xd.data_ptr(), rows, n, n, 1, seed, cd.data_ptr(), p, out.data_ptr(),
+                                             _stream()), lib)
+        got = out.cpu().numpy()
+        want = np.array([sampler.sample_from_x_nucleus(x[r], p, seed, *[int(c) for c in ctr[r]]) for r in range(rows)])
+        assert (got == want).all(), (p, np.nonzero(got != want)[0][:5], got[got != want][:5], want[got != want][:5])
+
+
+def test_rollout_with_nucleus_sampling_matches_oracle_port(cfg, dev):
+    """Closed loop with nucleus_sampling=True (cfgs/policy/ctrl_sim.yaml:10-11) == the oracle port, scene by scene."""
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    from ctrlsim_b200.weights import make_weights
+    from ctrlsim_b200.model import DeviceModel
+    from oracle.model_port import ModelPort
+    from oracle.policy_port import RolloutPort
+    weights = make_weights(cfg, seed=3, still_bias=2.0)
+    scenes = [make_scene(60 + i, n_vehicles=6 + 2 * i, n_roads=2, n_chunks=3) for i in range(2)]
+    steps = 4
+    pol = B200Policy(cfg, "synthetic", DeviceModel(cfg, weights, dev), seed=9, nucleus_sampling=True, nucleus_threshold=0.8)
+    ev = B200PolicyEvaluator(cfg, pol, scenes=scenes)
+    b = ev.build_batch(eval_threshold=64)
+    ev.rollout(b, max_steps=steps)
+    tr = b.trace()
+    port = RolloutPort(cfg, ModelPort(cfg, weights), seed=9, eval_threshold=64, nucleus=0.8)
+    for s, sc in enumerate(scenes):
+        rec = port.run_scene(s, sc["json"], sc["preproc"], max_steps=steps)
+        n = rec["n"]
+        assert (tr["tr_act_idx"][s, :n, :steps].T == rec["act_idx"][:steps]).all()
+        assert (tr["tr_rtg_idx"][s, :n, :steps].transpose(1, 0, 2) == rec["rtg_idx"][:steps]).all()
+        assert np.abs(tr["tr_pos"][s, :n, :steps] - rec["pos"][:, :steps]).max() < POS_TOL
+
+
 def test_geometry_known_answers(lib, dev):
     """Reference KATs: nocturne/cpp/tests/src/geometry/polygon_test.cc:60-86, intersection_test.cc:52-76."""
     eps = 1e-5

@@ -38,6 +38,37 @@ def test_sampler_is_a_faithful_multinomial():
     assert sampler.rtg_x(lg, 10.0)[-1] == np.float32(10.0) and sampler.rtg_x(lg, 10.0)[0] == 0
 
 
+def test_nucleus_keep_matches_the_reference_rule():
+    """oracle.sampler.nucleus_keep (integer weights) against the reference's own torch statement on float
+    probabilities (policies/autoregressive_policy.py:216-230): identical kept sets on generic inputs; hand cases for
+    ties, p = 0 (arg-max only) and p >= 1 (everything with a non-zero weight)."""
+    import torch
+    from oracle import sampler
+    rng = np.random.default_rng(5)
+    p = 0.8
+    for r in range(60):
+        x = (rng.standard_normal(1000) * rng.uniform(0.5, 6.0)).astype(np.float32)
+        probs = torch.softmax(torch.from_numpy(x), dim=0)
+        sp, si = torch.sort(probs, descending=True)
+        sel = torch.cumsum(sp, dim=-1) < p
+        sel = torch.cat([sel.new_ones(1), sel[:-1]])
+        ref_keep = np.zeros(1000, bool)
+        ref_keep[si[sel].numpy()] = True
+        got = sampler.nucleus_keep(sampler.weights_from_x(x), p)
+        assert (got == ref_keep).all(), (r, int(got.sum()), int(ref_keep.sum()))
+    w = np.array([4, 4, 8, 1, 4, 0], np.uint64)  # sorted: 8 | 4(i0) 4(i1) 4(i4) | 1 | 0 ; total 21
+    assert sampler.nucleus_keep(w, 0.0).tolist() == [False, False, True, False, False, False]
+    assert sampler.nucleus_keep(w, 0.5).tolist() == [True, False, True, False, False, False]      # 8 < 10.5 -> +4(i0): 12
+    assert sampler.nucleus_keep(w, 0.6).tolist() == [True, True, True, False, False, False]       # 12 < 12.6 -> +4(i1)
+    assert sampler.nucleus_keep(w, 1.0).tolist() == [True, True, True, True, True, False]         # 20 < 21 -> +1; 21 !< 21
+    assert sampler.nucleus_keep(w, 1.5).all()
+    # draws only ever land in the kept set
+    x = (rng.standard_normal(1000) * 3).astype(np.float32)
+    keep = sampler.nucleus_keep(sampler.weights_from_x(x), 0.8)
+    draws = {sampler.sample_from_x_nucleus(x, 0.8, 1, 2, a, 0, 3) for a in range(300)}
+    assert all(keep[d] for d in draws) and len(draws) > 1
+
+
 # ------------------------------------------------------------------------------------------------ simulator oracle
 def test_geometry_known_answers_c_oracle():
     """nocturne/cpp/tests/src/geometry/polygon_test.cc:60-86 and intersection_test.cc:52-76 on the C restatement."""
