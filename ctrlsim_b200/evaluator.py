@@ -189,9 +189,11 @@ class B200PolicyEvaluator:
             ids.append(i)
         return scenes, ids
 
-    def build_batch(self, eval_threshold=None):
+    def build_batch(self, eval_threshold=None, keep_replay_only=False):
         """Shard scenes over ranks (scene i -> rank i mod world) keeping the evaluated-vehicle draw of the
-        single-process evaluator: every rank walks all scenes in order with the same seeded generator."""
+        single-process evaluator: every rank walks all scenes in order with the same seeded generator.
+        ``keep_replay_only``: keep scenes without any evaluated vehicle (pure log replay, BASELINE config 4) instead of
+        skipping them like the reference evaluator does."""
         from .scenario import parse_scenario
         cfg = self.cfg
         rng = random.Random(cfg.eval.seed)
@@ -203,7 +205,7 @@ class B200PolicyEvaluator:
             p = parse_scenario(s["json"], self.steps, sc["moving_threshold"], sc["speed_threshold"])
             moving = [i for i in range(p["n"]) if p["moving"][i]]
             ev = rng.sample(moving, thr) if len(moving) > thr else moving
-            if not ev:
+            if not ev and not keep_replay_only:
                 continue  # no candidate agent: scene skipped (policy_evaluator.py:461-464)
             if own:
                 mine.append(s)

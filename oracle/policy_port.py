@@ -253,7 +253,9 @@ class RolloutPort:
         return self.model.forward(data)
 
     # ------------------------------------------------------------------------------------------------ loop
-    def run_scene(self, scene_idx, scen_json, preproc, logit_steps=(), max_steps=None):
+    def run_scene(self, scene_idx, scen_json, preproc, logit_steps=(), max_steps=None, replay_only=False):
+        """replay_only: no vehicle is policy-controlled - every vehicle is log-replayed through the inverse bicycle model
+        (BASELINE config 4; the reference evaluator itself skips scenes without evaluated vehicles)."""
         cfg, w = self.cfg, self.w
         steps, dt = self.steps, self.dt
         run_steps = steps if max_steps is None else max_steps
@@ -263,7 +265,9 @@ class RolloutPort:
         sim = sim_port.ScenePort(parsed)
         moving = [i for i in range(n) if parsed["moving"][i]]
         evaluated = random.sample(moving, self.eval_threshold) if len(moving) > self.eval_threshold else moving
-        if not evaluated:
+        if replay_only:
+            evaluated = []
+        elif not evaluated:
             return None
         # goals (evaluator.py:60-76)
         goal = np.zeros((n, 4))
@@ -404,5 +408,6 @@ class RolloutPort:
             sim.step(dt)
         if run_steps == steps:
             observe(steps)
-            self.metrics.add_scene(rec, evaluated)
+            if evaluated:
+                self.metrics.add_scene(rec, evaluated)
         return rec

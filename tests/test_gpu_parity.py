@@ -198,6 +198,60 @@ def test_rollout_with_nucleus_sampling_matches_oracle_port(cfg, dev):
         assert np.abs(tr["tr_pos"][s, :n, :steps] - rec["pos"][:, :steps]).max() < POS_TOL
 
 
+def test_log_replay_batch_matches_oracle(cfg, dev):
+    """BASELINE config 4 shape: every vehicle log-replayed (inverse bicycle -> FreeCar / Box2D integrate -> collision
+    and off-road checks -> rewards) for whole 90-step episodes, a batch of scenes on the GPU vs the C simulator oracle
+    scene by scene.  Compared up to a scene's first vehicle-vehicle contact (contact response is not modelled)."""
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    from ctrlsim_b200.weights import make_weights
+    from ctrlsim_b200.model import DeviceModel
+    from oracle.policy_port import RolloutPort
+    scenes = [make_scene(300 + i, n_vehicles=4 + (5 * i) % 29, n_roads=2 + i % 3, n_chunks=3 + i % 4, frac_short=0.25,
+                         frac_parked=0.2 if i % 2 else 0.0) for i in range(40)]
+    for sc in scenes[::5]:  # the first vehicle of some scenes leaves its lane at 20 degrees and crosses a road edge
+        o = sc["json"]["objects"][0]
+        th = math.radians(o["heading"][0]) + 0.35
+        sp = max(6.0, math.hypot(o["velocity"][0]["x"], o["velocity"][0]["y"]))
+        x0, y0 = o["position"][0]["x"], o["position"][0]["y"]
+        for t, ok in enumerate(o["valid"]):
+            if ok:
+                o["position"][t] = {"x": x0 + sp * 0.1 * t * math.cos(th), "y": y0 + sp * 0.1 * t * math.sin(th)}
+                o["heading"][t] = math.degrees(th)
+                o["velocity"][t] = {"x": sp * math.cos(th), "y": sp * math.sin(th)}
+        last = max(t for t, ok in enumerate(o["valid"]) if ok)
+        o["goalPosition"] = dict(o["position"][last])
+    pol = B200Policy(cfg, "synthetic", DeviceModel(cfg, make_weights(cfg, seed=0), dev), seed=0)
+    ev = B200PolicyEvaluator(cfg, pol, scenes=scenes)
+    b = ev.build_batch(eval_threshold=0, keep_replay_only=True)
+    assert b.n_evaluated() == 0 and b.S == len(scenes)
+    ev.rollout(b)
+    tr = b.trace()
+    port = RolloutPort(cfg, model=None, eval_threshold=0)
+    n_full, n_veh_steps, n_coll, n_off = 0, 0, 0, 0
+    for s, sc in enumerate(scenes):
+        rec = port.run_scene(s, sc["json"], sc["preproc"], replay_only=True)
+        n = rec["n"]
+        cv = ((rec["reward"][:, :, 6] > 0) & (rec["existence"] > 0)).any(0)  # absent vehicles all sit at one far point
+        T = int(np.argmax(cv)) if cv.any() else 91
+        n_full += T == 91
+        ex = rec["existence"][:, :T].astype(bool)
+        assert (tr["tr_exist"][s, :n, :T] == rec["existence"][:, :T]).all()
+        if not ex.any():
+            continue
+        assert np.abs(tr["tr_pos"][s, :n, :T].astype(np.float64) - rec["pos"][:, :T])[ex].max() < POS_TOL
+        assert np.abs(tr["tr_heading"][s, :n, :T].astype(np.float64) - rec["heading"][:, :T])[ex].max() < 1e-5
+        assert np.abs(tr["tr_vel"][s, :n, :T].astype(np.float64) - rec["vel"][:, :T])[ex].max() < 1e-4
+        assert np.abs(tr["tr_reward"][s, :n, :T].astype(np.float64) - rec["reward"][:, :T])[ex].max() < 1e-5  # incl. both collision flags
+        assert np.abs(tr["tr_nearest"][s, :n, :T, 0] - rec["nearest_dist"][:, :T])[ex].max() < 1e-3
+        n_veh_steps += int(ex.sum()); n_off += int((rec["reward"][:, :T, 7][ex] > 0).sum())
+        if T < 91:  # the contact itself is flagged identically
+            assert ((tr["tr_reward"][s, :n, T, 6] > 0) == (rec["reward"][:, T, 6] > 0)).all()
+            n_coll += 1
+    # the comparison is not vacuous: whole episodes, collisions and off-road events all occur
+    assert n_full >= 15 and n_veh_steps > 20000 and n_off > 0 and n_coll > 0, (n_full, n_veh_steps, n_off, n_coll)
+
+
 def test_geometry_known_answers(lib, dev):
     """Reference KATs: nocturne/cpp/tests/src/geometry/polygon_test.cc:60-86, intersection_test.cc:52-76."""
     eps = 1e-5
