@@ -171,6 +171,9 @@ class RolloutPort:
             if not ep["states"][focal, t, -1]:
                 dead.append(focal)
                 continue
+            if len(ep["road_points"]) == 0:  # scene without road polylines (autoregressive_policy.py:106-108)
+                dead.append(focal)
+                continue
             if t == 0:
                 ep["relevant"][focal] = []
             dist = np.linalg.norm(ep["states"][focal, t0, :2][None] - ep["states"][:, t0, :2], axis=-1)

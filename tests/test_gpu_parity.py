@@ -198,6 +198,49 @@ def test_rollout_with_nucleus_sampling_matches_oracle_port(cfg, dev):
         assert np.abs(tr["tr_pos"][s, :n, :steps] - rec["pos"][:, :steps]).max() < POS_TOL
 
 
+def test_edge_scenes_match_oracle_port(cfg, dev):
+    """Ragged / degenerate inputs in ONE batch: a scene without any road polyline (every focal is 'dead': action (0,0),
+    autoregressive_policy.py:106-108,249-251), a single-vehicle scene, a scene whose vehicles all vanish early, and a
+    64-vehicle scene (the grouping kernel's maximum) - against the oracle port, scene by scene."""
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene, preproc_from_json
+    from ctrlsim_b200.weights import make_weights
+    from ctrlsim_b200.model import DeviceModel
+    from oracle.model_port import ModelPort
+    from oracle.policy_port import RolloutPort
+    weights = make_weights(cfg, seed=2, still_bias=5.0)
+    no_roads = make_scene(80, n_vehicles=5, n_roads=1, n_chunks=2)
+    no_roads["json"]["roads"] = []
+    no_roads["preproc"] = preproc_from_json(no_roads["json"])
+    single = make_scene(81, n_vehicles=1, n_roads=1, n_chunks=2)
+    vanish = make_scene(82, n_vehicles=6, n_roads=1, n_chunks=3)
+    for o in vanish["json"]["objects"]:  # every vehicle disappears after step 11
+        for t in range(12, 91):
+            o["position"][t] = {"x": -10000.0, "y": -10000.0}; o["velocity"][t] = {"x": -10000.0, "y": -10000.0}
+            o["heading"][t] = -10000.0; o["valid"][t] = False
+        o["goalPosition"] = dict(o["position"][11])
+    full = make_scene(83, n_vehicles=64)
+    scenes = [no_roads, single, vanish, full]
+    steps = 14
+    pol = B200Policy(cfg, "synthetic", DeviceModel(cfg, weights, dev), seed=4)
+    ev = B200PolicyEvaluator(cfg, pol, scenes=scenes)
+    b = ev.build_batch(eval_threshold=64)
+    assert b.S == 4 and b.N == 64
+    ev.rollout(b, max_steps=steps)
+    tr = b.trace()
+    port = RolloutPort(cfg, ModelPort(cfg, weights), seed=4, eval_threshold=64)
+    for s, sc in enumerate(scenes):
+        rec = port.run_scene(s, sc["json"], sc["preproc"], max_steps=steps if s < 3 else 2)
+        n, T = rec["n"], (steps if s < 3 else 2)  # the 64-vehicle scene costs the CPU oracle ~24 forwards per step
+        assert (tr["tr_act_idx"][s, :n, :T].T == rec["act_idx"][:T]).all(), s
+        assert (tr["tr_rtg_idx"][s, :n, :T].transpose(1, 0, 2) == rec["rtg_idx"][:T]).all(), s
+        assert (tr["tr_exist"][s, :n, :T] == rec["existence"][:, :T]).all(), s
+        ex = rec["existence"][:, :T].astype(bool)
+        assert np.abs(tr["tr_pos"][s, :n, :T] - rec["pos"][:, :T])[ex].max() < POS_TOL, s
+        assert np.abs(tr["tr_action"][s, :n, :T] - np.stack([rec["accel"], rec["steer"]], -1)[:, :T])[ex].max() < 1e-4, s
+    assert (tr["tr_act_idx"][0] == -1).all()  # no road polylines: nothing is ever sampled
+
+
 def test_log_replay_batch_matches_oracle(cfg, dev):
     """BASELINE config 4 shape: every vehicle log-replayed (inverse bicycle -> FreeCar / Box2D integrate -> collision
     and off-road checks -> rewards) for whole 90-step episodes, a batch of scenes on the GPU vs the C simulator oracle
