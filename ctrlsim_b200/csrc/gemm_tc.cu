@@ -10,7 +10,9 @@
 // chained on one accumulator; the two small cross terms therefore go to a SECOND TMEM accumulator (their truncation
 // is 2^-11 smaller) and are added once, with round-to-nearest, in the epilogue: K/8 chained adds instead of 3K/8.
 //
-// Structure (one CTA per 128 x 256 output tile, 288 threads):
+// Two kernels: gemm_tc_tma_kernel further down is the product path (persistent, TMA-fed, see its header); the simple
+// gemm_tc_kernel right below serves the calls TMA cannot express (row gather, unaligned operands) and A/B runs.
+// Structure of gemm_tc_kernel (one CTA per 128 x 256 output tile, 288 threads):
 //   warps 0-7  producers: global fp32 -> registers -> hi/lo split -> st.shared into the canonical K-major SWIZZLE_128B
 //              layout (rows of 32 floats = 128 B, 8-row groups of 1024 B, 16-byte chunk index XOR (row & 7));
 //              fence.proxy.async + mbarrier arrive on full[stage].  Afterwards the same warps run the epilogue:
@@ -373,196 +375,12 @@ gemm_tc_kernel(const float* __restrict__ Aa, const float* __restrict__ W, const 
 
 
 // =====================================================================================================================
-// v2: persistent, warp-specialised (one CTA per SM loops over 128 x 128 output tiles).
-//   warps 0-7   producers only: global -> (register prefetch of the next k-slab) -> hi/lo split -> swizzled smem,
-//               3 stages x 64 KB (A_hi, A_lo, B_hi, B_lo of 128 x 32 floats each)
-//   warp  8     MMA issuer: 12 tcgen05.mma (M=128, N=128, K=8) per k-slab into TMEM buffer b = tile & 1
-//               (columns b*256 + [0,128): hi*hi, + [128,256): cross terms); commits free the smem stage / publish the tile
-//   warps 9-12  epilogue: tcgen05.ld of buffer b while the MMA warp already works on buffer b^1 for the next tile
+// Persistent kernel geometry (one CTA per SM loops over 128 x 128 output tiles, k-slabs of 32 floats = one 128-byte
+// swizzle row).
 constexpr int P_BM = 128, P_BN = 128, P_BK = 32, P_STAGES = 3;
-constexpr int P_PRODUCERS = 256, P_EPI = 128, P_THREADS = P_PRODUCERS + 32 + P_EPI;
-
-struct alignas(1024) PStage {
-  float a_hi[P_BM * P_BK];
-  float a_lo[P_BM * P_BK];
-  float b_hi[P_BN * P_BK];
-  float b_lo[P_BN * P_BK];
-};
-struct PSmem {
-  PStage stage[P_STAGES];
-  uint64_t full[P_STAGES];
-  uint64_t empty[P_STAGES];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
-  uint32_t tmem_base;
-};
-
-template <bool RELU>
-__global__ void __launch_bounds__(P_THREADS, 1)
-gemm_tc_persistent_kernel(const float* __restrict__ Aa, const float* __restrict__ W, const float* __restrict__ bias,
-                          const float* __restrict__ table, const int* __restrict__ tidx,
-                          const int* __restrict__ agather, float* __restrict__ C, int M, int N, int K, int lda, int ldw,
-                          int ldc, int ldt, int n_tiles_n, int n_tiles) {
-  extern __shared__ unsigned char tc_raw[];
-  PSmem& sm = *reinterpret_cast<PSmem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nk = K / P_BK;
-
-  if (tid == 0) {
-    for (int s = 0; s < P_STAGES; ++s) { tc_mbar_init(&sm.full[s], P_PRODUCERS); tc_mbar_init(&sm.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { tc_mbar_init(&sm.tmem_full[b], 1); tc_mbar_init(&sm.tmem_empty[b], P_EPI); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = sm.tmem_base;
-
-  if (warp < 8) {
-    // ------------------------------------------------------------------ producers
-    const int c = tid & 7, rbase = tid >> 3;
-    const int sc = (c ^ (rbase & 7)) << 2;
-    uint32_t it = 0;  // global k-slab counter (stage ring position)
-    float4 va[4], vb[4];
-    const float* ap[4];
-    const float* wp[4];
-    auto set_tile = [&](int tile) {
-      const int m0 = (tile / n_tiles_n) * P_BM, n0 = (tile % n_tiles_n) * P_BN;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = m0 + rbase + 32 * i, n = n0 + rbase + 32 * i;
-        ap[i] = m < M ? Aa + (size_t)(agather ? agather[m] : m) * lda + c * 4 : nullptr;
-        wp[i] = n < N ? W + (size_t)n * ldw + c * 4 : nullptr;
-      }
-    };
-    auto gload = [&](int k0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        va[i] = ap[i] ? *reinterpret_cast<const float4*>(ap[i] + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
-        vb[i] = wp[i] ? __ldg(reinterpret_cast<const float4*>(wp[i] + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    int tile = blockIdx.x;
-    if (tile < n_tiles) { set_tile(tile); gload(0); }
-    while (tile < n_tiles) {
-      for (int kc = 0; kc < nk; ++kc, ++it) {
-        const int s = it % P_STAGES;
-        tc_mbar_wait(&sm.empty[s], ((it / P_STAGES) & 1) ^ 1);
-        PStage& st = sm.stage[s];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          tc_split_store(st.a_hi, st.a_lo, (rbase + 32 * i) * P_BK + sc, va[i]);
-          tc_split_store(st.b_hi, st.b_lo, (rbase + 32 * i) * P_BK + sc, vb[i]);
-        }
-        // prefetch the next k-slab (possibly of the next tile) into registers before publishing this one
-        if (kc + 1 < nk) {
-          gload((kc + 1) * P_BK);
-        } else {
-          const int nt = tile + gridDim.x;
-          if (nt < n_tiles) { set_tile(nt); gload(0); }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_mbar_arrive(&sm.full[s]);
-      }
-      tile += gridDim.x;
-    }
-  } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = tc_make_idesc(P_BM, P_BN);
-    uint32_t it = 0, ti = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      const uint32_t buf = ti & 1;
-      tc_mbar_wait(&sm.tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d_main = tmem + buf * 256, d_cross = d_main + 128;
-      for (int kc = 0; kc < nk; ++kc, ++it) {
-        const int s = it % P_STAGES;
-        tc_mbar_wait(&sm.full[s], (it / P_STAGES) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
-          PStage& st = sm.stage[s];
-          const uint64_t dah = tc_make_desc(tc_smem_u32(st.a_hi)), dal = tc_make_desc(tc_smem_u32(st.a_lo));
-          const uint64_t dbh = tc_make_desc(tc_smem_u32(st.b_hi)), dbl = tc_make_desc(tc_smem_u32(st.b_lo));
-#pragma unroll
-          for (int ks = 0; ks < P_BK / 8; ++ks) {
-            const uint64_t o = (uint64_t)(2 * ks);
-            const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
-            tc_mma(d_cross, dal + o, dbh + o, idesc, acc);
-            tc_mma(d_cross, dah + o, dbl + o, idesc, 1u);
-            tc_mma(d_main, dah + o, dbh + o, idesc, acc);
-          }
-          tc_commit(&sm.empty[s]);
-          if (kc == nk - 1) tc_commit(&sm.tmem_full[buf]);
-        }
-        __syncwarp();
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  } else {
-    // ------------------------------------------------------------------ epilogue (warps 9..12)
-    const int lg = warp & 3;  // TMEM lane group this warp may access
-    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      const uint32_t buf = ti & 1;
-      const int m0 = (tile / n_tiles_n) * P_BM, n0 = (tile % n_tiles_n) * P_BN;
-      tc_mbar_wait(&sm.tmem_full[buf], (ti >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int m = m0 + 32 * lg + lane;
-      const float* trow = (table && m < M) ? table + (size_t)tidx[m] * ldt : nullptr;
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        const int col0 = j * 32;
-        uint32_t r[32], rx[32];
-        const uint32_t ta = tmem + ((uint32_t)(32 * lg) << 16) + buf * 256 + (uint32_t)col0;
-        tc_ld32(ta, r);
-        tc_ld32(ta + 128, rx);
-        const float bl = (bias && n0 + col0 + lane < N) ? __ldg(bias + n0 + col0 + lane) : 0.f;
-        tc_epilogue_chunk<RELU>(r, rx, m, M, n0 + col0, N, bl, trow, C, ldc, vec_ok);
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      tc_mbar_arrive(&sm.tmem_empty[buf]);
-    }
-  }
-  __syncthreads();
-  if (warp == 8) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-  }
-}
-
-static int launch_gemm_tc_persistent(const GemmArgs& g, cudaStream_t st) {
-  static int n_sm = 0;
-  const int smem = (int)sizeof(PSmem) + 1024;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { n_sm = 0; return set_error(-5, "gemm_tc_persistent smem attr: %s", cudaGetErrorString(e)); }
-  }
-  const int tn = (g.N + P_BN - 1) / P_BN, tm = (g.M + P_BM - 1) / P_BM;
-  const long long tiles = (long long)tn * tm;
-  if (tiles > 0x7fffffffLL) return set_error(-2, "gemm_tc: too many tiles");
-  const int grid = (int)(tiles < n_sm ? tiles : n_sm);
-  if (g.relu)
-    gemm_tc_persistent_kernel<true><<<grid, P_THREADS, smem, st>>>(g.A, g.W, g.bias, g.table, g.tidx, g.agather, g.C, g.M, g.N,
-                                                                   g.K, g.lda, g.ldw, g.ldc, g.ldt, tn, (int)tiles);
-  else
-    gemm_tc_persistent_kernel<false><<<grid, P_THREADS, smem, st>>>(g.A, g.W, g.bias, g.table, g.tidx, g.agather, g.C, g.M, g.N,
-                                                                    g.K, g.lda, g.ldw, g.ldc, g.ldt, tn, (int)tiles);
-  CS_CHECK_LAUNCH("gemm_tc_persistent");
-  return 0;
-}
-
 
 // =====================================================================================================================
-// v3: v2's persistent structure, but the operand tiles are fetched by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor
+// The product kernel: persistent, warp-specialised, operand tiles fetched by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor
 // maps) so that no warp ever waits on a global load: the raw fp32 tile lands in shared memory already in the canonical
 // K-major layout and is used DIRECTLY as the "hi" operand - kind::tf32 ignores the 13 low mantissa bits of its 32-bit
 // inputs, i.e. it sees trunc13(x) - while the 8 producer warps only derive the lo = x - trunc13(x) tiles from it.
@@ -853,14 +671,11 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0) return 0;
   if (g.K % TC_BK != 0 || (g.lda & 3) || (g.ldw & 3))
     return set_error(-2, "gemm_tc: K=%d must be a multiple of %d and lda/ldw multiples of 4", g.K, TC_BK);
-  {  // CTRLSIM_GEMM=tc1 keeps the one-tile-per-CTA kernel above for A/B runs
+  {  // CTRLSIM_GEMM=tc1 forces the one-tile-per-CTA kernel above (A/B runs); it also serves row-gather / unaligned calls
     static int v1 = -1;
     if (v1 < 0) { const char* e = getenv("CTRLSIM_GEMM"); v1 = (e && std::string(e) == "tc1") ? 1 : 0; }
-    static int v2 = -1;
-    if (v2 < 0) { const char* e = getenv("CTRLSIM_GEMM"); v2 = (e && std::string(e) == "tc2") ? 1 : 0; }
     const bool tma_ok = !g.agather && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.W) & 15) == 0);
-    if (!v1 && !v2 && tma_ok) return launch_gemm_tc_tma(g, st);
-    if (!v1 && v2) return launch_gemm_tc_persistent(g, st);
+    if (!v1 && tma_ok) return launch_gemm_tc_tma(g, st);
   }
   static bool attr_set = false;
   const int smem = (int)sizeof(TcSmem) + 1024;

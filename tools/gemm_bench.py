@@ -24,4 +24,4 @@ for M, N, K in shapes:
     ms = e0.elapsed_time(e1) / 5
     ref = torch.nn.functional.linear(A[:512].double(), W.double(), b.double())
     err = (C[:512].double() - ref).abs().max().item()
-    print(f"M={M} N={N} K={K}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s  max|err|={err:.2e}  env={os.environ.get('CTRLSIM_GEMM','tc2')}", flush=True)
+    print(f"M={M} N={N} K={K}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s  max|err|={err:.2e}  mode={os.environ.get('CTRLSIM_GEMM','default')}", flush=True)
