@@ -302,3 +302,33 @@ def test_product_path_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_c_abi_fails_loudly_without_a_gpu_and_on_bad_arguments(cfg):
+    """The product path has no CPU fallback: on a box without a CUDA device ctrlsim_create returns a negative status
+    and an explanatory message; argument errors are reported the same way (no exceptions cross the C boundary)."""
+    import ctypes as C
+    import torch
+    from ctrlsim_b200 import lib as L
+    so = L.load(build_if_missing=False)
+    # size queries are pure host arithmetic and must agree with the documented layouts
+    per_block = 200 * 256 * 4 + 200
+    assert so.ctrlsim_map_cache_bytes(3, 64) == 3 * 64 * per_block + 256
+    slot = so.ctrlsim_prefix_cache_bytes(8, 1)
+    assert slot >= 8 * (4 * 2304 * 512 * 4 + 4 * 224 * 512 * 4 + 224) and so.ctrlsim_prefix_cache_bytes(8, 5) == 5 * slot
+    assert so.ctrlsim_workspace_bytes(None, 2) > so.ctrlsim_workspace_bytes(None, 1) > 0
+    # bad arguments
+    h = C.c_void_p()
+    assert so.ctrlsim_create(None, C.byref(h)) < 0 and b"null" in so.ctrlsim_last_error()
+    cc = L.make_config(cfg)
+    cc.abi_version = 1  # stale ABI
+    assert so.ctrlsim_create(C.byref(cc), C.byref(h)) < 0 and b"ABI" in so.ctrlsim_last_error()
+    cc = L.make_config(cfg)
+    cc.hidden_dim = 128  # a geometry the kernels are not specialised to
+    assert so.ctrlsim_create(C.byref(cc), C.byref(h)) < 0 and b"specialised" in so.ctrlsim_last_error()
+    if not torch.cuda.is_available():
+        cc = L.make_config(cfg)
+        rc = so.ctrlsim_create(C.byref(cc), C.byref(h))
+        assert rc < 0, "ctrlsim_create must not succeed without a CUDA device"
+        msg = so.ctrlsim_last_error().decode()
+        assert "CUDA" in msg or "sm_100" in msg, msg
