@@ -230,10 +230,11 @@ small_mlp1_kernel(const float* __restrict__ X, const float* __restrict__ W1, con
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
   // this lane's 8 output channels: weights, bias and LN affine live in registers for all rows the warp processes
+  // lane owns channels 4 lane .. 4 lane + 3 and 128 + 4 lane .. + 3: every warp store is one contiguous 512-byte run
   float w[8][DIN], bb[8], gm[8], bt[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int o = lane * 8 + i;
+    const int o = (i < 4 ? 0 : H / 2) + lane * 4 + (i & 3);
     bb[i] = __ldg(b1 + o); gm[i] = __ldg(gamma + o); bt[i] = __ldg(beta + o);
 #pragma unroll
     for (int k = 0; k < DIN; ++k) w[i][k] = __ldg(W1 + o * DIN + k);
@@ -260,9 +261,9 @@ small_mlp1_kernel(const float* __restrict__ X, const float* __restrict__ W1, con
     float o8[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o8[i] = fmaxf((v[i] - mean) * rstd * gm[i] + bt[i], 0.f);
-    float* y = Y + row * H + lane * 8;
+    float* y = Y + row * H + lane * 4;
     *reinterpret_cast<float4*>(y) = make_float4(o8[0], o8[1], o8[2], o8[3]);
-    *reinterpret_cast<float4*>(y + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+    *reinterpret_cast<float4*>(y + H / 2) = make_float4(o8[4], o8[5], o8[6], o8[7]);
   }
 }
 
@@ -322,44 +323,46 @@ assemble_tokens_kernel(int n_rows, int n_t, const float* __restrict__ sg, TokenB
   const int ts = tk.ts[gl * n_t + tw];
   const float ex = tk.exist[sa] ? 1.f : 0.f;
   float v[8];
-  const int c0 = lane * 8;
+  // lane owns channels 4 lane .. + 3 and 128 + 4 lane .. + 3 (fully coalesced 512-byte warp accesses)
+#define CH(i) (((i) < 4 ? 0 : H / 2) + lane * 4 + ((i) & 3))
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __ldg(ew.ts + ts * H + c0 + i) + __ldg(ew.id + a * H + c0 + i);
+  for (int i = 0; i < 8; ++i) v[i] = __ldg(ew.ts + ts * H + CH(i)) + __ldg(ew.id + a * H + CH(i));
   if (k == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = sg[(size_t)sa * H + c0 + i] + v[i];
+    for (int i = 0; i < 8; ++i) v[i] = sg[(size_t)sa * H + CH(i)] + v[i];
   } else if (k == 1) {
     const int i0 = tk.rtg_idx[sa * 3], i1 = tk.rtg_idx[sa * 3 + 1], i2 = tk.rtg_idx[sa * 3 + 2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      v[i] = (((__ldg(ew.rtg_goal + i0 * H + c0 + i) + __ldg(ew.rtg_veh + i1 * H + c0 + i)) +
-               __ldg(ew.rtg_road + i2 * H + c0 + i)) + __ldg(ew.rtg_bias + c0 + i)) + v[i];
+      v[i] = (((__ldg(ew.rtg_goal + i0 * H + CH(i)) + __ldg(ew.rtg_veh + i1 * H + CH(i))) +
+               __ldg(ew.rtg_road + i2 * H + CH(i))) + __ldg(ew.rtg_bias + CH(i))) + v[i];
   } else {
     const int ia = tk.act_idx[sa];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __ldg(ew.act + ia * H + c0 + i) + v[i];
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(ew.act + ia * H + CH(i)) + v[i];
   }
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { v[i] *= ex; s += v[i]; }
   if (k == 0 && tw == 0 && mem) {
-    float* m = mem + ((size_t)gl * MEM + P + a) * H + c0;
+    float* m = mem + ((size_t)gl * MEM + P + a) * H + lane * 4;
     *reinterpret_cast<float4*>(m) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(m + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    *reinterpret_cast<float4*>(m + H / 2) = make_float4(v[4], v[5], v[6], v[7]);
   }
   const float mean = warp_sum(s) * (1.0f / H);
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + LN_EPS);
-  float* x = X + (size_t)r * H + c0;
+  float* x = X + (size_t)r * H + lane * 4;
   float o[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = (v[i] - mean) * rstd * __ldg(ew.ln_w + c0 + i) + __ldg(ew.ln_b + c0 + i);
+  for (int i = 0; i < 8; ++i) o[i] = (v[i] - mean) * rstd * __ldg(ew.ln_w + CH(i)) + __ldg(ew.ln_b + CH(i));
   *reinterpret_cast<float4*>(x) = make_float4(o[0], o[1], o[2], o[3]);
-  *reinterpret_cast<float4*>(x + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  *reinterpret_cast<float4*>(x + H / 2) = make_float4(o[4], o[5], o[6], o[7]);
 }
 
+#undef CH
 int launch_assemble_tokens(int G, int n_t, const float* sg, const TokenBufs& tk, const EmbedW& ew, float* X, float* mem,
                            cudaStream_t st) {
   const int n_rows = G * n_t * TOK_T;
@@ -381,14 +384,15 @@ assemble_rtg_rows_kernel(int n_rows, int n_t, int ti, const int* __restrict__ rt
   const int ts = tk.ts[gl * n_t + ti];
   const float ex = tk.exist[sa] ? 1.f : 0.f;
   const int i0 = rtg_new[r * 3], i1 = rtg_new[r * 3 + 1], i2 = rtg_new[r * 3 + 2];
-  const int c0 = lane * 8;
+  // lane owns channels 4 lane .. + 3 and 128 + 4 lane .. + 3 (fully coalesced 512-byte warp accesses)
+#define CH(i) (((i) < 4 ? 0 : H / 2) + lane * 4 + ((i) & 3))
   float v[8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float e = __ldg(ew.ts + ts * H + c0 + i) + __ldg(ew.id + a * H + c0 + i);
-    v[i] = ((((__ldg(ew.rtg_goal + i0 * H + c0 + i) + __ldg(ew.rtg_veh + i1 * H + c0 + i)) +
-              __ldg(ew.rtg_road + i2 * H + c0 + i)) + __ldg(ew.rtg_bias + c0 + i)) + e) * ex;
+    const float e = __ldg(ew.ts + ts * H + CH(i)) + __ldg(ew.id + a * H + CH(i));
+    v[i] = ((((__ldg(ew.rtg_goal + i0 * H + CH(i)) + __ldg(ew.rtg_veh + i1 * H + CH(i))) +
+              __ldg(ew.rtg_road + i2 * H + CH(i))) + __ldg(ew.rtg_bias + CH(i))) + e) * ex;
     s += v[i];
   }
   const float mean = warp_sum(s) * (1.0f / H);
@@ -396,14 +400,15 @@ assemble_rtg_rows_kernel(int n_rows, int n_t, int ti, const int* __restrict__ rt
 #pragma unroll
   for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + LN_EPS);
-  float* x = Xr + (size_t)r * H + c0;
+  float* x = Xr + (size_t)r * H + lane * 4;
   float o[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = (v[i] - mean) * rstd * __ldg(ew.ln_w + c0 + i) + __ldg(ew.ln_b + c0 + i);
+  for (int i = 0; i < 8; ++i) o[i] = (v[i] - mean) * rstd * __ldg(ew.ln_w + CH(i)) + __ldg(ew.ln_b + CH(i));
   *reinterpret_cast<float4*>(x) = make_float4(o[0], o[1], o[2], o[3]);
-  *reinterpret_cast<float4*>(x + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  *reinterpret_cast<float4*>(x + H / 2) = make_float4(o[4], o[5], o[6], o[7]);
 }
 
+#undef CH
 int launch_assemble_rtg_rows(int G, int n_t, int ti, const int* rtg_new, const TokenBufs& tk, const EmbedW& ew,
                              float* Xr, cudaStream_t st) {
   const int n_rows = G * A;
