@@ -1,0 +1,1111 @@
+// Tensor-core GEMM for the linear layers: C[M,N] = act(A[M,K] W[N,K]^T + bias + table[tidx]) on the 5th-generation
+// tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM), fp32 in / fp32 out with fp32-class accuracy.
+//
+// Accuracy: tf32 keeps 10 mantissa bits, which would put ~1e-3 relative error on every product and break sampled-bin
+// parity with the fp32 reference.  Each operand is therefore split on the fly into hi = x with the 13 low mantissa
+// bits cleared (exactly representable in tf32) and lo = x - hi (exact in fp32), and three MMAs are issued per k-step:
+//   D += A_lo B_hi ;  D += A_hi B_lo ;  D += A_hi B_hi          (the dropped A_lo B_lo term is ~2^-22 relative)
+// ("3xTF32").  Ceiling: 1/3 of the dense tf32 rate (~370 TFLOP/s nominal) instead of the 74 TFLOP/s FP32 FFMA peak.
+// The tensor core adds into its fp32 accumulator with truncation, so the error grows linearly with the number of MMAs
+// chained on one accumulator; the two small cross terms therefore go to a SECOND TMEM accumulator (their truncation
+// is 2^-11 smaller) and are added once, with round-to-nearest, in the epilogue: K/8 chained adds instead of 3K/8.
+//
+// Structure (one CTA per 128 x 256 output tile, 288 threads):
+//   warps 0-7  producers: global fp32 -> registers -> hi/lo split -> st.shared into the canonical K-major SWIZZLE_128B
+//              layout (rows of 32 floats = 128 B, 8-row groups of 1024 B, 16-byte chunk index XOR (row & 7));
+//              fence.proxy.async + mbarrier arrive on full[stage].  Afterwards the same warps run the epilogue:
+//              tcgen05.ld 32x32b.x32 (warp w owns TMEM lanes 32*(w%4).., column half w/4) -> bias/table/ReLU -> global.
+//   warp 8     allocates 256 TMEM columns, then one elected lane waits full[stage], issues 12 tcgen05.mma
+//              (4 k-steps of 8 x 3 split products, M=128, N=256) and tcgen05.commit's to empty[stage]; the last commit
+//              signals the epilogue.
+// 2 stages x 96 KB (A_hi, A_lo 16 KB each; B_hi, B_lo 32 KB each) of dynamic shared memory.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ctrlsim {
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 2;
+constexpr int TC_PRODUCERS = 256, TC_THREADS = TC_PRODUCERS + 32;
+constexpr uint32_t TC_TMEM_COLS = 512;  // columns [0,256): A_hi B_hi accumulator; [256,512): cross-term accumulator
+
+struct alignas(1024) TcStage {
+  float a_hi[TC_BM * TC_BK];
+  float a_lo[TC_BM * TC_BK];
+  float b_hi[TC_BN * TC_BK];
+  float b_lo[TC_BN * TC_BK];
+};
+struct TcSmem {
+  TcStage stage[TC_STAGES];
+  uint64_t full[TC_STAGES];
+  uint64_t empty[TC_STAGES];
+  uint64_t accum_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
+    if (!done && ++spins > (1u << 26)) __trap();  // a lost arrival must not hang the GPU box
+  }
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100): start>>4 | LBO=1 |
+// SBO = 1024 B (one 8-row group) | version 1 | layout_type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t tc_make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32: c_format F32 (1) @4, a/b_format TF32 (2) @7/@10, K-major both,
+// n_dim = N>>3 @17, m_dim = M>>4 @24.
+__device__ __forceinline__ uint32_t tc_make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_ld32x2(uint32_t ta, uint32_t (&r)[32], uint32_t tb, uint32_t (&q)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(ta));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
+        "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
+        "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+      : "r"(tb));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 16 TMEM lanes x 32 columns without waiting: register 4k + 2h + e = (lane (t >> 2) + 8 h, column 8 k + 2 (t & 3) + e)
+// (the m16n8 accumulator-fragment layout, repeated over 4 column blocks)
+__device__ __forceinline__ void tc_ld16x256_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// Epilogue of one 32-row x 32-column chunk of a warp's accumulator rows, coalesced: the accumulators are read in the
+// 16x256b fragment layout (4 lanes share a row), lane pairs swap half of their values so that every lane owns four
+// consecutive columns, and each store instruction writes 8 rows x 64 contiguous bytes (instead of 32 rows x 16 bytes
+// with one row per thread).  m_base: first row of the warp's 32 rows; nc0: first column of the chunk.
+template <bool RELU, bool FAST /* tile fully inside C, vector stores, no table: no per-element checks */>
+__device__ __forceinline__ void tc_epilogue_chunk_frag(uint32_t tmem_main, uint32_t tmem_cross, int m_base, int M, int nc0,
+                                                       int N, const float* __restrict__ bias,
+                                                       const float* __restrict__ table, const int* __restrict__ tidx,
+                                                       int ldt, float* __restrict__ C, int ldc, bool vec_ok, int lane,
+                                                       bool skip_store) {
+  const int t0 = lane & 3, t1 = lane >> 2, odd = t0 & 1;
+  // bias of the 8 columns this thread holds before the swap: columns nc0 + 8 k + 2 t0 + e
+  float bz[4][2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = nc0 + 8 * k + 2 * t0;
+    if (FAST) {
+      if (bias) { const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + c)); bz[k][0] = b2.x; bz[k][1] = b2.y; }
+      else { bz[k][0] = 0.f; bz[k][1] = 0.f; }
+    } else {
+      bz[k][0] = (bias && c < N) ? __ldg(bias + c) : 0.f;
+      bz[k][1] = (bias && c + 1 < N) ? __ldg(bias + c + 1) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {  // lanes 0..15, then 16..31 of the warp's lane quadrant
+  uint32_t a0[16], x0[16];                // main / cross accumulators
+  tc_ld16x256_x4(tmem_main + ((uint32_t)(16 * half) << 16), a0);
+  tc_ld16x256_x4(tmem_cross + ((uint32_t)(16 * half) << 16), x0);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {  // row t1 + 8 h of the warp's 32 rows
+    const int h = 2 * half + hh;
+    const int m = m_base + t1 + 8 * h;
+    const float* trow = (!FAST && table && m < M) ? table + (size_t)tidx[m] * ldt : nullptr;
+    float v[4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ri = 4 * k + 2 * hh + e;
+        const float acc = __uint_as_float(a0[ri]) + __uint_as_float(x0[ri]);
+        float x = acc + bz[k][e];
+        if (!FAST && trow) { const int c = nc0 + 8 * k + 2 * t0 + e; if (c < N) x += __ldg(trow + c); }
+        v[k][e] = RELU ? fmaxf(x, 0.f) : x;
+      }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {  // column blocks 2p (kept by even t0) and 2p+1 (kept by odd t0)
+      const float k0 = odd ? v[2 * p + 1][0] : v[2 * p][0], k1 = odd ? v[2 * p + 1][1] : v[2 * p][1];
+      const float s0 = odd ? v[2 * p][0] : v[2 * p + 1][0], s1 = odd ? v[2 * p][1] : v[2 * p + 1][1];
+      const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+      const float4 out = odd ? make_float4(g0, g1, k0, k1) : make_float4(k0, k1, g0, g1);
+      const int c = nc0 + 8 * (2 * p + odd) + 2 * (t0 & 2);  // first of this lane's four consecutive columns
+      if (FAST) {
+        if (!skip_store) *reinterpret_cast<float4*>(C + (size_t)m * ldc + c) = out;
+      } else if (m < M && !skip_store) {
+        float* dst = C + (size_t)m * ldc + c;
+        if (vec_ok && c + 3 < N) {
+          *reinterpret_cast<float4*>(dst) = out;
+        } else {
+          if (c < N) dst[0] = out.x;
+          if (c + 1 < N) dst[1] = out.y;
+          if (c + 2 < N) dst[2] = out.z;
+          if (c + 3 < N) dst[3] = out.w;
+        }
+      }
+    }
+  }
+  }
+}
+
+__device__ __forceinline__ void tc_split_store(float* hi, float* lo, int off, float4 v) {
+  float4 h, l;
+  h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+  h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+  h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+  h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+  *reinterpret_cast<float4*>(hi + off) = h;
+  *reinterpret_cast<float4*>(lo + off) = l;
+}
+
+// Epilogue of one 32-column chunk held by this thread (row m, columns nc0 .. nc0+31): main + cross accumulators, bias,
+// optional table row, ReLU, store.  The bias is fetched with ONE coalesced load per chunk and broadcast by shuffles
+// (a per-element __ldg serialises ~200 cycles of latency per output); must be called by all 32 lanes of the warp.
+template <bool RELU>
+__device__ __forceinline__ void tc_epilogue_chunk(const uint32_t (&r)[32], const uint32_t (&rx)[32], int m, int M, int nc0,
+                                                  int N, const float bl /* bias[nc0 + lane] or 0 */,
+                                                  const float* __restrict__ trow, float* __restrict__ C, int ldc,
+                                                  bool vec_ok) {
+  float t[32];
+  if (trow) {
+#pragma unroll
+    for (int q = 0; q < 32; q += 4) {
+      if (nc0 + q + 3 < N) {
+        const float4 tv = __ldg(reinterpret_cast<const float4*>(trow + nc0 + q));
+        t[q] = tv.x; t[q + 1] = tv.y; t[q + 2] = tv.z; t[q + 3] = tv.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) t[q + e] = (nc0 + q + e < N) ? __ldg(trow + nc0 + q + e) : 0.f;
+      }
+    }
+  }
+  float* dst = C + (size_t)m * ldc + nc0;
+#pragma unroll
+  for (int q = 0; q < 32; q += 4) {
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float x = __uint_as_float(r[q + e]) + __uint_as_float(rx[q + e]);
+      x += __shfl_sync(0xffffffffu, bl, q + e);
+      if (trow) x += t[q + e];
+      v[e] = RELU ? fmaxf(x, 0.f) : x;
+    }
+    if (m < M) {
+      if (vec_ok && nc0 + q + 3 < N) {
+        *reinterpret_cast<float4*>(dst + q) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (nc0 + q + e < N) dst[q + e] = v[e];
+      }
+    }
+  }
+}
+
+template <bool RELU>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const float* __restrict__ Aa, const float* __restrict__ W, const float* __restrict__ bias,
+               const float* __restrict__ table, const int* __restrict__ tidx, const int* __restrict__ agather,
+               float* __restrict__ C, int M, int N, int K, int lda, int ldw, int ldc, int ldt) {
+  extern __shared__ unsigned char tc_raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
+  const int nk = K / TC_BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(&sm.full[s], TC_PRODUCERS); tc_mbar_init(&sm.empty[s], 1); }
+    tc_mbar_init(&sm.accum_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sm.tmem_base)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ producers
+    const int c = tid & 7;                 // 16-byte chunk of the 128-byte k-slab
+    const int rbase = tid >> 3;            // 0..31
+    const int sc = (c ^ (rbase & 7)) << 2; // swizzled chunk, in floats (row & 7 == rbase & 7 for rows rbase + 32 i)
+    const float* ap[4];
+    const float* wp[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + rbase + 32 * i;
+      ap[i] = m < M ? Aa + (size_t)(agather ? agather[m] : m) * lda + c * 4 : nullptr;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + rbase + 32 * i;
+      wp[i] = n < N ? W + (size_t)n * ldw + c * 4 : nullptr;
+    }
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % TC_STAGES;
+      const int k0 = kc * TC_BK;
+      float4 va[4], vb[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) va[i] = ap[i] ? *reinterpret_cast<const float4*>(ap[i] + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) vb[i] = wp[i] ? __ldg(reinterpret_cast<const float4*>(wp[i] + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kc >= TC_STAGES) tc_mbar_wait(&sm.empty[s], ((kc / TC_STAGES) - 1) & 1);
+      TcStage& st = sm.stage[s];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tc_split_store(st.a_hi, st.a_lo, (rbase + 32 * i) * TC_BK + sc, va[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tc_split_store(st.b_hi, st.b_lo, (rbase + 32 * i) * TC_BK + sc, vb[i]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_mbar_arrive(&sm.full[s]);
+    }
+    // ------------------------------------------------------------------ epilogue
+    tc_mbar_wait(&sm.accum_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int lg = warp & 3, half = warp >> 2;
+    const int m = m0 + 32 * lg + lane;
+    const float* trow = (table && m < M) ? table + (size_t)tidx[m] * ldt : nullptr;
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int col0 = half * 128 + j * 32;
+      uint32_t r[32], rx[32];
+      tc_ld32(tmem + ((uint32_t)(32 * lg) << 16) + (uint32_t)col0, r);
+      tc_ld32(tmem + ((uint32_t)(32 * lg) << 16) + (uint32_t)(TC_BN + col0), rx);
+      const float bl = (bias && n0 + col0 + lane < N) ? __ldg(bias + n0 + col0 + lane) : 0.f;
+      tc_epilogue_chunk<RELU>(r, rx, m, M, n0 + col0, N, bl, trow, C, ldc, vec_ok);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (warp 8)
+    const uint32_t idesc = tc_make_idesc(TC_BM, TC_BN);
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % TC_STAGES;
+      tc_mbar_wait(&sm.full[s], (kc / TC_STAGES) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        TcStage& st = sm.stage[s];
+        const uint64_t dah = tc_make_desc(tc_smem_u32(st.a_hi)), dal = tc_make_desc(tc_smem_u32(st.a_lo));
+        const uint64_t dbh = tc_make_desc(tc_smem_u32(st.b_hi)), dbl = tc_make_desc(tc_smem_u32(st.b_lo));
+#pragma unroll
+        for (int ks = 0; ks < TC_BK / 8; ++ks) {   // UMMA_K = 8 tf32 = 32 bytes -> start address advances by 2 (x16 B)
+          const uint64_t o = (uint64_t)(2 * ks);
+          const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
+          tc_mma(tmem + TC_BN, dal + o, dbh + o, idesc, acc);
+          tc_mma(tmem + TC_BN, dah + o, dbl + o, idesc, 1u);
+          tc_mma(tmem, dah + o, dbh + o, idesc, acc);
+        }
+        tc_commit(&sm.empty[s]);
+        if (kc == nk - 1) tc_commit(&sm.accum_full);
+      }
+      __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+
+// =====================================================================================================================
+// v2: persistent, warp-specialised (one CTA per SM loops over 128 x 128 output tiles).
+//   warps 0-7   producers only: global -> (register prefetch of the next k-slab) -> hi/lo split -> swizzled smem,
+//               3 stages x 64 KB (A_hi, A_lo, B_hi, B_lo of 128 x 32 floats each)
+//   warp  8     MMA issuer: 12 tcgen05.mma (M=128, N=128, K=8) per k-slab into TMEM buffer b = tile & 1
+//               (columns b*256 + [0,128): hi*hi, + [128,256): cross terms); commits free the smem stage / publish the tile
+//   warps 9-12  epilogue: tcgen05.ld of buffer b while the MMA warp already works on buffer b^1 for the next tile
+constexpr int P_BM = 128, P_BN = 128, P_BK = 32, P_STAGES = 3;
+constexpr int P_PRODUCERS = 256, P_EPI = 128, P_THREADS = P_PRODUCERS + 32 + P_EPI;
+
+struct alignas(1024) PStage {
+  float a_hi[P_BM * P_BK];
+  float a_lo[P_BM * P_BK];
+  float b_hi[P_BN * P_BK];
+  float b_lo[P_BN * P_BK];
+};
+struct PSmem {
+  PStage stage[P_STAGES];
+  uint64_t full[P_STAGES];
+  uint64_t empty[P_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+template <bool RELU>
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_tc_persistent_kernel(const float* __restrict__ Aa, const float* __restrict__ W, const float* __restrict__ bias,
+                          const float* __restrict__ table, const int* __restrict__ tidx,
+                          const int* __restrict__ agather, float* __restrict__ C, int M, int N, int K, int lda, int ldw,
+                          int ldc, int ldt, int n_tiles_n, int n_tiles) {
+  extern __shared__ unsigned char tc_raw[];
+  PSmem& sm = *reinterpret_cast<PSmem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk = K / P_BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < P_STAGES; ++s) { tc_mbar_init(&sm.full[s], P_PRODUCERS); tc_mbar_init(&sm.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { tc_mbar_init(&sm.tmem_full[b], 1); tc_mbar_init(&sm.tmem_empty[b], P_EPI); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ producers
+    const int c = tid & 7, rbase = tid >> 3;
+    const int sc = (c ^ (rbase & 7)) << 2;
+    uint32_t it = 0;  // global k-slab counter (stage ring position)
+    float4 va[4], vb[4];
+    const float* ap[4];
+    const float* wp[4];
+    auto set_tile = [&](int tile) {
+      const int m0 = (tile / n_tiles_n) * P_BM, n0 = (tile % n_tiles_n) * P_BN;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + rbase + 32 * i, n = n0 + rbase + 32 * i;
+        ap[i] = m < M ? Aa + (size_t)(agather ? agather[m] : m) * lda + c * 4 : nullptr;
+        wp[i] = n < N ? W + (size_t)n * ldw + c * 4 : nullptr;
+      }
+    };
+    auto gload = [&](int k0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        va[i] = ap[i] ? *reinterpret_cast<const float4*>(ap[i] + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[i] = wp[i] ? __ldg(reinterpret_cast<const float4*>(wp[i] + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    int tile = blockIdx.x;
+    if (tile < n_tiles) { set_tile(tile); gload(0); }
+    while (tile < n_tiles) {
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int s = it % P_STAGES;
+        tc_mbar_wait(&sm.empty[s], ((it / P_STAGES) & 1) ^ 1);
+        PStage& st = sm.stage[s];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          tc_split_store(st.a_hi, st.a_lo, (rbase + 32 * i) * P_BK + sc, va[i]);
+          tc_split_store(st.b_hi, st.b_lo, (rbase + 32 * i) * P_BK + sc, vb[i]);
+        }
+        // prefetch the next k-slab (possibly of the next tile) into registers before publishing this one
+        if (kc + 1 < nk) {
+          gload((kc + 1) * P_BK);
+        } else {
+          const int nt = tile + gridDim.x;
+          if (nt < n_tiles) { set_tile(nt); gload(0); }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_mbar_arrive(&sm.full[s]);
+      }
+      tile += gridDim.x;
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = tc_make_idesc(P_BM, P_BN);
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1;
+      tc_mbar_wait(&sm.tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_main = tmem + buf * 256, d_cross = d_main + 128;
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int s = it % P_STAGES;
+        tc_mbar_wait(&sm.full[s], (it / P_STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          PStage& st = sm.stage[s];
+          const uint64_t dah = tc_make_desc(tc_smem_u32(st.a_hi)), dal = tc_make_desc(tc_smem_u32(st.a_lo));
+          const uint64_t dbh = tc_make_desc(tc_smem_u32(st.b_hi)), dbl = tc_make_desc(tc_smem_u32(st.b_lo));
+#pragma unroll
+          for (int ks = 0; ks < P_BK / 8; ++ks) {
+            const uint64_t o = (uint64_t)(2 * ks);
+            const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
+            tc_mma(d_cross, dal + o, dbh + o, idesc, acc);
+            tc_mma(d_cross, dah + o, dbl + o, idesc, 1u);
+            tc_mma(d_main, dah + o, dbh + o, idesc, acc);
+          }
+          tc_commit(&sm.empty[s]);
+          if (kc == nk - 1) tc_commit(&sm.tmem_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 9..12)
+    const int lg = warp & 3;  // TMEM lane group this warp may access
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1;
+      const int m0 = (tile / n_tiles_n) * P_BM, n0 = (tile % n_tiles_n) * P_BN;
+      tc_mbar_wait(&sm.tmem_full[buf], (ti >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = m0 + 32 * lg + lane;
+      const float* trow = (table && m < M) ? table + (size_t)tidx[m] * ldt : nullptr;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int col0 = j * 32;
+        uint32_t r[32], rx[32];
+        const uint32_t ta = tmem + ((uint32_t)(32 * lg) << 16) + buf * 256 + (uint32_t)col0;
+        tc_ld32(ta, r);
+        tc_ld32(ta + 128, rx);
+        const float bl = (bias && n0 + col0 + lane < N) ? __ldg(bias + n0 + col0 + lane) : 0.f;
+        tc_epilogue_chunk<RELU>(r, rx, m, M, n0 + col0, N, bl, trow, C, ldc, vec_ok);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      tc_mbar_arrive(&sm.tmem_empty[buf]);
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+static int launch_gemm_tc_persistent(const GemmArgs& g, cudaStream_t st) {
+  static int n_sm = 0;
+  const int smem = (int)sizeof(PSmem) + 1024;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { n_sm = 0; return set_error(-5, "gemm_tc_persistent smem attr: %s", cudaGetErrorString(e)); }
+  }
+  const int tn = (g.N + P_BN - 1) / P_BN, tm = (g.M + P_BM - 1) / P_BM;
+  const long long tiles = (long long)tn * tm;
+  if (tiles > 0x7fffffffLL) return set_error(-2, "gemm_tc: too many tiles");
+  const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+  if (g.relu)
+    gemm_tc_persistent_kernel<true><<<grid, P_THREADS, smem, st>>>(g.A, g.W, g.bias, g.table, g.tidx, g.agather, g.C, g.M, g.N,
+                                                                   g.K, g.lda, g.ldw, g.ldc, g.ldt, tn, (int)tiles);
+  else
+    gemm_tc_persistent_kernel<false><<<grid, P_THREADS, smem, st>>>(g.A, g.W, g.bias, g.table, g.tidx, g.agather, g.C, g.M, g.N,
+                                                                    g.K, g.lda, g.ldw, g.ldc, g.ldt, tn, (int)tiles);
+  CS_CHECK_LAUNCH("gemm_tc_persistent");
+  return 0;
+}
+
+
+// =====================================================================================================================
+// v3: v2's persistent structure, but the operand tiles are fetched by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor
+// maps) so that no warp ever waits on a global load: the raw fp32 tile lands in shared memory already in the canonical
+// K-major layout and is used DIRECTLY as the "hi" operand - kind::tf32 ignores the 13 low mantissa bits of its 32-bit
+// inputs, i.e. it sees trunc13(x) - while the 8 producer warps only derive the lo = x - trunc13(x) tiles from it.
+//   warp 9      TMA issuer (one lane): expect_tx + 2 tensor copies (A box 32 x 128, W box 32 x 128) per k-slab
+//   warps 0-7   lo producers; warp 8 MMA issuer; warps 10-17 epilogue (two per TMEM lane quadrant: a single warp per
+//               quadrant needs ~2100 dependent instructions per tile and could not keep up with K = 256 tiles)
+// Rows beyond M / N are zero-filled by the TMA unit.  Row gather (agather) is not expressible: those two small GEMMs
+// use the v1 kernel.
+struct alignas(1024) P3Stage {
+  float a_raw[P_BM * P_BK];
+  float a_lo[P_BM * P_BK];
+  float b_raw[P_BN * P_BK];
+  float b_lo[P_BN * P_BK];
+};
+struct P3Smem {
+  P3Stage stage[P_STAGES];
+  uint64_t tma_full[P_STAGES];
+  uint64_t full[P_STAGES];
+  uint64_t empty[P_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+constexpr int P3_EPI = 256;  // 8 epilogue warps: two per TMEM lane quadrant, each owns one 64-column half of the tile
+constexpr int P3_THREADS = 256 + 32 + 32 + P3_EPI;
+
+__device__ __forceinline__ void tc_tma_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(tc_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float4 tc_lo4(float4 v) {
+  float4 l;
+  l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+  l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+  l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+  l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+  return l;
+}
+
+__device__ int g_gemm_debug = 0;                // 1: record a timeline of CTA 0
+__device__ long long g_gemm_trace[4 * 128];     // [k-slab][event]: 0 TMA issued, 1 data landed, 2 lo tiles published, 3 MMAs issued
+__device__ long long g_gemm_epi_trace[4 * 64];  // [tile][event]: 0 accumulators ready, 1 first TMEM loads back, 2 first chunk stored, 3 buffer released
+#define GE_TRACE(slot) do { if (gtrace && ti < 64) g_gemm_epi_trace[ti * 4 + (slot)] = clock64(); } while (0)
+#define GT_TRACE(slot) do { if (gtrace && it < 128) g_gemm_trace[it * 4 + (slot)] = clock64(); } while (0)
+
+template <bool RELU, bool WLO>
+__global__ void __launch_bounds__(P3_THREADS, 1)
+gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                   const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* __restrict__ table, const int* __restrict__ tidx,
+                   float* __restrict__ C, int M, int N, int K, int ldc, int ldt, int n_tiles_n, int n_tiles) {
+  extern __shared__ unsigned char tc_raw[];
+  P3Smem& sm = *reinterpret_cast<P3Smem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk = K / P_BK;
+  const bool gtrace = g_gemm_debug >= 1 && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < P_STAGES; ++s) {
+      tc_mbar_init(&sm.tma_full[s], 1); tc_mbar_init(&sm.full[s], 8); tc_mbar_init(&sm.empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) { tc_mbar_init(&sm.tmem_full[b], 1); tc_mbar_init(&sm.tmem_empty[b], P3_EPI); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ lo producers
+    const int c = tid & 7, rbase = tid >> 3;
+    const int sc = (c ^ (rbase & 7)) << 2;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int s = it % P_STAGES;
+        tc_mbar_wait(&sm.tma_full[s], (it / P_STAGES) & 1);
+        if (warp == 0) GT_TRACE(1);
+        P3Stage& st = sm.stage[s];
+        const uint32_t a_raw = tc_smem_u32(st.a_raw), a_lo = tc_smem_u32(st.a_lo);
+        const uint32_t b_raw = tc_smem_u32(st.b_raw), b_lo = tc_smem_u32(st.b_lo);
+        float4 va[4], vb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t off = (uint32_t)((rbase + 32 * i) * P_BK + sc) * 4u;
+          va[i] = lds128(a_raw + off);
+          if (!WLO) vb[i] = lds128(b_raw + off);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t off = (uint32_t)((rbase + 32 * i) * P_BK + sc) * 4u;
+          sts128(a_lo + off, tc_lo4(va[i]));
+          if (!WLO) sts128(b_lo + off, tc_lo4(vb[i]));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(&sm.full[s]);
+        if (warp == 0) GT_TRACE(2);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    // Per k-step TWO instructions: A_hi x [B_hi ; B_lo] with N = 256 (b_raw and b_lo are adjacent in shared memory and
+    // the main / cross accumulators adjacent in TMEM, so one MMA yields main += A_hi B_hi and cross += A_hi B_lo while
+    // reading A_hi once), then cross += A_lo x B_hi with N = 128.
+    const uint32_t idesc2 = tc_make_idesc(P_BM, 2 * P_BN), idesc1 = tc_make_idesc(P_BM, P_BN);
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1;
+      tc_mbar_wait(&sm.tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_main = tmem + buf * 256, d_cross = d_main + 128;
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int s = it % P_STAGES;
+        tc_mbar_wait(&sm.full[s], (it / P_STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          P3Stage& st = sm.stage[s];
+          const uint64_t dah = tc_make_desc(tc_smem_u32(st.a_raw)), dal = tc_make_desc(tc_smem_u32(st.a_lo));
+          const uint64_t dbh = tc_make_desc(tc_smem_u32(st.b_raw));
+#pragma unroll
+          for (int ks = 0; ks < P_BK / 8; ++ks) {
+            const uint64_t o = (uint64_t)(2 * ks);
+            tc_mma(d_main, dah + o, dbh + o, idesc2, (kc > 0 || ks > 0) ? 1u : 0u);
+            tc_mma(d_cross, dal + o, dbh + o, idesc1, 1u);
+          }
+          GT_TRACE(3);
+          tc_commit(&sm.empty[s]);
+          if (kc == nk - 1) tc_commit(&sm.tmem_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ TMA issuer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles_n) * P_BM, n0 = (tile % n_tiles_n) * P_BN;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % P_STAGES;
+          tc_mbar_wait(&sm.empty[s], ((it / P_STAGES) & 1) ^ 1);
+          P3Stage& st = sm.stage[s];
+          GT_TRACE(0);
+          tc_expect_tx(&sm.tma_full[s], (P_BM + (WLO ? 2 : 1) * P_BN) * P_BK * 4);
+          tc_tma_2d(st.a_raw, &tmA, kc * P_BK, m0, &sm.tma_full[s]);
+          tc_tma_2d(st.b_raw, &tmW, kc * P_BK, n0, &sm.tma_full[s]);
+          if (WLO) tc_tma_2d(st.b_lo, &tmWlo, kc * P_BK, n0, &sm.tma_full[s]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 10..17)
+    const int lg = warp & 3;
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1;
+      const int m0 = (tile / n_tiles_n) * P_BM, n0 = (tile % n_tiles_n) * P_BN;
+      tc_mbar_wait(&sm.tmem_full[buf], (ti >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (warp == 10) GE_TRACE(0);
+      const bool fast = m0 + P_BM <= M && n0 + P_BN <= N && vec_ok && !table && (reinterpret_cast<uintptr_t>(bias) & 7) == 0;
+      const bool nostore = g_gemm_debug == 2;  // timing experiment: no global stores
+#pragma unroll 1
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = 2 * ((warp - 10) >> 2) + jj;  // this warp's 64-column half of the tile
+        const uint32_t ta = tmem + ((uint32_t)(32 * lg) << 16) + buf * 256 + (uint32_t)(32 * j);
+        if (fast)
+          tc_epilogue_chunk_frag<RELU, true>(ta, ta + 128, m0 + 32 * lg, M, n0 + 32 * j, N, bias, table, tidx, ldt, C, ldc, vec_ok, lane, nostore);
+        else
+          tc_epilogue_chunk_frag<RELU, false>(ta, ta + 128, m0 + 32 * lg, M, n0 + 32 * j, N, bias, table, tidx, ldt, C, ldc, vec_ok, lane, nostore);
+        if (warp == 10 && jj == 0) GE_TRACE(2);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      tc_mbar_arrive(&sm.tmem_empty[buf]);
+      if (warp == 10) GE_TRACE(3);
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// =====================================================================================================================
+// v4: CTA pair (cta_group::2).  Two CTAs of a cluster (the two SMs of a TPC) compute one 256 x 128 output tile: each
+// keeps its own 128 rows of A (raw + lo) and its own 128 accumulator rows, but the B operand of every MMA is SPLIT
+// between the two shared memories and read once for both tensor cores:
+//   MMA1  [main | cross] += A_hi x [B_hi ; B_lo]   M = 256, N = 256: CTA 0 stages B_hi (128 rows), CTA 1 stages B_lo
+//   MMA2  cross          += A_lo x B_hi            M = 256, N = 128: CTA 0 stages B_hi rows 0..63, CTA 1 rows 64..127
+// Shared-memory traffic per CTA and k-slab drops from 160 KB to 128 KB (the single-CTA kernel is bound by it) and the
+// 40 KB stages allow a 4-deep TMA ring.  Only the leader (rank 0) issues MMAs; its barriers collect the B tiles and
+// the A_lo tiles of both CTAs (remote arrivals from rank 1), its tcgen05.commit is multicast to both CTAs.
+constexpr int PP_STAGES = 4, PP_LO = 2;
+struct alignas(1024) PPStage {
+  float a_raw[P_BM * P_BK];       // own 128 rows of A
+  float b1[P_BN * P_BK];          // rank 0: W rows n0..n0+127 (B_hi); rank 1: the same rows of W_lo (B_lo)
+  float b2[(P_BN / 2) * P_BK];    // W rows n0 + 64 rank .. + 63
+};
+struct PPSmem {
+  PPStage stage[PP_STAGES];
+  float a_lo[PP_LO][P_BM * P_BK];
+  uint64_t a_full[PP_STAGES];     // local:  own A tile landed
+  uint64_t b_full[PP_STAGES];     // LEADER: B tiles of both CTAs landed
+  uint64_t empty[PP_STAGES];      // local:  stage consumed (leader's commit, multicast)
+  uint64_t lo_full[PP_LO];        // LEADER: A_lo of both CTAs published (2 x 8 warps)
+  uint64_t lo_empty[PP_LO];       // local:  (commit multicast)
+  uint64_t tmem_full[2];          // local:  (commit multicast)
+  uint64_t tmem_empty[2];         // LEADER: both epilogues drained the buffer (2 x 8 warps)
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pp_cta_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void pp_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA 0 of the pair (cutlass Sm100MmaPeerBitMask)
+__device__ __forceinline__ uint32_t pp_leader(const void* p) { return tc_smem_u32(p) & 0xFEFFFFFFu; }
+__device__ __forceinline__ void pp_arrive_leader(const uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(pp_leader(bar)) : "memory");
+}
+__device__ __forceinline__ void pp_expect_tx_leader(const uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(pp_leader(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pp_tma_2d_leader(void* dst, const CUtensorMap* map, int c0, int c1, const uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(tc_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(pp_leader(bar)) : "memory");
+}
+__device__ __forceinline__ void pp_commit(uint64_t* bar) {  // arrives on `bar` of BOTH CTAs when the prior MMAs retire
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(tc_smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void pp_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+template <bool RELU>
+__global__ void __launch_bounds__(P3_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmW64,
+                    const float* __restrict__ bias, const float* __restrict__ table, const int* __restrict__ tidx,
+                    float* __restrict__ C, int M, int N, int K, int ldc, int ldt, int n_tiles_n, int n_pair_tiles) {
+  extern __shared__ unsigned char tc_raw[];
+  PPSmem& sm = *reinterpret_cast<PPSmem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk = K / P_BK;
+  const uint32_t rank = pp_cta_rank();
+  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < PP_STAGES; ++s) { tc_mbar_init(&sm.a_full[s], 1); tc_mbar_init(&sm.b_full[s], 2); tc_mbar_init(&sm.empty[s], 1); }
+    for (int b = 0; b < PP_LO; ++b) { tc_mbar_init(&sm.lo_full[b], 16); tc_mbar_init(&sm.lo_empty[b], 1); }
+    for (int b = 0; b < 2; ++b) { tc_mbar_init(&sm.tmem_full[b], 1); tc_mbar_init(&sm.tmem_empty[b], 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  pp_cluster_sync();  // the peer's barriers are initialised before anything arrives on them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ A_lo producers (both CTAs)
+    const int c = tid & 7, rbase = tid >> 3;
+    const int sc = (c ^ (rbase & 7)) << 2;
+    uint32_t it = 0;
+    for (int pt = pair0; pt < n_pair_tiles; pt += pair_stride) {
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int s = it % PP_STAGES, lb = it % PP_LO;
+        tc_mbar_wait(&sm.a_full[s], (it / PP_STAGES) & 1);
+        tc_mbar_wait(&sm.lo_empty[lb], ((it / PP_LO) & 1) ^ 1);
+        const uint32_t a_raw = tc_smem_u32(sm.stage[s].a_raw), a_lo = tc_smem_u32(sm.a_lo[lb]);
+        float4 va[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) va[i] = lds128(a_raw + (uint32_t)((rbase + 32 * i) * P_BK + sc) * 4u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sts128(a_lo + (uint32_t)((rbase + 32 * i) * P_BK + sc) * 4u, tc_lo4(va[i]));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) pp_arrive_leader(&sm.lo_full[lb]);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      const uint32_t idesc2 = tc_make_idesc(2 * P_BM, 2 * P_BN), idesc1 = tc_make_idesc(2 * P_BM, P_BN);
+      uint32_t it = 0, ti = 0;
+      for (int pt = pair0; pt < n_pair_tiles; pt += pair_stride, ++ti) {
+        const uint32_t buf = ti & 1;
+        tc_mbar_wait(&sm.tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_main = tmem + buf * 256, d_cross = d_main + 128;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % PP_STAGES, lb = it % PP_LO;
+          tc_mbar_wait(&sm.b_full[s], (it / PP_STAGES) & 1);
+          tc_mbar_wait(&sm.lo_full[lb], (it / PP_LO) & 1);  // implies that both A tiles have landed
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            PPStage& st = sm.stage[s];
+            const uint64_t dah = tc_make_desc(tc_smem_u32(st.a_raw)), dal = tc_make_desc(tc_smem_u32(sm.a_lo[lb]));
+            const uint64_t db1 = tc_make_desc(tc_smem_u32(st.b1)), db2 = tc_make_desc(tc_smem_u32(st.b2));
+#pragma unroll
+            for (int ks = 0; ks < P_BK / 8; ++ks) {
+              const uint64_t o = (uint64_t)(2 * ks);
+              pp_mma(d_main, dah + o, db1 + o, idesc2, (kc > 0 || ks > 0) ? 1u : 0u);
+              pp_mma(d_cross, dal + o, db2 + o, idesc1, 1u);
+            }
+            pp_commit(&sm.empty[s]);
+            pp_commit(&sm.lo_empty[lb]);
+            if (kc == nk - 1) pp_commit(&sm.tmem_full[buf]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ TMA issuer (both CTAs)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int pt = pair0; pt < n_pair_tiles; pt += pair_stride) {
+        const int m0 = (2 * (pt / n_tiles_n) + (int)rank) * P_BM, n0 = (pt % n_tiles_n) * P_BN;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % PP_STAGES;
+          tc_mbar_wait(&sm.empty[s], ((it / PP_STAGES) & 1) ^ 1);
+          PPStage& st = sm.stage[s];
+          tc_expect_tx(&sm.a_full[s], P_BM * P_BK * 4);
+          tc_tma_2d(st.a_raw, &tmA, kc * P_BK, m0, &sm.a_full[s]);
+          pp_expect_tx_leader(&sm.b_full[s], (P_BN + P_BN / 2) * P_BK * 4);
+          pp_tma_2d_leader(st.b1, rank == 0 ? &tmW : &tmWlo, kc * P_BK, n0, &sm.b_full[s]);
+          pp_tma_2d_leader(st.b2, &tmW64, kc * P_BK, n0 + (int)rank * (P_BN / 2), &sm.b_full[s]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 10..17, both CTAs)
+    const int lg = warp & 3;
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    uint32_t ti = 0;
+    for (int pt = pair0; pt < n_pair_tiles; pt += pair_stride, ++ti) {
+      const uint32_t buf = ti & 1;
+      const int m0 = (2 * (pt / n_tiles_n) + (int)rank) * P_BM, n0 = (pt % n_tiles_n) * P_BN;
+      tc_mbar_wait(&sm.tmem_full[buf], (ti >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool fast = m0 + P_BM <= M && n0 + P_BN <= N && vec_ok && !table && (reinterpret_cast<uintptr_t>(bias) & 7) == 0;
+#pragma unroll 1
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = 2 * ((warp - 10) >> 2) + jj;
+        const uint32_t ta = tmem + ((uint32_t)(32 * lg) << 16) + buf * 256 + (uint32_t)(32 * j);
+        if (fast)
+          tc_epilogue_chunk_frag<RELU, true>(ta, ta + 128, m0 + 32 * lg, M, n0 + 32 * j, N, bias, table, tidx, ldt, C, ldc, vec_ok, lane, false);
+        else
+          tc_epilogue_chunk_frag<RELU, false>(ta, ta + 128, m0 + 32 * lg, M, n0 + 32 * j, N, bias, table, tidx, ldt, C, ldc, vec_ok, lane, false);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) pp_arrive_leader(&sm.tmem_empty[buf]);
+    }
+  }
+  __syncthreads();
+  pp_cluster_sync();  // nobody leaves (or frees TMEM) while the peer may still read its operands or signal its barriers
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(EncodeTiledFn enc, CUtensorMap* map, const float* base, int rows, int K, int ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)P_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(-5, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld);
+  return 0;
+}
+
+// lo = x - trunc13(x) copies of the registered weights (ctrlsim_finalize_weights): when the W operand of a GEMM lies
+// inside a registered tensor its lo tile is fetched by TMA instead of being derived in shared memory by the producers.
+struct LoRange { const void* owner; const float* base; size_t count; const float* lo; };
+static std::vector<LoRange> g_lo_ranges;
+void gemm_clear_weight_lo(const void* owner) {
+  for (size_t i = 0; i < g_lo_ranges.size();)
+    if (g_lo_ranges[i].owner == owner) g_lo_ranges.erase(g_lo_ranges.begin() + i); else ++i;
+}
+void gemm_register_weight_lo(const void* owner, const float* base, size_t count, const float* lo) {
+  for (size_t i = 0; i < g_lo_ranges.size();) {  // a range overlapping the new one describes memory that was re-used
+    const LoRange& r = g_lo_ranges[i];
+    if (base < r.base + r.count && r.base < base + count) g_lo_ranges.erase(g_lo_ranges.begin() + i); else ++i;
+  }
+  g_lo_ranges.push_back({owner, base, count, lo});
+}
+static const float* find_weight_lo(const float* W, size_t span) {
+  for (const LoRange& r : g_lo_ranges)
+    if (W >= r.base && W + span <= r.base + r.count) return r.lo + (W - r.base);
+  return nullptr;
+}
+__global__ void weight_lo_kernel(const float* __restrict__ w, float* __restrict__ lo, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float x = w[i]; lo[i] = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+}
+int launch_weight_lo(const float* w, float* lo, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  weight_lo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, lo, n);
+  CS_CHECK_LAUNCH("weight_lo");
+  return 0;
+}
+
+static int launch_gemm_tc_tma(const GemmArgs& g, cudaStream_t st) {
+  static int n_sm = 0;
+  static EncodeTiledFn enc = nullptr;
+  const int smem = (int)sizeof(P3Smem) + 1024;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) { n_sm = 0; return set_error(-5, "cuTensorMapEncodeTiled entry point unavailable"); }
+    enc = reinterpret_cast<EncodeTiledFn>(fn);
+    e = cudaFuncSetAttribute(gemm_tc_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { n_sm = 0; return set_error(-5, "gemm_tc_tma smem attr: %s", cudaGetErrorString(e)); }
+  }
+  CUtensorMap tmA, tmW, tmWlo;
+  int rc;
+  if ((rc = make_map(enc, &tmA, g.A, g.M, g.K, g.lda, P_BM))) return rc;
+  if ((rc = make_map(enc, &tmW, g.W, g.N, g.K, g.ldw, P_BN))) return rc;
+  const float* wlo = find_weight_lo(g.W, (size_t)(g.N - 1) * g.ldw + g.K);
+  if (wlo && (reinterpret_cast<uintptr_t>(wlo) & 15)) wlo = nullptr;
+  if (wlo) { if ((rc = make_map(enc, &tmWlo, wlo, g.N, g.K, g.ldw, P_BN))) return rc; }
+  else tmWlo = tmW;
+  const int tn = (g.N + P_BN - 1) / P_BN, tm = (g.M + P_BM - 1) / P_BM;
+  const long long tiles = (long long)tn * tm;
+  {  // CTA-pair kernel for the big GEMMs (registered weights, whole 128-row W tiles); CTRLSIM_GEMM=tc3 keeps v3
+    static int pair_mode = -1;
+    if (pair_mode < 0) {
+      const char* e = getenv("CTRLSIM_GEMM");
+      pair_mode = (e && std::string(e) == "tc3") ? 0 : 1;
+      if (pair_mode) {
+        const int psmem = (int)sizeof(PPSmem) + 1024;
+        cudaError_t pe = cudaFuncSetAttribute(gemm_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
+        if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gemm_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
+        if (pe != cudaSuccess) { pair_mode = -1; return set_error(-5, "gemm_tc_pair smem attr: %s", cudaGetErrorString(pe)); }
+      }
+    }
+    if (pair_mode == 1 && wlo && tm >= 8 && g.N % (P_BN / 2) == 0 && g.N >= P_BN) {
+      CUtensorMap tmW64;
+      if ((rc = make_map(enc, &tmW64, g.W, g.N, g.K, g.ldw, P_BN / 2))) return rc;
+      const int pair_tiles = ((tm + 1) / 2) * tn;
+      const int pairs = pair_tiles < n_sm / 2 ? pair_tiles : n_sm / 2;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(P3_THREADS);
+      cfg.dynamicSmemBytes = sizeof(PPSmem) + 1024; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      cudaError_t le;
+      if (g.relu) le = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<true>, tmA, tmW, tmWlo, tmW64, g.bias, g.table, g.tidx, g.C, g.M, g.N, g.K, g.ldc, g.ldt, tn, pair_tiles);
+      else le = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<false>, tmA, tmW, tmWlo, tmW64, g.bias, g.table, g.tidx, g.C, g.M, g.N, g.K, g.ldc, g.ldt, tn, pair_tiles);
+      if (le != cudaSuccess) return set_error(-5, "gemm_tc_pair launch: %s", cudaGetErrorString(le));
+      CS_CHECK_LAUNCH("gemm_tc_pair");
+      return 0;
+    }
+  }
+  const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+#define CS_LAUNCH_TMA(R, L) gemm_tc_tma_kernel<R, L><<<grid, P3_THREADS, smem, st>>>(tmA, tmW, tmWlo, g.bias, g.table, g.tidx, g.C, g.M, g.N, g.K, g.ldc, g.ldt, tn, (int)tiles)
+  if (g.relu) { if (wlo) CS_LAUNCH_TMA(true, true); else CS_LAUNCH_TMA(true, false); }
+  else { if (wlo) CS_LAUNCH_TMA(false, true); else CS_LAUNCH_TMA(false, false); }
+#undef CS_LAUNCH_TMA
+  CS_CHECK_LAUNCH("gemm_tc_tma");
+  return 0;
+}
+
+void set_gemm_debug(int v) { cudaMemcpyToSymbol(g_gemm_debug, &v, sizeof(int)); }
+void read_gemm_trace(long long* out) {
+  cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(long long) * 4 * 128);
+  cudaMemcpyFromSymbol(out + 4 * 128, g_gemm_epi_trace, sizeof(long long) * 4 * 64);
+}
+
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
+  if (g.M <= 0) return 0;
+  if (g.K % TC_BK != 0 || (g.lda & 3) || (g.ldw & 3))
+    return set_error(-2, "gemm_tc: K=%d must be a multiple of %d and lda/ldw multiples of 4", g.K, TC_BK);
+  {  // CTRLSIM_GEMM=tc1 keeps the one-tile-per-CTA kernel above for A/B runs
+    static int v1 = -1;
+    if (v1 < 0) { const char* e = getenv("CTRLSIM_GEMM"); v1 = (e && std::string(e) == "tc1") ? 1 : 0; }
+    static int v2 = -1;
+    if (v2 < 0) { const char* e = getenv("CTRLSIM_GEMM"); v2 = (e && std::string(e) == "tc2") ? 1 : 0; }
+    const bool tma_ok = !g.agather && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.W) & 15) == 0);
+    if (!v1 && !v2 && tma_ok) return launch_gemm_tc_tma(g, st);
+    if (!v1 && v2) return launch_gemm_tc_persistent(g, st);
+  }
+  static bool attr_set = false;
+  const int smem = (int)sizeof(TcSmem) + 1024;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(-5, "gemm_tc smem attr: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.N + TC_BN - 1) / TC_BN);
+  if (g.relu)
+    gemm_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(g.A, g.W, g.bias, g.table, g.tidx, g.agather, g.C, g.M, g.N, g.K,
+                                                         g.lda, g.ldw, g.ldc, g.ldt);
+  else
+    gemm_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(g.A, g.W, g.bias, g.table, g.tidx, g.agather, g.C, g.M, g.N, g.K,
+                                                          g.lda, g.ldw, g.ldc, g.ldt);
+  CS_CHECK_LAUNCH("gemm_tc");
+  return 0;
+}
+
+}  // namespace ctrlsim
