@@ -332,3 +332,62 @@ def test_c_abi_fails_loudly_without_a_gpu_and_on_bad_arguments(cfg):
         assert rc < 0, "ctrlsim_create must not succeed without a CUDA device"
         msg = so.ctrlsim_last_error().decode()
         assert "CUDA" in msg or "sm_100" in msg, msg
+
+
+def _parse_scenario_scalar(scen, steps=90, moving_threshold=0.2, speed_threshold=0.05):
+    """Element-by-element statement of the loader rules (scenario.cc:893-1057, utils/sim.py:20-65) the vectorised
+    ctrlsim_b200.scenario.parse_scenario must reproduce bit for bit."""
+    import math
+    from ctrlsim_b200.scenario import _normalize_angle_f32
+    objs = [o for o in scen["objects"] if bool(o["valid"][0]) and o["type"] == "vehicle"]
+    n, T1 = len(objs), steps + 1
+    gt = np.zeros((n, T1, 4), np.float32)
+    gt_valid = np.zeros((n, T1), np.uint8)
+    target = np.zeros((n, 4), np.float32)
+    moving = np.zeros(n, bool)
+    for i, o in enumerate(objs):
+        gp = o.get("goalPosition", {"x": 0.0, "y": 0.0})
+        target[i, :2] = (gp["x"], gp["y"])
+        for t in range(len(o["position"])):
+            x, y = np.float32(o["position"][t]["x"]), np.float32(o["position"][t]["y"])
+            h = _normalize_angle_f32(o["heading"][t])
+            vx, vy = np.float32(o["velocity"][t]["x"]), np.float32(o["velocity"][t]["y"])
+            sp = np.sqrt(np.float32(vx * vx + vy * vy))
+            if t < T1:
+                gt[i, t] = (x, y, h, sp)
+                gt_valid[i, t] = x != np.float32(-10000.0)
+            if bool(o["valid"][t]):
+                target[i, 2], target[i, 3] = h, sp
+                dx, dy = x - target[i, 0], y - target[i, 1]
+                dist = np.sqrt(np.float32(dx * dx + dy * dy))
+                if sp > np.float32(speed_threshold) or dist > np.float32(moving_threshold):
+                    moving[i] = True
+    segs = []
+    for road in scen["roads"]:
+        g = road["geometry"]
+        if road["type"] != "road_edge" or isinstance(g, dict):
+            continue
+        for k in range(len(g) - 1):
+            segs.append((g[k]["x"], g[k]["y"], g[k + 1]["x"], g[k + 1]["y"]))
+    return dict(gt=gt, gt_valid=gt_valid, moving=moving, target=target, segs=np.asarray(segs, np.float32).reshape(-1, 4))
+
+
+def test_vectorised_scenario_parser_is_bit_identical_to_the_scalar_rules():
+    from ctrlsim_b200.scenario import parse_scenario
+    from ctrlsim_b200.synth import make_scene
+    cases = [make_scene(0, n_vehicles=12, n_roads=2, n_chunks=3),
+             make_scene(3, n_vehicles=9, n_roads=1, n_chunks=2, frac_short=0.5, frac_parked=0.3)]
+    # a track with odd headings (wrap-around on both sides) and an early disappearance
+    o = cases[1]["json"]["objects"][0]
+    for t in range(len(o["heading"])):
+        if o["valid"][t]:
+            o["heading"][t] = -540.0 + 13.7 * t
+    for sc in cases:
+        a = _parse_scenario_scalar(sc["json"])
+        b = parse_scenario(sc["json"], 90, 0.2, 0.05)
+        assert np.array_equal(a["gt"], b["gt"]) and a["gt"].dtype == b["gt"].dtype
+        assert np.array_equal(a["gt_valid"], b["gt_valid"]) and np.array_equal(a["moving"], b["moving"])
+        assert np.array_equal(a["segs"], b["segs"]) and a["segs"].dtype == b["segs"].dtype
+        # goal heading / speed of vehicles that never disappear = the last valid state
+        keep = b["gt_valid"].all(1)
+        assert np.array_equal(a["target"][keep, 2:].astype(np.float64), b["goal"][keep, 2:])
