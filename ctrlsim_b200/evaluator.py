@@ -163,21 +163,19 @@ class B200PolicyEvaluator:
         self.steps, self.dt, self.history_steps = cfg.nocturne.steps, cfg.nocturne.dt, cfg.nocturne.history_steps
         self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
-        if scenes is None:
-            scenes, scene_ids = self._load_files()
-        self.scenes = scenes
-        self.scene_ids = list(range(len(scenes))) if scene_ids is None else list(scene_ids)
+        # reading from disk: the reference stops after num_files_to_evaluate // partitions scenes that were actually
+        # EVALUATED - scenes without preprocessed data or without a candidate agent do not count
+        # (policy_evaluator.py:436-437,445-446,461-464,492), so files are read lazily while scenes are selected
+        self._from_files = scenes is None
+        self.scenes = [] if scenes is None else scenes
+        self.scene_ids = list(range(len(self.scenes))) if scene_ids is None else list(scene_ids)
         self.batch = None
         self.last_summary = None
 
-    def _load_files(self):
+    def _iter_files(self):
         with open(os.path.join(self.cfg.dataset_root, "test_filenames.pkl"), "rb") as f:
             names = pickle.load(f)["test_filenames"]
-        scenes, ids = [], []
-        limit = self.cfg.eval.num_files_to_evaluate // self.cfg.eval.partitions
         for i, name in enumerate(names):
-            if len(scenes) == limit:
-                break
             pkl = os.path.join(self.cfg.dataset_root, "preprocess/test", f"{name[:-5]}_physics.pkl")
             if not os.path.exists(pkl):
                 continue  # the reference silently skips scenes without preprocessed data (policy_evaluator.py:445-446)
@@ -185,35 +183,54 @@ class B200PolicyEvaluator:
                 js = json.load(f)
             with open(pkl, "rb") as f:
                 pre = pickle.load(f)
-            scenes.append({"name": name, "json": js, "preproc": pre})
-            ids.append(i)
-        return scenes, ids
+            yield i, {"name": name, "json": js, "preproc": pre}
 
-    def build_batch(self, eval_threshold=None, keep_replay_only=False):
-        """Shard scenes over ranks (scene i -> rank i mod world) keeping the evaluated-vehicle draw of the
-        single-process evaluator: every rank walks all scenes in order with the same seeded generator.
-        ``keep_replay_only``: keep scenes without any evaluated vehicle (pure log replay, BASELINE config 4) instead of
-        skipping them like the reference evaluator does."""
+    def select_scenes(self, eval_threshold=None, keep_replay_only=False):
+        """Host half of build_batch: walk the scenes in file order with the evaluation's seeded generator, draw the
+        evaluated vehicles of each (policy_evaluator.py:450-464) and keep this rank's share (scene k -> rank k mod
+        world, k counting accepted scenes). Returns (scenes, ids, parsed, evaluated_sets, threshold)."""
         from .scenario import parse_scenario
         cfg = self.cfg
         rng = random.Random(cfg.eval.seed)
         thr = cfg.eval.multi_agent_eval_threshold if eval_threshold is None else eval_threshold
         sc = cfg.nocturne["scenario"]
-        mine, mine_ids, mine_parsed, mine_rng = [], [], [], []
-        for k, s in enumerate(self.scenes):
-            own = k % self.world == self.rank
+        if self._from_files:
+            source = self._iter_files()
+            limit = cfg.eval.num_files_to_evaluate // cfg.eval.partitions
+            self.scenes, self.scene_ids = [], []
+        else:
+            source = zip(self.scene_ids, self.scenes)
+            limit = None
+        mine, mine_ids, mine_parsed, mine_ev = [], [], [], []
+        accepted = 0
+        for sid, s in source:
+            if limit is not None and accepted == limit:
+                break
             p = parse_scenario(s["json"], self.steps, sc["moving_threshold"], sc["speed_threshold"])
             moving = [i for i in range(p["n"]) if p["moving"][i]]
             ev = rng.sample(moving, thr) if len(moving) > thr else moving
             if not ev and not keep_replay_only:
                 continue  # no candidate agent: scene skipped (policy_evaluator.py:461-464)
+            own = accepted % self.world == self.rank
+            accepted += 1
+            if self._from_files:
+                self.scenes.append(s if own else None)  # other ranks' scenes are not kept in memory
+                self.scene_ids.append(sid)
             if own:
                 mine.append(s)
-                mine_ids.append(self.scene_ids[k])
+                mine_ids.append(sid)
                 mine_parsed.append(p)
-                mine_rng.append(ev)
-        self.batch = SceneBatch(cfg, mine, mine_ids, self.policy.model.device, thr, parsed=mine_parsed,
-                                evaluated_sets=mine_rng)
+                mine_ev.append(ev)
+        return mine, mine_ids, mine_parsed, mine_ev, thr
+
+    def build_batch(self, eval_threshold=None, keep_replay_only=False):
+        """Shard scenes over ranks keeping the evaluated-vehicle draw of the single-process evaluator: every rank walks
+        all scenes in order with the same seeded generator (select_scenes).
+        ``keep_replay_only``: keep scenes without any evaluated vehicle (pure log replay, BASELINE config 4) instead of
+        skipping them like the reference evaluator does."""
+        mine, mine_ids, mine_parsed, mine_ev, thr = self.select_scenes(eval_threshold, keep_replay_only)
+        self.batch = SceneBatch(self.cfg, mine, mine_ids, self.policy.model.device, thr, parsed=mine_parsed,
+                                evaluated_sets=mine_ev)
         return self.batch
 
     def rollout(self, batch=None, max_steps=None):

@@ -84,6 +84,13 @@ class DeviceModel:
         self._ws = None
         self._ws_groups = 0
 
+    @classmethod
+    def load_from_checkpoint(cls, model_path, cfg, device="cuda:0"):
+        """Mirror of ``CtRLSim.load_from_checkpoint(model_path)`` (eval_sim.py:52): a Lightning ``.ckpt`` -> device model.
+        Names and shapes are checked against ``cfg`` before anything is uploaded (checkpoint.load_checkpoint)."""
+        from .checkpoint import load_checkpoint
+        return cls(cfg, load_checkpoint(model_path, cfg), device)
+
     def workspace(self, groups: int):
         if self._ws is None or self._ws_groups < groups:
             nbytes = int(self.lib.ctrlsim_workspace_bytes(self.handle, groups))

@@ -391,3 +391,74 @@ def test_vectorised_scenario_parser_is_bit_identical_to_the_scalar_rules():
         # goal heading / speed of vehicles that never disappear = the last valid state
         keep = b["gt_valid"].all(1)
         assert np.array_equal(a["target"][keep, 2:].astype(np.float64), b["goal"][keep, 2:])
+
+
+# ---- on-disk formats: checkpoint import and the evaluator's file reader ------------------------------
+def test_param_spec_matches_the_reference_state_dict(cfg):
+    """tests/golden/state_dict_spec.json = names and shapes of the unmodified reference CtRLSim().state_dict()
+    (oracle/make_state_dict_spec.py): the checkpoint importer must expect exactly these tensors."""
+    import json
+    from ctrlsim_b200.weights import param_spec
+    with open(os.path.join(ROOT, "tests", "golden", "state_dict_spec.json")) as f:
+        ref = json.load(f)
+    mine = {k: list(s) for k, s, _ in param_spec(cfg)}
+    assert mine == ref
+    assert sum(int(np.prod(s)) for s in ref.values()) == 8285762  # 8.29 M parameters (SURVEY 8(a))
+
+
+def test_lightning_checkpoint_import_round_trip_and_errors(tmp_path, cfg):
+    import torch
+    from ctrlsim_b200.checkpoint import CheckpointError, check_state_dict, load_checkpoint, save_checkpoint
+    from ctrlsim_b200.weights import make_weights
+    w = make_weights(cfg, seed=3)
+    path = str(tmp_path / "model.ckpt")
+    save_checkpoint(w, path, cfg)
+    blob = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(blob) >= {"state_dict", "pytorch-lightning_version", "hyper_parameters"}  # what load_from_checkpoint reads
+    got = load_checkpoint(path, cfg)
+    assert list(got) == list(w)
+    assert all(got[k].dtype == np.float32 and np.array_equal(got[k], w[k]) for k in w)
+    # wrapper prefixes (EMA / DataParallel / compiled modules) and a bare state_dict file
+    torch.save({"model." + k: torch.from_numpy(v) for k, v in w.items()}, path)
+    got = load_checkpoint(path, cfg)
+    assert all(np.array_equal(got[k], w[k]) for k in w)
+    # the unused future-state head may be absent; anything else missing or mis-shaped is named in the error
+    slim = {k: v for k, v in w.items() if not k.startswith("decoder.predict_future_states")}
+    assert len(check_state_dict(slim, cfg)) == len(slim) < len(w)
+    broken = dict(w)
+    del broken["encoder.map_encoder.map_seeds"]
+    broken["decoder.predict_action.mlp.3.weight"] = broken["decoder.predict_action.mlp.3.weight"][:999]
+    with pytest.raises(CheckpointError) as e:
+        check_state_dict(broken, cfg)
+    assert "encoder.map_encoder.map_seeds" in str(e.value) and "(999, 256)" in str(e.value)
+    with pytest.raises(CheckpointError):
+        check_state_dict(dict(w, stray=np.zeros(3, np.float32)), cfg, strict_unexpected=True)
+
+
+def test_file_reader_counts_only_evaluated_scenes_like_the_reference(tmp_path, cfg):
+    """evaluate_policy stops after num_files_to_evaluate // partitions EVALUATED scenes; scenes without a *_physics.pkl
+    or without a candidate agent are skipped and do not count (policy_evaluator.py:436-437,445-446,461-464,492)."""
+    import copy
+    import types
+    from ctrlsim_b200.evaluator import B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene, write_dataset
+    scenes = [make_scene(70 + i, n_vehicles=6, n_roads=2, n_chunks=2) for i in range(6)]
+    for o in scenes[1]["json"]["objects"]:  # scene 1: nobody moves -> no candidate agent
+        o["position"] = [dict(o["position"][0]) for _ in o["position"]]
+        o["velocity"] = [{"x": 0.0, "y": 0.0} for _ in o["velocity"]]
+        o["goalPosition"] = dict(o["position"][0])
+    paths = write_dataset(str(tmp_path), scenes)
+    os.remove(os.path.join(paths["preprocess_dir"], "test", scenes[2]["name"] + "_physics.pkl"))  # scene 2: no preproc
+    c = copy.deepcopy(cfg)
+    c.dataset_root, c.nocturne_waymo_val_folder = paths["dataset_root"], paths["nocturne_waymo_val_folder"]
+    c.eval.num_files_to_evaluate, c.eval.partitions = 6, 2  # -> 3 evaluated scenes
+    stub = types.SimpleNamespace(model=types.SimpleNamespace(device="cpu"))
+    ev = B200PolicyEvaluator(c, stub)
+    mine, ids, parsed, evs, thr = ev.select_scenes()
+    assert ids == [0, 3, 4]  # file indices: 1 and 2 skipped, 5 beyond the limit
+    assert [s["name"] for s in mine] == [scenes[i]["name"] + ".json" for i in ids]
+    assert all(len(e) > 0 for e in evs) and thr == c.eval.multi_agent_eval_threshold
+    # the same draw as an in-memory evaluation of the accepted scenes (one seeded stream over all scenes walked)
+    ev_mem = B200PolicyEvaluator(c, stub, scenes=[scenes[i] for i in (0, 1, 3, 4)], scene_ids=[0, 1, 3, 4])
+    _, ids_mem, _, evs_mem, _ = ev_mem.select_scenes()
+    assert ids_mem == ids and evs_mem == evs
