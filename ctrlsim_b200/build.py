@@ -54,7 +54,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(LIB, objs):
-        subprocess.check_call([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"])
+        subprocess.check_call([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"])
     return LIB
 
 

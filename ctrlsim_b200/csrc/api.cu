@@ -7,10 +7,23 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "model.h"
 #include "model_ws.h"
+
+namespace {
+// NVTX range over the host-side enqueue of one phase (a no-op unless a profiler is attached): nsys / ncu --nvtx
+// attribute the kernels launched inside to the phase
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+}  // namespace
 
 namespace ctrlsim {
 long long g_launch_count = 0;
@@ -277,7 +290,10 @@ int ctrlsim_observe(CtrlSim* h, CtrlSimBatch* b, int32_t t, void* stream) { retu
 int ctrlsim_plan_groups(CtrlSim* h, CtrlSimBatch* b, int32_t t, int32_t* n_groups_total, void* stream) {
   return launch_plan_groups(*b, t, h->mc, n_groups_total, S(stream));
 }
-int ctrlsim_sim_step(CtrlSim* h, CtrlSimBatch* b, int32_t t, void* stream) { return launch_sim_step(*b, t, h->mc, S(stream)); }
+int ctrlsim_sim_step(CtrlSim* h, CtrlSimBatch* b, int32_t t, void* stream) {
+  NvtxRange r("ctrlsim_sim_step");
+  return launch_sim_step(*b, t, h->mc, S(stream));
+}
 int ctrlsim_metrics(CtrlSim* h, const CtrlSimBatch* b, double* out_scene, int64_t* out_hist, void* stream) {
   return launch_metrics(*b, h->mc, out_scene, reinterpret_cast<long long*>(out_hist), S(stream));
 }
@@ -286,6 +302,7 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
                         void* workspace, int64_t workspace_bytes, int32_t chunk_groups, void* stream) {
   if (!h || !h->finalized) return set_error(-3, "ctrlsim_policy_step: weights not finalized");
   if (n_groups_total <= 0) return 0;
+  NvtxRange nvtx_step("ctrlsim_policy_step");
   cudaStream_t st = S(stream);
   const int Sn = b->n_scenes;
   h->h_group_off.resize(Sn + 1);
@@ -371,6 +388,9 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
       }
       ++chunk_idx;
       MapPlan mp;
+      NvtxRange nvtx_chunk(pc && pc->incr ? "chunk (incremental decode)" : "chunk (full window)");
+      {
+      NvtxRange r_tok("tokenize");
       if (pc && pc->incr) {
         // nothing upstream of the decoder is recomputed; tokenise the last two window steps only
         if ((rc = launch_tokenize(*b, g0, ng, t, 2, ws.tk, h->mc, st, ws.map_sel, 0, t - 1))) return rc;
@@ -395,10 +415,21 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
       } else {
         if ((rc = launch_tokenize(*b, g0, ng, t, n_t, ws.tk, h->mc, st))) return rc;
       }
-      if ((rc = forward_pass1(h->w, ws, ng, n_t, h->n_sm, st, mp, pc))) return rc;
-      if ((rc = launch_resolve_rtg_range(*b, *p, t, s0, s1, g0, h->mc.steps, ws.rtg_logits, st))) return rc;
-      if ((rc = launch_gather_rtg_steps(*b, g0, ng, t, h->mc.steps, ws.rtg_new, st))) return rc;
-      if ((rc = forward_pass2(h->w, ws, ng, n_t, st, pc))) return rc;
+      }
+      {
+        NvtxRange r("pass 1: encoders + decoder -> RTG logits");
+        if ((rc = forward_pass1(h->w, ws, ng, n_t, h->n_sm, st, mp, pc))) return rc;
+      }
+      {
+        NvtxRange r("sample RTG");
+        if ((rc = launch_resolve_rtg_range(*b, *p, t, s0, s1, g0, h->mc.steps, ws.rtg_logits, st))) return rc;
+        if ((rc = launch_gather_rtg_steps(*b, g0, ng, t, h->mc.steps, ws.rtg_new, st))) return rc;
+      }
+      {
+        NvtxRange r("pass 2: last-step rows -> action logits");
+        if ((rc = forward_pass2(h->w, ws, ng, n_t, st, pc))) return rc;
+      }
+      NvtxRange r("sample actions");
       if ((rc = launch_sample_actions(*b, *p, g0, ng, t, ws.act_logits, h->mc, st))) return rc;
     } else {
       int rc;  // scenes without any group still owe their vehicles the "(0,0,0) RTG appended" bookkeeping
