@@ -10,6 +10,13 @@ import torch
 from . import lib as _lib
 from .scenario import parse_scenario, road_arrays
 
+# per-policy state: everything a Policy object owns in the reference (policies/policy.py:45-59: buffers, relevant agent
+# sets) plus the focal groups of the current step; a policy_view() gets its own copies, everything else is the shared world
+POLICY_FIELDS = ("evaluated", "eval_order", "hist_rtg", "relevant", "next_action", "tr_rtg_idx", "tr_act_idx", "n_groups",
+                 "group_off", "group_focal", "group_members", "group_served", "group_scene", "group_local")
+STATIC_FIELDS = {"scene_id", "n_veh", "veh_len", "veh_wid", "gt", "gt_valid", "goal", "goal_norm", "evaluated",
+                 "eval_order", "road_xy", "road_valid", "road_type", "n_poly", "segs", "n_seg"}
+
 _DT = {"int64": torch.int64, "int32": torch.int32, "int16": torch.int16, "int8": torch.int8, "uint8": torch.uint8,
        "float32": torch.float32, "float64": torch.float64}
 MAX_VEH = 64
@@ -56,6 +63,7 @@ class SceneBatch:
         host["tr_rtg_idx"][:] = -1
         host["tr_act_idx"][:] = -1
         self.evaluated_ids = []
+        self._gt_len = [p["gt_valid"].astype(np.float64).sum(axis=1).astype(np.int64) for p in parsed]
         ids = list(range(S)) if scene_ids is None else list(scene_ids)
         for s, (p, (rxy, rvalid, rtype)) in enumerate(zip(parsed, roads)):
             n = p["n"]
@@ -86,6 +94,47 @@ class SceneBatch:
         self.struct = _lib.CtrlSimBatch(n_scenes=S, max_veh=N, max_poly=Pm, max_seg=E,
                                         **{k: self.t[k].data_ptr() for k, _, _ in _lib.BATCH_FIELDS})
         self.n_total = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._owned = set(self.t)
+
+    def policy_view(self, evaluated_sets, gt=None):
+        """A second policy's view of the SAME world (planner-vs-adversary evaluation, evaluators/
+        planner_adversary_evaluator.py:466-540: two Policy objects share one vehicle_data_dict and one simulator).
+        The view shares every world array (static scene data, simulator state, history of states and actions, trace)
+        with this batch and owns fresh per-policy state (POLICY_FIELDS) for its own set of controlled vehicles.
+        ``gt``: optional replacement of the log-replay targets [S,N,T1,4] (a scripted trajectory for some vehicle)."""
+        v = object.__new__(SceneBatch)
+        v.__dict__.update({k: getattr(self, k) for k in ("cfg", "device", "steps", "S", "N", "Pm", "E", "_gt_len")})
+        v.t = dict(self.t)
+        own = {}
+        for k in POLICY_FIELDS:
+            own[k] = torch.zeros_like(self.t[k])
+        own["eval_order"].fill_(-1)
+        own["hist_rtg"][..., 1:] = 35
+        own["tr_rtg_idx"].fill_(-1)
+        own["tr_act_idx"].fill_(-1)
+        ev_host = np.zeros((self.S, self.N), np.uint8)
+        order_host = -np.ones((self.S, self.N), np.int32)
+        v.evaluated_ids = []
+        for s, ev in enumerate(evaluated_sets):
+            ev = [int(x) for x in ev]
+            v.evaluated_ids.append(sorted(ev))
+            ev_host[s, ev] = 1
+            if ev:  # descending GT length like SceneBatch.__init__ (autoregressive_policy.py:88-94)
+                order = np.argsort(np.array([int(self._gt_len[s][x]) for x in ev]))[::-1]
+                order_host[s, :len(ev)] = np.array(ev)[order]
+        own["evaluated"].copy_(torch.from_numpy(ev_host))
+        own["eval_order"].copy_(torch.from_numpy(order_host))
+        v._init_dynamic = {k: own[k].cpu().numpy() for k in ("hist_rtg", "tr_rtg_idx", "tr_act_idx")}
+        v.t.update(own)
+        v._owned = set(POLICY_FIELDS)
+        if gt is not None:
+            v.t["gt"] = torch.as_tensor(np.ascontiguousarray(gt, np.float64)).to(self.device)
+            assert v.t["gt"].shape == self.t["gt"].shape
+            v._owned.add("gt")
+        v.struct = _lib.CtrlSimBatch(n_scenes=self.S, max_veh=self.N, max_poly=self.Pm, max_seg=self.E,
+                                     **{k: v.t[k].data_ptr() for k, _, _ in _lib.BATCH_FIELDS})
+        v.n_total = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return v
 
     @property
     def ptr(self):
@@ -93,10 +142,8 @@ class SceneBatch:
 
     def reset_dynamic(self):
         """Policy.reset (policies/policy.py:45-59): clear history, trace and group state for a new episode."""
-        static = {"scene_id", "n_veh", "veh_len", "veh_wid", "gt", "gt_valid", "goal", "goal_norm", "evaluated",
-                  "eval_order", "road_xy", "road_valid", "road_type", "n_poly", "segs", "n_seg"}
         for k, v in self.t.items():
-            if k in static:
+            if k in STATIC_FIELDS or k not in self._owned:
                 continue
             if k in self._init_dynamic:
                 v.copy_(torch.from_numpy(self._init_dynamic[k]))

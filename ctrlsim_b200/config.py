@@ -10,6 +10,7 @@ Values follow (reference file:line):
   cfgs/model/base.yaml:1-18, cfgs/model/ctrl_sim.yaml:4-9   model sizes
   cfgs/config.yaml:41-90              nocturne steps/dt/history, scenario dict, reward config
   cfgs/eval/base.yaml:5-15, cfgs/policy/ctrl_sim.yaml:5-13  eval + policy defaults
+  cfgs/eval_planner_adversary/base.yaml:1-10, cfgs/policy/ctrl_sim_{planner,adversary}.yaml  planner-vs-adversary defaults
 """
 from __future__ import annotations
 
@@ -96,10 +97,18 @@ def default_config() -> AttrDict:
         multi_agent_eval_threshold=8, num_files_to_evaluate=1000, eval_mode="multi_agent", verbose=False,
         seed=0, partitions=1, policy=policy,
     )
+    # cfgs/eval_planner_adversary/base.yaml, cfgs/policy/ctrl_sim_planner.yaml, cfgs/policy/ctrl_sim_adversary.yaml
+    epa = dict(
+        history_steps=10, verbose=False, seed=0, visualize=False, visualization_data_path="",
+        num_files_to_evaluate=1000,
+        planner=dict(policy, goal_tilt=10, veh_veh_tilt=10, veh_edge_tilt=10),
+        adversary=dict(policy, goal_tilt=0, veh_veh_tilt=-10, veh_edge_tilt=0),
+    )
     train = dict(seed=0, max_steps=200000, warmup_steps=500, lr=5e-4, weight_decay=1e-4, finetuning=False)
     cfg = AttrDict.wrap(dict(
-        dataset_root="", project_root="", nocturne_waymo_val_folder="",
+        dataset_root="", project_root="", nocturne_waymo_val_folder="", nocturne_waymo_val_interactive_folder="",
         dataset=dict(waymo=waymo), model=model, nocturne=nocturne, eval=evalc, train=train,
+        eval_planner_adversary=epa, cat=dict(dict_path=""),
     ))
     # the scenario dict is handed to pybind as-is by the reference: keep it a plain dict
     cfg.nocturne["scenario"] = dict(nocturne["scenario"])

@@ -299,8 +299,8 @@ sim_reset_kernel(CtrlSimBatch b, int T1) {  // T1 = steps + 1
   const bool present = i < n;
   float x = 0, y = 0, heading = 0, speed = 0, len = 1, wid = 1;
   if (present) {
-    const float* g0 = b.gt + (((size_t)s * N + i) * T1 + 0) * 4;
-    x = g0[0]; y = g0[1]; heading = g0[2]; speed = g0[3];
+    const double* g0 = b.gt + (((size_t)s * N + i) * T1 + 0) * 4;  // float32-valued (expert states of the simulator)
+    x = (float)g0[0]; y = (float)g0[1]; heading = (float)g0[2]; speed = (float)g0[3];
     len = b.veh_len[(size_t)s * N + i]; wid = b.veh_wid[(size_t)s * N + i];
     Body B;
     B.thr = B.brk = B.steer = 0.f; B.awake = 1.f; B.sleep_t = 0.f; B.om = 0.f; B.vx = B.vy = 0.f;
@@ -378,7 +378,7 @@ observe_kernel(CtrlSimBatch b, int t, ModelCfg mc) {
       hs[0] = px; hs[1] = py; hs[2] = vx; hs[3] = vy; hs[4] = head;
       hs[5] = b.veh_len[vi]; hs[6] = b.veh_wid[vi]; hs[7] = ex;
     }
-    const float* g = b.gt + (vi * T1 + t) * 4;
+    const double* g = b.gt + (vi * T1 + t) * 4;
     gx[i] = g[0]; gy[i] = g[1];
   }
   sx[i] = px; sy[i] = py; sex[i] = ex;
@@ -582,7 +582,7 @@ sim_step_kernel(CtrlSimBatch b, int t, ModelCfg mc) {
       if (t > 0 && !exists_t) ex = false;
       if (!ex) teleport = true;
       else {
-        const float* g1 = b.gt + (vi * T1 + t + 1) * 4;
+        const double* g1 = b.gt + (vi * T1 + t + 1) * 4;  // float64: a scripted target need not be float32-valued
         const double vel_gt = g1[3], theta_gt = g1[2], L = len;
         const double sim_vel = o[O_SPEED * N + i], sim_theta = o[O_HEAD * N + i];
         acc = (vel_gt - sim_vel) / mc.dt_d;
@@ -659,7 +659,7 @@ metrics_kernel(CtrlSimBatch b, ModelCfg mc, double* __restrict__ out_scene, long
         if (rw[0] == 1.f) goal = 1;
         if (rw[6] == 1.f) coll = 1;
         if (rw[7] == 1.f) off = 1;
-        const float* g = b.gt + (vi * T1 + t) * 4;
+        const double* g = b.gt + (vi * T1 + t) * 4;
         const double dx = (double)b.tr_pos[(vi * T1 + t) * 2] - (double)g[0];
         const double dy = (double)b.tr_pos[(vi * T1 + t) * 2 + 1] - (double)g[1];
         const double d = sqrt(dx * dx + dy * dy);

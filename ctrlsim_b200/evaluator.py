@@ -78,8 +78,8 @@ class B200Policy:
         return torch.cuda.current_stream(self.model.device).cuda_stream
 
     # ---- the reference's four verbs, batched -----------------------------------------------------------------------
-    def reset(self, batch: SceneBatch):
-        batch.reset_dynamic()
+    def attach_caches(self, batch: SceneBatch):
+        """(Re)attach this policy's polyline-encoder cache, sized for ``batch``, to its model handle."""
         if self.use_map_cache:
             need = int(self.lib.ctrlsim_map_cache_bytes(batch.S, batch.N))
             if self._map_cache is None or self._map_cache.numel() < need:
@@ -88,6 +88,10 @@ class B200Policy:
                                                          self._map_cache.numel()), "ctrlsim_attach_map_cache")
         else:
             _lib.check(self.lib.ctrlsim_attach_map_cache(self.model.handle, None, 0), "ctrlsim_attach_map_cache")
+
+    def reset(self, batch: SceneBatch):
+        batch.reset_dynamic()
+        self.attach_caches(batch)
         _lib.check(self.lib.ctrlsim_sim_reset(self.model.handle, batch.ptr, self._stream()), "ctrlsim_sim_reset")
 
     def update_state(self, batch: SceneBatch, t: int):

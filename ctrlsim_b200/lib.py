@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libctrlsim_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class CtrlSimConfig(C.Structure):
@@ -34,7 +34,7 @@ class CtrlSimConfig(C.Structure):
 # (field name, torch dtype name, shape expression) in the exact order of struct CtrlSimBatch
 BATCH_FIELDS = [
     ("scene_id", "int64", "S"), ("n_veh", "int32", "S"), ("veh_len", "float32", "S,N"), ("veh_wid", "float32", "S,N"),
-    ("gt", "float32", "S,N,T1,4"), ("gt_valid", "uint8", "S,N,T1"), ("goal", "float64", "S,N,4"),
+    ("gt", "float64", "S,N,T1,4"), ("gt_valid", "uint8", "S,N,T1"), ("goal", "float64", "S,N,4"),
     ("goal_norm", "float64", "S,N"), ("evaluated", "uint8", "S,N"), ("eval_order", "int32", "S,N"),
     ("road_xy", "float64", "S,Pm,100,2"), ("road_valid", "uint8", "S,Pm,100"), ("road_type", "int8", "S,Pm"),
     ("n_poly", "int32", "S"), ("segs", "float32", "S,E,4"), ("n_seg", "int32", "S"),

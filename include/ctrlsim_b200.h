@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define CTRLSIM_ABI_VERSION 2
+#define CTRLSIM_ABI_VERSION 3
 #define CTRLSIM_MAX_VEH 64 /* vehicles per scene supported by the grouping kernel (bitmask width) */
 
 /* Model / episode geometry. The kernels are specialised to the reference defaults (cfgs/model/base.yaml:1-9,
@@ -43,7 +43,8 @@ typedef struct CtrlSimBatch {
   const int32_t* n_veh;       /* [S]                                                                               */
   const float* veh_len;       /* [S,N]                                                                             */
   const float* veh_wid;       /* [S,N]                                                                             */
-  const float* gt;            /* [S,N,T1,4] expert x, y, heading, speed (utils/sim.py:20-65)                       */
+  const double* gt;           /* [S,N,T1,4] log-replay targets x, y, heading, speed: the expert states          */
+                              /* (utils/sim.py:20-65, float32-valued) or a scripted track (float64, CAT adversary)  */
   const uint8_t* gt_valid;    /* [S,N,T1]                                                                          */
   const double* goal;         /* [S,N,4] goal x, y, heading, speed (evaluators/evaluator.py:60-76)                 */
   const double* goal_norm;    /* [S,N] initial distance to goal (evaluator.py:79-84)                               */

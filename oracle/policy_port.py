@@ -256,23 +256,13 @@ class RolloutPort:
         return self.model.forward(data)
 
     # ------------------------------------------------------------------------------------------------ loop
-    def run_scene(self, scene_idx, scen_json, preproc, logit_steps=(), max_steps=None, replay_only=False):
-        """replay_only: no vehicle is policy-controlled - every vehicle is log-replayed through the inverse bicycle model
-        (BASELINE config 4; the reference evaluator itself skips scenes without evaluated vehicles)."""
-        cfg, w = self.cfg, self.w
+    def setup_scene(self, scene_idx, scen_json):
+        """Simulator, ground truth, goals and the empty per-scene record (evaluator.py:60-84, policy_evaluator.py:69-96)."""
         steps, dt = self.steps, self.dt
-        run_steps = steps if max_steps is None else max_steps
         parsed = sim_port.parse_scenario(scen_json)
         n = parsed["n"]
         gt = sim_port.ground_truth(parsed, steps)
         sim = sim_port.ScenePort(parsed)
-        moving = [i for i in range(n) if parsed["moving"][i]]
-        evaluated = random.sample(moving, self.eval_threshold) if len(moving) > self.eval_threshold else moving
-        if replay_only:
-            evaluated = []
-        elif not evaluated:
-            return None
-        # goals (evaluator.py:60-76)
         goal = np.zeros((n, 4))
         for i in range(n):
             gp, gh, gs = parsed["target"][i, :2].astype(np.float64), float(parsed["target"][i, 2]), float(parsed["target"][i, 3])
@@ -283,134 +273,176 @@ class RolloutPort:
                     gp, gh, gs = gt[i, k, :2], gt[i, k, 2], gt[i, k, 3]
             goal[i] = (gp[0], gp[1], gh, gs)
         normalizer = np.linalg.norm(sim.position() - goal[:, :2], axis=1)
+        T1 = steps + 1
+        rec = {"scene": scene_idx, "n": n, "pos": np.zeros((n, T1, 2)), "vel": np.zeros((n, T1, 2)),
+               "heading": np.zeros((n, T1)), "existence": np.zeros((n, T1)), "accel": np.zeros((n, T1)),
+               "steer": np.zeros((n, T1)), "reward": np.zeros((n, T1, 8)),
+               "nearest_dist": np.zeros((n, T1)), "gt_nearest_dist": np.zeros((n, T1)),
+               "gt_pos": gt[:, :, :2].copy(), "gt_heading": gt[:, :, 2].copy(), "gt_speed": gt[:, :, 3].copy(),
+               "gt_accel": np.zeros((n, T1)), "goal": goal, "size": parsed["size"].astype(np.float64)}
+        rec["gt_accel"][:, 1:steps - 1] = (gt[:, 2:steps, 3] - gt[:, 0:steps - 2, 3]) / (2 * dt)
+        return {"parsed": parsed, "n": n, "gt": gt, "sim": sim, "goal": goal, "normalizer": normalizer, "rec": rec}
+
+    def policy_record(self, n):
+        """What one Policy object adds to the scene record: sampled bins, RTGs (its key_dict['rtgs']), focal groups."""
+        steps = self.steps
+        return {"rtgs": np.zeros((n, steps, 3)), "rtg_idx": -np.ones((steps, n, 3), np.int32),
+                "act_idx": -np.ones((steps, n), np.int32), "groups": [[] for _ in range(steps)], "logits": {}}
+
+    def new_episode(self, ctx, evaluated, preproc):
+        """Policy.reset (policies/policy.py:45-59) + the served order of get_data (autoregressive_policy.py:88-94)."""
+        n, steps, w, gt = ctx["n"], self.steps, self.w, ctx["gt"]
         lengths = [int(gt[v][:, 4].sum()) for v in evaluated]
         order = np.argsort(np.array(lengths))[::-1]
-        ep = {
+        return {
             "states": np.zeros((n, steps, 8)), "actions": np.zeros((n, steps, 2)), "rtgs": np.zeros((n, steps, 3)),
             "goals": np.zeros((n, steps, w.goal_dim)), "timesteps": np.zeros((n, steps, 1)),
             "types": np.tile(np.eye(5)[1], (n, 1)), "relevant": {},
             "eval_order": list(np.array(evaluated)[order]),
             "road_points": preproc["road_points"], "road_types": preproc["road_types"],
         }
-        T1 = steps + 1
-        rec = {"scene": scene_idx, "n": n, "pos": np.zeros((n, T1, 2)), "vel": np.zeros((n, T1, 2)),
-               "heading": np.zeros((n, T1)), "existence": np.zeros((n, T1)), "accel": np.zeros((n, T1)),
-               "steer": np.zeros((n, T1)), "reward": np.zeros((n, T1, 8)), "rtgs": np.zeros((n, steps, 3)),
-               "nearest_dist": np.zeros((n, T1)), "gt_nearest_dist": np.zeros((n, T1)),
-               "gt_pos": gt[:, :, :2].copy(), "gt_heading": gt[:, :, 2].copy(), "gt_speed": gt[:, :, 3].copy(),
-               "gt_accel": np.zeros((n, T1)), "goal": goal, "size": parsed["size"].astype(np.float64),
-               "evaluated": np.array(sorted(evaluated), np.int32),
-               "rtg_idx": -np.ones((steps, n, 3), np.int32), "act_idx": -np.ones((steps, n), np.int32),
-               "groups": [[] for _ in range(steps)], "logits": {}}
-        rec["gt_accel"][:, 1:steps - 1] = (gt[:, 2:steps, 3] - gt[:, 0:steps - 2, 3]) / (2 * dt)
-        next_act = np.zeros((n, 2))
-        rew_cfg = cfg.nocturne["rew_cfg"]
 
-        def observe(t):
-            pos, head, spd, vel = sim.position(), sim.heading(), sim.speed(), sim.velocity()
-            cv, ce = sim.collisions()
-            rec["pos"][:, t], rec["vel"][:, t], rec["heading"][:, t] = pos, vel, head
-            ex = gt[:, t, 4].copy()
-            if t > 0:
-                ex[rec["existence"][:, t - 1] == 0] = 0
-            rec["existence"][:, t] = ex
-            for i in range(n):
-                prev = t > 0 and rec["reward"][i, t - 1, 0]
-                dist = np.linalg.norm(goal[i, :2] - pos[i])
-                r0 = 1.0 if prev else float(dist < rew_cfg["position_target_tolerance"])
-                r2 = float(np.abs(goal[i, 3] - spd[i]) < rew_cfg["speed_target_tolerance"])
-                r1 = float(np.abs(angle_sub(goal[i, 2], head[i])) < rew_cfg["heading_target_tolerance"])
-                gds, rs = rew_cfg["shaped_goal_distance_scaling"], rew_cfg["reward_scaling"]
-                nz = normalizer[i] if normalizer[i] != 0.0 else 1.0
-                r3 = gds / rs if prev else gds * (1 - dist / nz) / rs
-                r4 = gds * (1 - np.abs(spd[i] - goal[i, 3]) / 40.0) / rs
-                r5 = gds * (1 - np.abs(angle_sub(head[i], goal[i, 2])) / (2 * np.pi)) / rs
-                rec["reward"][i, t] = (r0, r1, r2, r3, r4, r5, float(cv[i]), float(ce[i]))
-            for key, P in (("nearest_dist", pos), ("gt_nearest_dist", gt[:, t, :2])):
-                Pm = np.where(ex[:, None].astype(bool), P, np.inf)
-                with np.errstate(invalid="ignore"):
-                    d2 = ((Pm[:, None] - Pm[None]) ** 2).sum(-1)
-                np.fill_diagonal(d2, np.inf)
-                with np.errstate(invalid="ignore"):
-                    d = np.sqrt(np.min(d2, axis=1))
-                d[d == np.inf] = np.nan
-                rec[key][:, t] = np.nan_to_num(d * ex, nan=0.0) * ex
+    def observe(self, ctx, t):
+        """update_vehicle_data_dict (policy_evaluator.py:99-159) incl. compute_reward (utils/sim.py:83-141)."""
+        sim, rec, gt, goal, normalizer, n = ctx["sim"], ctx["rec"], ctx["gt"], ctx["goal"], ctx["normalizer"], ctx["n"]
+        rew_cfg = self.cfg.nocturne["rew_cfg"]
+        pos, head, spd, vel = sim.position(), sim.heading(), sim.speed(), sim.velocity()
+        cv, ce = sim.collisions()
+        rec["pos"][:, t], rec["vel"][:, t], rec["heading"][:, t] = pos, vel, head
+        ex = gt[:, t, 4].copy()
+        if t > 0:
+            ex[rec["existence"][:, t - 1] == 0] = 0
+        rec["existence"][:, t] = ex
+        for i in range(n):
+            prev = t > 0 and rec["reward"][i, t - 1, 0]
+            dist = np.linalg.norm(goal[i, :2] - pos[i])
+            r0 = 1.0 if prev else float(dist < rew_cfg["position_target_tolerance"])
+            r2 = float(np.abs(goal[i, 3] - spd[i]) < rew_cfg["speed_target_tolerance"])
+            r1 = float(np.abs(angle_sub(goal[i, 2], head[i])) < rew_cfg["heading_target_tolerance"])
+            gds, rs = rew_cfg["shaped_goal_distance_scaling"], rew_cfg["reward_scaling"]
+            nz = normalizer[i] if normalizer[i] != 0.0 else 1.0
+            r3 = gds / rs if prev else gds * (1 - dist / nz) / rs
+            r4 = gds * (1 - np.abs(spd[i] - goal[i, 3]) / 40.0) / rs
+            r5 = gds * (1 - np.abs(angle_sub(head[i], goal[i, 2])) / (2 * np.pi)) / rs
+            rec["reward"][i, t] = (r0, r1, r2, r3, r4, r5, float(cv[i]), float(ce[i]))
+        for key, P in (("nearest_dist", pos), ("gt_nearest_dist", gt[:, t, :2])):
+            Pm = np.where(ex[:, None].astype(bool), P, np.inf)
+            with np.errstate(invalid="ignore"):
+                d2 = ((Pm[:, None] - Pm[None]) ** 2).sum(-1)
+            np.fill_diagonal(d2, np.inf)
+            with np.errstate(invalid="ignore"):
+                d = np.sqrt(np.min(d2, axis=1))
+            d[d == np.inf] = np.nan
+            rec[key][:, t] = np.nan_to_num(d * ex, nan=0.0) * ex
 
-        for t in range(run_steps):
-            observe(t)
-            # T1
-            ep["states"][:, t, :2], ep["states"][:, t, 2:4] = rec["pos"][:, t], rec["vel"][:, t]
-            ep["states"][:, t, 4], ep["states"][:, t, 5:7] = rec["heading"][:, t], parsed["size"]
-            ep["states"][:, t, 7] = rec["existence"][:, t]
-            ep["timesteps"][:, t, 0] = t
-            if t > 0:
-                ep["actions"][:, t - 1, 0], ep["actions"][:, t - 1, 1] = rec["accel"][:, t - 1], rec["steer"][:, t - 1]
-                ep["rtgs"][:, t - 1] = rec["rtgs"][:, t - 1]
-            ep["goals"][:, t] = np.stack([goal[:, 0], goal[:, 1], goal[:, 3] * np.cos(goal[:, 2]),
-                                          goal[:, 3] * np.sin(goal[:, 2]), goal[:, 2]], -1)[:, : w.goal_dim]
-            # predict
-            groups, dead = self.plan_groups(ep, t)
-            ti = t if t < w.train_context_length else w.train_context_length - 1
-            done = {}
-            for g, (focal, closest, served, rel) in enumerate(groups):
-                members = -np.ones(w.max_num_agents, np.int32)
-                members[: len(closest)] = closest
-                rec["groups"][t].append({"focal": focal, "members": members, "served": [int(v) for v in served]})
-                slot = {int(a): k for k, a in enumerate(closest)}
-                tok = self.tokenize(ep, t, focal, closest)
-                out = self._forward(tok)
-                rtg_logits = out["rtg_preds"][0, :, ti].numpy()
-                for a in rel:
-                    if a not in done:
-                        tilted = a in served
-                        lg = rtg_logits[slot[a]].reshape(w.rtg_discretization, 3)
-                        done[a] = [sampler.sample_from_x(sampler.rtg_x(lg[:, c], self.tilts[c] if tilted else 0),
-                                                         self.seed, scene_idx, a, t, c) for c in range(3)]
-                        rec["rtg_idx"][t, a] = done[a]
-                    tok["rtgs"][slot[a], ti] = done[a]
-                out2 = self._forward(tok)
-                act_logits = out2["action_preds"][0, :, ti].numpy()
-                if t in logit_steps:
-                    rec["logits"][(t, g)] = {"rtg_logits": rtg_logits.copy(), "action_logits": act_logits.copy()}
-                for v in served:
-                    ax = sampler.action_x(act_logits[slot[v]], self.temperature)
-                    if self.nucleus is None:
-                        idx = sampler.sample_from_x(ax, self.seed, scene_idx, v, t, sampler.COMP_ACTION)
-                    else:
-                        idx = sampler.sample_from_x_nucleus(ax, self.nucleus, self.seed, scene_idx, v, t, sampler.COMP_ACTION)
-                    rec["act_idx"][t, v] = idx
-                    next_act[v, 0] = (idx // w.steer_discretization) / (w.accel_discretization - 1) * (w.max_accel - w.min_accel) + w.min_accel
-                    next_act[v, 1] = (idx % w.steer_discretization) / (w.steer_discretization - 1) * (w.max_steer - w.min_steer) + w.min_steer
-            R = w.rtg_discretization - 1
-            for a, idx in done.items():
-                rec["rtgs"][a, t] = (idx[0] / R * (w.max_rtg_pos - w.min_rtg_pos) + w.min_rtg_pos,
-                                     idx[1] / R * (w.max_rtg_veh - w.min_rtg_veh) + w.min_rtg_veh,
-                                     idx[2] / R * (w.max_rtg_road - w.min_rtg_road) + w.min_rtg_road)
-            for v in dead:
-                next_act[v] = 0.0
-            # act / log replay
-            pos, head, spd = sim.position(), sim.heading(), sim.speed()
-            for i in range(n):
-                if t >= self.hist - 1 and i in evaluated:
-                    if not rec["existence"][i, t]:
-                        a, s = 0.0, 0.0
-                        sim.teleport(i, -1000000, -1000000)
-                    else:
-                        a, s = next_act[i]
+    def update_state(self, ep, ctx, prec, t):
+        """Policy.update_state (policies/policy.py:68-105): world record -> this policy's buffers; RTGs from its own key."""
+        rec, goal, w = ctx["rec"], ctx["goal"], self.w
+        ep["states"][:, t, :2], ep["states"][:, t, 2:4] = rec["pos"][:, t], rec["vel"][:, t]
+        ep["states"][:, t, 4], ep["states"][:, t, 5:7] = rec["heading"][:, t], ctx["parsed"]["size"]
+        ep["states"][:, t, 7] = rec["existence"][:, t]
+        ep["timesteps"][:, t, 0] = t
+        if t > 0:
+            ep["actions"][:, t - 1, 0], ep["actions"][:, t - 1, 1] = rec["accel"][:, t - 1], rec["steer"][:, t - 1]
+            ep["rtgs"][:, t - 1] = prec["rtgs"][:, t - 1]
+        ep["goals"][:, t] = np.stack([goal[:, 0], goal[:, 1], goal[:, 3] * np.cos(goal[:, 2]),
+                                      goal[:, 3] * np.sin(goal[:, 2]), goal[:, 2]], -1)[:, : w.goal_dim]
+
+    def predict_step(self, ep, prec, t, scene_idx, next_act, logit_steps=()):
+        """AutoregressivePolicy.predict (autoregressive_policy.py:168-253) for this policy's served vehicles: writes the
+        sampled bins / RTGs / groups into ``prec`` and the continuous actions into ``next_act`` (its key_dict slots)."""
+        w = self.w
+        groups, dead = self.plan_groups(ep, t)
+        ti = t if t < w.train_context_length else w.train_context_length - 1
+        done = {}
+        for g, (focal, closest, served, rel) in enumerate(groups):
+            members = -np.ones(w.max_num_agents, np.int32)
+            members[: len(closest)] = closest
+            prec["groups"][t].append({"focal": focal, "members": members, "served": [int(v) for v in served]})
+            slot = {int(a): k for k, a in enumerate(closest)}
+            tok = self.tokenize(ep, t, focal, closest)
+            out = self._forward(tok)
+            rtg_logits = out["rtg_preds"][0, :, ti].numpy()
+            for a in rel:
+                if a not in done:
+                    tilted = a in served
+                    lg = rtg_logits[slot[a]].reshape(w.rtg_discretization, 3)
+                    done[a] = [sampler.sample_from_x(sampler.rtg_x(lg[:, c], self.tilts[c] if tilted else 0),
+                                                     self.seed, scene_idx, a, t, c) for c in range(3)]
+                    prec["rtg_idx"][t, a] = done[a]
+                tok["rtgs"][slot[a], ti] = done[a]
+            out2 = self._forward(tok)
+            act_logits = out2["action_preds"][0, :, ti].numpy()
+            if t in logit_steps:
+                prec["logits"][(t, g)] = {"rtg_logits": rtg_logits.copy(), "action_logits": act_logits.copy()}
+            for v in served:
+                ax = sampler.action_x(act_logits[slot[v]], self.temperature)
+                if self.nucleus is None:
+                    idx = sampler.sample_from_x(ax, self.seed, scene_idx, v, t, sampler.COMP_ACTION)
                 else:
-                    exists = gt[i, t, 4] and gt[i, t + 1, 4]
-                    if t > 0 and rec["existence"][i, t] == 0:
-                        exists = 0
-                    if not exists:
-                        a, s = 0.0, 0.0
-                        sim.teleport(i, -1000000, -1000000)
-                    else:
-                        a, s = inverse_bicycle(gt[i, t + 1], pos[i], head[i], spd[i], dt)
-                sim.set_action(i, a, s)
-                rec["accel"][i, t], rec["steer"][i, t] = a, s
+                    idx = sampler.sample_from_x_nucleus(ax, self.nucleus, self.seed, scene_idx, v, t, sampler.COMP_ACTION)
+                prec["act_idx"][t, v] = idx
+                next_act[v, 0] = (idx // w.steer_discretization) / (w.accel_discretization - 1) * (w.max_accel - w.min_accel) + w.min_accel
+                next_act[v, 1] = (idx % w.steer_discretization) / (w.steer_discretization - 1) * (w.max_steer - w.min_steer) + w.min_steer
+        R = w.rtg_discretization - 1
+        for a, idx in done.items():
+            prec["rtgs"][a, t] = (idx[0] / R * (w.max_rtg_pos - w.min_rtg_pos) + w.min_rtg_pos,
+                                  idx[1] / R * (w.max_rtg_veh - w.min_rtg_veh) + w.min_rtg_veh,
+                                  idx[2] / R * (w.max_rtg_road - w.min_rtg_road) + w.min_rtg_road)
+        for v in dead:
+            next_act[v] = 0.0
+
+    def apply_controls(self, ctx, t, controlled, next_act, targets=None):
+        """The per-vehicle loop of evaluate_policy (policy_evaluator.py:526-535): policy.act for controlled vehicles
+        from step history_steps - 1 on, apply_gt_action (evaluator.py:160-193) otherwise.  ``targets`` optionally
+        replaces the log-replay target states of some vehicles ({vehicle: [T1, 8] array})."""
+        sim, rec, gt, n, dt = ctx["sim"], ctx["rec"], ctx["gt"], ctx["n"], self.dt
+        pos, head, spd = sim.position(), sim.heading(), sim.speed()
+        for i in range(n):
+            if t >= self.hist - 1 and i in controlled:
+                if not rec["existence"][i, t]:
+                    a, s = 0.0, 0.0
+                    sim.teleport(i, -1000000, -1000000)
+                else:
+                    a, s = next_act[i]
+            else:
+                exists = gt[i, t, 4] and gt[i, t + 1, 4]
+                if t > 0 and rec["existence"][i, t] == 0:
+                    exists = 0
+                if not exists:
+                    a, s = 0.0, 0.0
+                    sim.teleport(i, -1000000, -1000000)
+                else:
+                    tgt = gt[i, t + 1] if targets is None or i not in targets else targets[i][t + 1]
+                    a, s = inverse_bicycle(tgt, pos[i], head[i], spd[i], dt)
+            sim.set_action(i, a, s)
+            rec["accel"][i, t], rec["steer"][i, t] = a, s
+
+    def run_scene(self, scene_idx, scen_json, preproc, logit_steps=(), max_steps=None, replay_only=False):
+        """replay_only: no vehicle is policy-controlled - every vehicle is log-replayed through the inverse bicycle model
+        (BASELINE config 4; the reference evaluator itself skips scenes without evaluated vehicles)."""
+        steps, dt = self.steps, self.dt
+        run_steps = steps if max_steps is None else max_steps
+        ctx = self.setup_scene(scene_idx, scen_json)
+        n, sim, rec = ctx["n"], ctx["sim"], ctx["rec"]
+        moving = [i for i in range(n) if ctx["parsed"]["moving"][i]]
+        evaluated = random.sample(moving, self.eval_threshold) if len(moving) > self.eval_threshold else moving
+        if replay_only:
+            evaluated = []
+        elif not evaluated:
+            return None
+        ep = self.new_episode(ctx, evaluated, preproc)
+        rec.update(self.policy_record(n))
+        rec["evaluated"] = np.array(sorted(evaluated), np.int32)
+        next_act = np.zeros((n, 2))
+        for t in range(run_steps):
+            self.observe(ctx, t)
+            self.update_state(ep, ctx, rec, t)
+            self.predict_step(ep, rec, t, scene_idx, next_act, logit_steps)
+            self.apply_controls(ctx, t, evaluated, next_act)
             sim.step(dt)
         if run_steps == steps:
-            observe(steps)
+            self.observe(ctx, steps)
             if evaluated:
                 self.metrics.add_scene(rec, evaluated)
         return rec

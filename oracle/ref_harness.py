@@ -238,3 +238,157 @@ def run_reference(scenes, weights=None, seed=0, tilts=(0, 0, 0), temperature=1.0
     finally:
         torch.multinomial = orig_multinomial
     return {k: float(v) for k, v in metrics.items()}, records
+
+
+def run_reference_planner_adversary(scenes, pairs, adv_positions=None, weights=None, seeds=(1, 2),
+                                    tilts_planner=(10, 10, 10), tilts_adversary=(0, -10, 0), cat=False, steps=90,
+                                    workdir=None):
+    """The UNMODIFIED ``PlannerAdversaryEvaluator.evaluate_planner_adversary()``
+    (evaluators/planner_adversary_evaluator.py:466-593) on synthetic scenes.
+
+    ``pairs``: per scene (ego, adversary) JSON object indices; ``adv_positions``: per scene the CAT trajectory [steps+1, 2]
+    (the evaluator requires one in its table even when the adversary is a CtRL-Sim policy, :447-448).
+    ``cat``: the adversary follows that trajectory instead of a policy (cfgs/policy/cat.yaml).
+    Returns (metrics, [per-scene record]); a record holds the world arrays plus 'planner' / 'adversary' sub-records
+    (sampled bins, RTGs, focal groups) like oracle/planner_adversary_port.py."""
+    import pickle
+    import shutil
+    ref_shims.install()
+    import policies.policy as ref_policy_mod
+    import policies.autoregressive_policy as ref_ar_mod
+    from policies import AutoregressivePolicy
+    from evaluators import PlannerAdversaryEvaluator
+
+    tmp = workdir or tempfile.mkdtemp(prefix="ctrlsim_ref_pa_")
+    paths = write_dataset(tmp, scenes)
+    shutil.copytree(os.path.join(paths["preprocess_dir"], "test"), os.path.join(paths["preprocess_dir"], "val_interactive"),
+                    dirs_exist_ok=True)
+    table = {}
+    for k, sc in enumerate(scenes):
+        ent = {"nocturne_path": "x" * 66 + sc["name"] + ".json", "nocturne_sdc_id": int(pairs[k][0]),
+               "nocturne_adversary_id": int(pairs[k][1])}
+        if adv_positions is not None and adv_positions[k] is not None:
+            ent["adv_traj"] = np.asarray(adv_positions[k], np.float64)
+        table[k] = ent
+    dict_path = os.path.join(tmp, "eval_planner_dict.pkl")
+    with open(dict_path, "wb") as f:
+        pickle.dump(table, f)
+    cfg = build_cfg(paths, 2, len(scenes))
+    cfg.nocturne.steps = steps
+    cfg.nocturne_waymo_val_interactive_folder = paths["nocturne_waymo_val_folder"]
+    cfg.cat.dict_path = dict_path
+    cfg.eval_planner_adversary.num_files_to_evaluate = len(scenes)
+    cfg.eval_planner_adversary.verbose = False
+    cfg.eval_planner_adversary.visualize = False
+    if weights is None:
+        weights = make_weights(cfg)
+    model = build_reference_model(cfg, weights)
+
+    Fshim = types.SimpleNamespace(softmax=_softmax_shim)
+    ref_policy_mod.F = Fshim
+    ref_ar_mod.F = Fshim
+    orig_multinomial = torch.multinomial
+    torch.multinomial = _multinomial_shim
+
+    def make_policy(name, tilts, keys):
+        return AutoregressivePolicy(
+            cfg=cfg, model_path="synthetic", model=model, use_rtg=True, predict_rtgs=True, discretize_rtgs=True,
+            real_time_rewards=False, privileged_return=False, max_return=False, min_return=False, key_dict=keys,
+            tilt_dict={"tilt": True, "goal_tilt": tilts[0], "veh_veh_tilt": tilts[1], "veh_edge_tilt": tilts[2]},
+            name=name, action_temperature=1.0, nucleus_sampling=False, nucleus_threshold=0.8)
+
+    planner = make_policy("ctrl_sim", tilts_planner, {"next_acceleration": "next_planner_acceleration",
+                                                      "next_steering": "next_planner_steering", "rtgs": "planner_rtgs"})
+    if cat:
+        adversary = types.SimpleNamespace(name="cat", real_time_rewards=False, model_path="cat", reset=lambda d: None)
+    else:
+        adversary = make_policy("ctrl_sim", tilts_adversary, {"next_acceleration": "next_adversary_acceleration",
+                                                              "next_steering": "next_adversary_steering",
+                                                              "rtgs": "adversary_rtgs"})
+    evaluator = PlannerAdversaryEvaluator(cfg, planner, adversary)
+    records = []
+    scene = {"rec": None}
+
+    def policy_record(n):
+        return {"rtg_idx": -np.ones((steps, n, 3), np.int32), "act_idx": -np.ones((steps, n), np.int32),
+                "groups": [[] for _ in range(steps)], "logits": {}}
+
+    orig_load = evaluator.load_scenario
+
+    def load_scenario(file_path, file):
+        n = len(scenes[int(file)]["json"]["objects"])
+        _Ctx.scene = int(file)
+        scene["rec"] = {"scene": int(file), "n": n, "planner": policy_record(n),
+                        "adversary": None if cat else policy_record(n)}
+        return orig_load(file_path, file)
+
+    evaluator.load_scenario = load_scenario
+
+    def instrument(policy, role, seed):
+        orig_get_data = policy.get_data
+
+        def get_data(gt_data_dict, preproc_data, dset, vehicles_to_evaluate, t):
+            out = orig_get_data(gt_data_dict, preproc_data, dset, vehicles_to_evaluate, t)
+            motion_datas, dead, new_idx, data_veh_ids = out
+            _Ctx.seed, _Ctx.step, _Ctx.rec = seed, int(t), scene["rec"][role]
+            _Ctx.action_queue = [int(v) for f in motion_datas.keys() for v in data_veh_ids[f]]
+            for f in motion_datas.keys():
+                members = -np.ones(24, np.int32)
+                for old, new in new_idx[f].items():
+                    members[new] = int(old)
+                _Ctx.rec["groups"][t].append({"focal": int(f), "members": members,
+                                              "served": [int(v) for v in data_veh_ids[f]]})
+            return out
+
+        policy.get_data = get_data
+        orig_ppr = policy.process_predicted_rtg
+
+        def process_predicted_rtg(rtg_logits, token_index, veh_id, *a, **k):
+            _Ctx.agent, _Ctx.comp = int(veh_id), 0
+            return orig_ppr(rtg_logits, token_index, veh_id, *a, **k)
+
+        policy.process_predicted_rtg = process_predicted_rtg
+
+    instrument(planner, "planner", seeds[0])
+    if not cat:
+        instrument(adversary, "adversary", seeds[1])
+
+    orig_stats = evaluator.update_running_statistics
+
+    def update_running_statistics(data_dict):
+        rec = scene["rec"]
+        ids = sorted(data_dict.keys())
+        T = steps + 1
+
+        def arr(key, sub=None):
+            if sub is None:
+                return np.array([[data_dict[v][key][t] for t in range(T)] for v in ids], dtype=np.float64)
+            return np.array([[[data_dict[v][key][t][s] for s in sub] for t in range(T)] for v in ids], np.float64)
+
+        rec["veh_ids"] = np.array(ids, np.int32)
+        rec["pos"], rec["vel"] = arr("position", ("x", "y")), arr("velocity", ("x", "y"))
+        for dst, src in (("heading", "heading"), ("existence", "existence"), ("accel", "acceleration"),
+                         ("steer", "steering"), ("nearest_dist", "nearest_dist"), ("gt_nearest_dist", "gt_nearest_dist"),
+                         ("gt_heading", "gt_heading"), ("gt_speed", "gt_speed"), ("gt_accel", "gt_acceleration")):
+            rec[dst] = arr(src)
+        rec["gt_pos"] = arr("gt_position", ("x", "y"))
+        rec["reward"] = np.array([[data_dict[v]["reward"][t] for t in range(T)] for v in ids], np.float64)
+        rec["planner"]["rtgs"] = np.array([[data_dict[v]["planner_rtgs"][t] for t in range(steps)] for v in ids], np.float64)
+        if not cat:
+            rec["adversary"]["rtgs"] = np.array([[data_dict[v]["adversary_rtgs"][t] for t in range(steps)] for v in ids],
+                                                np.float64)
+        rec["size"] = np.array([[data_dict[v]["length"], data_dict[v]["width"]] for v in ids], np.float64)
+        rec["ego"], rec["adv"] = int(evaluator.ego_vehicle), int(evaluator.adversary_vehicle)
+        records.append(rec)
+        return orig_stats(data_dict)
+
+    evaluator.update_running_statistics = update_running_statistics
+    try:
+        with torch.no_grad(), np.errstate(invalid="ignore"):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                metrics, _ = evaluator.evaluate_planner_adversary()
+    finally:
+        torch.multinomial = orig_multinomial
+    return {k: float(v) for k, v in metrics.items()}, records

@@ -25,3 +25,18 @@ def load_golden(name):
     spec = json.loads(bytes(g["spec_json"]).decode())
     metrics = json.loads(bytes(g["metrics_json"]).decode())
     return g, spec, metrics
+
+
+def load_planner_adversary_golden(name):
+    """tests/golden/planner_adversary_<name>.npz (oracle/make_golden_planner_adversary.py): per-scene records of the
+    unmodified reference PlannerAdversaryEvaluator, its metrics and the generator arguments."""
+    import json
+    import numpy as np
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"planner_adversary_{name}.npz"))
+    spec = json.loads(bytes(g["spec_json"]).decode())
+    metrics = json.loads(bytes(g["metrics_json"]).decode())
+    recs = []
+    for k in range(len(spec["scenes"])):
+        pre = f"s{k}_"
+        recs.append({key[len(pre):]: g[key] for key in g.files if key.startswith(pre)})
+    return recs, spec, metrics

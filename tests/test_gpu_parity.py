@@ -495,3 +495,79 @@ def test_scene_results_do_not_depend_on_batch_composition(cfg, dev):
         for sid, rec in other.items():
             for f, v in rec.items():
                 assert np.array_equal(v, base[sid][f]), (sid, f, order, chunk)
+
+
+# ---------------------------------------------------------------------------------------------- planner vs adversary
+@pytest.mark.parametrize("name", ["policies", "cat"])
+def test_planner_adversary_matches_reference(cfg, dev, name):
+    """ego driven by the planner policy, one other vehicle by the adversary (a second policy with its
+    own tilts and sampler seed, or the scripted CAT trajectory), everyone else log-replayed - the whole 90-step episode
+    of every scene at once vs the unmodified reference PlannerAdversaryEvaluator (tests/golden/planner_adversary_*.npz,
+    contact-free scenes).
+
+    Sampled bins are compared bit for bit.  Two fp32-class implementations agree on a categorical draw unless the
+    uniform lands within their logit difference (here ~7e-6) of a CDF boundary; with ~60 effective RTG bins that is
+    a few draws in 10^4, and these fixtures sample ~3000.  Such a marginal draw may move an RTG sample to the
+    ADJACENT bin; from there on the two rollouts legitimately differ (a different RTG token is in the context).  So:
+    every draw before a policy's first marginal flip must be identical, the flip must come after the sliding-window
+    regime has started (t >= 32: log replay, hand-over at t = 9, cached and full-window steps are all covered bit-exact),
+    it must be an adjacent-bin flip of an RTG component, and trajectories are compared up to it."""
+    from conftest import load_planner_adversary_golden
+    from ctrlsim_b200.evaluator import B200Policy
+    from ctrlsim_b200.model import DeviceModel
+    from ctrlsim_b200.planner_adversary import B200PlannerAdversaryEvaluator, CatAdversary, vehicle_index_of_object
+    from ctrlsim_b200.synth import make_scene
+    from ctrlsim_b200.weights import make_weights
+    recs, spec, ref_metrics = load_planner_adversary_golden(name)
+    scenes = [make_scene(**s) for s in spec["scenes"]]
+    weights = make_weights(cfg, **spec["weights"])
+    tp, ta = spec["tilts_planner"], spec["tilts_adversary"]
+    tilt = lambda t: {"tilt": True, "goal_tilt": t[0], "veh_veh_tilt": t[1], "veh_edge_tilt": t[2]}
+    planner = B200Policy(cfg, "synthetic", DeviceModel(cfg, weights, dev), tilt_dict=tilt(tp), seed=spec["seeds"][0])
+    if spec["cat"]:
+        adversary = CatAdversary()
+    else:
+        adversary = B200Policy(cfg, "synthetic", DeviceModel(cfg, weights, dev), tilt_dict=tilt(ta), seed=spec["seeds"][1])
+    pairs = [tuple(vehicle_index_of_object(sc["json"], o) for o in p) for sc, p in zip(scenes, spec["pairs"])]
+    ev = B200PlannerAdversaryEvaluator(cfg, planner, adversary, scenes=scenes, pairs=pairs,
+                                       adv_trajs=[r["adv_pos"] for r in recs])
+    metrics, _ = ev.evaluate_planner_adversary()
+    tr = ev.batch.trace()
+    T = 90
+    views = {"planner": ev.view_planner, "adversary": ev.view_adversary}
+    exact = True
+    for s, g in enumerate(recs):
+        assert not (g["reward"][:, :, 6] * g["existence"]).any(), "fixture must be contact-free"
+        n = g["pos"].shape[0]
+        assert tuple(int(x) for x in g["ego_adv"]) == pairs[s]
+        assert (tr["tr_exist"][s, :n, :T + 1] == g["existence"]).all()
+        t_ok = T  # steps [0, t_ok) are free of marginal flips in every policy of this scene
+        for role, view in views.items():
+            if view is None:
+                continue
+            act = view.t["tr_act_idx"][s, :n, :T].cpu().numpy().T
+            rtg = view.t["tr_rtg_idx"][s, :n, :T].cpu().numpy().transpose(1, 0, 2).astype(np.int64)
+            bad_r = np.argwhere(rtg != g[f"{role}_rtg_idx"])
+            bad_a = np.argwhere(act != g[f"{role}_act_idx"])
+            t_r = int(bad_r[:, 0].min()) if len(bad_r) else T
+            t_a = int(bad_a[:, 0].min()) if len(bad_a) else T
+            assert t_a > t_r or t_a == T, (role, "an action draw differs before any RTG draw did", t_a, t_r)
+            if t_r < T:
+                exact = False
+                assert t_r >= 32, (role, s, "draws differ before the sliding-window regime", bad_r[:4].tolist())
+                first = bad_r[bad_r[:, 0] == t_r]
+                for t, v, c in first:
+                    assert abs(int(rtg[t, v, c]) - int(g[f"{role}_rtg_idx"][t, v, c])) == 1, (role, t, v, c)
+            t_ok = min(t_ok, t_r)
+        ex = g["existence"][:, :t_ok + 1].astype(bool)
+        dpos = np.abs(tr["tr_pos"][s, :n, :t_ok + 1].astype(np.float64) - g["pos"][:, :t_ok + 1])[ex].max()
+        ga = np.stack([g["accel"], g["steer"]], -1)
+        dacc = np.abs(tr["tr_action"][s, :n, :t_ok] - ga[:, :t_ok])[ex[:, :t_ok]].max()  # controls applied before the flip
+        assert dpos < POS_TOL and dacc < 2e-4, (s, t_ok, dpos, dacc)
+    for k, v in ref_metrics.items():
+        if isinstance(v, float) and math.isnan(v):
+            assert math.isnan(metrics[k]), (k, metrics[k])
+        elif exact:
+            assert abs(metrics[k] - v) < 1e-4 * max(1.0, abs(v)), (k, metrics[k], v)
+        else:  # a marginal flip happened late in some episode: the aggregate metrics can only move a little
+            assert abs(metrics[k] - v) < 0.05 * max(1.0, abs(v)), (k, metrics[k], v)

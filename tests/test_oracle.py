@@ -462,3 +462,82 @@ def test_file_reader_counts_only_evaluated_scenes_like_the_reference(tmp_path, c
     ev_mem = B200PolicyEvaluator(c, stub, scenes=[scenes[i] for i in (0, 1, 3, 4)], scene_ids=[0, 1, 3, 4])
     _, ids_mem, _, evs_mem, _ = ev_mem.select_scenes()
     assert ids_mem == ids and evs_mem == evs
+
+
+# ---- planner vs adversary --------------------------------------------------------------------------
+def _pa_setup(cfg, spec):
+    from ctrlsim_b200.synth import make_scene
+    from ctrlsim_b200.weights import make_weights
+    scenes = [make_scene(**s) for s in spec["scenes"]]
+    return scenes, make_weights(cfg, **spec["weights"])
+
+
+def _same_metrics(got, ref, tol=1e-9):
+    assert set(got) == set(ref)
+    for k, v in ref.items():
+        if isinstance(v, float) and np.isnan(v):
+            assert np.isnan(got[k]), (k, got[k])
+        else:
+            assert abs(got[k] - v) <= tol * max(1.0, abs(v)), (k, got[k], v)
+
+
+@pytest.mark.parametrize("name", ["policies", "cat"])
+def test_planner_adversary_metrics_match_the_reference(cfg, name):
+    """Both restatements of update_running_statistics / compute_metrics (planner_adversary_evaluator.py:201-428) - the
+    oracle's and the product's host-side PlannerAdversaryStats - on the reference's own per-scene records."""
+    from conftest import load_planner_adversary_golden
+    from ctrlsim_b200.planner_adversary import PlannerAdversaryStats
+    from oracle.planner_adversary_port import PlannerAdversaryMetricsPort
+    recs, spec, ref = load_planner_adversary_golden(name)
+    port, stats = PlannerAdversaryMetricsPort(cfg), PlannerAdversaryStats(cfg)
+    for rec in recs:
+        ego, adv = (int(x) for x in rec["ego_adv"])
+        port.add_scene(rec, ego, adv)
+        stats.add_scene(rec, ego, adv)
+    _same_metrics(port.compute(), ref)
+    _same_metrics(stats.compute(), ref)
+
+
+def test_planner_adversary_port_matches_reference_prefix(cfg):
+    """Two policies on one world (own RTG series, context sets and sampler seeds): first steps of the oracle port vs
+    the unmodified reference evaluator - sampled bins bit-exact, trajectories within float tolerance."""
+    from conftest import load_planner_adversary_golden
+    from oracle.model_port import ModelPort
+    from oracle.planner_adversary_port import PlannerAdversaryPort
+    from oracle.policy_port import RolloutPort
+    recs, spec, _ = load_planner_adversary_golden("policies")
+    scenes, weights = _pa_setup(cfg, spec)
+    mp = ModelPort(cfg, weights)
+    port = PlannerAdversaryPort(cfg, RolloutPort(cfg, mp, seed=spec["seeds"][0], tilts=spec["tilts_planner"]),
+                                RolloutPort(cfg, mp, seed=spec["seeds"][1], tilts=spec["tilts_adversary"]))
+    steps, k = 11, 1  # crosses t = 9, where the policies take over from log replay
+    g, sc, (ego, adv) = recs[k], scenes[k], spec["pairs"][k]
+    rec = port.run_scene(k, sc["json"], sc["preproc"], ego, adv, max_steps=steps)
+    for role in ("planner", "adversary"):
+        assert (rec[role]["act_idx"][:steps] == g[f"{role}_act_idx"][:steps]).all()
+        assert (rec[role]["rtg_idx"][:steps] == g[f"{role}_rtg_idx"][:steps]).all()
+        assert np.abs(rec[role]["rtgs"][:, :steps] - g[f"{role}_rtgs"][:, :steps]).max() < 1e-12
+    assert (rec["planner"]["act_idx"][:steps, ego] >= 0).all() and (rec["adversary"]["act_idx"][:steps, adv] >= 0).all()
+    assert np.abs(rec["pos"][:, :steps] - g["pos"][:, :steps]).max() < 1e-3
+    assert np.abs(rec["accel"][:, :steps] - g["accel"][:, :steps]).max() < 1e-6
+
+
+def test_scripted_adversary_port_matches_reference_prefix(cfg):
+    """CAT adversary: log replay until step 8, then the scripted trajectory through the inverse bicycle model."""
+    from conftest import load_planner_adversary_golden
+    from oracle.model_port import ModelPort
+    from oracle.planner_adversary_port import PlannerAdversaryPort
+    from oracle.policy_port import RolloutPort
+    recs, spec, _ = load_planner_adversary_golden("cat")
+    scenes, weights = _pa_setup(cfg, spec)
+    port = PlannerAdversaryPort(cfg, RolloutPort(cfg, ModelPort(cfg, weights), seed=spec["seeds"][0],
+                                                 tilts=spec["tilts_planner"]), None)
+    steps = 14
+    g, sc, (ego, adv) = recs[0], scenes[0], spec["pairs"][0]
+    rec = port.run_scene(0, sc["json"], sc["preproc"], ego, adv, adv_pos=g["adv_pos"], max_steps=steps)
+    assert (rec["planner"]["act_idx"][:steps] == g["planner_act_idx"][:steps]).all()
+    assert np.abs(rec["pos"][:, :steps] - g["pos"][:, :steps]).max() < 1e-3
+    assert np.abs(rec["accel"][:, :steps] - g["accel"][:, :steps]).max() < 1e-6
+    assert np.abs(rec["steer"][:, :steps] - g["steer"][:, :steps]).max() < 1e-6
+    # the scripted track really differs from the logged one after the hand-over
+    assert np.abs(g["accel"][adv, 9:steps]).max() > 1e-2
