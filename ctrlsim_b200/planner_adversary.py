@@ -340,18 +340,22 @@ class B200PlannerAdversaryEvaluator:
                         "gt_accel": gt_acc, "size": size[s, :n]})
         return out
 
+    def gather(self, stats: PlannerAdversaryStats) -> PlannerAdversaryStats:
+        """The one exchange of an evaluation: every rank contributes the per-scene lists of its scenes (a few hundred
+        floats per scene) and all ranks end up with the statistics of the whole job.  Every metric is a mean or a
+        histogram over these lists, so the rank order of the concatenation only matters at float-summation level."""
+        if self.world == 1:
+            return stats
+        parts = [None] * self.world
+        torch.distributed.all_gather_object(parts, stats.data)
+        merged = PlannerAdversaryStats(self.cfg)
+        merged.merge(parts)
+        return merged
+
     def evaluate_planner_adversary(self):
         self.rollout()
         stats = PlannerAdversaryStats(self.cfg)
         for rec, (ego, adv) in zip(self.records(), self.pairs):
             stats.add_scene(rec, ego, adv)
-        if self.world > 1:
-            parts = [None] * self.world
-            torch.distributed.all_gather_object(parts, stats.data)
-            # scene k lives on rank k mod world: interleave back into file order so that every mean sees the
-            # reference's order (the metrics are order-free up to float summation)
-            merged = PlannerAdversaryStats(self.cfg)
-            merged.merge(parts)
-            stats = merged
-        m = stats.compute()
+        m = self.gather(stats).compute()
         return m, ["{}: {:.6f}".format(k, v) for k, v in m.items()]

@@ -66,6 +66,20 @@ def _worker(rank, world, port, out):
     dist.all_reduce(s)
     if rank == 0:
         np.save(out, s.numpy())
+    # (3) planner-vs-adversary: scenes k -> rank k mod world, per-scene statistics exchanged with all_gather_object
+    from conftest import load_planner_adversary_golden
+    from ctrlsim_b200.planner_adversary import B200PlannerAdversaryEvaluator, CatAdversary, PlannerAdversaryStats
+    recs, spec, ref = load_planner_adversary_golden("policies")
+    pa_scenes = [{"json": {"objects": []}, "preproc": {}, "tag": k} for k in range(len(recs))]
+    pa = B200PlannerAdversaryEvaluator(cfg, stub, CatAdversary(), scenes=pa_scenes, pairs=spec["pairs"],
+                                       adv_trajs=[r["adv_pos"] for r in recs])
+    assert [sc["tag"] for sc in pa.scenes] == [k for k in range(len(recs)) if k % world == rank]
+    st = PlannerAdversaryStats(cfg)
+    for sc, (ego, adv) in zip(pa.scenes, pa.pairs):
+        st.add_scene(recs[sc["tag"]], ego, adv)
+    got = pa.gather(st).compute()
+    for k, v in ref.items():
+        assert (np.isnan(v) and np.isnan(got[k])) or abs(got[k] - v) < 1e-9 * max(1.0, abs(v)), (k, got[k], v)
     dist.barrier()
     dist.destroy_process_group()
 
