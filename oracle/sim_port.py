@@ -47,6 +47,14 @@ def lib():
         L.simo_teleport.argtypes = [P, ctypes.c_int, f, f]
         L.simo_step.argtypes = [P, f, _F, ctypes.c_int]
         L.simo_update_collision.argtypes = [P, _F, ctypes.c_int]
+        L.simc_create.restype = ctypes.c_void_p
+        L.simc_create.argtypes = [ctypes.c_int]
+        L.simc_free.argtypes = [ctypes.c_void_p]
+        L.simc_init_body.argtypes = [P, ctypes.c_void_p, ctypes.c_int]
+        L.simc_teleport.argtypes = [P, ctypes.c_void_p, ctypes.c_int]
+        L.simc_step.argtypes = [P, ctypes.c_void_p, f, _F, ctypes.c_int]
+        L.simc_num_contacts.argtypes = [ctypes.c_void_p]
+        L.simc_num_touching.argtypes = [ctypes.c_void_p]
         L.simo_poly_intersects.argtypes = [ctypes.c_int, _F, _F, ctypes.c_int, _F, _F]
         L.simo_poly_segment_intersects.argtypes = [ctypes.c_int, _F, _F, f, f, f, f]
         _LIB = L
@@ -126,8 +134,11 @@ def parse_scenario(scen: dict):
 class ScenePort:
     """All vehicles of one scene as FreeCars (evaluators/evaluator.py:33-41)."""
 
-    def __init__(self, parsed: dict):
+    def __init__(self, parsed: dict, contacts: bool = False):
+        """``contacts``: run the world step with the Box2D contact restatement (sim_oracle.c, second half) instead of the
+        contact-free subset."""
         self.p = parsed
+        self.contacts = None
         n = parsed["n"]
         self.n = n
         self.arr = {k: np.zeros(n, np.float32) for k in
@@ -143,16 +154,36 @@ class ScenePort:
         for i in range(n):
             L.simo_spawn(ctypes.byref(self.s), i, parsed["pos"][i, 0, 0], parsed["pos"][i, 0, 1],
                          parsed["heading"][i, 0], parsed["speed"][i, 0], parsed["size"][i, 0], parsed["size"][i, 1])
+        if contacts:
+            self.contacts = L.simc_create(n)
+            for i in range(n):
+                L.simc_init_body(ctypes.byref(self.s), self.contacts, i)
         L.simo_update_collision(ctypes.byref(self.s), _fp(self.segs), len(self.segs))  # scenario.cc:263
+
+    def __del__(self):
+        if getattr(self, "contacts", None) and _LIB is not None:
+            try:
+                _LIB.simc_free(self.contacts)
+            except Exception:  # interpreter shutdown
+                pass
+            self.contacts = None
 
     def set_action(self, i, accel, steer):
         lib().simo_set_action(ctypes.byref(self.s), i, np.float32(accel), np.float32(steer))
 
     def teleport(self, i, x, y):
         lib().simo_teleport(ctypes.byref(self.s), i, np.float32(x), np.float32(y))
+        if self.contacts:
+            lib().simc_teleport(ctypes.byref(self.s), self.contacts, i)
 
     def step(self, dt=0.1):
-        lib().simo_step(ctypes.byref(self.s), np.float32(dt), _fp(self.segs), len(self.segs))
+        if self.contacts:
+            lib().simc_step(ctypes.byref(self.s), self.contacts, np.float32(dt), _fp(self.segs), len(self.segs))
+        else:
+            lib().simo_step(ctypes.byref(self.s), np.float32(dt), _fp(self.segs), len(self.segs))
+
+    def n_touching(self):
+        return int(lib().simc_num_touching(self.contacts)) if self.contacts else 0
 
     # getters (float32 values widened to python float, like pybind)
     def position(self):

@@ -3,6 +3,7 @@ the unmodified reference (tests/golden/, oracle/make_golden.py); plus host logic
 import ctypes
 import math
 import os
+import sys
 import re
 
 import numpy as np
@@ -541,3 +542,18 @@ def test_scripted_adversary_port_matches_reference_prefix(cfg):
     assert np.abs(rec["steer"][:, :steps] - g["steer"][:, :steps]).max() < 1e-6
     # the scripted track really differs from the logged one after the hand-over
     assert np.abs(g["accel"][adv, 9:steps]).max() > 1e-2
+
+
+# ---- Box2D contact response (SURVEY 7.3-1 stage 2) --------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["rear", "side", "head", "pile"])
+def test_contact_solver_bit_exact_vs_reference_nocturne(mode):
+    """Vehicles that hit each other: the C restatement of Box2D's broad phase bookkeeping, polygon manifold, warm-started
+    sequential-impulse solver (block solver, 8 + 3 iterations) and island sleeping is bit-identical to the real
+    nocturne_cpp / Box2D for the whole run - through the impact, the pushing phase, a vehicle vanishing mid-contact
+    and the separation.  Each case runs in a fresh process: the reference's b2World is a process singleton whose
+    dynamic tree recycles node ids, and which fixture of a pair is "A" follows those ids (tests/contact_case.py)."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "contact_case.py"), mode], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "bit-exact" in r.stdout, r.stdout[-500:]
