@@ -114,6 +114,7 @@ int ctrlsim_create(const CtrlSimConfig* c, CtrlSim** out) {
   h->mc.min_accel = c->min_accel; h->mc.max_accel = c->max_accel; h->mc.min_steer = c->min_steer; h->mc.max_steer = c->max_steer;
   h->mc.pos_tol = c->pos_tol; h->mc.heading_tol = c->heading_tol; h->mc.speed_tol = c->speed_tol;
   h->mc.goal_dist_scaling = c->goal_dist_scaling; h->mc.reward_scaling = c->reward_scaling;
+  { const char* e = getenv("CTRLSIM_CONTACTS"); h->mc.contacts = !(e && e[0] == '0'); }
   *out = h;
   return 0;
 }

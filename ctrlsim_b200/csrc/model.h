@@ -14,6 +14,7 @@ struct ModelCfg {
   double agent_dist = 60.0;
   double min_accel = -10, max_accel = 10, min_steer = -0.7, max_steer = 0.7;
   double pos_tol = 1.0, heading_tol = 0.3, speed_tol = 1.0, goal_dist_scaling = 0.2, reward_scaling = 1.0;
+  int contacts = 1;     // Box2D contact response between vehicles (sim_contacts.cuh); 0 = contact-free subset
 };
 
 struct MlpW {  // utils/layers.py MLPLayer: Linear - LayerNorm - ReLU - Linear

@@ -18,7 +18,8 @@
 //   S6 act / apply_gt_action / inverse bicycle  policies/autoregressive_policy.py:256-274 ; evaluators/evaluator.py:160-193 ;
 //      nocturne/bicycle_model.py:51-109
 //   S7 update_running_statistics / histograms   evaluators/policy_evaluator.py:162-305
-// Box2D's contact solver is not modelled: overlapping bodies pass through each other (flags are still raised).
+// Box2D's contact response for vehicle-vehicle contacts: sim_contacts.cuh (one thread per scene between the parallel
+// FreeCar step and the parallel Vehicle::Step / collision flags); CTRLSIM_CONTACTS=0 falls back to the contact-free subset.
 //
 // libm: the reference calls glibc sinf/cosf/tanf (results are the correctly rounded fp32 value in all but ~1e-9 of
 // cases).  CUDA's fp32 versions are 1-2 ulp, so those calls are evaluated in fp64 and rounded once.
@@ -97,6 +98,8 @@ __device__ void box_local_center(float hx, float hy, float& lcx, float& lcy) {
   const float inv_mass = 1.0f / mass;
   lcx = lx * inv_mass; lcy = ly * inv_mass;
 }
+
+#include "sim_contacts.cuh"
 
 __device__ __forceinline__ float dampen(float speed, float target, float damping, float dt) {
   const float red = damping * dt;
@@ -311,6 +314,15 @@ sim_reset_kernel(CtrlSimBatch b, int T1) {  // T1 = steps + 1
     body_store(b.body + (size_t)s * B_FIELDS * N, N, i, B);
     float* o = b.obj + (size_t)s * O_FIELDS * N;
     o[O_X * N + i] = x; o[O_Y * N + i] = y; o[O_HEAD * N + i] = heading; o[O_SPEED * N + i] = speed;
+  }
+  __syncthreads();
+  if (i == 0 && b.cstate) {  // contact state: every proxy freshly inserted, no contacts, first step has dtRatio 0
+    __shared__ int scratch[CS_SCRATCH_WORDS];
+    float* w = b.cstate + (size_t)s * cs_words(N);
+    SV sv{b.body + (size_t)s * B_FIELDS * N, b.veh_len + (size_t)s * N, b.veh_wid + (size_t)s * N, N, n};
+    SC c = cs_view(w, N, n, scratch);
+    *c.new_contacts = 1; *c.n_contacts = 0; *c.inv_dt0 = 0.0f;
+    for (int k = 0; k < n; ++k) cs_init_body(sv, c, k);
   }
   update_collision(b, s, i, n, present, x, y, heading, len, wid, sh_obb, sh_seg);
 }
@@ -561,9 +573,13 @@ __global__ void __launch_bounds__(SIM_THREADS)
 sim_step_kernel(CtrlSimBatch b, int t, ModelCfg mc) {
   __shared__ Obb sh_obb[SIM_THREADS];
   __shared__ float4 sh_seg[SEG_TILE];
+  __shared__ int sh_scratch[CS_SCRATCH_WORDS];
+  __shared__ CsScratch sh_solver;
+  __shared__ bool sh_tele[SIM_THREADS];
   const int s = blockIdx.x, i = threadIdx.x, N = b.max_veh, T1 = mc.steps + 1;
   const int n = b.n_veh[s];
   const bool present = i < n;
+  const bool use_contacts = mc.contacts && b.cstate != nullptr;
   const size_t vi = (size_t)s * N + i;
   float ox = 0, oy = 0, heading = 0, len = 1, wid = 1;
   if (present) {
@@ -610,8 +626,26 @@ sim_step_kernel(CtrlSimBatch b, int t, ModelCfg mc) {
     }
     B.steer = (float)steer;
     freecar_step(B, len, mc.dt);
-    island_solve(B, mc.dt);
+    if (!use_contacts) island_solve(B, mc.dt);
     body_store(b.body + (size_t)s * B_FIELDS * N, N, i, B);
+    sh_tele[i] = teleport;
+  }
+  if (use_contacts) {  // b2World::Step with contacts: one thread per scene (sim_contacts.cuh)
+    __syncthreads();
+    if (i == 0) {
+      float* w = b.cstate + (size_t)s * cs_words(N);
+      SV sv{b.body + (size_t)s * B_FIELDS * N, b.veh_len + (size_t)s * N, b.veh_wid + (size_t)s * N, N, n};
+      SC c = cs_view(w, N, n, sh_scratch);
+      for (int k = 0; k < n; ++k)
+        if (sh_tele[k]) { cs_teleport(sv, c, k); *c.new_contacts = 1; }  // SetTransform happened before the FreeCar steps
+      world_step(sv, c, mc.dt, &sh_solver);
+    }
+    __syncthreads();
+  }
+  if (present) {
+    Body B;
+    body_load(b.body + (size_t)s * B_FIELDS * N, N, i, B);
+    float* o = b.obj + (size_t)s * O_FIELDS * N;
     ox = B.px; oy = B.py;
     heading = (float)((double)B.ang + 3.14159265358979323846 * 0.5f);
     o[O_X * N + i] = ox; o[O_Y * N + i] = oy; o[O_HEAD * N + i] = heading;

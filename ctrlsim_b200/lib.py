@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libctrlsim_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class CtrlSimConfig(C.Structure):
@@ -46,7 +46,7 @@ BATCH_FIELDS = [
     ("tr_nearest", "float64", "S,N,T1,2"), ("tr_rtg_idx", "int16", "S,N,T,3"), ("tr_act_idx", "int16", "S,N,T"),
     ("n_groups", "int32", "S"), ("group_off", "int32", "S+1"), ("group_focal", "int32", "S,N"),
     ("group_members", "int32", "S,N,24"), ("group_served", "int32", "S,N"), ("group_scene", "int32", "S*N"),
-    ("group_local", "int32", "S*N"),
+    ("group_local", "int32", "S*N"), ("cstate", "float32", "S,4+8*N+20*128"),
 ]
 
 

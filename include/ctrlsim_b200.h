@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define CTRLSIM_ABI_VERSION 3
+#define CTRLSIM_ABI_VERSION 4
 #define CTRLSIM_MAX_VEH 64 /* vehicles per scene supported by the grouping kernel (bitmask width) */
 
 /* Model / episode geometry. The kernels are specialised to the reference defaults (cfgs/model/base.yaml:1-9,
@@ -84,6 +84,9 @@ typedef struct CtrlSimBatch {
   uint32_t* group_served;     /* [S,N]      bit k = member slot k is served by this group */
   int32_t* group_scene;       /* [S*N] compact group -> scene          */
   int32_t* group_local;       /* [S*N] compact group -> scene-local id */
+  /* ---- Box2D contact state of the vehicle bodies (simulator state, owned by the library) ------------------------ */
+  float* cstate;              /* [S, 4 + 8*N + 20*128] per scene: header, proxy AABBs, mass data, contact manifolds with */
+                              /* their warm-start impulses (ctrlsim_b200/csrc/sim_contacts.cuh); NULL = contact-free sim */
 } CtrlSimBatch;
 
 /* Sampling / control knobs of AutoregressivePolicy (cfgs/policy/ctrl_sim.yaml:6-11). */

@@ -13,7 +13,7 @@ Rows of SURVEY 8(a) restated here (reference file:line):
   S6  apply_gt_action, BicycleModel.backward             evaluators/evaluator.py:160-193, nocturne/bicycle_model.py:51-109
   S7  update_running_statistics, compute_metrics         evaluators/policy_evaluator.py:162-305
   loop evaluate_policy                                   evaluators/policy_evaluator.py:426-595
-The simulator is oracle/sim_port.py (C restatement) and the network is oracle/model_port.py; sampling uses the
+The simulator is oracle/sim_port.py (C restatement, incl. Box2D's vehicle-vehicle contact response) and the network is oracle/model_port.py; sampling uses the
 explicit sampler contract of oracle/sampler.py.  Pinned against the reference itself by the fixtures under
 tests/golden/ (oracle/make_golden.py).
 
@@ -147,11 +147,14 @@ class MetricsPort:
 
 
 class RolloutPort:
-    def __init__(self, cfg, model, seed=0, tilts=(0, 0, 0), temperature=1.0, eval_threshold=None, nucleus=None):
+    def __init__(self, cfg, model, seed=0, tilts=(0, 0, 0), temperature=1.0, eval_threshold=None, nucleus=None,
+                 contacts=True, fp64_trig=False):
         self.cfg, self.model = cfg, model
         self.w, self.m = cfg.dataset.waymo, cfg.model
         self.seed, self.tilts, self.temperature = seed, tilts, float(temperature)
         self.nucleus = nucleus  # None, or the nucleus threshold p (autoregressive_policy.py:216-230)
+        self.contacts = contacts  # simulator with Box2D contact response (sim_oracle.c second half) or contact-free
+        self.fp64_trig = fp64_trig  # simulator trig rounded like the GPU path's (sim_oracle.c SIMO_TRIG_FP64)
         self.steps, self.dt, self.hist = cfg.nocturne.steps, cfg.nocturne.dt, cfg.nocturne.history_steps
         self.eval_threshold = eval_threshold if eval_threshold is not None else cfg.eval.multi_agent_eval_threshold
         self.metrics = MetricsPort(cfg)
@@ -262,7 +265,7 @@ class RolloutPort:
         parsed = sim_port.parse_scenario(scen_json)
         n = parsed["n"]
         gt = sim_port.ground_truth(parsed, steps)
-        sim = sim_port.ScenePort(parsed)
+        sim = sim_port.ScenePort(parsed, contacts=self.contacts, fp64_trig=self.fp64_trig)
         goal = np.zeros((n, 4))
         for i in range(n):
             gp, gh, gs = parsed["target"][i, :2].astype(np.float64), float(parsed["target"][i, 2]), float(parsed["target"][i, 3])

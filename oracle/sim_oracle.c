@@ -22,6 +22,19 @@
 #include <stdint.h>
 #include <string.h>
 
+#ifdef SIMO_TRIG_FP64
+/* Variant library (oracle/_build/libsim_oracle_fp64trig.so): sinf / cosf / tanf evaluated in fp64 and rounded once, the
+ * way the GPU path evaluates them (ctrlsim_b200/csrc/sim.cu cr_sinf ...).  glibc's are within 1 ulp but not always
+ * correctly rounded, so the two libraries differ by an ulp in rare calls; the tests use this variant to predict, on the
+ * CPU, how far the GPU simulator may drift from the reference while vehicles push each other. */
+static inline float simo_sinf(float x) { return (float)sin((double)x); }
+static inline float simo_cosf(float x) { return (float)cos((double)x); }
+static inline float simo_tanf(float x) { return (float)tan((double)x); }
+#define sinf simo_sinf
+#define cosf simo_cosf
+#define tanf simo_tanf
+#endif
+
 #define B2_PI 3.14159265359f
 static const float kMaxTranslation = 5.0f;
 static const float kMaxRotation = 0.5f * B2_PI;

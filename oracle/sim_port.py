@@ -33,13 +33,27 @@ def build():
     subprocess.check_call(["make", "-s", "-C", HERE, "port"])
 
 
-def lib():
-    global _LIB
+_LIB_FP64 = None
+
+
+def lib(fp64_trig: bool = False):
+    """The C restatement; ``fp64_trig`` selects the variant built with the GPU's trig (see sim_oracle.c)."""
+    global _LIB, _LIB_FP64
+    if fp64_trig:
+        if _LIB_FP64 is None:
+            _LIB_FP64 = _load("libsim_oracle_fp64trig.so")
+        return _LIB_FP64
     if _LIB is None:
-        path = os.path.join(HERE, "_build", "libsim_oracle.so")
-        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(HERE, "sim_oracle.c")):
-            build()
-        L = ctypes.CDLL(path)
+        _LIB = _load("libsim_oracle.so")
+    return _LIB
+
+
+def _load(name):
+    path = os.path.join(HERE, "_build", name)
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(HERE, "sim_oracle.c")):
+        build()
+    L = ctypes.CDLL(path)
+    if True:
         P = ctypes.POINTER(_SimO)
         f = ctypes.c_float
         L.simo_spawn.argtypes = [P, ctypes.c_int, f, f, f, f, f, f]
@@ -57,8 +71,8 @@ def lib():
         L.simc_num_touching.argtypes = [ctypes.c_void_p]
         L.simo_poly_intersects.argtypes = [ctypes.c_int, _F, _F, ctypes.c_int, _F, _F]
         L.simo_poly_segment_intersects.argtypes = [ctypes.c_int, _F, _F, f, f, f, f]
-        _LIB = L
-    return _LIB
+        L.simo_velocity.argtypes = [P, ctypes.c_int, _F, _F]
+    return L
 
 
 def _fp(a):
@@ -134,11 +148,12 @@ def parse_scenario(scen: dict):
 class ScenePort:
     """All vehicles of one scene as FreeCars (evaluators/evaluator.py:33-41)."""
 
-    def __init__(self, parsed: dict, contacts: bool = False):
+    def __init__(self, parsed: dict, contacts: bool = False, fp64_trig: bool = False):
         """``contacts``: run the world step with the Box2D contact restatement (sim_oracle.c, second half) instead of the
         contact-free subset."""
         self.p = parsed
         self.contacts = None
+        self.L = lib(fp64_trig)  # fp64_trig: the variant with the GPU's trig rounding (sim_oracle.c SIMO_TRIG_FP64)
         n = parsed["n"]
         self.n = n
         self.arr = {k: np.zeros(n, np.float32) for k in
@@ -150,7 +165,7 @@ class ScenePort:
         for k, a in self.arr.items():
             setattr(self.s, k, a.ctypes.data_as(_U8 if a.dtype == np.uint8 else _F))
         self.segs = np.ascontiguousarray(parsed["segs"], np.float32)
-        L = lib()
+        L = self.L
         for i in range(n):
             L.simo_spawn(ctypes.byref(self.s), i, parsed["pos"][i, 0, 0], parsed["pos"][i, 0, 1],
                          parsed["heading"][i, 0], parsed["speed"][i, 0], parsed["size"][i, 0], parsed["size"][i, 1])
@@ -161,29 +176,29 @@ class ScenePort:
         L.simo_update_collision(ctypes.byref(self.s), _fp(self.segs), len(self.segs))  # scenario.cc:263
 
     def __del__(self):
-        if getattr(self, "contacts", None) and _LIB is not None:
+        if getattr(self, "contacts", None) and getattr(self, "L", None) is not None:
             try:
-                _LIB.simc_free(self.contacts)
+                self.L.simc_free(self.contacts)
             except Exception:  # interpreter shutdown
                 pass
             self.contacts = None
 
     def set_action(self, i, accel, steer):
-        lib().simo_set_action(ctypes.byref(self.s), i, np.float32(accel), np.float32(steer))
+        self.L.simo_set_action(ctypes.byref(self.s), i, np.float32(accel), np.float32(steer))
 
     def teleport(self, i, x, y):
-        lib().simo_teleport(ctypes.byref(self.s), i, np.float32(x), np.float32(y))
+        self.L.simo_teleport(ctypes.byref(self.s), i, np.float32(x), np.float32(y))
         if self.contacts:
-            lib().simc_teleport(ctypes.byref(self.s), self.contacts, i)
+            self.L.simc_teleport(ctypes.byref(self.s), self.contacts, i)
 
     def step(self, dt=0.1):
         if self.contacts:
-            lib().simc_step(ctypes.byref(self.s), self.contacts, np.float32(dt), _fp(self.segs), len(self.segs))
+            self.L.simc_step(ctypes.byref(self.s), self.contacts, np.float32(dt), _fp(self.segs), len(self.segs))
         else:
-            lib().simo_step(ctypes.byref(self.s), np.float32(dt), _fp(self.segs), len(self.segs))
+            self.L.simo_step(ctypes.byref(self.s), np.float32(dt), _fp(self.segs), len(self.segs))
 
     def n_touching(self):
-        return int(lib().simc_num_touching(self.contacts)) if self.contacts else 0
+        return int(self.L.simc_num_touching(self.contacts)) if self.contacts else 0
 
     # getters (float32 values widened to python float, like pybind)
     def position(self):
@@ -200,8 +215,7 @@ class ScenePort:
         # PolarToVector2D(speed, heading) with std::cos/std::sin(float): evaluate with the same libm via C
         vx = np.zeros(self.n, np.float32)
         vy = np.zeros(self.n, np.float32)
-        L = lib()
-        L.simo_velocity.argtypes = [ctypes.POINTER(_SimO), ctypes.c_int, _F, _F]
+        L = self.L
         for i in range(self.n):
             L.simo_velocity(ctypes.byref(self.s), i, _fp(vx[i:i + 1]), _fp(vy[i:i + 1]))
         return np.stack([vx, vy], -1).astype(np.float64)

@@ -11,6 +11,7 @@ import pytest
 import torch
 
 from conftest import load_golden
+from parity_checks import check_rollout_vs_reference
 
 pytestmark = pytest.mark.gpu
 
@@ -372,32 +373,55 @@ def _first_contact(g):
 
 @pytest.mark.parametrize("name", ["plumbing", "crowded", "sparse"])
 def test_rollout_matches_reference(cfg, dev, name):
-    """Free-running closed loop vs the unmodified reference evaluator on the same scene JSON, weights and sampler seed.
-    Compared up to the first vehicle-vehicle contact (Box2D's contact response is not modelled)."""
+    """Free-running closed loop vs the unmodified reference evaluator on the same scene JSON, weights and sampler seed,
+    THROUGH vehicle-vehicle contacts (plumbing: from step 12, crowded: from step 16; Box2D contact response,
+    sim_contacts.cuh).  Sampled bins are compared bit for bit up to the first marginal draw (see
+    test_planner_adversary_matches_reference: a uniform within ~1e-5 of a CDF boundary, a few in 10^4 draws), which
+    must lie well past the first contact and be an adjacent-bin flip of an RTG component; everything else is compared
+    up to that step.  No such draw: whole episode and the final metrics."""
     g, spec, ref_metrics = load_golden(name)
-    n = g["pos"].shape[0]
-    tc = _first_contact(g)
-    ev, b, tr = _rollout(cfg, spec, dev, max_steps=None if tc > 90 else tc)
-    T = min(tc, 90)
-    ex = g["existence"][:, :T].astype(bool)
-    assert (tr["tr_exist"][0, :n, :T] == g["existence"][:, :T]).all()
-    # sampled indices: bit-exact under the shared explicit sampler
-    assert (tr["tr_rtg_idx"][0, :n, :T].transpose(1, 0, 2) == g["rtg_idx"][:T]).all()
-    assert (tr["tr_act_idx"][0, :n, :T].T == g["act_idx"][:T]).all()
-    dpos = np.abs(tr["tr_pos"][0, :n, :T].astype(np.float64) - g["pos"][:, :T])[ex].max()
-    dhead = np.abs(tr["tr_heading"][0, :n, :T].astype(np.float64) - g["heading"][:, :T])[ex].max()
-    dvel = np.abs(tr["tr_vel"][0, :n, :T].astype(np.float64) - g["vel"][:, :T])[ex].max()
-    assert dpos < POS_TOL and dhead < 1e-5 and dvel < 1e-4, (dpos, dhead, dvel)
-    dacc = np.abs(tr["tr_action"][0, :n, :T] - np.stack([g["accel"], g["steer"]], -1)[:, :T])[ex].max()
-    assert dacc < 1e-4, dacc
-    drew = np.abs(tr["tr_reward"][0, :n, :T].astype(np.float64) - g["reward"][:, :T])[ex].max()
-    assert drew < 1e-5, drew
-    dnd = np.abs(tr["tr_nearest"][0, :n, :T, 0] - g["nearest_dist"][:, :T])[ex].max()
-    assert dnd < 1e-3, dnd
-    if tc > 90:  # whole episode contact-free: the summary metrics must match the reference's compute_metrics
+    ev, b, tr = _rollout(cfg, spec, dev)
+    t_r = check_rollout_vs_reference(tr, g, name)
+    if t_r == 90:  # no marginal draw: the summary metrics must match the reference's compute_metrics
         m = ev.metrics_from_summary(ev.summarize(b))
         for k, v in ref_metrics.items():
             assert abs(m[k] - v) < 1e-4 * max(1.0, abs(v)), (k, m[k], v)
+
+
+@pytest.mark.parametrize("name", ["plumbing", "crowded", "sparse"])
+def test_simulator_with_contacts_reproduces_reference_episodes(cfg, dev, name):
+    """Simulator only, no sampling: the controls the reference evaluator applied to the policy-controlled vehicles are
+    fed to ctrlsim_sim_step step by step (log-replayed vehicles compute their own inverse-bicycle controls); the
+    trajectories of ALL 90 steps must be the reference's - through the contacts of 'plumbing' (from step 12) and
+    'crowded' (30 vehicles, from step 16), where a contact-free simulator is metres off."""
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    g, spec, _ = load_golden(name)
+    sc = make_scene(**spec["scene"])
+    pol = B200Policy(cfg, "synthetic", _model(cfg, spec, dev), seed=0)
+    ev = B200PolicyEvaluator(cfg, pol, scenes=[sc])
+    b = ev.build_batch(eval_threshold=64)
+    assert b.evaluated_ids[0] == sorted(int(v) for v in g["evaluated"])
+    pol.reset(b)
+    n = g["pos"].shape[0]
+    ctrl = torch.from_numpy(np.stack([g["accel"], g["steer"]], -1)).to(dev)  # [n, 91, 2]
+    for t in range(90):
+        pol.update_state(b, t)
+        b.t["next_action"][0, :n] = ctrl[:, t]
+        pol.act(b, t)
+    pol.update_state(b, 90)
+    tr = b.trace()
+    ex = g["existence"].astype(bool)
+    assert (tr["tr_exist"][0, :n] == g["existence"]).all()
+    dpos = np.abs(tr["tr_pos"][0, :n].astype(np.float64) - g["pos"])[ex].max()
+    dhead = np.abs(tr["tr_heading"][0, :n].astype(np.float64) - g["heading"])[ex].max()
+    coll = (tr["tr_reward"][0, :n, :, 6] == 1)[ex]
+    # bit-exact until glibc's sinf / cosf (not always correctly rounded) and the GPU's (fp64, rounded once) first
+    # disagree by an ulp while vehicles are pushing each other: crowded step 47, 0.73 mm / 2.3e-5 rad by step 90
+    assert dpos < POS_TOL and dhead < 2e-4, (name, dpos, dhead)
+    assert (coll == (g["reward"][:, :, 6] == 1)[ex]).mean() > 0.999
+    if name != "sparse":
+        assert coll.any()
 
 
 def test_rollout_matches_oracle_port_multi_scene(cfg, dev):
