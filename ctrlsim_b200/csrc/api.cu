@@ -115,6 +115,11 @@ int ctrlsim_create(const CtrlSimConfig* c, CtrlSim** out) {
   h->mc.pos_tol = c->pos_tol; h->mc.heading_tol = c->heading_tol; h->mc.speed_tol = c->speed_tol;
   h->mc.goal_dist_scaling = c->goal_dist_scaling; h->mc.reward_scaling = c->reward_scaling;
   { const char* e = getenv("CTRLSIM_CONTACTS"); h->mc.contacts = !(e && e[0] == '0'); }
+  {  // process-wide (a __constant__ of the simulator kernels): CTRLSIM_TRIG=glibc selects glibc's sinf / cosf algorithm
+    const char* e = getenv("CTRLSIM_TRIG");
+    const int rc = set_trig_mode(e && strcmp(e, "glibc") == 0);
+    if (rc) { delete h; return rc; }
+  }
   *out = h;
   return 0;
 }

@@ -87,6 +87,7 @@ int launch_gather_rows(int n, const float* X, const int* idx, float* Y, cudaStre
 int launch_clamp_type_index(int n, const int* in, int* out, cudaStream_t st);
 
 // sim.cu
+int set_trig_mode(int glibc);  // sim.cu: 1 = sinf / cosf by glibc's algorithm (glibc_trig.h), 0 = fp64 and round once
 int launch_sim_reset(const CtrlSimBatch& b, const ModelCfg& mc, cudaStream_t st);
 int launch_observe(const CtrlSimBatch& b, int t, const ModelCfg& mc, cudaStream_t st);
 int launch_plan_groups(const CtrlSimBatch& b, int t, const ModelCfg& mc, int* n_total, cudaStream_t st);

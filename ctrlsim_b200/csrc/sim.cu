@@ -24,13 +24,25 @@
 // libm: the reference calls glibc sinf/cosf/tanf (results are the correctly rounded fp32 value in all but ~1e-9 of
 // cases).  CUDA's fp32 versions are 1-2 ulp, so those calls are evaluated in fp64 and rounded once.
 #include "common.cuh"
+#include "glibc_trig.h"
 #include "kernels.h"
 #include "model.h"
 
 namespace ctrlsim {
 
-__device__ __forceinline__ float cr_sinf(float x) { return (float)sin((double)x); }
-__device__ __forceinline__ float cr_cosf(float x) { return (float)cos((double)x); }
+// 0: sinf / cosf evaluated in fp64 and rounded once (correctly rounded; differs from glibc's in ~1 % of calls by 1 ulp)
+// 1: glibc's own algorithm (glibc_trig.h; identical to the x86-64 FMA build of glibc in 1.2e8 of 1.2e8 arguments)
+__constant__ int g_trig_glibc = 0;
+__device__ __forceinline__ float cr_sinf(float x) {
+  float r;
+  if (g_trig_glibc && glibc_trig::sinf_fast(x, &r)) return r;
+  return (float)sin((double)x);
+}
+__device__ __forceinline__ float cr_cosf(float x) {
+  float r;
+  if (g_trig_glibc && glibc_trig::cosf_fast(x, &r)) return r;
+  return (float)cos((double)x);
+}
 __device__ __forceinline__ float cr_tanf(float x) { return (float)tan((double)x); }
 
 #define B2_PI 3.14159265359f
@@ -325,6 +337,13 @@ sim_reset_kernel(CtrlSimBatch b, int T1) {  // T1 = steps + 1
     for (int k = 0; k < n; ++k) cs_init_body(sv, c, k);
   }
   update_collision(b, s, i, n, present, x, y, heading, len, wid, sh_obb, sh_seg);
+}
+
+int set_trig_mode(int glibc) {
+  const int v = glibc ? 1 : 0;
+  const cudaError_t e = cudaMemcpyToSymbol(g_trig_glibc, &v, sizeof(int));
+  if (e != cudaSuccess) return set_error(-5, "set_trig_mode: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 int launch_sim_reset(const CtrlSimBatch& b, const ModelCfg& mc, cudaStream_t st) {

@@ -22,6 +22,20 @@
 #include <stdint.h>
 #include <string.h>
 
+#ifdef SIMO_TRIG_GLIBC_PORT
+/* Variant library (oracle/_build/libsim_oracle_glibcport.so, compiled as C++): sinf / cosf from
+ * ctrlsim_b200/csrc/glibc_trig.h - the restatement of glibc's algorithm the GPU uses under CTRLSIM_TRIG=glibc - instead
+ * of this machine's libm.  Emulates that GPU mode on the CPU. */
+#include "../ctrlsim_b200/csrc/glibc_trig.h"
+static inline float simo_sinf(float x) { float r; return glibc_trig::sinf_fast(x, &r) ? r : (float)sin((double)x); }
+static inline float simo_cosf(float x) { float r; return glibc_trig::cosf_fast(x, &r) ? r : (float)cos((double)x); }
+#define sinf simo_sinf
+#define cosf simo_cosf
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
 #ifdef SIMO_TRIG_FP64
 /* Variant library (oracle/_build/libsim_oracle_fp64trig.so): sinf / cosf / tanf evaluated in fp64 and rounded once, the
  * way the GPU path evaluates them (ctrlsim_b200/csrc/sim.cu cr_sinf ...).  glibc's are within 1 ulp but not always
@@ -1105,3 +1119,7 @@ void simc_step(SimO* s, SimC* c, float dt, const float* segs, int nseg) {
 }
 int simc_num_contacts(const SimC* c) { return c->n_contacts; }
 int simc_num_touching(const SimC* c) { int t = 0; for (int k = 0; k < c->n_contacts; ++k) t += c->ct[k].touching; return t; }
+
+#ifdef __cplusplus
+}
+#endif

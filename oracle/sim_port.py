@@ -36,9 +36,17 @@ def build():
 _LIB_FP64 = None
 
 
-def lib(fp64_trig: bool = False):
-    """The C restatement; ``fp64_trig`` selects the variant built with the GPU's trig (see sim_oracle.c)."""
-    global _LIB, _LIB_FP64
+_LIB_PORT = None
+
+
+def lib(fp64_trig=False):
+    """The C restatement; ``fp64_trig`` True selects the variant built with the GPU's default trig (fp64, rounded once),
+    "glibc_port" the variant built with the product's restatement of glibc's sinf / cosf (see sim_oracle.c)."""
+    global _LIB, _LIB_FP64, _LIB_PORT
+    if fp64_trig == "glibc_port":
+        if _LIB_PORT is None:
+            _LIB_PORT = _load("libsim_oracle_glibcport.so")
+        return _LIB_PORT
     if fp64_trig:
         if _LIB_FP64 is None:
             _LIB_FP64 = _load("libsim_oracle_fp64trig.so")

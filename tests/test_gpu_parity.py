@@ -595,3 +595,35 @@ def test_planner_adversary_matches_reference(cfg, dev, name):
             assert abs(metrics[k] - v) < 1e-4 * max(1.0, abs(v)), (k, metrics[k], v)
         else:  # a marginal flip happened late in some episode: the aggregate metrics can only move a little
             assert abs(metrics[k] - v) < 0.05 * max(1.0, abs(v)), (k, metrics[k], v)
+
+
+@pytest.mark.xfail(strict=False, reason="CTRLSIM_TRIG=glibc was added after the last GPU session of round 1: verified on the "
+                                        "host (tools/trig_check.cpp, oracle glibc-port variant), not yet on a B200")
+def test_glibc_trig_mode_is_bit_exact_through_contacts(cfg, dev, monkeypatch):
+    """With glibc's own sinf / cosf algorithm on the GPU (CTRLSIM_TRIG=glibc, glibc_trig.h) the simulator has no
+    arithmetic difference to the reference left: 'crowded' (30 vehicles pushing each other from step 16 on) replayed
+    with the reference's controls must be bit-identical for all 90 steps (default mode: 0.73 mm)."""
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    g, spec, _ = load_golden("crowded")
+    monkeypatch.setenv("CTRLSIM_TRIG", "glibc")
+    try:
+        model = _model(cfg, spec, dev)  # ctrlsim_create reads the switch
+        pol = B200Policy(cfg, "synthetic", model, seed=0)
+        ev = B200PolicyEvaluator(cfg, pol, scenes=[make_scene(**spec["scene"])])
+        b = ev.build_batch(eval_threshold=64)
+        pol.reset(b)
+        n = g["pos"].shape[0]
+        ctrl = torch.from_numpy(np.stack([g["accel"], g["steer"]], -1)).to(dev)
+        for t in range(90):
+            pol.update_state(b, t)
+            b.t["next_action"][0, :n] = ctrl[:, t]
+            pol.act(b, t)
+        pol.update_state(b, 90)
+        tr = b.trace()
+    finally:
+        monkeypatch.delenv("CTRLSIM_TRIG")
+        _model(cfg, spec, dev)  # the switch is process-wide: the next handle sets it back to the default
+    ex = g["existence"].astype(bool)
+    assert (tr["tr_pos"][0, :n].astype(np.float64)[ex] == g["pos"][ex]).all()
+    assert (tr["tr_heading"][0, :n].astype(np.float64)[ex] == g["heading"][ex]).all()

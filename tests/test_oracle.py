@@ -629,3 +629,40 @@ def test_gpu_acceptance_logic_on_cpu_emulation_of_gpu_arithmetic(cfg, name):
         assert abs(dpos - 0.000732421875) < 1e-12 and abs(dhead - 2.3126602172851562e-05) < 1e-12, (dpos, dhead)
     if name == "sparse":
         assert dpos == 0.0
+
+
+def test_glibc_trig_restatement_equals_this_machines_libm(tmp_path):
+    """ctrlsim_b200/csrc/glibc_trig.h (the sinf / cosf the GPU simulator uses under CTRLSIM_TRIG=glibc) compiled for the
+    host - same source as the device build - against sinf / cosf of this machine's libm over 6e6 arguments in
+    [-8, 8], [-0.9, 0.9] and [-119, 119]: no difference.  (1.2e8 arguments: none; 'evaluate in fp64 and round once'
+    differs in 1.3 % of them, tools/trig_check.cpp.)"""
+    import subprocess
+    exe = str(tmp_path / "trig_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", os.path.join(ROOT, "tools", "trig_check.cpp"), "-o", exe])
+    r = subprocess.run([exe, "3000000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "differs from libm in 0 sinf / 0 cosf" in r.stdout, r.stdout[-600:]
+
+
+@pytest.mark.parametrize("name", ["plumbing", "crowded"])
+def test_glibc_trig_mode_makes_the_contact_episodes_bit_exact(cfg, name):
+    """CPU emulation of the GPU's CTRLSIM_TRIG=glibc mode (oracle built on the product's glibc_trig.h instead of libm):
+    the reference's controls reproduce the reference's trajectories bit for bit over all 90 steps - also 'crowded',
+    where the default mode (fp64 trig) drifts by 0.73 mm while vehicles push each other."""
+    from ctrlsim_b200.synth import make_scene
+    from oracle.policy_port import RolloutPort
+    g, spec, _ = load_golden(name)
+    sc = make_scene(**spec["scene"])
+    port = RolloutPort(cfg, None, contacts=True, fp64_trig="glibc_port")
+    ctx = port.setup_scene(0, sc["json"])
+    n, sim, rec = ctx["n"], ctx["sim"], ctx["rec"]
+    evaluated = [int(v) for v in g["evaluated"]]
+    next_act = np.zeros((n, 2))
+    for t in range(90):
+        port.observe(ctx, t)
+        next_act[:, 0], next_act[:, 1] = g["accel"][:, t], g["steer"][:, t]
+        port.apply_controls(ctx, t, evaluated, next_act)
+        sim.step(0.1)
+    port.observe(ctx, 90)
+    ex = g["existence"].astype(bool)
+    assert (rec["pos"][ex] == g["pos"][ex]).all() and (rec["heading"][ex] == g["heading"][ex]).all()
+    assert (rec["reward"][:, :, 6][ex] == g["reward"][:, :, 6][ex]).all() and g["reward"][:, :, 6][ex].any()
