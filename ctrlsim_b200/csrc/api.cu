@@ -116,9 +116,16 @@ int ctrlsim_create(const CtrlSimConfig* c, CtrlSim** out) {
   h->mc.goal_dist_scaling = c->goal_dist_scaling; h->mc.reward_scaling = c->reward_scaling;
   { const char* e = getenv("CTRLSIM_CONTACTS"); h->mc.contacts = !(e && e[0] == '0'); }
   {  // process-wide (a __constant__ of the simulator kernels): CTRLSIM_TRIG=glibc selects glibc's sinf / cosf algorithm
+    // The constant is statically 0; it is only written when the switch is asked for (or has to be taken back), so the
+    // default flow performs no extra CUDA call.
+    static bool trig_is_glibc = false;
     const char* e = getenv("CTRLSIM_TRIG");
-    const int rc = set_trig_mode(e && strcmp(e, "glibc") == 0);
-    if (rc) { delete h; return rc; }
+    const bool want = e && strcmp(e, "glibc") == 0;
+    if (want != trig_is_glibc) {
+      const int rc = set_trig_mode(want ? 1 : 0);
+      if (rc) { delete h; return rc; }
+      trig_is_glibc = want;
+    }
   }
   *out = h;
   return 0;
