@@ -104,4 +104,46 @@ GLT_FN bool cosf_fast(float y, float* out) {
   return false;
 }
 
+// tanf for |x| <= pi/4 (the steering range is [-0.7, 0.7]) as glibc computes it: the float-arithmetic fdlibm kernel
+// (sysdeps/ieee754/flt-32/k_tanf.c with y = 0, iy = 1; s_tanf.c).  No fused operations: this file of glibc has no
+// FMA build.  Returns false outside the range.
+GLT_FN bool tanf_fast(float x, float* out) {
+  uint32_t ux;
+  memcpy(&ux, &x, 4);
+  const int32_t hx = (int32_t)ux;
+  const int32_t ix = hx & 0x7fffffff;
+  if (ix > 0x3f490fda) return false;  // |x| > pi/4: range reduction not restated
+  const float T[13] = {3.3333334327e-01f, 1.3333334029e-01f, 5.3968254477e-02f, 2.1869488060e-02f, 8.8632395491e-03f,
+                       3.5920790397e-03f, 1.4562094584e-03f, 5.8804126456e-04f, 2.4646313977e-04f, 7.8179444245e-05f,
+                       7.1407252108e-05f, -1.8558637748e-05f, 2.5907305826e-05f};
+  const float pio4 = 7.8539812565e-01f, pio4lo = 3.7748947079e-08f;
+  float y = 0.0f, z, r, v, w, s;
+  if (ix < 0x39000000) {  // |x| < 2**-13
+    if ((int)x == 0) { *out = x; return true; }
+  }
+  if (ix >= 0x3f2ca140) {  // |x| >= 0.6744
+    if (hx < 0) { x = -x; y = -y; }
+    z = pio4 - x;
+    w = pio4lo - y;
+    x = z + w;
+    y = 0.0f;
+    if (fabsf(x) < 0x1p-13f) { *out = (float)(1 - ((hx >> 30) & 2)) * 1 * (1.0f - 2 * 1 * x); return true; }
+  }
+  z = x * x;
+  w = z * z;
+  r = T[1] + w * (T[3] + w * (T[5] + w * (T[7] + w * (T[9] + w * T[11]))));
+  v = z * (T[2] + w * (T[4] + w * (T[6] + w * (T[8] + w * (T[10] + w * T[12])))));
+  s = z * x;
+  r = y + z * (s * (r + v) + y);
+  r += T[0] * s;
+  w = x + r;
+  if (ix >= 0x3f2ca140) {
+    v = 1.0f;
+    *out = (float)(1 - ((hx >> 30) & 2)) * (v - 2.0f * (x - (w * w / (w + v) - r)));
+    return true;
+  }
+  *out = w;
+  return true;
+}
+
 }  // namespace glibc_trig

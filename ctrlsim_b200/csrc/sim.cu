@@ -43,7 +43,12 @@ __device__ __forceinline__ float cr_cosf(float x) {
   if (g_trig_glibc && glibc_trig::cosf_fast(x, &r)) return r;
   return (float)cos((double)x);
 }
-__device__ __forceinline__ float cr_tanf(float x) { return (float)tan((double)x); }
+__device__ __forceinline__ float cr_tanf(float x) {
+  float r;
+  if (g_trig_glibc && glibc_trig::tanf_fast(x, &r)) return r;
+  return (float)tan((double)x);
+}
+
 
 #define B2_PI 3.14159265359f
 enum { B_PX, B_PY, B_CX, B_CY, B_LCX, B_LCY, B_ANG, B_VX, B_VY, B_OM, B_SLEEP, B_THR, B_BRK, B_STEER, B_AWAKE, B_PAD, B_FIELDS };

@@ -24,13 +24,15 @@
 
 #ifdef SIMO_TRIG_GLIBC_PORT
 /* Variant library (oracle/_build/libsim_oracle_glibcport.so, compiled as C++): sinf / cosf from
- * ctrlsim_b200/csrc/glibc_trig.h - the restatement of glibc's algorithm the GPU uses under CTRLSIM_TRIG=glibc - instead
+ * ctrlsim_b200/csrc/glibc_trig.h (sinf, cosf, tanf) - the restatement of glibc's algorithms the GPU uses under CTRLSIM_TRIG=glibc - instead
  * of this machine's libm.  Emulates that GPU mode on the CPU. */
 #include "../ctrlsim_b200/csrc/glibc_trig.h"
 static inline float simo_sinf(float x) { float r; return glibc_trig::sinf_fast(x, &r) ? r : (float)sin((double)x); }
 static inline float simo_cosf(float x) { float r; return glibc_trig::cosf_fast(x, &r) ? r : (float)cos((double)x); }
+static inline float simo_tanf(float x) { float r; return glibc_trig::tanf_fast(x, &r) ? r : (float)tan((double)x); }
 #define sinf simo_sinf
 #define cosf simo_cosf
+#define tanf simo_tanf
 #endif
 #ifdef __cplusplus
 extern "C" {

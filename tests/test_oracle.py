@@ -634,13 +634,14 @@ def test_gpu_acceptance_logic_on_cpu_emulation_of_gpu_arithmetic(cfg, name):
 def test_glibc_trig_restatement_equals_this_machines_libm(tmp_path):
     """ctrlsim_b200/csrc/glibc_trig.h (the sinf / cosf the GPU simulator uses under CTRLSIM_TRIG=glibc) compiled for the
     host - same source as the device build - against sinf / cosf of this machine's libm over 6e6 arguments in
-    [-8, 8], [-0.9, 0.9] and [-119, 119]: no difference.  (1.2e8 arguments: none; 'evaluate in fp64 and round once'
+    [-8, 8], [-0.9, 0.9] and [-119, 119], and tanf on [-pi/4, pi/4]: no difference.  (1.2e8 arguments: none; 'evaluate in fp64 and round once'
     differs in 1.3 % of them, tools/trig_check.cpp.)"""
     import subprocess
     exe = str(tmp_path / "trig_check")
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", os.path.join(ROOT, "tools", "trig_check.cpp"), "-o", exe])
     r = subprocess.run([exe, "3000000"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "differs from libm in 0 sinf / 0 cosf" in r.stdout, r.stdout[-600:]
+    assert "tanf on [-pi/4, pi/4]: port differs from libm in 0 of" in r.stdout, r.stdout[-600:]
 
 
 @pytest.mark.parametrize("name", ["plumbing", "crowded"])

@@ -23,6 +23,18 @@ int main(int argc, char** argv) {
     bad_c64 += (float)cos((double)x) != rc;
     if ((s != rs || c != rc) && bad_s + bad_c <= 5) printf("  x=%a port sin %a cos %a  libm sin %a cos %a\n", x, s, c, rs, rc);
   }
+  long bad_t = 0, bad_t64 = 0;
+  for (long i = 0; i < N; ++i) {
+    const float x = (float)((double)(rng() >> 11) * (1.0 / 9007199254740992.0) * 1.5707 - 0.78535);
+    float t;
+    if (!glibc_trig::tanf_fast(x, &t)) continue;
+    const float rt = tanf(x);
+    bad_t += t != rt;
+    bad_t64 += (float)tan((double)x) != rt;
+    if (t != rt && bad_t <= 5) printf("  x=%a port tan %a libm tan %a\n", x, t, rt);
+  }
+  printf("tanf on [-pi/4, pi/4]: port differs from libm in %ld of %ld; fp64-and-round differs in %ld\n", bad_t, N, bad_t64);
+  if (bad_t) return 1;
   printf("%ld arguments: glibc port differs from libm in %ld sinf / %ld cosf; fp64-and-round differs in %ld / %ld; %ld outside the fast path\n",
          N, bad_s, bad_c, bad_s64, bad_c64, miss);
   return (bad_s || bad_c) ? 1 : 0;
