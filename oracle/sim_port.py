@@ -61,25 +61,24 @@ def _load(name):
     if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(HERE, "sim_oracle.c")):
         build()
     L = ctypes.CDLL(path)
-    if True:
-        P = ctypes.POINTER(_SimO)
-        f = ctypes.c_float
-        L.simo_spawn.argtypes = [P, ctypes.c_int, f, f, f, f, f, f]
-        L.simo_set_action.argtypes = [P, ctypes.c_int, f, f]
-        L.simo_teleport.argtypes = [P, ctypes.c_int, f, f]
-        L.simo_step.argtypes = [P, f, _F, ctypes.c_int]
-        L.simo_update_collision.argtypes = [P, _F, ctypes.c_int]
-        L.simc_create.restype = ctypes.c_void_p
-        L.simc_create.argtypes = [ctypes.c_int]
-        L.simc_free.argtypes = [ctypes.c_void_p]
-        L.simc_init_body.argtypes = [P, ctypes.c_void_p, ctypes.c_int]
-        L.simc_teleport.argtypes = [P, ctypes.c_void_p, ctypes.c_int]
-        L.simc_step.argtypes = [P, ctypes.c_void_p, f, _F, ctypes.c_int]
-        L.simc_num_contacts.argtypes = [ctypes.c_void_p]
-        L.simc_num_touching.argtypes = [ctypes.c_void_p]
-        L.simo_poly_intersects.argtypes = [ctypes.c_int, _F, _F, ctypes.c_int, _F, _F]
-        L.simo_poly_segment_intersects.argtypes = [ctypes.c_int, _F, _F, f, f, f, f]
-        L.simo_velocity.argtypes = [P, ctypes.c_int, _F, _F]
+    P = ctypes.POINTER(_SimO)
+    f = ctypes.c_float
+    L.simo_spawn.argtypes = [P, ctypes.c_int, f, f, f, f, f, f]
+    L.simo_set_action.argtypes = [P, ctypes.c_int, f, f]
+    L.simo_teleport.argtypes = [P, ctypes.c_int, f, f]
+    L.simo_step.argtypes = [P, f, _F, ctypes.c_int]
+    L.simo_update_collision.argtypes = [P, _F, ctypes.c_int]
+    L.simc_create.restype = ctypes.c_void_p
+    L.simc_create.argtypes = [ctypes.c_int]
+    L.simc_free.argtypes = [ctypes.c_void_p]
+    L.simc_init_body.argtypes = [P, ctypes.c_void_p, ctypes.c_int]
+    L.simc_teleport.argtypes = [P, ctypes.c_void_p, ctypes.c_int]
+    L.simc_step.argtypes = [P, ctypes.c_void_p, f, _F, ctypes.c_int]
+    L.simc_num_contacts.argtypes = [ctypes.c_void_p]
+    L.simc_num_touching.argtypes = [ctypes.c_void_p]
+    L.simo_poly_intersects.argtypes = [ctypes.c_int, _F, _F, ctypes.c_int, _F, _F]
+    L.simo_poly_segment_intersects.argtypes = [ctypes.c_int, _F, _F, f, f, f, f]
+    L.simo_velocity.argtypes = [P, ctypes.c_int, _F, _F]
     return L
 
 

@@ -365,12 +365,6 @@ def _rollout(cfg, spec, dev, max_steps=None):
     return ev, b, b.trace()
 
 
-def _first_contact(g):
-    cv = (g["reward"][:, :, 6] * g["existence"]).any(0)
-    idx = np.where(cv)[0]
-    return int(idx[0]) if len(idx) else 91
-
-
 @pytest.mark.parametrize("name", ["plumbing", "crowded", "sparse"])
 def test_rollout_matches_reference(cfg, dev, name):
     """Free-running closed loop vs the unmodified reference evaluator on the same scene JSON, weights and sampler seed,
