@@ -1119,6 +1119,19 @@ void simc_step(SimO* s, SimC* c, float dt, const float* segs, int nseg) {
   }
   simo_update_collision(s, segs, nseg);
 }
+/* the two halves of a step around the world step (used by tests that put another world step in between) */
+void simo_freecar_all(SimO* s, float dt) {
+  for (int i = 0; i < s->n; ++i) freecar_step(s, i, dt);
+}
+void simo_finish_step(SimO* s, const float* segs, int nseg) {
+  for (int i = 0; i < s->n; ++i) {
+    s->ox[i] = s->px[i];
+    s->oy[i] = s->py[i];
+    s->speed[i] = sqrtf(s->vx[i] * s->vx[i] + s->vy[i] * s->vy[i]);
+    s->heading[i] = (float)((double)s->ang[i] + M_PI * 0.5f);
+  }
+  simo_update_collision(s, segs, nseg);
+}
 int simc_num_contacts(const SimC* c) { return c->n_contacts; }
 int simc_num_touching(const SimC* c) { int t = 0; for (int k = 0; k < c->n_contacts; ++k) t += c->ct[k].touching; return t; }
 

@@ -79,6 +79,8 @@ def _load(name):
     L.simo_poly_intersects.argtypes = [ctypes.c_int, _F, _F, ctypes.c_int, _F, _F]
     L.simo_poly_segment_intersects.argtypes = [ctypes.c_int, _F, _F, f, f, f, f]
     L.simo_velocity.argtypes = [P, ctypes.c_int, _F, _F]
+    L.simo_freecar_all.argtypes = [P, f]
+    L.simo_finish_step.argtypes = [P, _F, ctypes.c_int]
     return L
 
 

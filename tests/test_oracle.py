@@ -667,3 +667,65 @@ def test_glibc_trig_mode_makes_the_contact_episodes_bit_exact(cfg, name):
     ex = g["existence"].astype(bool)
     assert (rec["pos"][ex] == g["pos"][ex]).all() and (rec["heading"][ex] == g["heading"][ex]).all()
     assert (rec["reward"][:, :, 6][ex] == g["reward"][:, :, 6][ex]).all() and g["reward"][:, :, 6][ex].any()
+
+
+@pytest.mark.parametrize("mode", ["rear", "side", "head", "pile"])
+def test_product_contact_code_equals_oracle_on_the_host(tmp_path, mode):
+    """The PRODUCT's contact code (ctrlsim_b200/csrc/sim_contacts.cuh - what sim.cu compiles for the GPU), built for the
+    host (tests/host_contacts_shim.cpp) and put between the oracle's FreeCar step and its Vehicle::Step / collision
+    flags, against the oracle's own world step: bit-identical bodies every step of the collision cases (impact, pushing,
+    a vehicle teleported away mid-contact, three-car pile-up).  Keeps the CUDA source checkable without a GPU."""
+    import ctypes
+    import subprocess
+    from contact_case import collision_scene
+    from oracle import sim_port
+    so = str(tmp_path / "libhc.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-w",
+                           os.path.join(ROOT, "tests", "host_contacts_shim.cpp"), "-o", so])
+    H = ctypes.CDLL(so)
+    F, U8 = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint8)
+    H.hc_init.argtypes = [F, F, F, ctypes.c_int, ctypes.c_int, F]
+    H.hc_world_step.argtypes = [F, F, F, ctypes.c_int, ctypes.c_int, F, U8, ctypes.c_float]
+    H.hc_num_touching.argtypes = [F, ctypes.c_int, ctypes.c_int]
+    fields = ("px", "py", "cx", "cy", "lcx", "lcy", "ang", "vx", "vy", "om", "sleep_t", "thr", "brk", "steer", "awake")
+    assert H.hc_body_fields() == len(fields) + 1
+    parsed = sim_port.parse_scenario(collision_scene(mode)["json"])
+    A = sim_port.ScenePort(parsed, contacts=True)   # oracle, its own world step
+    B = sim_port.ScenePort(parsed, contacts=False)  # oracle FreeCar / Vehicle::Step around the product's world step
+    n = N = parsed["n"]
+    L = sim_port.lib()
+    fp = lambda a: a.ctypes.data_as(F)
+
+    def pack():
+        return np.ascontiguousarray(np.stack([B.arr[k].astype(np.float32) for k in fields] + [np.zeros(n, np.float32)]))
+
+    def unpack(body):
+        for k, row in zip(fields, body):
+            B.arr[k][:] = row.astype(B.arr[k].dtype)
+
+    cstate = np.zeros(H.hc_words(N), np.float32)
+    body = pack()
+    H.hc_init(fp(body), fp(B.arr["len"]), fp(B.arr["wid"]), N, n, fp(cstate))
+    rng = np.random.default_rng(1)
+    touched = 0
+    for t in range(45):
+        for k in ("px", "py", "ang", "vx", "vy", "om", "sleep_t", "awake", "ox", "oy", "heading", "speed", "coll_veh"):
+            assert (A.arr[k] == B.arr[k]).all(), (mode, t, k)
+        tele = np.zeros(n, np.uint8)
+        for i in range(n):
+            a, s = (0.5, 0.0) if i < 3 else (rng.uniform(-2, 2), rng.uniform(-0.2, 0.2))
+            if t == 30 and i == 1:
+                A.teleport(i, -1000000, -1000000)
+                B.teleport(i, -1000000, -1000000)
+                tele[i] = 1
+            A.set_action(i, a, s)
+            B.set_action(i, a, s)
+        A.step(0.1)
+        L.simo_freecar_all(ctypes.byref(B.s), np.float32(0.1))
+        body = pack()
+        H.hc_world_step(fp(body), fp(B.arr["len"]), fp(B.arr["wid"]), N, n, fp(cstate), tele.ctypes.data_as(U8), np.float32(0.1))
+        unpack(body)
+        L.simo_finish_step(ctypes.byref(B.s), sim_port._fp(B.segs), len(B.segs))
+        assert H.hc_num_touching(fp(cstate), N, n) == A.n_touching(), (mode, t)
+        touched = max(touched, A.n_touching())
+    assert touched >= (2 if mode == "pile" else 1)
