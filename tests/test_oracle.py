@@ -669,7 +669,7 @@ def test_glibc_trig_mode_makes_the_contact_episodes_bit_exact(cfg, name):
     assert (rec["reward"][:, :, 6][ex] == g["reward"][:, :, 6][ex]).all() and g["reward"][:, :, 6][ex].any()
 
 
-@pytest.mark.parametrize("mode", ["rear", "side", "head", "pile"])
+@pytest.mark.parametrize("mode", ["rear", "side", "head", "pile", "dense"])
 def test_product_contact_code_equals_oracle_on_the_host(tmp_path, mode):
     """The PRODUCT's contact code (ctrlsim_b200/csrc/sim_contacts.cuh - what sim.cu compiles for the GPU), built for the
     host (tests/host_contacts_shim.cpp) and put between the oracle's FreeCar step and its Vehicle::Step / collision
@@ -689,7 +689,11 @@ def test_product_contact_code_equals_oracle_on_the_host(tmp_path, mode):
     H.hc_num_touching.argtypes = [F, ctypes.c_int, ctypes.c_int]
     fields = ("px", "py", "cx", "cy", "lcx", "lcy", "ang", "vx", "vy", "om", "sleep_t", "thr", "brk", "steer", "awake")
     assert H.hc_body_fields() == len(fields) + 1
-    parsed = sim_port.parse_scenario(collision_scene(mode)["json"])
+    if mode == "dense":  # BASELINE config-2 scene: 64 vehicles, random controls -> dozens of pairs, islands of several contacts
+        from ctrlsim_b200.synth import make_scene
+        parsed = sim_port.parse_scenario(make_scene(2)["json"])
+    else:
+        parsed = sim_port.parse_scenario(collision_scene(mode)["json"])
     A = sim_port.ScenePort(parsed, contacts=True)   # oracle, its own world step
     B = sim_port.ScenePort(parsed, contacts=False)  # oracle FreeCar / Vehicle::Step around the product's world step
     n = N = parsed["n"]
@@ -708,13 +712,13 @@ def test_product_contact_code_equals_oracle_on_the_host(tmp_path, mode):
     H.hc_init(fp(body), fp(B.arr["len"]), fp(B.arr["wid"]), N, n, fp(cstate))
     rng = np.random.default_rng(1)
     touched = 0
-    for t in range(45):
+    for t in range(90 if mode == "dense" else 45):
         for k in ("px", "py", "ang", "vx", "vy", "om", "sleep_t", "awake", "ox", "oy", "heading", "speed", "coll_veh"):
             assert (A.arr[k] == B.arr[k]).all(), (mode, t, k)
         tele = np.zeros(n, np.uint8)
         for i in range(n):
-            a, s = (0.5, 0.0) if i < 3 else (rng.uniform(-2, 2), rng.uniform(-0.2, 0.2))
-            if t == 30 and i == 1:
+            a, s = (0.5, 0.0) if (i < 3 and mode != "dense") else (rng.uniform(-3, 3), rng.uniform(-0.3, 0.3))
+            if (t == 30 and i == 1) or (mode == "dense" and t >= 60 and i % 7 == 3):
                 A.teleport(i, -1000000, -1000000)
                 B.teleport(i, -1000000, -1000000)
                 tele[i] = 1
@@ -728,4 +732,4 @@ def test_product_contact_code_equals_oracle_on_the_host(tmp_path, mode):
         L.simo_finish_step(ctypes.byref(B.s), sim_port._fp(B.segs), len(B.segs))
         assert H.hc_num_touching(fp(cstate), N, n) == A.n_touching(), (mode, t)
         touched = max(touched, A.n_touching())
-    assert touched >= (2 if mode == "pile" else 1)
+    assert touched >= {"pile": 2, "dense": 6}.get(mode, 1), (mode, touched)
