@@ -43,7 +43,56 @@ def collision_scene(mode):
     return sc
 
 
+def dense(sid=2):
+    """BASELINE config-2 scene (64 vehicles), uniformly random controls for everyone, vehicles vanishing from step 60:
+    up to 15 simultaneous touching contacts in islands of several vehicles.  Vehicles parked at (-1e6, -1e6) are not
+    compared: the reference solves the contacts among them, the restatement skips them (never observed)."""
+    from ctrlsim_b200.config import default_config
+    from ctrlsim_b200.synth import make_scene
+    from oracle import ref_shims, sim_port
+    ref_shims.install()
+    import nocturne
+    cfg = default_config()
+    sc = make_scene(sid)
+    path = tempfile.mktemp(suffix=".json")
+    with open(path, "w") as f:
+        json.dump(sc["json"], f)
+    sim = nocturne.Simulation(scenario_path=path, config=cfg.nocturne["scenario"])
+    vehs = sim.getScenario().vehicles()
+    for v in vehs:
+        v.expert_control = False
+        v.physics_simulated = True
+    port = sim_port.ScenePort(sim_port.parse_scenario(sc["json"]), contacts=True)
+    rng = np.random.default_rng(sid)
+    touched = 0
+    for t in range(91):
+        p = np.array([[v.getPosition().x, v.getPosition().y] for v in vehs])
+        live = p[:, 0] > -500000
+        assert (p[live] == port.position()[live]).all(), ("dense", t, np.abs(p - port.position())[live].max())
+        assert (np.array([v.getHeading() for v in vehs])[live] == port.heading()[live]).all(), ("dense", t)
+        assert (np.array([v.getSpeed() for v in vehs])[live] == port.speed()[live]).all(), ("dense", t)
+        touched = max(touched, port.n_touching())
+        for i, v in enumerate(vehs):
+            a, s = rng.uniform(-3, 3), rng.uniform(-0.3, 0.3)
+            if t >= 60 and i % 7 == 3:
+                v.setPosition(-1000000, -1000000)
+                port.teleport(i, -1000000, -1000000)
+            if a > 0:
+                v.acceleration = a
+            else:
+                v.brake(abs(a))
+            v.steering = s
+            port.set_action(i, a, s)
+        sim.step(0.1)
+        port.step(0.1)
+    assert touched >= 8, touched
+    os.remove(path)
+    print(f"dense: bit-exact for 90 steps, up to {touched} touching contacts at once")
+
+
 def main(mode):
+    if mode == "dense":
+        return dense()
     from ctrlsim_b200.config import default_config
     from oracle import ref_shims, sim_port
     ref_shims.install()
