@@ -13,9 +13,9 @@
 //                        b2_contact_solver.cpp:51-755 (block solver; 8 velocity / 3 position iterations,
 //                        PhysicsSimulation.cpp:22-24), b2WorldManifold::Initialize b2_collision.cpp:26-90
 // Same statement of the algorithm as the CPU oracle (oracle/sim_oracle.c, which is pinned bit for bit against the real
-// nocturne_cpp); the limits of both are the same: fixture "A" of a pair is the vehicle created first and the contacts of
-// one island are solved in creation order (what a fresh b2World does; the reference's process-wide world recycles tree
-// node ids between scenes), continuous collision never acts on two non-bullet dynamic bodies, pairs of vehicles
+// nocturne_cpp); the limits of both are the same: fixture "A" of a pair is the vehicle created first (what the reference's
+// dynamic tree gives, also after the evaluator's per-file world wipe), pairs found by one broad-phase update become
+// contacts in (moved body, other body) order, continuous collision never acts on two non-bullet dynamic bodies, pairs of vehicles
 // parked at (-1e6, -1e6) are skipped (never observed, re-teleported before every step).  Capacity: CS_MAX_CONTACTS
 // broad-phase pairs per scene and CS_MAX_ISLAND_CONTACTS touching contacts per island; beyond that the newest are dropped.
 #pragma once

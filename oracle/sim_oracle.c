@@ -380,10 +380,12 @@ void simo_velocity(const SimO* s, int i, float* vx, float* vy) {
  *   islands + solver     b2World::Solve b2_world.cpp:394-582, b2Island::Solve b2_island.cpp:188-388,
  *                        b2ContactSolver b2_contact_solver.cpp:51-755 (block solver, 8 velocity / 3 position iterations,
  *                        PhysicsSimulation.cpp:22-24), b2WorldManifold::Initialize b2_collision.cpp:26-90
- * Not restated: the dynamic tree itself.  It decides (a) which fixture of a pair is "A" - here the vehicle created
- * first, which is what a fresh b2World gives (leaf ids grow with creation order) - and (b) the order in which
- * several contacts of one island are solved - here creation order; an island with a single contact (two vehicles)
- * does not depend on it.  Continuous collision (SolveTOI) never acts on two non-bullet dynamic bodies
+ * Not restated: the dynamic tree itself.  It decides (a) which fixture of a pair is "A" - the smaller leaf id, i.e. the
+ * vehicle created first: true in a fresh b2World and also in the evaluator's flow, where DeleteScene() (utils/sim.py:64
+ * -> Simulation::Reset) wipes the world newest body first before every evaluated file and the LIFO free list hands the
+ * ids out again in creation order; (b) the order in which the pairs of one broad-phase update become contacts - here
+ * (moved body, other body) index order; it only matters inside islands with several contacts and was bit-exact on every
+ * case tried (tests/contact_case.py).  Continuous collision (SolveTOI) never acts on two non-bullet dynamic bodies
  * (b2_world.cpp: "collideA == false && collideB == false -> continue").  Vehicles parked at (-1e6, -1e6) by the
  * evaluator overlap each other there; the reference solves those contacts too, but those vehicles are re-teleported
  * before every step and never observed (existence 0), so pairs with both bodies beyond x < -5e5 are skipped.

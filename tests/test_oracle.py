@@ -550,8 +550,9 @@ def test_contact_solver_bit_exact_vs_reference_nocturne(mode):
     """Vehicles that hit each other: the C restatement of Box2D's broad phase bookkeeping, polygon manifold, warm-started
     sequential-impulse solver (block solver, 8 + 3 iterations) and island sleeping is bit-identical to the real
     nocturne_cpp / Box2D for the whole run - through the impact, the pushing phase, a vehicle vanishing mid-contact
-    and the separation; "dense" = 64 vehicles with random controls, up to 15 touching contacts at once.  Each case runs in a fresh process: the reference's b2World is a process singleton whose
-    dynamic tree recycles node ids, and which fixture of a pair is "A" follows those ids (tests/contact_case.py)."""
+    and the separation; "dense" = 64 vehicles with random controls, up to 15 touching contacts at once.  Each case runs
+    in a fresh process: the reference's b2World is a process singleton and a Simulation dropped without reset() leaves
+    its bodies in it, where they collide with the next case at the same coordinates (tests/contact_case.py)."""
     import subprocess
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "contact_case.py"), mode], capture_output=True,
                        text=True, timeout=300)
