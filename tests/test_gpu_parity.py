@@ -591,12 +591,11 @@ def test_planner_adversary_matches_reference(cfg, dev, name):
             assert abs(metrics[k] - v) < 0.05 * max(1.0, abs(v)), (k, metrics[k], v)
 
 
-@pytest.mark.xfail(strict=False, reason="CTRLSIM_TRIG=glibc was added after the last GPU session of round 1: verified on the "
-                                        "host (tools/trig_check.cpp, oracle glibc-port variant), not yet on a B200")
 def test_glibc_trig_mode_is_bit_exact_through_contacts(cfg, dev, monkeypatch):
     """With glibc's own sinf / cosf algorithm on the GPU (CTRLSIM_TRIG=glibc, glibc_trig.h) the simulator has no
     arithmetic difference to the reference left: 'crowded' (30 vehicles pushing each other from step 16 on) replayed
-    with the reference's controls must be bit-identical for all 90 steps (default mode: 0.73 mm)."""
+    with the reference's controls must be bit-identical for all 90 steps (default mode: 0.73 mm).  First run on a B200 in
+    the last GPU call of round 1 (profiles/r01_glibc_trig_gpu.txt)."""
     from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
     from ctrlsim_b200.synth import make_scene
     g, spec, _ = load_golden("crowded")
