@@ -734,3 +734,48 @@ def test_product_contact_code_equals_oracle_on_the_host(tmp_path, mode):
         assert H.hc_num_touching(fp(cstate), N, n) == A.n_touching(), (mode, t)
         touched = max(touched, A.n_touching())
     assert touched >= {"pile": 2, "dense": 6}.get(mode, 1), (mode, touched)
+
+
+# ---- groundwork for SURVEY 8(f) N1: dense real-time reward ------------------------------------------------------------
+def test_dense_reward_port_matches_the_reference_functions(cfg):
+    """oracle/dense_reward_port.py (scalar loops) against the reference's own array code: signed distance to road-edge
+    polylines (utils/data.py:152-290), nearest-vehicle distance and compute_rewards (datasets/rl_waymo/dataset.py:
+    202-275) as evaluators/evaluator.py:106-140 combines them.  No product counterpart yet (next round)."""
+    from oracle import ref_shims
+    from oracle.dense_reward_port import dense_reward_step, signed_distance_to_polylines
+    ref_shims.install()
+    from utils.data import compute_distance_to_road_edge
+    from datasets.rl_waymo import RLWaymoDatasetCtRLSim
+    rng = np.random.default_rng(0)
+    th = np.linspace(0, 2 * np.pi, 41)
+    ring = np.stack([30 * np.cos(th), 20 * np.sin(th)], -1)                      # closed, counter-clockwise
+    ring[-1] = ring[0]
+    edge = np.stack([np.linspace(-60, 60, 25), 35 + 3 * np.sin(np.linspace(0, 6, 25))], -1)  # open, wavy
+    zig = np.array([[-50.0, -40.0], [-20.0, -30.0], [0.0, -45.0], [25.0, -28.0], [55.0, -42.0]])
+    polys = [ring, edge, zig]
+    pts = rng.uniform(-70, 70, size=(400, 2))
+    pts = np.concatenate([pts, ring[::5] * 1.0, edge[::4] + 1e-9, np.array([[30.0, 0.0], [-60.0, 35.0]])])
+    ref = compute_distance_to_road_edge(pts[:, 0][None], pts[:, 1][None], polys)
+    got = np.array([signed_distance_to_polylines(x, y, polys) for x, y in pts])
+    assert np.abs(got - ref).max() < 1e-9, np.abs(got - ref).max()
+    assert (np.sign(got[np.abs(got) > 1e-6]) == np.sign(ref[np.abs(got) > 1e-6])).all()
+    # one step of compute_dense_reward
+    dset = RLWaymoDatasetCtRLSim.__new__(RLWaymoDatasetCtRLSim)
+    dset.cfg_dataset = cfg.dataset.waymo
+    n = 12
+    pos = rng.uniform(-40, 40, size=(n, 2))
+    exist = (rng.uniform(size=n) > 0.25).astype(np.float64)
+    rew = rng.uniform(0, 1, size=(n, 8))
+    rew[:, [0, 1, 2, 6, 7]] = (rew[:, [0, 1, 2, 6, 7]] > 0.7).astype(np.float64)
+    proc = rew[:, None, :] * exist[:, None, None]
+    ag = pos[:, None, :]
+    edge_r = dset.compute_dist_to_nearest_road_edge_rewards(ag, polys) * exist[:, None]
+    agx = np.concatenate([pos, exist[:, None]], 1)[:, None, :]
+    vv = dset.compute_dist_to_nearest_vehicle_rewards(agx.copy(), normalize=False) * exist[:, None]
+    w = cfg.dataset.waymo
+    vvn = np.clip(vv, 0.0, w.max_veh_veh_distance) / w.max_veh_veh_distance
+    allr = dset.compute_rewards(agx, proc, edge_r, vvn)
+    ref_dense = np.concatenate([allr[:, :, :1], allr[:, :, 3:]], -1)[:, 0]
+    dense, nearest = dense_reward_step(w, pos, exist, rew, polys)
+    assert np.abs(dense - ref_dense).max() < 1e-9, np.abs(dense - ref_dense).max()
+    assert np.abs(nearest - vv[:, 0]).max() < 1e-9
