@@ -24,7 +24,7 @@ import torch
 import torch.nn.functional as F
 
 
-def causal_mask_rule(A: int, T: int, K: int = 3) -> torch.Tensor:
+def causal_mask_rule(A: int, T: int, K: int = 3, state_index: int = 0) -> torch.Tensor:
     """Boolean [L,L] 'allowed' matrix, token index = (t*A + a)*K + k with k in (state, rtg, action).
 
     Rule M1 (attend_own_return_action = False): j is visible from i iff t_j < t_i, or t_j == t_i and
@@ -36,7 +36,9 @@ def causal_mask_rule(A: int, T: int, K: int = 3) -> torch.Tensor:
     k = idx % K
     ti, tj = t[:, None], t[None, :]
     same_agent = a[:, None] == a[None, :]
-    allowed = (tj < ti) | ((tj == ti) & ((k[None, :] == 0) | (same_agent & (k[None, :] <= k[:, None]))))
+    # state_index: position of the state token inside a (step, agent) triple - 0 for CtRL-Sim (state, rtg, action),
+    # 1 for the decision-transformer baseline (rtg, state, action) (utils/train_utils.py:85-88)
+    allowed = (tj < ti) | ((tj == ti) & ((k[None, :] == state_index) | (same_agent & (k[None, :] <= k[:, None]))))
     return allowed
 
 
@@ -80,7 +82,8 @@ class ModelPort:
         self.m, self.w = cfg.model, cfg.dataset.waymo
         self.sd = {k: torch.as_tensor(v, dtype=torch.float32) for k, v in weights.items()}
         A, T = self.w.max_num_agents, self.w.train_context_length
-        allowed = causal_mask_rule(A, T, 3)
+        self.dt = bool(getattr(self.m, "decision_transformer", False))
+        allowed = causal_mask_rule(A, T, 3, state_index=1 if self.dt else 0)
         self.add_mask = torch.zeros(allowed.shape, dtype=torch.float32).masked_fill(~allowed, float("-inf"))
 
     # ---- M2 ------------------------------------------------------------------------------------------------
@@ -120,15 +123,23 @@ class ModelPort:
         s_emb = F.linear(torch.cat([s_emb, g_emb], dim=-1), sd["encoder.embed_state_goal.weight"],
                          sd["encoder.embed_state_goal.bias"]) + ts_emb + id_emb
         a_emb = sd["encoder.embed_action.weight"][actions] + ts_emb + id_emb
-        r_cat = torch.cat([sd["encoder.embed_rtg_goal.weight"][rtgs[..., 0]],
-                           sd["encoder.embed_rtg_veh.weight"][rtgs[..., 1]],
-                           sd["encoder.embed_rtg_road.weight"][rtgs[..., 2]]], dim=-1)
+        if getattr(self.m, "decision_transformer", False):
+            # DT baseline (cfgs/model/dt.yaml; modules/encoder.py:27-30,116-120): continuous, clip-normalised RTGs through
+            # Linear(1 -> H) per component instead of embedding tables.  Oracle groundwork for SURVEY 8(f) N1.
+            rc = data["rtgs"].transpose(1, 2).float()
+            r_cat = torch.cat([F.linear(rc[..., k:k + 1], sd[f"encoder.embed_rtg_{nm}.weight"], sd[f"encoder.embed_rtg_{nm}.bias"])
+                               for k, nm in enumerate(("goal", "veh", "road"))], dim=-1)
+        else:
+            r_cat = torch.cat([sd["encoder.embed_rtg_goal.weight"][rtgs[..., 0]],
+                               sd["encoder.embed_rtg_veh.weight"][rtgs[..., 1]],
+                               sd["encoder.embed_rtg_road.weight"][rtgs[..., 2]]], dim=-1)
         r_emb = F.linear(r_cat, sd["encoder.embed_rtg.weight"], sd["encoder.embed_rtg.bias"]) + ts_emb + id_emb
         ex = exist.float()
         s_emb, a_emb, r_emb = s_emb * ex, a_emb * ex, r_emb * ex
         init_emb = s_emb[:, 0]                                                   # [B,A,H] (pre-LN, encoder.py:111-112)
         init_exist = exist[:, 0, :, 0].bool()
-        stacked = torch.stack([s_emb, r_emb, a_emb], dim=3).reshape(B, T * A * 3, H)
+        order = [r_emb, s_emb, a_emb] if self.dt else [s_emb, r_emb, a_emb]  # modules/encoder.py:139-152
+        stacked = torch.stack(order, dim=3).reshape(B, T * A * 3, H)
         stacked = _ln(sd, "encoder.embed_ln", stacked)
         poly, valid = self.map_encoder(data["road_points"].float(), data["road_types"].float())
         x = torch.cat([poly, init_emb], dim=1)
@@ -165,5 +176,7 @@ class ModelPort:
         T = stacked.shape[1] // (A * 3)
         out = self.decoder(stacked, memory, pad).view(B, T * A, 3, -1)
         action_preds = _mlp(self.sd, "decoder.predict_action", out[:, :, 1]).view(B, T, A, -1).permute(0, 2, 1, 3)
-        rtg_preds = _mlp(self.sd, "decoder.predict_rtg", out[:, :, 0]).view(B, T, A, -1).permute(0, 2, 1, 3)
-        return {"action_preds": action_preds, "rtg_preds": rtg_preds, "hidden": out}
+        preds = {"action_preds": action_preds, "hidden": out}
+        if getattr(self.m, "predict_rtg", True):  # the DT baseline has no RTG head (cfgs/model/dt.yaml)
+            preds["rtg_preds"] = _mlp(self.sd, "decoder.predict_rtg", out[:, :, 0]).view(B, T, A, -1).permute(0, 2, 1, 3)
+        return preds

@@ -182,6 +182,10 @@ def test_mask_rule_equals_reference_get_causal_mask(cfg):
     small.dataset.waymo.max_num_agents = 4
     ref = get_causal_mask(small, 5, 3)
     assert ((ref == 0).numpy() == causal_mask_rule(4, 5, 3).numpy()).all()
+    import copy
+    dt = copy.deepcopy(small)  # decision-transformer token order (rtg, state, action): the state token sits at index 1
+    dt.model.decision_transformer = True
+    assert ((get_causal_mask(dt, 5, 3) == 0).numpy() == causal_mask_rule(4, 5, 3, state_index=1).numpy()).all()
 
 
 @pytest.mark.parametrize("name,step", [("plumbing", 9), ("crowded", 33), ("sparse", 89)])
@@ -779,3 +783,49 @@ def test_dense_reward_port_matches_the_reference_functions(cfg):
     dense, nearest = dense_reward_step(w, pos, exist, rew, polys)
     assert np.abs(dense - ref_dense).max() < 1e-9, np.abs(dense - ref_dense).max()
     assert np.abs(nearest - vv[:, 0]).max() < 1e-9
+
+
+def test_model_port_dt_variant_matches_the_reference_modules(cfg):
+    """Decision-transformer baseline (cfgs/model/dt.yaml: continuous RTG inputs, no RTG head): oracle/model_port.py against
+    the reference Encoder / Decoder built with that configuration and its own random initialisation.  Oracle groundwork
+    for SURVEY 8(f) N1 - no product counterpart yet."""
+    import copy
+    import torch
+    from oracle import ref_shims
+    from oracle.model_port import ModelPort
+    ref_shims.install()
+    from models import CtRLSim
+    c = copy.deepcopy(cfg)
+    c.model.decision_transformer, c.model.predict_rtg, c.model.predict_future_states = True, False, False
+    torch.manual_seed(0)
+    ref = CtRLSim(c).eval()
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    assert sd["encoder.embed_rtg_goal.weight"].shape == (c.model.hidden_dim, 1) and "decoder.predict_rtg.mlp.0.weight" not in sd
+    A, T, P = c.dataset.waymo.max_num_agents, c.dataset.waymo.train_context_length, c.dataset.waymo.max_num_road_polylines
+    g = torch.Generator().manual_seed(1)
+    n = 7
+    st = torch.zeros(1, A, T, 8, dtype=torch.float64)
+    st[0, :n, :, :7] = torch.randn(n, T, 7, generator=g, dtype=torch.float64) * torch.tensor([20, 20, 5, 5, 1, 0.1, 0.1]) + torch.tensor([0, 0, 0, 0, 0, 4.8, 2.0])
+    st[0, :n, :, 7] = (torch.rand(n, T, generator=g) > 0.1).double()
+    types = -torch.ones(1, A, 5, dtype=torch.float64)
+    types[0, :n] = torch.eye(5, dtype=torch.float64)[1]
+    rp = torch.zeros(1, P, 100, 3, dtype=torch.float64)
+    rp[0, :40, :, :2] = torch.randn(40, 100, 2, generator=g, dtype=torch.float64) * 30
+    rp[0, :40, :, 2] = (torch.rand(40, 100, generator=g) > 0.2).double()
+    rt = -torch.ones(1, P, 8, dtype=torch.float64)
+    rt[0, :40] = torch.eye(8, dtype=torch.float64)[torch.randint(0, 8, (40,), generator=g)]
+    data = {"agent_states": st, "agent_types": types, "goals": torch.randn(1, A, 5, generator=g, dtype=torch.float64) * 10,
+            "actions": torch.randint(0, 1000, (1, A, T), generator=g).double(),
+            "rtgs": torch.rand(1, A, T, 3, generator=g, dtype=torch.float64),
+            "timesteps": torch.arange(T)[None, None, :, None].expand(1, A, T, 1).clone(),
+            "road_points": rp, "road_types": rt}
+    from torch_geometric.data import HeteroData
+    md = HeteroData({"agent": {k: data[k] for k in ("agent_states", "agent_types", "goals", "actions", "rtgs", "timesteps")},
+                     "map": {"road_points": data["road_points"], "road_types": data["road_types"]}})
+    md["agent"]["moving_agent_mask"] = torch.ones(1, A)
+    with torch.no_grad():
+        want = ref(md, eval=True)["action_preds"]
+    got = ModelPort(c, sd).forward(data)
+    assert "rtg_preds" not in got
+    d = (got["action_preds"][0, :n] - want[0, :n]).abs().max().item()
+    assert d < 5e-5, d
