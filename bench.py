@@ -262,7 +262,8 @@ def main():
                    "focal_groups_per_step_avg": groups_all / args.steps / world, "chunk_groups": args.chunk,
                    "l2": "per-step working set (>10 GB of activations per chunk) far exceeds the 126 MB L2; no explicit flush",
                    "weights": "random-init (deterministic generator), reference architecture",
-                   "map_cache": "per-focal polyline-encoder cache for steps 0..31 (ctrlsim_attach_map_cache): " + ("on" if pol.use_map_cache else "off")},
+                   "map_cache": "per-focal polyline-encoder cache for steps 0..31 (ctrlsim_attach_map_cache): " + ("on" if pol.use_map_cache else "off"),
+                   "simulator": "FreeCar + Box2D vehicle-vehicle contact response: " + ("off" if os.environ.get("CTRLSIM_CONTACTS", "1") == "0" else "on")},
         "gpu_launches": int(launches_all),
         "clocks": clk,
         "roofline": {"kernel": "gemm_tc_tma_kernel (every nn.Linear: tcgen05 kind::tf32, 3-product hi/lo split = fp32-accurate, 3 tensor flops per counted flop)", "bound": "tensor", "achieved": gemm_tf,
