@@ -3,12 +3,19 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--scenes S] [--impl b200|reference]
 
 Workload (BASELINE.json configs[1], per GPU): S=256 synthetic Waymo-shaped scenes x 64 policy-controlled vehicles x
-256 polylines, RTG-conditioned autoregressive policy, 90-step episodes.  A "step" is one simulator step of the whole
-scene batch: observe -> focal grouping -> tokenise -> two-pass network -> RTG/action sampling -> log-replay/act ->
-physics + collision.  The timed region continues the running episode (and wraps into the next one), so with the
-default K=90 it covers exactly one episode's mix of short (t<32) and full 32-step windows.  Scenes shard over
-ranks with no data-path collective ("weak": per-GPU work fixed); the only collective is the summary all-reduce at
-the end of an evaluation, exercised in the e2e leg.
+256 polylines, RTG-conditioned autoregressive policy, 90-step episodes (evaluators/policy_evaluator.py:514-557).
+A "step" is one simulator step of the whole scene batch: observe -> focal grouping -> tokenise -> two-pass network ->
+RTG/action sampling -> log-replay/act -> physics + collision.
+
+An episode has two very different phases: steps 0..31 (the 32-step window still starts at t=0, prefix + map caches
+apply, ~6 % of the episode's time) and steps 32..89 (window slides, everything is recomputed).  Whatever K is, the
+timed steps are drawn from both phases IN EPISODE PROPORTION (58 : 32): K = 90 q + r is timed as q whole episodes plus
+round(r 58/90) full-window steps (t >= 32) plus the remaining steps of the cached phase, ending at t = 31.  Each timed
+segment is bracketed by barrier + synchronize and timed with CUDA events; between segments the episode is
+fast-forwarded untimed.  W warm-up steps run untimed in front of each phase's segment.  So `value` is the whole-episode
+throughput for every K (the `phases` object gives the per-step time of either phase).  Scenes shard over ranks with
+no data-path collective ("weak": per-GPU work fixed); the only collective is the summary all-reduce at the end of an
+evaluation, exercised in the e2e leg.
 
   value          agent-steps/s, state resident in HBM, CUDA-event timed, max over ranks
   e2e            the same metric through the public API from HOST scene arrays: B200PolicyEvaluator.evaluate_policy()
@@ -16,8 +23,11 @@ the end of an evaluation, exercised in the e2e leg.
                  device -> host read of the summary and of the full per-vehicle trace
   roofline       dominant kernel class of the step, timed live with CUDA events on the launching stream
   encoder_attn   the polyline-pooling attention kernel (HBM-bound), the kernel BASELINE.json's metric names
-  cpu_baseline   the oracle port (numpy/torch CPU restatement of the reference policy + C restatement of the simulator)
-                 timed on this box's host cores on a bounded sample (1 scene of the same workload, a few steps)
+  cpu_baseline   the reference's algorithm on this box's host cores (oracle port: two full B=1 2304-token forwards per
+                 focal group per step + C simulator), process-parallel: one single-threaded process per core, one scene
+                 of the same workload each, a stated prefix of the episode
+  gpu_torch_baseline  the same port's network on cuda:0 with stock torch ops at B=1 (the reference's GPU cost structure,
+                 policies/autoregressive_policy.py:183-210): forward time only, so an upper bound for that path
 """
 from __future__ import annotations
 
@@ -33,7 +43,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-WORKLOAD = "256 synthetic 64-agent/256-polyline scenes per GPU, 90-step episodes, RTG-conditioned autoregressive policy"
+T_WIN = 32  # context length: steps t < 32 are the cached phase
+
+
+def workload_name(scenes, wide):
+    geom = "wide model caps A=64/P=256 (one focal group per scene)" if wide else "reference-default caps A=24/P=200 (~11.6 focal groups per scene)"
+    return (f"{scenes} synthetic 64-agent/256-polyline scenes per GPU, 90-step episodes, RTG-conditioned autoregressive "
+            f"policy, {geom}")
 
 
 def _peaks():
@@ -42,6 +58,13 @@ def _peaks():
         d = json.load(open(p))
         return {"hbm": d["hbm_gbs"], "hbm_src": "measured", "tf": d["bf16_tflops_sustained"], "tf_src": "measured (sustained bf16 cuBLAS)"}
     return {"hbm": 6650.0, "hbm_src": "fallback", "tf": 1400.0, "tf_src": "fallback"}
+
+
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep files)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
 
 
 class ClockSampler:
@@ -62,14 +85,19 @@ class ClockSampler:
         for line in self.p.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, spans=None):
+        """spans: list of (row_begin, row_end) index pairs of the timed segments; only those samples count."""
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = self.rows if not spans else [r for a, b in spans for r in self.rows[a:max(b, a + 1)]]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -79,25 +107,108 @@ def make_scenes(n, first_id, stride, **kw):
     return [make_scene(first_id + i * stride, **kw) for i in range(n)], [first_id + i * stride for i in range(n)]
 
 
-def cpu_reference_run(cfg, weights, steps, n_scenes=1):
-    """The reference's algorithm on host cores: oracle policy port (2 full B=1 forwards per focal group per step, like
-    policies/autoregressive_policy.py:190,210) + C simulator restatement. Returns (agent_steps_per_s, cores, sample)."""
+# ---- the reference's CPU cost structure on host cores --------------------------------------------------------------
+def cpu_worker(scene_id, steps, wide):
+    """One single-threaded process = one scene of the workload, first `steps` steps of its episode."""
     import torch
+    torch.set_num_threads(1)
+    from ctrlsim_b200.config import default_config
+    from ctrlsim_b200.weights import make_weights
     from oracle.model_port import ModelPort
     from oracle.policy_port import RolloutPort
-    try:  # torchrun exports OMP_NUM_THREADS=1 to its workers: take every host core this process may use
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except (AttributeError, RuntimeError):
-        pass
-    scenes, ids = make_scenes(n_scenes, 10_000, 1)
+    cfg = default_config(wide=wide)
+    weights = make_weights(cfg, seed=0)
+    scenes, ids = make_scenes(1, scene_id, 1)
     port = RolloutPort(cfg, ModelPort(cfg, weights), seed=0, eval_threshold=64)
+    print("READY", flush=True)
+    sys.stdin.readline()  # all workers start together
     t0 = time.perf_counter()
-    agents = 0
-    for sid, sc in zip(ids, scenes):
-        rec = port.run_scene(sid, sc["json"], sc["preproc"], max_steps=steps)
-        agents += len(rec["evaluated"])
+    rec = port.run_scene(ids[0], scenes[0]["json"], scenes[0]["preproc"], max_steps=steps)
     wall = time.perf_counter() - t0
-    return agents * steps / wall, torch.get_num_threads(), f"{n_scenes} scene(s) x 64 agents x 256 polylines, first {steps} steps of the episode, {port.n_forwards} full 2304-token forwards"
+    print(json.dumps({"agents": len(rec["evaluated"]), "steps": steps, "wall": wall, "forwards": port.n_forwards}), flush=True)
+
+
+def cpu_reference_run(steps, wide=False, n_proc=None):
+    """N_proc = host cores, one single-threaded process per core, each running whole scenes of
+    the workload (here: the first `steps` steps of one scene each).  Returns (agent-steps/s, cores, sample, detail)."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    n_proc = n_proc or max(1, cores)
+    env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", str(10_000 + i), "--cpu-steps",
+                               str(steps)] + (["--wide"] if wide else []), stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                              text=True, env=env, cwd=ROOT) for i in range(n_proc)]
+    for p in procs:
+        line = p.stdout.readline()
+        assert line.strip() == "READY", f"cpu worker failed to start: {line!r}"
+    t0 = time.perf_counter()
+    for p in procs:
+        p.stdin.write("go\n")
+        p.stdin.flush()
+    recs = [json.loads(p.stdout.readline()) for p in procs]
+    wall = time.perf_counter() - t0
+    for p in procs:
+        p.wait()
+    agent_steps = sum(r["agents"] * r["steps"] for r in recs)
+    fw = sum(r["forwards"] for r in recs)
+    sample = (f"{n_proc} processes x 1 thread, one scene (64 agents x 256 polylines) each, first {steps} step(s) of the "
+              f"episode, {fw} full-window B=1 forwards in total (the reference pads every window to 32 steps, so its "
+              f"cost per step does not depend on t)")
+    return agent_steps / wall, n_proc, sample, {"wall_s": wall, "forwards": fw, "s_per_forward_1thread": sum(r["wall"] for r in recs) / max(fw, 1)}
+
+
+def gpu_torch_run(cfg, weights, dev, groups_per_scene, agents_per_scene, reps=6):
+    """Stock torch ops on the same B200 at B=1, two full forwards per focal group per step - the reference's own GPU
+    cost structure (policies/autoregressive_policy.py:183-210).  Forward time only (tokenisation, the .cpu() syncs and
+    the CPU simulator of the reference are NOT included), so this is an upper bound for that path."""
+    import numpy as np
+    import torch
+    from oracle.model_port import ModelPort
+    w = cfg.dataset.waymo
+    A, T, P = w.max_num_agents, w.train_context_length, w.max_num_road_polylines
+    port = ModelPort(cfg, weights).to(dev)
+    rng = np.random.default_rng(0)
+    data = {"agent_states": np.concatenate([rng.normal(size=(1, A, T, 7)), np.ones((1, A, T, 1))], -1),
+            "agent_types": np.eye(5)[rng.integers(0, 5, (1, A))], "goals": rng.normal(size=(1, A, 5)),
+            "actions": rng.integers(0, 1000, (1, A, T)), "rtgs": rng.integers(0, 350, (1, A, T, 3)),
+            "timesteps": np.tile(np.arange(T)[None, None, :, None], (1, A, 1, 1)),
+            "road_points": np.concatenate([rng.normal(size=(1, P, 100, 2)), np.ones((1, P, 100, 1))], -1),
+            "road_types": np.eye(8)[rng.integers(0, 8, (1, P))]}
+    data = {k: torch.from_numpy(v).to(dev) for k, v in data.items()}
+    for _ in range(3):
+        port.forward(data)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = port.forward(data)
+        out["action_preds"][0, 0, -1, 0].item()  # the reference reads logits back every forward
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    v = agents_per_scene / (groups_per_scene * 2 * ms * 1e-3)
+    return {"value": v, "unit": "agent-steps/s", "ms_per_forward": ms, "kind": "port (stock torch ops, fp32, TF32 off)",
+            "sample": f"{reps} B=1 forwards of one {A * T * 3}-token group on cuda; value = {agents_per_scene} agents / "
+                      f"({groups_per_scene:.2f} groups per scene x 2 forwards x ms_per_forward); network time only"}
+
+
+def plan_segments(K, W, steps=90):
+    """-> list of timed segments (t_first, n_steps, warm_from) whose phase mix is the episode's (see module docstring).
+    warm_from: episode step the untimed run-up to the segment must at least start from (W steps earlier when possible)."""
+    q, r = divmod(K, steps)
+    n_full = int(round(r * (steps - T_WIN) / steps))
+    n_cached = r - n_full
+    segs = []
+    if n_full:
+        t0 = min(T_WIN + W, steps - n_full)
+        segs.append((t0, n_full))
+    if n_cached:
+        segs.append((T_WIN - n_cached, n_cached))
+    for _ in range(q):
+        segs.append((0, steps))
+    return segs
 
 
 def main():
@@ -108,10 +219,17 @@ def main():
     ap.add_argument("--scenes", type=int, default=256, help="scenes per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk", type=int, default=256, help="focal groups per workspace chunk")
+    ap.add_argument("--wide", action="store_true", help="wide model variant: A=64 agents / P=256 polylines per group")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-torch-gpu", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=1)
+    ap.add_argument("--cpu-worker", type=int, default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+
+    if args.cpu_worker is not None:
+        cpu_worker(args.cpu_worker, args.cpu_steps, args.wide)
+        return
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -119,24 +237,29 @@ def main():
 
     from ctrlsim_b200.config import default_config
     from ctrlsim_b200.weights import make_weights
-    cfg = default_config()
+    cfg = default_config(wide=args.wide)
     weights = make_weights(cfg, seed=0)
+    n_ep = cfg.nocturne.steps
 
     if args.impl == "reference":
         if rank != 0:
             return
-        # bounded sample of the same workload: the first min(K, 6) steps of ONE of its scenes (each step = 64 agent-steps
-        # = 2 full forwards for each of the scene's ~12 focal groups); ms_per_step extrapolates to one step of the
-        # whole N-GPU job (256 scenes x 64 agents per GPU) at the measured rate
-        steps = max(1, args.steps)
-        v, cores, sample = cpu_reference_run(cfg, weights, steps=min(steps, 6))
+        # bounded sample of the same workload: one scene per host core, min(K, 2) steps each (every step of the
+        # reference costs the same: two full padded-window forwards per focal group); ms_per_step is the MEASURED wall
+        # time per step of that sample, not an extrapolation to the 256-scene batch
+        steps_run = max(1, min(args.steps, 2))
+        t0 = time.perf_counter()
+        v, cores, sample, det = cpu_reference_run(steps_run, wide=args.wide)
         line = {"impl": "reference", "metric": "agent-steps/s", "value": v, "unit": "agent-steps/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.scenes * 64 * args.gpus / v,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * det["wall_s"] / steps_run,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "note": "bounded sample: one scene of the workload on this box's host "
-                           "cores (the CPU path does not use the GPUs; value is the same for every N)"},
-                "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
-                "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "config": {"workload": workload_name(args.scenes, args.wide), "steps_run": steps_run,
+                           "note": "bounded sample: one scene of the workload per host core, the first steps_run steps "
+                                   "of the episode; ms_per_step is the measured wall time per step of that sample (the "
+                                   "CPU path does not use the GPUs; value is the same for every N)"},
+                "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample, **det},
+                "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "wall_s_total": time.perf_counter() - t0}
         print(json.dumps(line), flush=True)
         return
 
@@ -151,10 +274,10 @@ def main():
     dev = torch.device(f"cuda:{local}")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lib = L.load()
 
     scenes, ids = make_scenes(args.scenes, rank, world)
     model = DeviceModel(cfg, weights, dev)
+    lib = model.lib
     pol = B200Policy(cfg, "synthetic", model, seed=0, chunk_groups=args.chunk)
     ev = B200PolicyEvaluator(cfg, pol, scenes=scenes, scene_ids=ids)
     ev.rank, ev.world = 0, 1  # every rank owns all of ITS scenes (already sharded above)
@@ -171,36 +294,57 @@ def main():
         pol.update_state(batch, t)
         g = pol.predict(batch, t)
         pol.act(batch, t)
-        state["t"] = (t + 1) % cfg.nocturne.steps
+        state["t"] = (t + 1) % n_ep
         return g
 
-    for _ in range(args.warmup):
-        one_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    def goto(t):  # untimed fast-forward of the running episode to step t (restarting it when t lies behind)
+        while state["t"] != t:
+            one_step()
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    lib.ctrlsim_profile_enable(1)
-    launches0 = lib.ctrlsim_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    groups = 0
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        groups += one_step()
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    launches = lib.ctrlsim_launch_count() - launches0
     import ctypes
-    prof = (ctypes.c_double * 12)()
-    lib.ctrlsim_profile_read(prof)
-    lib.ctrlsim_profile_enable(0)
-    clk = clocks.stop() if rank == 0 else None
+    segs = plan_segments(args.steps, args.warmup, n_ep)
+    ms_total, groups, launches = 0.0, 0, 0
+    phase_ms = {"cached": [0.0, 0], "full_window": [0.0, 0]}
+    prof = [0.0] * 12
+    spans = []
+    for t_first, n in segs:
+        # run-up: W untimed warm-up steps of the same phase directly in front of the segment (wrapping into the
+        # previous episode for a segment that starts at t = 0)
+        goto((t_first - args.warmup) % n_ep if t_first >= args.warmup or state["t"] > t_first else 0)
+        goto(t_first)
+        fence()
+        lib.ctrlsim_profile_enable(1)
+        l0 = lib.ctrlsim_launch_count()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        r0 = clocks.mark()
+        torch.cuda.synchronize()
+        evs[0].record()
+        for i in range(n):
+            groups += one_step()
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        fence()
+        spans.append((r0, clocks.mark()))
+        ms_total += evs[0].elapsed_time(evs[n])
+        launches += lib.ctrlsim_launch_count() - l0
+        for i in range(n):
+            ph = phase_ms["cached" if (t_first + i) % n_ep < T_WIN else "full_window"]
+            ph[0] += evs[i].elapsed_time(evs[i + 1])
+            ph[1] += 1
+        buf = (ctypes.c_double * 12)()
+        lib.ctrlsim_profile_read(buf)
+        lib.ctrlsim_profile_enable(0)
+        prof = [a + b for a, b in zip(prof, buf)]
+    clk = clocks.stop(spans) if rank == 0 else None
+    ms = ms_total
 
     tt = torch.tensor([ms, float(n_agents * args.steps), float(launches), float(groups)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -215,9 +359,7 @@ def main():
     # ---- e2e: public API from host arrays, one full evaluation ----------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        fence()
         host_bytes = sum(v.numel() * v.element_size() for k, v in batch.t.items())
         t0 = time.perf_counter()
         ev2 = B200PolicyEvaluator(cfg, pol, scenes=scenes, scene_ids=ids)
@@ -233,13 +375,14 @@ def main():
         wall = time.perf_counter() - t0
         d2h = sum(v.nbytes for v in tr.values()) + summ.nbytes
         w = torch.tensor([wall], dtype=torch.float64, device=dev)
-        a = torch.tensor([float(b2.n_evaluated() * cfg.nocturne.steps)], dtype=torch.float64, device=dev)
+        a = torch.tensor([float(b2.n_evaluated() * n_ep)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(w, op=dist.ReduceOp.MAX)
             dist.all_reduce(a, op=dist.ReduceOp.SUM)
         e2e = {"value": a.item() / w.item(), "unit": "agent-steps/s",
-               "h2d_bytes_per_step": int(host_bytes / cfg.nocturne.steps), "d2h_bytes_per_step": int(d2h / cfg.nocturne.steps),
+               "h2d_bytes_per_step": int(host_bytes / n_ep), "d2h_bytes_per_step": int(d2h / n_ep),
                "episode_wall_s": w.item(), "host_parse_and_upload_s": t_h2d - t0,
+               "what": "B200PolicyEvaluator.evaluate_policy() pieces from host scene arrays: one whole 90-step episode",
                "metrics": ev2.metrics_from_summary(summ) if rank == 0 else None}
 
     if rank != 0:
@@ -248,32 +391,45 @@ def main():
         return
 
     pk = _peaks()
+    traffic = _ncu_traffic()
     gemm_ms, gemm_fl, gemm_n = prof[0], prof[1], prof[2]
     pool_ms, pool_by, pool_n = prof[3], prof[4], prof[5]
     sa_ms, sa_fl, sa_n = prof[6], prof[7], prof[8]
     ca_ms, ca_fl, ca_n = prof[9], prof[10], prof[11]
     gemm_tf = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     pool_gbs = pool_by / (pool_ms * 1e-3) / 1e9 if pool_ms > 0 else 0.0
+    n_full = phase_ms["full_window"][1]
+    enc = {"kernel": "map_pool_kernel (polyline pooling attention, TMA bulk + mbarrier ring)", "bound": "hbm",
+           "peak": pk["hbm"], "unit": "GB/s", "peak_source": pk["hbm_src"], "launches": int(pool_n),
+           "traffic": traffic.get("map_pool_kernel")}
+    if pool_n > 0:
+        enc.update({"achieved": pool_gbs, "frac": pool_gbs / pk["hbm"], "share_of_step": pool_ms / ms,
+                    "avg_launch_ms": pool_ms / pool_n, "algorithmic_bytes_per_launch": pool_by / pool_n})
+    else:
+        enc.update({"achieved": None, "frac": None, "note": "not exercised: no full-window step in the timed region"})
     line = {
         "metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "scenes_per_gpu": args.scenes, "controlled_agents_rank0": n_agents,
+        "config": {"workload": workload_name(args.scenes, args.wide), "scenes_per_gpu": args.scenes,
+                   "controlled_agents_rank0": n_agents,
                    "focal_groups_per_step_avg": groups_all / args.steps / world, "chunk_groups": args.chunk,
+                   "timed_segments": [{"t_first": a, "steps": b} for a, b in segs],
                    "l2": "per-step working set (>10 GB of activations per chunk) far exceeds the 126 MB L2; no explicit flush",
                    "weights": "random-init (deterministic generator), reference architecture",
                    "map_cache": "per-focal polyline-encoder cache for steps 0..31 (ctrlsim_attach_map_cache): " + ("on" if pol.use_map_cache else "off"),
                    "simulator": "FreeCar + Box2D vehicle-vehicle contact response: " + ("off" if os.environ.get("CTRLSIM_CONTACTS", "1") == "0" else "on")},
+        "phases": {"cached_ms_per_step": phase_ms["cached"][0] / max(phase_ms["cached"][1], 1), "cached_steps": phase_ms["cached"][1],
+                   "full_window_ms_per_step": phase_ms["full_window"][0] / max(n_full, 1), "full_window_steps": n_full,
+                   "episode_mix": "58 full-window : 32 cached steps per 90-step episode"},
         "gpu_launches": int(launches_all),
         "clocks": clk,
         "roofline": {"kernel": "gemm_tc_tma_kernel (every nn.Linear: tcgen05 kind::tf32, 3-product hi/lo split = fp32-accurate, 3 tensor flops per counted flop)", "bound": "tensor", "achieved": gemm_tf,
-                     "peak": pk["tf"] / 1.0, "unit": "TFLOP/s", "frac": gemm_tf / pk["tf"], "traffic": None,
+                     "peak": pk["tf"] / 1.0, "unit": "TFLOP/s", "frac": gemm_tf / pk["tf"],
+                     "traffic": traffic.get("gemm_tc_tma_kernel"),
                      "peak_source": pk["tf_src"], "share_of_step": gemm_ms / ms, "launches": int(gemm_n),
-                     "avg_launch_ms": gemm_ms / max(gemm_n, 1)},
-        "encoder_attn": {"kernel": "map_pool_kernel (polyline pooling attention, TMA bulk + mbarrier ring)",
-                         "bound": "hbm", "achieved": pool_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                         "frac": pool_gbs / pk["hbm"], "traffic": None, "peak_source": pk["hbm_src"],
-                         "share_of_step": pool_ms / ms, "launches": int(pool_n), "avg_launch_ms": pool_ms / max(pool_n, 1)},
+                     "avg_launch_ms": gemm_ms / max(gemm_n, 1), "algorithmic_flops_per_launch": gemm_fl / max(gemm_n, 1)},
+        "encoder_attn": enc,
         "kernel_shares": {"gemm": gemm_ms / ms, "map_pool": pool_ms / ms, "decoder_self_attn": sa_ms / ms,
                           "decoder_cross_attn": ca_ms / ms,
                           "decoder_self_attn_tflops": sa_fl / (sa_ms * 1e-3) / 1e12 if sa_ms > 0 else 0.0,
@@ -281,9 +437,14 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
-    if not args.no_cpu and world == 1:  # the CPU baseline is reported by the single-GPU run only
-        v, cores, sample = cpu_reference_run(cfg, weights, steps=args.cpu_steps)
-        line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample}
+    if world == 1:  # the baselines are reported by the single-GPU run only
+        if not args.no_torch_gpu:
+            line["gpu_torch_baseline"] = gpu_torch_run(cfg, weights, dev, groups_all / args.steps / args.scenes,
+                                                       n_agents / args.scenes)
+        if not args.no_cpu:
+            del model, pol, ev, batch
+            v, cores, sample, det = cpu_reference_run(args.cpu_steps, wide=args.wide)
+            line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample, **det}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

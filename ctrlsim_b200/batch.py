@@ -45,11 +45,11 @@ class SceneBatch:
             parsed = [parse_scenario(s["json"], steps, sc_cfg["moving_threshold"], sc_cfg["speed_threshold"]) for s in scenes]
         roads = [road_arrays(s["preproc"]) for s in scenes]
         S = len(scenes)
-        N = max(1, max(p["n"] for p in parsed))
+        N = max(1, max((p["n"] for p in parsed), default=0))  # S == 0: a rank without scenes (more ranks than scenes)
         if N > MAX_VEH:
             raise ValueError(f"at most {MAX_VEH} vehicles per scene are supported (got {N})")
-        Pm = max(1, max(r[0].shape[0] for r in roads))
-        E = max(1, max(p["segs"].shape[0] for p in parsed))
+        Pm = max(1, max((r[0].shape[0] for r in roads), default=0))
+        E = max(1, max((p["segs"].shape[0] for p in parsed), default=0))
         T1 = steps + 1
         dims = {"S": S, "N": N, "Pm": Pm, "E": E, "T": steps, "T1": T1}
         self.S, self.N, self.Pm, self.E = S, N, Pm, E
@@ -149,6 +149,14 @@ class SceneBatch:
                 v.copy_(torch.from_numpy(self._init_dynamic[k]))
             else:
                 v.zero_()
+
+    def contact_overflow(self) -> int:
+        """Broad-phase pairs / island contacts the simulator had to drop since the last reset because a capacity of
+        sim_contacts.cuh (128 pairs per scene, 32 contacts per island) was exceeded; > 0 means the episode is no longer
+        the reference's (Box2D has no such caps)."""
+        if self.S == 0:
+            return 0
+        return int(self.t["cstate"][:, 3].contiguous().view(torch.int32).sum().item())
 
     def n_evaluated(self) -> int:
         return sum(len(e) for e in self.evaluated_ids)

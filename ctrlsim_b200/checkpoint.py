@@ -9,6 +9,8 @@ shape, nothing silently skipped) and returns the float32 numpy dict ``model.Devi
 """
 from __future__ import annotations
 
+import pickle
+
 from collections import OrderedDict
 
 import numpy as np
@@ -65,13 +67,19 @@ def check_state_dict(state_dict, cfg, strict_unexpected: bool = False):
     return out
 
 
-def load_checkpoint(path: str, cfg, strict_unexpected: bool = False):
-    """Read a Lightning ``.ckpt`` (or a bare ``state_dict`` file) -> OrderedDict[str, np.float32 array]."""
+def load_checkpoint(path: str, cfg, strict_unexpected: bool = False, trusted: bool = False):
+    """Read a Lightning ``.ckpt`` (or a bare ``state_dict`` file) -> OrderedDict[str, np.float32 array].
+
+    The file is read with ``weights_only=True``.  Lightning checkpoints pickle their hyper-parameters (an omegaconf tree
+    in the reference, train.py:46), which that mode refuses; ``trusted=True`` - the caller vouches for the file, as the
+    reference's ``load_from_checkpoint`` implicitly does - falls back to full unpickling for exactly that error.  Any
+    other failure (missing file, corrupt archive) propagates unchanged."""
     try:
         blob = torch.load(path, map_location="cpu", weights_only=True)
-    except Exception:
-        # Lightning checkpoints pickle their hyper-parameters (an omegaconf tree in the reference); the tensors are all
-        # this loader needs, and the file is the user's own model, as it is for the reference's load_from_checkpoint
+    except pickle.UnpicklingError as e:
+        if not trusted:
+            raise CheckpointError(f"{path}: holds pickled objects besides tensors ({e}); pass trusted=True to unpickle a "
+                                  "checkpoint you trust") from e
         blob = torch.load(path, map_location="cpu", weights_only=False)
     if isinstance(blob, dict) and "state_dict" in blob:
         blob = blob["state_dict"]

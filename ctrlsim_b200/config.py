@@ -44,7 +44,10 @@ class AttrDict(dict):
         return d
 
 
-def default_config() -> AttrDict:
+def default_config(wide: bool = False) -> AttrDict:
+    """``wide``: SURVEY 8(d) config 2 "wide" variant - the caps of cfgs/dataset/waymo/base.yaml:38-39 raised to 64 agents
+    and 256 polylines per focal group, so that one group covers a whole 64-vehicle / 256-polyline scene (6144 decoder
+    tokens, 320 memory tokens); everything else as the reference default."""
     waymo = dict(
         train_context_length=32, num_agent_types=5, num_road_types=8, map_attr=2, k_attr=7,
         agent_dist_threshold=60.0, map_dist_threshold=100.0, max_timestep=90,
@@ -110,6 +113,9 @@ def default_config() -> AttrDict:
         dataset=dict(waymo=waymo), model=model, nocturne=nocturne, eval=evalc, train=train,
         eval_planner_adversary=epa, cat=dict(dict_path=""),
     ))
+    if wide:
+        cfg.dataset.waymo.max_num_agents = 64
+        cfg.dataset.waymo.max_num_road_polylines = 256
     # the scenario dict is handed to pybind as-is by the reference: keep it a plain dict
     cfg.nocturne["scenario"] = dict(nocturne["scenario"])
     cfg.nocturne["rew_cfg"] = AttrDict(nocturne["rew_cfg"])

@@ -101,6 +101,9 @@ int ctrlsim_create(const CtrlSimConfig* c, CtrlSim** out) {
       c->pts_per_polyline != NP || c->n_action_bins != N_ACT || c->n_rtg_bins != N_RTG)
     return set_error(-2, "ctrlsim_create: kernels are specialised to the reference default model geometry "
                          "(H=256, heads=8, FF=1024, 2+4 layers, 24 agents, 32 steps, 200x100 map, 1000/350 bins)");
+  // the accel_jsd histogram (metrics_kernel) and the action un-discretisation assume the 20 x 50 factorisation
+  if (c->n_steer_bins != 50)
+    return set_error(-2, "ctrlsim_create: n_steer_bins=%d; the kernels assume the reference's 20 accel x 50 steer bins", c->n_steer_bins);
   int dev = 0, cc_major = 0, n_sm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return set_error(-5, "no CUDA device: the product path has no CPU fallback");
   cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev);
@@ -115,12 +118,13 @@ int ctrlsim_create(const CtrlSimConfig* c, CtrlSim** out) {
   h->mc.pos_tol = c->pos_tol; h->mc.heading_tol = c->heading_tol; h->mc.speed_tol = c->speed_tol;
   h->mc.goal_dist_scaling = c->goal_dist_scaling; h->mc.reward_scaling = c->reward_scaling;
   { const char* e = getenv("CTRLSIM_CONTACTS"); h->mc.contacts = !(e && e[0] == '0'); }
-  {  // process-wide (a __constant__ of the simulator kernels): CTRLSIM_TRIG=glibc selects glibc's sinf / cosf algorithm
-    // The constant is statically 0; it is only written when the switch is asked for (or has to be taken back), so the
-    // default flow performs no extra CUDA call.
-    static bool trig_is_glibc = false;
+  {  // process-wide (a __constant__ of the simulator kernels): sinf / cosf / tanf follow glibc's own algorithm
+    // (glibc_trig.h) so that the simulator is bit-identical to the reference's through contacts; CTRLSIM_TRIG=fp64
+    // selects "evaluate in fp64 and round once" (correctly rounded, 1 ulp off glibc in ~1 % of calls).
+    // The constant is statically 1; it is only written when the other mode is asked for (or has to be taken back).
+    static bool trig_is_glibc = true;
     const char* e = getenv("CTRLSIM_TRIG");
-    const bool want = e && strcmp(e, "glibc") == 0;
+    const bool want = !(e && strcmp(e, "fp64") == 0);
     if (want != trig_is_glibc) {
       const int rc = set_trig_mode(want ? 1 : 0);
       if (rc) { delete h; return rc; }

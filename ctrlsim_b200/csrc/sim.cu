@@ -32,7 +32,7 @@ namespace ctrlsim {
 
 // 0: sinf / cosf evaluated in fp64 and rounded once (correctly rounded; differs from glibc's in ~1 % of calls by 1 ulp)
 // 1: glibc's own algorithm (glibc_trig.h; identical to the x86-64 FMA build of glibc in 1.2e8 of 1.2e8 arguments)
-__constant__ int g_trig_glibc = 0;
+__constant__ int g_trig_glibc = 1;  // default since round 2: bit-exact with the reference through contacts
 __device__ __forceinline__ float cr_sinf(float x) {
   float r;
   if (g_trig_glibc && glibc_trig::sinf_fast(x, &r)) return r;
@@ -338,7 +338,7 @@ sim_reset_kernel(CtrlSimBatch b, int T1) {  // T1 = steps + 1
     float* w = b.cstate + (size_t)s * cs_words(N);
     SV sv{b.body + (size_t)s * B_FIELDS * N, b.veh_len + (size_t)s * N, b.veh_wid + (size_t)s * N, N, n};
     SC c = cs_view(w, N, n, scratch);
-    *c.new_contacts = 1; *c.n_contacts = 0; *c.inv_dt0 = 0.0f;
+    *c.new_contacts = 1; *c.n_contacts = 0; *c.inv_dt0 = 0.0f; *c.overflow = 0;
     for (int k = 0; k < n; ++k) cs_init_body(sv, c, k);
   }
   update_collision(b, s, i, n, present, x, y, heading, len, wid, sh_obb, sh_seg);

@@ -79,6 +79,7 @@ typedef struct {
   Contact* ct;
   int* new_contacts;
   float* inv_dt0;
+  int* overflow;  // broad-phase pairs / island contacts dropped because a capacity was exceeded (parity no longer holds)
   float friction;
   int *island_flag, *stack, *ibody, *iidx; /* island scratch */
 } SC;
@@ -217,7 +218,7 @@ __device__ static void find_new_contacts(const SV& s, SC& c) {
       int a = i < j ? i : j, b = i < j ? j : i;
       if (s.px(a) < -500000.f && s.px(b) < -500000.f) continue; /* parked pairs, see header */
       if (find_contact(c, a, b) >= 0) continue;
-      if ((*c.n_contacts) == CS_MAX_CONTACTS) continue;
+      if ((*c.n_contacts) == CS_MAX_CONTACTS) { ++(*c.overflow); continue; }
       Contact* k = &c.ct[(*c.n_contacts)++];
       *k = Contact{};
       k->a = a; k->b = b;
@@ -387,7 +388,7 @@ __device__ static void solve_island(SV& s, SC& c, const int* bodies, int nb, con
   V2* pc_ = sc->pc_; float* pa = sc->pa;  // shared memory of the block (only this thread uses it)
   V2* vv = sc->vv;   float* vw = sc->vw;
   VC* vcs = sc->vcs;
-  if (nc > CS_MAX_ISLAND_CONTACTS) nc = CS_MAX_ISLAND_CONTACTS;  // see the header: larger islands drop their newest contacts
+  if (nc > CS_MAX_ISLAND_CONTACTS) { (*c.overflow) += nc - CS_MAX_ISLAND_CONTACTS; nc = CS_MAX_ISLAND_CONTACTS; }  // see the header: larger islands drop their newest contacts
   for (int i = 0; i < nb; ++i) {
     int b = bodies[i];
     c.iidx[b] = i;
@@ -738,7 +739,7 @@ __device__ static void world_step(SV& s, SC& c, float dt, CsScratch* sc) {
 
 
 // persistent contact state of one scene inside CtrlSimBatch.cstate (float words; ints stored bit-wise):
-//   [0] new_contacts  [1] n_contacts  [2] inv_dt0  [3] -   | fat[4N] | moved[N] | mass, inv_mass, inv_i [3N] | contacts
+//   [0] new_contacts  [1] n_contacts  [2] inv_dt0  [3] overflow count   | fat[4N] | moved[N] | mass, inv_mass, inv_i [3N] | contacts
 __host__ __device__ inline int cs_words(int N) { return 4 + 8 * N + CS_CONTACT_WORDS * CS_MAX_CONTACTS; }
 static_assert(sizeof(Contact) == CS_CONTACT_WORDS * 4, "Contact must stay 20 words");
 
@@ -748,6 +749,7 @@ __device__ inline SC cs_view(float* w, int N, int n, int* scratch) {
   c.new_contacts = reinterpret_cast<int*>(w + 0);
   c.n_contacts = reinterpret_cast<int*>(w + 1);
   c.inv_dt0 = w + 2;
+  c.overflow = reinterpret_cast<int*>(w + 3);
   c.fat = w + 4;
   c.moved = reinterpret_cast<int*>(w + 4 + 4 * N);
   c.mass = w + 4 + 5 * N;

@@ -19,6 +19,7 @@ import json
 import os
 import pickle
 import random
+import warnings
 
 import numpy as np
 import torch
@@ -90,16 +91,22 @@ class B200Policy:
             _lib.check(self.lib.ctrlsim_attach_map_cache(self.model.handle, None, 0), "ctrlsim_attach_map_cache")
 
     def reset(self, batch: SceneBatch):
+        if batch.S == 0:  # a rank that owns no scene (fewer scenes than ranks) only takes part in the collective
+            return
         batch.reset_dynamic()
         self.attach_caches(batch)
         _lib.check(self.lib.ctrlsim_sim_reset(self.model.handle, batch.ptr, self._stream()), "ctrlsim_sim_reset")
 
     def update_state(self, batch: SceneBatch, t: int):
         """update_vehicle_data_dict + Policy.update_state for step t (observation, reward, history append)."""
+        if batch.S == 0:
+            return
         _lib.check(self.lib.ctrlsim_observe(self.model.handle, batch.ptr, t, self._stream()), "ctrlsim_observe")
 
     def predict(self, batch: SceneBatch, t: int):
         """Focal grouping, tokenisation, two-pass network, RTG + action sampling; leaves next_action on the device."""
+        if batch.S == 0:
+            return 0
         st = self._stream()
         _lib.check(self.lib.ctrlsim_plan_groups(self.model.handle, batch.ptr, t, batch.n_total.data_ptr(), st),
                    "ctrlsim_plan_groups")
@@ -143,6 +150,8 @@ class B200Policy:
 
     def act(self, batch: SceneBatch, t: int):
         """policy.act / apply_gt_action for every vehicle, then Simulation.step(dt)."""
+        if batch.S == 0:
+            return
         _lib.check(self.lib.ctrlsim_sim_step(self.model.handle, batch.ptr, t, self._stream()), "ctrlsim_sim_step")
 
 
@@ -155,6 +164,9 @@ def _jsd(p, q):
     left = np.where(p > 0, p * np.log(np.where(p > 0, p, 1.0) / np.where(m > 0, m, 1.0)), 0.0)
     right = np.where(q > 0, q * np.log(np.where(q > 0, q, 1.0) / np.where(m > 0, m, 1.0)), 0.0)
     return float(np.sqrt((left.sum() + right.sum()) / 2.0))
+
+
+EVAL_MODES = ("multi_agent", "one_agent", "two_agent")
 
 
 class B200PolicyEvaluator:
@@ -175,6 +187,7 @@ class B200PolicyEvaluator:
         self.scene_ids = list(range(len(self.scenes))) if scene_ids is None else list(scene_ids)
         self.batch = None
         self.last_summary = None
+        self.contact_overflow = 0
 
     def _iter_files(self):
         with open(os.path.join(self.cfg.dataset_root, "test_filenames.pkl"), "rb") as f:
@@ -193,8 +206,11 @@ class B200PolicyEvaluator:
         """Host half of build_batch: walk the scenes in file order with the evaluation's seeded generator, draw the
         evaluated vehicles of each (policy_evaluator.py:450-464) and keep this rank's share (scene k -> rank k mod
         world, k counting accepted scenes). Returns (scenes, ids, parsed, evaluated_sets, threshold)."""
-        from .scenario import parse_scenario
+        from .scenario import interesting_pairs, parse_scenario
         cfg = self.cfg
+        mode = cfg.eval.eval_mode
+        if mode not in EVAL_MODES:
+            raise ValueError(f"cfg.eval.eval_mode={mode!r}: expected one of {EVAL_MODES} (cfgs/eval/base.yaml:13-14)")
         rng = random.Random(cfg.eval.seed)
         thr = cfg.eval.multi_agent_eval_threshold if eval_threshold is None else eval_threshold
         sc = cfg.nocturne["scenario"]
@@ -212,7 +228,14 @@ class B200PolicyEvaluator:
                 break
             p = parse_scenario(s["json"], self.steps, sc["moving_threshold"], sc["speed_threshold"])
             moving = [i for i in range(p["n"]) if p["moving"][i]]
-            ev = rng.sample(moving, thr) if len(moving) > thr else moving
+            if mode == "multi_agent":  # policy_evaluator.py:450-454
+                ev = rng.sample(moving, thr) if len(moving) > thr else moving
+            else:  # one_agent / two_agent: a random "interesting" pair, or its first vehicle (policy_evaluator.py:455-459)
+                e = cfg.eval
+                pairs = interesting_pairs(p, moving, self.history_steps, e.interesting_traj_len_threshold,
+                                          e.interesting_goal_dist_threshold, e.interesting_timestep_diff_threshold)
+                pick = rng.choice(pairs) if pairs else None  # the only use of the generator, only when a pair exists
+                ev = [] if pick is None else ([pick[0]] if mode == "one_agent" else [pick[0], pick[1]])
             if not ev and not keep_replay_only:
                 continue  # no candidate agent: scene skipped (policy_evaluator.py:461-464)
             own = accepted % self.world == self.rank
@@ -256,9 +279,15 @@ class B200PolicyEvaluator:
         dev = self.policy.model.device
         out_scene = torch.zeros(b.S, 8, dtype=torch.float64, device=dev)
         out_hist = torch.zeros(8, 200, dtype=torch.int64, device=dev)
-        st = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(self.policy.lib.ctrlsim_metrics(self.policy.model.handle, b.ptr, out_scene.data_ptr(),
-                                                   out_hist.data_ptr(), st), "ctrlsim_metrics")
+        if b.S > 0:  # a rank without scenes contributes zeros to the all-reduce below
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self.policy.lib.ctrlsim_metrics(self.policy.model.handle, b.ptr, out_scene.data_ptr(),
+                                                       out_hist.data_ptr(), st), "ctrlsim_metrics")
+            self.contact_overflow = b.contact_overflow()
+            if self.contact_overflow:
+                warnings.warn(f"{self.contact_overflow} contact(s) exceeded the simulator's capacity (128 broad-phase pairs "
+                              "per scene / 32 contacts per island, sim_contacts.cuh) and were dropped: the affected "
+                              "scenes no longer follow the reference's Box2D step")
         # flat summary: [goal_sum, n_agents, sum_scene_coll, sum_scene_off, n_scenes_with_agents, ade_sum, fde_sum, 0]
         summ = torch.cat([out_scene.sum(0), out_hist.to(torch.float64).flatten()])
         if self.world > 1:
@@ -267,18 +296,20 @@ class B200PolicyEvaluator:
         return self.last_summary
 
     @staticmethod
-    def metrics_from_summary(s):
+    def metrics_from_summary(s, accel_bins=20):
         goal_sum, n_ag, coll_sum, off_sum, n_sc, ade_sum, fde_sum = s[:7]
         h = s[8:].reshape(8, 200)
+        if n_ag == 0 or n_sc == 0:
+            raise ValueError("no scene with an evaluated vehicle was accepted: there is nothing to report")
         m = {"goal": goal_sum / n_ag, "collision_rate": coll_sum / n_sc, "offroad_rate": off_sum / n_sc,
              "fde": fde_sum / n_ag, "ade": ade_sum / n_ag,
              "lin_speed_jsd": _jsd(h[0], h[1]), "ang_speed_jsd": _jsd(h[2], h[3]),
-             "accel_jsd": _jsd(h[4][:20], h[5][:20]), "nearest_dist_jsd": _jsd(h[6], h[7])}
+             "accel_jsd": _jsd(h[4][:accel_bins], h[5][:accel_bins]), "nearest_dist_jsd": _jsd(h[6], h[7])}
         return {k: float(v) for k, v in m.items()}
 
     def evaluate_policy(self):
         if self.batch is None:
             self.build_batch()
         self.rollout()
-        m = self.metrics_from_summary(self.summarize())
+        m = self.metrics_from_summary(self.summarize(), self.cfg_rl_waymo.accel_discretization)
         return m, ["{}: {:.6f}".format(k, v) for k, v in m.items()]

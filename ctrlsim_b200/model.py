@@ -85,11 +85,11 @@ class DeviceModel:
         self._ws_groups = 0
 
     @classmethod
-    def load_from_checkpoint(cls, model_path, cfg, device="cuda:0"):
+    def load_from_checkpoint(cls, model_path, cfg, device="cuda:0", trusted=False):
         """Mirror of ``CtRLSim.load_from_checkpoint(model_path)`` (eval_sim.py:52): a Lightning ``.ckpt`` -> device model.
         Names and shapes are checked against ``cfg`` before anything is uploaded (checkpoint.load_checkpoint)."""
         from .checkpoint import load_checkpoint
-        return cls(cfg, load_checkpoint(model_path, cfg), device)
+        return cls(cfg, load_checkpoint(model_path, cfg, trusted=trusted), device)
 
     def workspace(self, groups: int):
         if self._ws is None or self._ws_groups < groups:

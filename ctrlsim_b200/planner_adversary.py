@@ -221,6 +221,11 @@ class B200PlannerAdversaryEvaluator:
         self.is_cat = getattr(adversary, "name", "") == "cat"
         if not self.is_cat and not isinstance(adversary, B200Policy):
             raise TypeError("adversary must be a B200Policy or a CatAdversary")
+        if not self.is_cat and adversary.seed == planner.seed:
+            # the explicit sampler is keyed by (seed; scene, vehicle, step, component): with equal seeds the two policies
+            # would draw IDENTICAL Philox bits for the RTG of the same (scene, vehicle, step) - correlated draws where
+            # the reference's two policies consume independent stretches of the torch generator
+            raise ValueError("planner and adversary need distinct sampler seeds (B200Policy(..., seed=...))")
         if scenes is None:
             scenes, pairs, adv_trajs, scene_ids = self._load_files()
         if pairs is None or len(pairs) != len(scenes):

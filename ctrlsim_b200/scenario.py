@@ -73,19 +73,41 @@ def parse_scenario(scen: dict, steps: int = 90, moving_threshold: float = 0.2, s
     segs = np.concatenate(segs, axis=0) if segs else np.zeros((0, 4), np.float32)
     # goals (evaluators/evaluator.py:60-76), float64 views of float32 values
     goal = np.zeros((n, 4), np.float64)
+    goal_idx = np.full(n, steps - 1, np.int64)  # step of the goal state (policy_evaluator.py:324-331)
     for i in range(n):
         gp = target[i, :2].astype(np.float64)
         gh, gs = float(target[i, 2]), float(target[i, 3])
         gone = np.where(gt_valid[i] == 0)[0]
         if len(gone) > 0:
             k = gone[0] - 1
+            goal_idx[i] = k
             g64 = gt[i, k].astype(np.float64)
             if np.linalg.norm(g64[:2] - gp) > 0.0:
                 gp, gh, gs = g64[:2], g64[2], g64[3]
         goal[i] = (gp[0], gp[1], gh, gs)
     goal_norm = np.linalg.norm(gt[:, 0, :2].astype(np.float64) - goal[:, :2], axis=1)
     return dict(n=n, gt=gt, gt_valid=gt_valid, size=size, moving=moving, goal=goal, goal_norm=goal_norm,
-                segs=segs)
+                segs=segs, goal_idx=goal_idx)
+
+
+def interesting_pairs(parsed: dict, candidates, history_steps: int = 10, traj_len_threshold: int = 60,
+                      goal_dist_threshold: float = 10.0, timestep_diff_threshold: int = 20):
+    """The ordered vehicle pairs ``PolicyEvaluator.find_interesting_agent`` / ``find_interesting_pair`` draw from
+    (evaluators/policy_evaluator.py:308-360,362-416): among the candidate (moving) vehicles, in scenario order, pairs
+    (a, b) whose goals are distinct but less than ``goal_dist_threshold`` apart, reached within
+    ``timestep_diff_threshold`` steps of each other, both with at least ``traj_len_threshold`` valid states after the
+    history.  Row-major order of ``np.where`` over the candidate list, like the reference's ``valid_pairs``."""
+    ids = [int(v) for v in candidates]
+    if not ids:
+        return []
+    goals = parsed["goal"][ids, :2]
+    goal_t = parsed["goal_idx"][ids] - history_steps
+    long_enough = (parsed["gt_valid"][ids][:, history_steps:].astype(np.int64).sum(axis=1) >= traj_len_threshold).astype(np.int64)
+    dists = np.linalg.norm(goals[None, :, :] - goals[:, None, :], 2, -1)
+    mask = ((dists < goal_dist_threshold) * (dists > 0) * long_enough[:, None] * long_enough[None, :]
+            * (np.abs(goal_t[:, None] - goal_t[None, :]) < timestep_diff_threshold))
+    rows, cols = np.where(mask == 1)
+    return [(ids[a], ids[b]) for a, b in zip(rows, cols)]
 
 
 def road_arrays(preproc: dict):

@@ -86,6 +86,12 @@ class ModelPort:
         allowed = causal_mask_rule(A, T, 3, state_index=1 if self.dt else 0)
         self.add_mask = torch.zeros(allowed.shape, dtype=torch.float32).masked_fill(~allowed, float("-inf"))
 
+    def to(self, device):
+        """Move the weights and the mask (bench.py gpu_torch_baseline: the same stock torch ops on a CUDA device)."""
+        self.sd = {k: v.to(device) for k, v in self.sd.items()}
+        self.add_mask = self.add_mask.to(device)
+        return self
+
     # ---- M2 ------------------------------------------------------------------------------------------------
     def map_encoder(self, road_points, road_types):
         sd, H = self.sd, self.m.hidden_dim
@@ -115,7 +121,7 @@ class ModelPort:
         actions = data["actions"].transpose(1, 2).long()
         rtgs = data["rtgs"].transpose(1, 2).long()
         ts = data["timesteps"].transpose(1, 2)[..., 0].long()
-        ids = torch.arange(A)[None, None, :].expand(B, T, A)
+        ids = torch.arange(A, device=st.device)[None, None, :].expand(B, T, A)
         ts_emb = sd["encoder.embed_timestep.weight"][ts]
         id_emb = sd["encoder.embed_agent_id.weight"][ids]
         s_emb = _mlp(sd, "encoder.embed_state", states)

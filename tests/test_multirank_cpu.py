@@ -80,6 +80,25 @@ def _worker(rank, world, port, out):
     got = pa.gather(st).compute()
     for k, v in ref.items():
         assert (np.isnan(v) and np.isnan(got[k])) or abs(got[k] - v) < 1e-9 * max(1.0, abs(v)), (k, got[k], v)
+    # (4) fewer scenes than ranks: the rank without a scene builds an empty batch, skips the rollout (its policy stub
+    # has no verbs: any call would raise) and still joins the one all-reduce with a zero summary
+    ev0 = B200PolicyEvaluator(cfg, stub, scenes=scenes[:1], scene_ids=[100])
+    b0 = ev0.build_batch(eval_threshold=4)
+    assert b0.S == (1 if rank == 0 else 0)
+    if rank == 0:
+        s1 = torch.from_numpy(summary_from_record(cfg, load_golden("sparse")[0]))
+        dist.all_reduce(s1)
+    else:
+        from ctrlsim_b200.evaluator import B200Policy
+        stub.reset = lambda b: B200Policy.reset(stub, b)
+        stub.update_state = lambda b, t: B200Policy.update_state(stub, b, t)
+        stub.predict = lambda b, t: B200Policy.predict(stub, b, t)
+        stub.act = lambda b, t: B200Policy.act(stub, b, t)
+        ev0.rollout(b0)
+        assert b0.n_evaluated() == 0 and b0.contact_overflow() == 0
+        s1 = torch.from_numpy(ev0.summarize(b0))
+        want = summary_from_record(cfg, load_golden("sparse")[0])
+        assert np.array_equal(s1.numpy(), want)  # zeros + rank 0's part
     dist.barrier()
     dist.destroy_process_group()
 

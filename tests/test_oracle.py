@@ -442,6 +442,16 @@ def test_lightning_checkpoint_import_round_trip_and_errors(tmp_path, cfg):
     assert "encoder.map_encoder.map_seeds" in str(e.value) and "(999, 256)" in str(e.value)
     with pytest.raises(CheckpointError):
         check_state_dict(dict(w, stray=np.zeros(3, np.float32)), cfg, strict_unexpected=True)
+    # arbitrary pickled objects (an omegaconf tree in the reference's checkpoints) are refused unless the caller vouches
+    # for the file; a missing file is reported as such, not retried
+    import fractions
+    torch.save({"state_dict": {k: torch.from_numpy(v) for k, v in w.items()}, "hyper_parameters": fractions.Fraction(1, 3)}, path)
+    with pytest.raises(CheckpointError, match="trusted=True"):
+        load_checkpoint(path, cfg)
+    got = load_checkpoint(path, cfg, trusted=True)
+    assert all(np.array_equal(got[k], w[k]) for k in w)
+    with pytest.raises(FileNotFoundError):
+        load_checkpoint(str(tmp_path / "absent.ckpt"), cfg, trusted=True)
 
 
 def test_file_reader_counts_only_evaluated_scenes_like_the_reference(tmp_path, cfg):
@@ -631,7 +641,7 @@ def test_gpu_acceptance_logic_on_cpu_emulation_of_gpu_arithmetic(cfg, name):
           "tr_exist": rec["existence"][None], "tr_action": np.stack([rec["accel"], rec["steer"]], -1)[None],
           "tr_reward": rec["reward"][None], "tr_nearest": np.stack([rec["nearest_dist"], rec["gt_nearest_dist"]], -1)[None],
           "tr_rtg_idx": g["rtg_idx"].transpose(1, 0, 2)[None], "tr_act_idx": g["act_idx"].T[None]}
-    assert check_rollout_vs_reference(tr, g, name) == 90
+    assert check_rollout_vs_reference(tr, g, name, trig="fp64") == 90
     ex = g["existence"].astype(bool)
     dpos = np.abs(rec["pos"] - g["pos"])[ex].max()
     dhead = np.abs(rec["heading"] - g["heading"])[ex].max()
@@ -677,6 +687,13 @@ def test_glibc_trig_mode_makes_the_contact_episodes_bit_exact(cfg, name):
     ex = g["existence"].astype(bool)
     assert (rec["pos"][ex] == g["pos"][ex]).all() and (rec["heading"][ex] == g["heading"][ex]).all()
     assert (rec["reward"][:, :, 6][ex] == g["reward"][:, :, 6][ex]).all() and g["reward"][:, :, 6][ex].any()
+    # ... and passes the (strict, default-mode) acceptance function of the GPU parity test
+    from parity_checks import check_rollout_vs_reference
+    tr = {"tr_pos": rec["pos"][None], "tr_vel": rec["vel"][None], "tr_heading": rec["heading"][None],
+          "tr_exist": rec["existence"][None], "tr_action": np.stack([rec["accel"], rec["steer"]], -1)[None],
+          "tr_reward": rec["reward"][None], "tr_nearest": np.stack([rec["nearest_dist"], rec["gt_nearest_dist"]], -1)[None],
+          "tr_rtg_idx": g["rtg_idx"].transpose(1, 0, 2)[None], "tr_act_idx": g["act_idx"].T[None]}
+    assert check_rollout_vs_reference(tr, g, name, trig="glibc") == 90
 
 
 @pytest.mark.parametrize("mode", ["rear", "side", "head", "pile", "dense"])
@@ -836,3 +853,59 @@ def test_model_port_dt_variant_matches_the_reference_modules(cfg):
     assert "rtg_preds" not in got
     d = (got["action_preds"][0, :n] - want[0, :n]).abs().max().item()
     assert d < 5e-5, d
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref")) or not os.path.isdir("/root/reference"),
+                    reason="needs the reference tree and its built simulator (build container only)")
+def test_one_agent_and_two_agent_selection_match_the_reference_functions(tmp_path, cfg):
+    """cfg.eval.eval_mode = one_agent / two_agent (cfgs/eval/base.yaml:13-14; one_agent is the reference's default):
+    the evaluated vehicles are a random "interesting" pair (or its first vehicle).  The host-side restatement
+    (scenario.interesting_pairs + B200PolicyEvaluator.select_scenes) is compared with the UNMODIFIED
+    PolicyEvaluator.find_interesting_agent / find_interesting_pair (policy_evaluator.py:308-416) run on the real
+    nocturne_cpp objects of the same scenes, draw for draw with the same seeded generator."""
+    import random
+    import types
+    from ctrlsim_b200.evaluator import B200PolicyEvaluator
+    from ctrlsim_b200.scenario import interesting_pairs, parse_scenario
+    from ctrlsim_b200.synth import make_scene, write_dataset
+    from oracle import ref_harness, ref_shims
+    ref_shims.install()
+    from evaluators import PolicyEvaluator
+    from utils.sim import get_ground_truth_states, get_moving_vehicles
+    scenes = [make_scene(700 + i, n_vehicles=10 + 6 * i, n_roads=1 + i % 2, n_chunks=3, frac_short=0.4) for i in range(5)]
+    scenes.append(make_scene(710, n_vehicles=2, n_roads=2, n_chunks=3, lane_ids=[0]))  # no interesting pair
+    paths = write_dataset(str(tmp_path), scenes)
+    rcfg = ref_harness.build_cfg(paths, 64, len(scenes))
+    stub_policy = types.SimpleNamespace(real_time_rewards=False, model_path="x", cfg=rcfg, name="ctrl_sim",
+                                        tilt_dict={"tilt": False})
+    ref = PolicyEvaluator(rcfg, stub_policy)
+    n_pairs = []
+    for mode in ("one_agent", "two_agent"):
+        random.seed(rcfg.eval.seed)
+        want = []
+        for f in range(len(scenes)):
+            gt = get_ground_truth_states(rcfg, rcfg.nocturne_waymo_val_folder, ref.test_filenames, f, ref.dt, ref.steps)
+            sim, scenario, vehicles = ref.load_scenario(rcfg.nocturne_waymo_val_folder, f)
+            ref.vehicles_to_evaluate = get_moving_vehicles(scenario)
+            if mode == "one_agent":
+                v = ref.find_interesting_agent(vehicles, gt.copy())
+                want.append(None if v is None else [int(v)])
+            else:
+                pr = ref.find_interesting_pair(vehicles, gt.copy())
+                want.append(None if pr is None else [int(x) for x in pr])
+            sim.reset()
+        c = cfg.copy()
+        c.eval = cfg.eval.copy()
+        c.eval.eval_mode = mode
+        ev = B200PolicyEvaluator(c, types.SimpleNamespace(model=types.SimpleNamespace(device="cpu")), scenes=scenes)
+        _, ids, _, evs, _ = ev.select_scenes()
+        assert ids == [f for f, w in enumerate(want) if w is not None]  # scenes without a pair are skipped
+        assert evs == [w for w in want if w is not None], (mode, evs, want)
+        n_pairs = [len(interesting_pairs(parse_scenario(s["json"]), [i for i, m in enumerate(parse_scenario(s["json"])["moving"]) if m]))
+                   for s in scenes]
+    assert sum(n > 2 for n in n_pairs) >= 3 and n_pairs[-1] == 0, n_pairs  # the draw is a real choice, and one scene has none
+    c = cfg.copy()
+    c.eval = cfg.eval.copy()
+    c.eval.eval_mode = "three_agent"
+    with pytest.raises(ValueError):
+        B200PolicyEvaluator(c, types.SimpleNamespace(model=types.SimpleNamespace(device="cpu")), scenes=scenes).select_scenes()
