@@ -489,6 +489,12 @@ int ctrlsim_attn_padded(const float* Q, int32_t ldq, const float* K, const float
 int ctrlsim_attn_causal(const float* QKV, float* O, int32_t G, int32_t n_t, void* stream) {
   return launch_attn_causal(QKV, O, G, n_t, S(stream));
 }
+int ctrlsim_attn_step(const float* KV, int32_t ld, int32_t k_off, int32_t v_off, int32_t group_rows, const float* qkv_rows,
+                      float* O, int32_t G, int32_t ti, int32_t own_row, void* stream) {
+  if (ti < 0 || ti >= T || (ti + 1) * TOK_T > group_rows) return set_error(-2, "ctrlsim_attn_step: need 0 <= ti < %d and (ti + 1) * %d <= group_rows", T, TOK_T);
+  KvView v; v.base = KV; v.ld = ld; v.k_off = k_off; v.v_off = v_off; v.group_rows = group_rows;
+  return launch_attn_step(v, qkv_rows, O, G, ti, own_row != 0, S(stream));
+}
 int ctrlsim_map_pool(const float* feats, const uint8_t* pt_valid, const uint8_t* poly_valid, const float* U,
                      float* pooled, int32_t n_poly, void* stream) {
   int dev = 0, n_sm = 148;

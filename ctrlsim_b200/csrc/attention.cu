@@ -227,103 +227,7 @@ int launch_attn_causal_tail(const float* Q, int ldq, const KvView& kv, float* O,
                         Lk - n_q, kv.group_rows);
 }
 
-// -------------------------------------------------------------------------------------------------------------
-// Second pass: queries are the A rtg-token rows (ti, a, 1) of each group, recomputed after RTG sampling.
-// Visible keys: every first-pass token of timesteps < ti, the A state tokens of timestep ti (first pass), and the
-// row's own (new) rtg key/value.  QKV_full: first-pass [G*Lfull, 768]; qkv_rows: [G*A, 768]; O: [G*A, 256].
-constexpr int SCH = 32;  // keys per per-warp tile in attn_step
-
-// 4 warps per (group, head): warp w streams key tiles w, w+4, ... for all 24 query rows (thread = query), then the
-// partial online-softmax states are merged through shared memory.
-__global__ void __launch_bounds__(128)
-attn_step_kernel(const float* __restrict__ KVbuf, int ld, int k_off, int v_off, int group_rows,
-                 const float* __restrict__ qkv_rows, float* __restrict__ O, int ti, int own_row) {
-  __shared__ __align__(16) KVTile<SCH> sm[4];
-  __shared__ float part[4][A][DH + 2];
-  const int g = blockIdx.y, h = blockIdx.x;
-  const int warp = threadIdx.x >> 5, a = threadIdx.x & 31;
-  const bool active = a < A;
-  float q[DH], acc[DH];
-  float m = -INFINITY, l = 0.f;
-#pragma unroll
-  for (int c = 0; c < DH; ++c) acc[c] = 0.f;
-  const float* myrow = qkv_rows + ((size_t)g * A + (active ? a : 0)) * (3 * H) + h * DH;
-  if (active) load_q(myrow, q);
-  const float* base = KVbuf + (size_t)g * group_rows * ld;
-  const int n_hist = ti * TOK_T;          // all tokens of earlier timesteps
-  const int n_keys = n_hist + A;          // + state tokens of timestep ti
-  KVTile<SCH>& t = sm[warp];
-  for (int k0 = warp * SCH; k0 < n_keys; k0 += 4 * SCH) {
-    const int nk = min(SCH, n_keys - k0);
-    __syncwarp();
-    for (int i = a; i < nk * (DH / 4); i += 32) {
-      const int r = i >> 3, c = (i & 7) << 2;
-      const int key = k0 + r;
-      const int tok = key < n_hist ? key : n_hist + (key - n_hist) * KT;  // state token of agent (key - n_hist)
-      const float* src = base + (size_t)tok * ld + h * DH + c;
-      *reinterpret_cast<float4*>(&t.k[r][c]) = *reinterpret_cast<const float4*>(src + k_off);
-      *reinterpret_cast<float4*>(&t.v[r][c]) = *reinterpret_cast<const float4*>(src + v_off);
-    }
-    __syncwarp();
-    if (active) {
-      for (int b = 0; b < nk; b += 8) {
-        bool ok[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ok[j] = b + j < nk;
-        online_block8(q, t.k, t.v, b, ok, m, l, acc);
-      }
-    }
-  }
-  if (own_row && warp == 3) {  // own (new) rtg key/value of the second pass: each thread uses only its own row
-    __syncwarp();
-    for (int i = a; i < A * (DH / 4); i += 32) {
-      const int r = i >> 3, c = (i & 7) << 2;
-      const float* src = qkv_rows + ((size_t)g * A + r) * (3 * H) + h * DH + c;
-      *reinterpret_cast<float4*>(&t.k[r][c]) = *reinterpret_cast<const float4*>(src + H);
-      *reinterpret_cast<float4*>(&t.v[r][c]) = *reinterpret_cast<const float4*>(src + 2 * H);
-    }
-    __syncwarp();
-    if (active) {
-      const int b = (a >> 3) << 3;
-      bool ok[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) ok[j] = (b + j) == a;
-      online_block8(q, t.k, t.v, b, ok, m, l, acc);
-    }
-  }
-  if (active) {
-    part[warp][a][DH] = m;
-    part[warp][a][DH + 1] = l;
-#pragma unroll
-    for (int c = 0; c < DH; ++c) part[warp][a][c] = acc[c];
-  }
-  __syncthreads();
-  if (warp == 0 && active) {
-    float ms = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) ms = fmaxf(ms, part[w][a][DH]);
-    float lt = 0.f;
-#pragma unroll
-    for (int c = 0; c < DH; ++c) acc[c] = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float mw = part[w][a][DH];
-      const float f = mw == -INFINITY ? 0.f : exp2f(mw - ms);
-      lt = fmaf(part[w][a][DH + 1], f, lt);
-#pragma unroll
-      for (int c = 0; c < DH; ++c) acc[c] = fmaf(part[w][a][c], f, acc[c]);
-    }
-    store_o(O + ((size_t)g * A + a) * H + h * DH, acc, lt);
-  }
-}
-
-int launch_attn_step(const KvView& kv, const float* qkv_rows, float* O, int G, int ti, bool own_row, cudaStream_t st) {
-  if (G <= 0) return 0;
-  dim3 grid(NH, G);
-  attn_step_kernel<<<grid, 128, 0, st>>>(kv.base, kv.ld, kv.k_off, kv.v_off, kv.group_rows, qkv_rows, O, ti, own_row ? 1 : 0);
-  CS_CHECK_LAUNCH("attn_step");
-  return 0;
-}
+// attn_step (the A rows of the current window step against the first pass' K/V rows) lives in attention_step.cu
 
 // -------------------------------------------------------------------------------------------------------------
 // map_pool: persistent CTAs, 2-stage TMA bulk pipeline over polylines.
@@ -384,6 +288,7 @@ map_pool_kernel(const float* __restrict__ feats, const uint8_t* __restrict__ pt_
     const int s = it & 1;
     const int nxt = pid + stride;
     if (tid == 0 && nxt < n_poly) {  // stage s^1 was fully consumed before the __syncthreads that ended iteration it-1
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // ... also as a reduction buffer (generic writes)
       mbar_expect_tx(&sm.full[s ^ 1], TILE_BYTES);
       tma_bulk_g2s(&sm.feats[s ^ 1][0][0], feats + (size_t)nxt * NP * H, TILE_BYTES, &sm.full[s ^ 1]);
     }
@@ -460,23 +365,41 @@ map_pool_kernel(const float* __restrict__ feats, const uint8_t* __restrict__ pt_
       }
     }
     __syncthreads();
-    // pooled[h][d] = sum_p prob[p][h] * feats[p][d]; thread owns column d
+    // pooled[h][d] = sum_p prob[p][h] * feats[p][d].  Thread = (point group pg, column quad cq): one 128-bit read of the
+    // tile and two broadcast reads of the weights feed 32 FMAs (thread-per-column needed the two weight reads for 8);
+    // the four point groups are then added through the consumed tile.
     {
-      float accp[NH];
+      const int pg = tid >> 6, cq = tid & 63;
+      float accp[NH][4];
 #pragma unroll
-      for (int hh = 0; hh < NH; ++hh) accp[hh] = 0.f;
-#pragma unroll 4
-      for (int p = 0; p < NP; ++p) {
-        const float f = sm.feats[s][p][tid];
+      for (int hh = 0; hh < NH; ++hh) accp[hh][0] = accp[hh][1] = accp[hh][2] = accp[hh][3] = 0.f;
+#pragma unroll 5
+      for (int p = pg; p < NP; p += POOL_THREADS / 64) {
+        const float4 f = *reinterpret_cast<const float4*>(&sm.feats[s][p][4 * cq]);
         const float4 pa = *reinterpret_cast<const float4*>(&sm.prob[p][0]);
         const float4 pb = *reinterpret_cast<const float4*>(&sm.prob[p][4]);
-        accp[0] = fmaf(pa.x, f, accp[0]); accp[1] = fmaf(pa.y, f, accp[1]);
-        accp[2] = fmaf(pa.z, f, accp[2]); accp[3] = fmaf(pa.w, f, accp[3]);
-        accp[4] = fmaf(pb.x, f, accp[4]); accp[5] = fmaf(pb.y, f, accp[5]);
-        accp[6] = fmaf(pb.z, f, accp[6]); accp[7] = fmaf(pb.w, f, accp[7]);
-      }
+        const float w[NH] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
-      for (int hh = 0; hh < NH; ++hh) out[hh * H + tid] = accp[hh];
+        for (int hh = 0; hh < NH; ++hh) {
+          accp[hh][0] = fmaf(w[hh], f.x, accp[hh][0]); accp[hh][1] = fmaf(w[hh], f.y, accp[hh][1]);
+          accp[hh][2] = fmaf(w[hh], f.z, accp[hh][2]); accp[hh][3] = fmaf(w[hh], f.w, accp[hh][3]);
+        }
+      }
+      __syncthreads();  // every thread is done with the tile: its first 32 KB become the reduction buffer [4][NH][H]
+      float* red = &sm.feats[s][0][0];
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh)
+        *reinterpret_cast<float4*>(&red[(pg * NH + hh) * H + 4 * cq]) = make_float4(accp[hh][0], accp[hh][1], accp[hh][2], accp[hh][3]);
+      __syncthreads();
+      for (int i = tid; i < NH * H / 4; i += POOL_THREADS) {
+        float4 a = *reinterpret_cast<const float4*>(&red[4 * i]);
+#pragma unroll
+        for (int k = 1; k < POOL_THREADS / 64; ++k) {
+          const float4 b = *reinterpret_cast<const float4*>(&red[k * NH * H + 4 * i]);
+          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        *reinterpret_cast<float4*>(&out[4 * i]) = a;
+      }
     }
     __syncthreads();  // stage s and prob[] free for reuse
   }

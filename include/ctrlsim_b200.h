@@ -176,6 +176,12 @@ int ctrlsim_layernorm(const float* X, const float* R, const float* gamma, const 
 int ctrlsim_attn_padded(const float* Q, int32_t ldq, const float* K, const float* V, int32_t ldkv,
                         const uint8_t* key_pad, float* O, int32_t G, int32_t Lq, int32_t Lk, void* stream);
 int ctrlsim_attn_causal(const float* QKV, float* O, int32_t G, int32_t n_t, void* stream);
+/* decoder self-attention of the max_agents rows of window step ti only (state rows of the last layer / rtg rows of the
+ * second pass, policies/autoregressive_policy.py:190-210): queries = columns [0, 256) of qkv_rows [G * max_agents, 768];
+ * keys / values = rows of KV [G * group_rows, ld] at column offsets k_off / v_off: every token of steps < ti, the state
+ * tokens of step ti and - own_row - the row's own key / value (columns [256, 768) of qkv_rows). O [G * max_agents, 256]. */
+int ctrlsim_attn_step(const float* KV, int32_t ld, int32_t k_off, int32_t v_off, int32_t group_rows, const float* qkv_rows,
+                      float* O, int32_t G, int32_t ti, int32_t own_row, void* stream);
 int ctrlsim_map_pool(const float* feats, const uint8_t* pt_valid, const uint8_t* poly_valid, const float* U,
                      float* pooled, int32_t n_poly, void* stream);
 /* one categorical draw per row with the explicit sampler: x [rows, n] fp32 (already tilted / tempered) */

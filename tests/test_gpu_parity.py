@@ -108,6 +108,41 @@ def test_attn_causal_matches_mask_rule(lib, dev, n_t):
     assert (O - ref).abs().max().item() < 3e-5
 
 
+@pytest.mark.parametrize("ti,own_row,cache_layout", [(0, True, False), (0, False, False), (1, True, True), (5, False, False),
+                                                      (31, True, False), (31, False, True)])
+def test_attn_step_matches_mask_rule(lib, dev, ti, own_row, cache_layout):
+    """The 24 rows of the current window step only (attention_step.cu): state rows of the last first-pass layer
+    (own_row = False) and rtg rows of the second pass (own_row = True: the row's own NEW key replaces the first pass'
+    rtg token) against the dense mask rule M1, for both K/V layouts (workspace QKV buffer / prefix-cache slot)."""
+    from oracle.model_port import causal_mask_rule
+    A, G, n_t = 24, 3, ti + 1
+    L = n_t * 72
+    g = torch.Generator(device="cpu").manual_seed(100 * ti + own_row)
+    qkv = torch.randn(G, L, 768, generator=g).to(dev)          # first-pass rows
+    rows = torch.randn(G, A, 768, generator=g).to(dev)         # recomputed rows of step ti (q | k | v)
+    O = torch.empty(G, A, 256, device=dev)
+    if cache_layout:  # [G, 2304, 512]: K | V, rows past the current length are stale
+        group_rows = 2304
+        kv = torch.randn(G, group_rows, 512, generator=g).to(dev)
+        kv[:, :L] = qkv[..., 256:]
+        args = (kv.data_ptr(), 512, 0, 256, group_rows)
+    else:
+        args = (qkv.data_ptr(), 768, 256, 512, L)
+    _chk(lib.ctrlsim_attn_step(*args, rows.data_ptr(), O.data_ptr(), G, ti, 1 if own_row else 0, _stream()), lib)
+    k_tok = 1 if own_row else 0
+    idx = torch.tensor([(ti * A + a) * 3 + k_tok for a in range(A)], device=dev)
+    full = qkv.clone()
+    if own_row:  # the rows' own keys / values are the new ones
+        full[:, idx, 256:] = rows[..., 256:]
+    allowed = causal_mask_rule(A, n_t, 3).to(dev)[idx]           # [A, L]
+    qh = rows[..., :256].reshape(G, A, 8, 32).transpose(1, 2)
+    kh = full[..., 256:512].reshape(G, L, 8, 32).transpose(1, 2)
+    vh = full[..., 512:].reshape(G, L, 8, 32).transpose(1, 2)
+    s = ((qh / math.sqrt(32)) @ kh.transpose(-1, -2)).masked_fill(~allowed, float("-inf"))
+    ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(G, A, 256)
+    assert (O - ref).abs().max().item() < 2e-5
+
+
 def test_map_pool_matches_torch(lib, dev):
     n_poly = 301  # more polylines than SMs: exercises the 2-stage TMA ring and the phase bookkeeping
     g = torch.Generator(device="cpu").manual_seed(5)
