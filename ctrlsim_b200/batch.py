@@ -51,7 +51,7 @@ class SceneBatch:
         Pm = max(1, max((r[0].shape[0] for r in roads), default=0))
         E = max(1, max((p["segs"].shape[0] for p in parsed), default=0))
         T1 = steps + 1
-        dims = {"S": S, "N": N, "Pm": Pm, "E": E, "T": steps, "T1": T1}
+        dims = {"S": S, "N": N, "Pm": Pm, "E": E, "T": steps, "T1": T1, "A": cfg.dataset.waymo.max_num_agents}
         self.S, self.N, self.Pm, self.E = S, N, Pm, E
         host = {}
         for name, dt, shp in _lib.BATCH_FIELDS:

@@ -99,8 +99,9 @@ int ctrlsim_create(const CtrlSimConfig* c, CtrlSim** out) {
   if (c->hidden_dim != H || c->num_heads != NH || c->dim_feedforward != FF || c->enc_layers != N_ENC ||
       c->dec_layers != N_DEC || c->max_agents != A || c->context_len != T || c->max_polylines != P ||
       c->pts_per_polyline != NP || c->n_action_bins != N_ACT || c->n_rtg_bins != N_RTG)
-    return set_error(-2, "ctrlsim_create: kernels are specialised to the reference default model geometry "
-                         "(H=256, heads=8, FF=1024, 2+4 layers, 24 agents, 32 steps, 200x100 map, 1000/350 bins)");
+    return set_error(-2, "ctrlsim_create: this library is specialised to H=256, heads=8, FF=1024, 2+4 layers, %d agents, "
+                         "32 steps, %dx100 map, 1000/350 bins (got %d agents, %d polylines; the default and the wide "
+                         "geometry live in libctrlsim_b200.so / libctrlsim_b200_wide.so)", A, P, c->max_agents, c->max_polylines);
   // the accel_jsd histogram (metrics_kernel) and the action un-discretisation assume the 20 x 50 factorisation
   if (c->n_steer_bins != 50)
     return set_error(-2, "ctrlsim_create: n_steer_bins=%d; the kernels assume the reference's 20 accel x 50 steer bins", c->n_steer_bins);

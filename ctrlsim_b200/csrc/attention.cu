@@ -137,7 +137,7 @@ static bool use_mma_attn() { return attn_mode() >= 1; }
 int launch_attn_padded(const float* Q, int ldq, const float* Kp, const float* Vp, int ldkv, const uint8_t* key_pad,
                        float* O, int ldo, int G, int Lq, int Lk, cudaStream_t st) {
   if (G <= 0 || Lq <= 0) return 0;
-  if (attn_mode() == 2 && Lq >= 128 && Lk <= 256 && Vp > Kp && ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(Kp)) & 15) == 0)
+  if (attn_mode() == 2 && Lq >= 128 && Lk <= 512 && Vp > Kp && ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(Kp)) & 15) == 0)
     return launch_attn_tc(false, Q, ldq, H, 0, Kp, ldkv, (int)(Vp - Kp) + H, 0, (int)(Vp - Kp), key_pad, O, ldo, G, Lq, Lk, st);
   if (use_mma_attn()) return launch_attn_padded_mma(Q, ldq, Kp, Vp, ldkv, key_pad, O, ldo, G, Lq, Lk, st);
   if (Lk % 8 != 0) return set_error(-2, "attn_padded: Lk=%d must be a multiple of 8", Lk);

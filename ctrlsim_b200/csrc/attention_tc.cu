@@ -54,7 +54,7 @@ struct AtSmem {
   uint64_t q_full, q_lo_ready, k_full[AT_STAGES], k_ready[AT_STAGES], k_empty[AT_STAGES], v_ready[AT_STAGES],
       v_empty[AT_STAGES], s_full[2], p_ready, o_full;
   uint32_t tmem_base;
-  unsigned long long pad_mask[4];  // padded mode: bit c of word j = key 64 j + c is valid and inside Lk
+  unsigned long long pad_mask[8];  // padded mode: bit c of word j = key 64 j + c is valid and inside Lk (Lk <= 512)
 };
 
 __device__ __forceinline__ uint32_t at_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -218,10 +218,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     at_mbar_init(&sm.p_ready, 128); at_mbar_init(&sm.o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (!CAUSAL) {  // key-padding bits: thread = key (Lk <= 256), one ballot per warp = one 32-bit half of a tile's mask
-    const bool ok = tid < Lk && !key_pad[(size_t)g * Lk + tid];
-    const unsigned bal = __ballot_sync(0xffffffffu, ok);
-    if (lane == 0) reinterpret_cast<unsigned*>(sm.pad_mask)[warp] = bal;
+  if (!CAUSAL) {  // key-padding bits: thread = key (Lk <= 512), one ballot per warp = one 32-bit half of a tile's mask
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      const int key = tid + rep * AT_THREADS;
+      const bool ok = key < Lk && !key_pad[(size_t)g * Lk + key];
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) reinterpret_cast<unsigned*>(sm.pad_mask)[warp + 8 * rep] = bal;
+    }
   }
   if (warp == 6) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(at_u32(&sm.tmem_base)), "r"(AT_TMEM_COLS) : "memory");
@@ -239,17 +243,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int row = r0 + 32 * warp + lane;
     const bool row_ok = row < Lq;
     int tq = 0;
-    // visibility pattern of the 72 keys of the row's own timestep (rule M1): every state token, plus the row's own
-    // rtg / action token if the row is at or past it.  Bit b <-> key tq * 72 + b; bits 64..71 live in pat_hi.
-    unsigned long long pat_lo = 0x9249249249249249ull, pat_hi = 0x24ull;
+    // rule M1 for the TOK_T keys of the row's own timestep: every state token (offsets 0, 3, 6, ...), plus the row's own
+    // rtg / action token if the row is at or past it (offsets 3 aq + 1 .. 3 aq + kq)
+    int aq = 0, kq = 0;
     if (CAUSAL) {
       tq = (q_pos0 + row) / TOK_T;
       const int rem = (q_pos0 + row) - tq * TOK_T;
-      const int aq = rem / KT, kq = rem - aq * KT;
-      for (int kk = 1; kk <= kq; ++kk) {
-        const int bpos = 3 * aq + kk;
-        if (bpos < 64) pat_lo |= 1ull << bpos; else pat_hi |= 1ull << (bpos - 64);
-      }
+      aq = rem / KT; kq = rem - aq * KT;
     }
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16);
     const float scale = 0.17677669529663687f * 1.4426950408889634f;  // d_h^-0.5 * log2(e)
@@ -265,12 +265,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       unsigned long long okm;
       if (CAUSAL) {
         const int base = tq * TOK_T - k0;  // position of the row's own timestep relative to the tile
-        if (!row_ok) okm = 0ull;
-        else if (base >= AT_KT) okm = ~0ull;
-        else if (base >= 0) okm = ((1ull << base) - 1ull) | (pat_lo << base);
-        else if (base > -64) okm = (pat_lo >> (-base)) | (pat_hi << (64 + base));
-        else if (base > -TOK_T) okm = pat_hi >> (-base - 64);
-        else okm = 0ull;
+        if (!row_ok || base <= -TOK_T) okm = 0ull;           // padding row / the tile lies past the row's timestep
+        else if (base >= AT_KT) okm = ~0ull;                  // the tile lies entirely in earlier timesteps
+        else {
+          const unsigned long long every3 = 0x9249249249249249ull;  // bits 0, 3, 6, ..., 63
+          // keys of earlier timesteps (bits below base) are visible; state tokens of the own timestep sit at offsets
+          // = 0 (mod 3) from base
+          okm = base >= 0 ? (((1ull << base) - 1ull) | (every3 << base)) : (every3 >> ((-base) % 3));
+          const int end = base + TOK_T;                        // first key of the next timestep (> 0 here)
+          if (end < AT_KT) okm &= (1ull << end) - 1ull;
+          for (int kk = 1; kk <= kq; ++kk) {
+            const int c = base + 3 * aq + kk;
+            if (c >= 0 && c < AT_KT) okm |= 1ull << c;
+          }
+        }
       } else {
         okm = sm.pad_mask[j];
       }
@@ -507,7 +515,7 @@ int launch_attn_tc(bool causal, const float* Qbase, int ldq, int q_cols, int q_c
     if (e != cudaSuccess) return set_error(-5, "attn_tc smem attr: %s", cudaGetErrorString(e));
     enc = reinterpret_cast<AtEncodeFn>(fn);
   }
-  if (!causal && Lk > 256) return set_error(-2, "attn_tc: padded mode supports at most 256 keys");
+  if (!causal && Lk > 512) return set_error(-2, "attn_tc: padded mode supports at most 512 keys");
   CUtensorMap tmQ, tmKV;
   int rc;
   if ((rc = at_make_map(enc, &tmQ, Qbase, (long long)G * Lq, q_cols, ldq, AT_QT))) return rc;

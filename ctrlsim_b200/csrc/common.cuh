@@ -10,18 +10,30 @@ namespace ctrlsim {
 
 // Fixed model geometry of the reference default config (cfgs/model/base.yaml:1-9, cfgs/dataset/waymo/base.yaml:4,38-43).
 // The kernels are specialised to these; ctrlsim_create() rejects any other configuration loudly.
+// The library is built twice from the same sources: libctrlsim_b200.so with the reference caps (24 agents, 200
+// polylines per focal group) and - with -DCTRLSIM_WIDE - libctrlsim_b200_wide.so with the caps of cfgs/dataset/waymo/
+// base.yaml:38-39 raised to 64 agents and 256 polylines, so that ONE focal group covers a whole 64-vehicle /
+// 256-polyline scene ("wide" variant: 6144 decoder tokens, 320 memory tokens).
 constexpr int H = 256;         // hidden_dim
 constexpr int NH = 8;          // num_heads
 constexpr int DH = 32;         // head dim
 constexpr int FF = 1024;       // dim_feedforward
+#ifdef CTRLSIM_WIDE
+constexpr int A = 64;          // max_num_agents per focal group (wide variant)
+#else
 constexpr int A = 24;          // max_num_agents per focal group
+#endif
 constexpr int T = 32;          // train_context_length
 constexpr int KT = 3;          // token types (state, rtg, action)
-constexpr int TOK_T = A * KT;  // 72 tokens per timestep
-constexpr int L = T * TOK_T;   // 2304 decoder tokens
+constexpr int TOK_T = A * KT;  // 72 (192) tokens per timestep
+constexpr int L = T * TOK_T;   // 2304 (6144) decoder tokens
+#ifdef CTRLSIM_WIDE
+constexpr int P = 256;         // max_num_road_polylines (wide variant)
+#else
 constexpr int P = 200;         // max_num_road_polylines
+#endif
 constexpr int NP = 100;        // points per polyline
-constexpr int MEM = P + A;     // 224 memory tokens
+constexpr int MEM = P + A;     // 224 (320) memory tokens
 constexpr int N_ACT = 1000;    // 20 x 50 action bins
 constexpr int N_RTG = 350;     // rtg bins per component
 constexpr int N_ENC = 2;       // encoder layers

@@ -48,15 +48,17 @@ resolve_rtg_kernel(CtrlSimBatch b, CtrlSimPolicyParams p, int t, int s0, int s1,
   int hit_g = -1, hit_k = -1;
   for (int lg = 0; lg < ng && hit_g < 0; ++lg) {
     const int* mem = b.group_members + ((size_t)s * N + lg) * A;
-    const int mv = lane < A ? mem[lane] : -1;
-    const unsigned m = __ballot_sync(0xffffffffu, mv == v);
-    if (m) { hit_g = lg; hit_k = __ffs(m) - 1; }
+    for (int a0 = 0; a0 < A && hit_g < 0; a0 += 32) {
+      const int mv = a0 + lane < A ? mem[a0 + lane] : -1;
+      const unsigned m = __ballot_sync(0xffffffffu, mv == v);
+      if (m) { hit_g = lg; hit_k = a0 + __ffs(m) - 1; }
+    }
   }
   if (hit_g < 0) {  // in no context this step: RTG (0,0,0) is appended (autoregressive_policy.py:246-247) -> bins (0,35,35)
     if (lane == 0) { tr[0] = tr[1] = tr[2] = -1; hr[0] = 0; hr[1] = 35; hr[2] = 35; }
     return;
   }
-  const bool tilted = p.tilt_enabled && ((b.group_served[(size_t)s * N + hit_g] >> hit_k) & 1u);
+  const bool tilted = p.tilt_enabled && ((b.group_served[(size_t)s * N + hit_g] >> hit_k) & 1ull);
   const float* row = rtg_logits + ((size_t)(b.group_off[s] + hit_g - g_base) * A + hit_k) * (N_RTG * 3);
   const uint32_t scene = (uint32_t)b.scene_id[s];
   for (int c = 0; c < 3; ++c) {
@@ -112,7 +114,7 @@ sample_actions_kernel(CtrlSimBatch b, CtrlSimPolicyParams p, int g0, int ng, int
   const int g = g0 + gl;
   const int s = b.group_scene[g], lg = b.group_local[g];
   const int N = b.max_veh;
-  if (!((b.group_served[(size_t)s * N + lg] >> a) & 1u)) return;
+  if (!((b.group_served[(size_t)s * N + lg] >> a) & 1ull)) return;
   const int v = b.group_members[((size_t)s * N + lg) * A + a];
   const float* row = act_logits + (size_t)w * N_ACT;
   const float temp = p.temperature;

@@ -538,12 +538,12 @@ plan_groups_kernel(CtrlSimBatch b, int t, ModelCfg mc) {
     // emit the group
     if (lane == 0) {
       int* mem = b.group_members + ((size_t)s * N + ng) * A;
-      unsigned served_slots = 0;
+      unsigned long long served_slots = 0;
       int k = 0;
       for (int v = 0; v < n && k < A; ++v)
         if ((closest >> v) & 1ull) {
           mem[k] = v;
-          if ((served_v >> v) & 1ull) served_slots |= 1u << k;
+          if ((served_v >> v) & 1ull) served_slots |= 1ull << k;
           ++k;
         }
       for (; k < A; ++k) mem[k] = -1;

@@ -11,7 +11,9 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libctrlsim_b200.so")
-ABI_VERSION = 4
+LIB_PATH_WIDE = os.path.join(HERE, "lib", "libctrlsim_b200_wide.so")  # -DCTRLSIM_WIDE: 64 agents / 256 polylines per group
+ABI_VERSION = 5
+GEOMETRY = {False: (24, 200), True: (64, 256)}  # (max_num_agents, max_num_road_polylines) of the two builds
 
 
 class CtrlSimConfig(C.Structure):
@@ -31,7 +33,8 @@ class CtrlSimConfig(C.Structure):
     ]
 
 
-# (field name, torch dtype name, shape expression) in the exact order of struct CtrlSimBatch
+# (field name, torch dtype name, shape expression) in the exact order of struct CtrlSimBatch; A = max_agents of the
+# library the batch is stepped with (24, or 64 for the wide build)
 BATCH_FIELDS = [
     ("scene_id", "int64", "S"), ("n_veh", "int32", "S"), ("veh_len", "float32", "S,N"), ("veh_wid", "float32", "S,N"),
     ("gt", "float64", "S,N,T1,4"), ("gt_valid", "uint8", "S,N,T1"), ("goal", "float64", "S,N,4"),
@@ -45,7 +48,7 @@ BATCH_FIELDS = [
     ("tr_exist", "uint8", "S,N,T1"), ("tr_action", "float64", "S,N,T1,2"), ("tr_reward", "float32", "S,N,T1,8"),
     ("tr_nearest", "float64", "S,N,T1,2"), ("tr_rtg_idx", "int16", "S,N,T,3"), ("tr_act_idx", "int16", "S,N,T"),
     ("n_groups", "int32", "S"), ("group_off", "int32", "S+1"), ("group_focal", "int32", "S,N"),
-    ("group_members", "int32", "S,N,24"), ("group_served", "int32", "S,N"), ("group_scene", "int32", "S*N"),
+    ("group_members", "int32", "S,N,A"), ("group_served", "int64", "S,N"), ("group_scene", "int32", "S*N"),
     ("group_local", "int32", "S*N"), ("cstate", "float32", "S,4+8*N+20*128"),
 ]
 
@@ -64,7 +67,7 @@ class CtrlSimError(RuntimeError):
     pass
 
 
-_lib = None
+_lib = {}
 
 _SIGS = {
     "ctrlsim_last_error": (C.c_char_p, []),
@@ -114,29 +117,41 @@ _SIGS = {
 EXPORTS = tuple(_SIGS)
 
 
-def load(build_if_missing: bool = True):
-    """Load libctrlsim_b200.so and declare every prototype of include/ctrlsim_b200.h."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def is_wide(cfg) -> bool:
+    """Which build serves ``cfg``: the reference-default geometry or the wide one; anything else is an error."""
+    w = cfg.dataset.waymo
+    geom = (w.max_num_agents, w.max_num_road_polylines)
+    for wide, g in GEOMETRY.items():
+        if geom == g:
+            return wide
+    raise CtrlSimError(f"no build of the library serves max_num_agents={geom[0]} / max_num_road_polylines={geom[1]}; "
+                       f"available: {sorted(GEOMETRY.values())}")
+
+
+def load(build_if_missing: bool = True, wide: bool = False):
+    """Load libctrlsim_b200[_wide].so and declare every prototype of include/ctrlsim_b200.h."""
+    if wide in _lib:
+        return _lib[wide]
+    path = LIB_PATH_WIDE if wide else LIB_PATH
+    if not os.path.exists(path):
         if not build_if_missing:
-            raise CtrlSimError(f"{LIB_PATH} is missing; run `python -m ctrlsim_b200.build`")
+            raise CtrlSimError(f"{path} is missing; run `python -m ctrlsim_b200.build`")
         from .build import build
-        build()
-    lib = C.CDLL(LIB_PATH)
+        build(wide=wide)
+    lib = C.CDLL(path)
     for name, (res, args) in _SIGS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
     if lib.ctrlsim_abi_version() != ABI_VERSION:
-        raise CtrlSimError("libctrlsim_b200.so ABI version mismatch; rebuild with `python -m ctrlsim_b200.build -f`")
-    _lib = lib
+        raise CtrlSimError(f"{os.path.basename(path)} ABI version mismatch; rebuild with `python -m ctrlsim_b200.build -f`")
+    _lib[wide] = lib
     return lib
 
 
 def check(rc: int, what: str = ""):
     if rc != 0:
-        msg = load().ctrlsim_last_error()
+        # the message is thread-local inside the library that failed; ask every loaded build
+        msg = b"; ".join(m for m in (l.ctrlsim_last_error() for l in _lib.values()) if m) if _lib else load().ctrlsim_last_error()
         raise CtrlSimError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
 
 

@@ -66,7 +66,8 @@ class DeviceModel:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.CtrlSimError("ctrlsim_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
-        self.lib = _lib.load()
+        self.wide = _lib.is_wide(cfg)  # which build of the library serves this geometry (24/200 or 64/256)
+        self.lib = _lib.load(wide=self.wide)
         torch.cuda.set_device(self.device)
         h = C.c_void_p()
         cc = _lib.make_config(cfg)
@@ -122,8 +123,9 @@ class DeviceModel:
             rtypes = np.where(rtypes.sum(-1) > 0, rtypes.argmax(-1), -1)
         rty = i32(rtypes)
         r2 = i32(rtg_idx_pass2)
-        rtg_logits = torch.empty(G, 24, 1050, dtype=torch.float32, device=dev)
-        act_logits = torch.empty(G, 24, 1000, dtype=torch.float32, device=dev)
+        A = self.cfg.dataset.waymo.max_num_agents
+        rtg_logits = torch.empty(G, A, 1050, dtype=torch.float32, device=dev)
+        act_logits = torch.empty(G, A, 1000, dtype=torch.float32, device=dev)
         ws = self.workspace(G)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(self.lib.ctrlsim_forward_tokens(

@@ -17,15 +17,17 @@
 extern "C" {
 #endif
 
-#define CTRLSIM_ABI_VERSION 4
+#define CTRLSIM_ABI_VERSION 5
 #define CTRLSIM_MAX_VEH 64 /* vehicles per scene supported by the grouping kernel (bitmask width) */
 
-/* Model / episode geometry. The kernels are specialised to the reference defaults (cfgs/model/base.yaml:1-9,
- * cfgs/dataset/waymo/base.yaml:4,38-43, cfgs/config.yaml:44-46); ctrlsim_create rejects anything else. */
+/* Model / episode geometry. The kernels are specialised at compile time: libctrlsim_b200.so to the reference defaults
+ * (cfgs/model/base.yaml:1-9, cfgs/dataset/waymo/base.yaml:4,38-43, cfgs/config.yaml:44-46), libctrlsim_b200_wide.so
+ * (same sources, -DCTRLSIM_WIDE, same ABI) to max_agents = 64 / max_polylines = 256 - one focal group per 64-vehicle /
+ * 256-polyline scene. ctrlsim_create of either library rejects any other geometry. */
 typedef struct CtrlSimConfig {
   int32_t abi_version;
   int32_t hidden_dim, num_heads, dim_feedforward, enc_layers, dec_layers;       /* 256, 8, 1024, 2, 4 */
-  int32_t max_agents, context_len, max_polylines, pts_per_polyline;              /* 24, 32, 200, 100 */
+  int32_t max_agents, context_len, max_polylines, pts_per_polyline;              /* 24, 32, 200, 100 (wide: 64, 32, 256, 100) */
   int32_t n_action_bins, n_steer_bins, n_rtg_bins;                               /* 1000, 50, 350 */
   int32_t steps, history_steps;                                                  /* 90, 10 */
   float dt;                                                                      /* 0.1 */
@@ -80,8 +82,8 @@ typedef struct CtrlSimBatch {
   int32_t* n_groups;          /* [S]                                   */
   int32_t* group_off;         /* [S+1] exclusive scan of n_groups      */
   int32_t* group_focal;       /* [S,N]      scene-local group -> focal vehicle */
-  int32_t* group_members;     /* [S,N,24]   vehicle ids ascending, -1 padded   */
-  uint32_t* group_served;     /* [S,N]      bit k = member slot k is served by this group */
+  int32_t* group_members;     /* [S,N,max_agents] vehicle ids ascending, -1 padded */
+  uint64_t* group_served;     /* [S,N]      bit k = member slot k is served by this group */
   int32_t* group_scene;       /* [S*N] compact group -> scene          */
   int32_t* group_local;       /* [S*N] compact group -> scene-local id */
   /* ---- Box2D contact state of the vehicle bodies (simulator state, owned by the library) ------------------------ */

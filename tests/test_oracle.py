@@ -283,17 +283,19 @@ def test_tokenizer_port_matches_reference_inputs(cfg):
 # ------------------------------------------------------------------------------------------------ C-ABI surface
 def test_library_loads_and_exports_every_declared_symbol():
     from ctrlsim_b200 import lib
-    from ctrlsim_b200.build import build
-    path = build()
-    so = ctypes.CDLL(path)
+    from ctrlsim_b200.build import build_all
     header = open(os.path.join(ROOT, "include", "ctrlsim_b200.h")).read()
     declared = set(re.findall(r"\b(ctrlsim_[a-z_0-9]+)\s*\(", header))
     assert declared, "no prototypes parsed from the header"
-    for name in declared:
-        assert hasattr(so, name), f"{name} declared in include/ctrlsim_b200.h but not exported"
     assert set(lib.EXPORTS) == declared
-    so.ctrlsim_abi_version.restype = ctypes.c_int
-    assert so.ctrlsim_abi_version() == lib.ABI_VERSION
+    paths = build_all()  # the reference-default geometry and the wide one (-DCTRLSIM_WIDE), same ABI
+    assert len(paths) == 2
+    for path in paths:
+        so = ctypes.CDLL(path)
+        for name in declared:
+            assert hasattr(so, name), f"{name} declared in include/ctrlsim_b200.h but not exported by {path}"
+        so.ctrlsim_abi_version.restype = ctypes.c_int
+        assert so.ctrlsim_abi_version() == lib.ABI_VERSION
 
 
 def test_batch_struct_matches_header_field_order():
