@@ -439,7 +439,8 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   P3Smem& sm = *reinterpret_cast<P3Smem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nk = K / P_BK;
-  const bool gtrace = g_gemm_debug >= 1 && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
+  const int dbg = g_gemm_debug;  // experiments (results are wrong): 4 = no A_lo derivation, 8 = no A_lo x B_hi MMAs, 16 = no W_lo TMA
+  const bool gtrace = (dbg == 1) && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
 
   if (tid == 0) {
     for (int s = 0; s < P_STAGES; ++s) {
@@ -471,6 +472,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint32_t a_raw = tc_smem_u32(st.a_raw), a_lo = tc_smem_u32(st.a_lo);
         const uint32_t b_raw = tc_smem_u32(st.b_raw), b_lo = tc_smem_u32(st.b_lo);
         float4 va[4], vb[4];
+        if (!(dbg & 4)) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t off = (uint32_t)((rbase + 32 * i) * P_BK + sc) * 4u;
@@ -482,6 +484,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t off = (uint32_t)((rbase + 32 * i) * P_BK + sc) * 4u;
           sts128(a_lo + off, tc_lo4(va[i]));
           if (!WLO) sts128(b_lo + off, tc_lo4(vb[i]));
+        }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -513,7 +516,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int ks = 0; ks < P_BK / 8; ++ks) {
             const uint64_t o = (uint64_t)(2 * ks);
             tc_mma(d_main, dah + o, dbh + o, idesc2, (kc > 0 || ks > 0) ? 1u : 0u);
-            tc_mma(d_cross, dal + o, dbh + o, idesc1, 1u);
+            if (!(dbg & 8)) tc_mma(d_cross, dal + o, dbh + o, idesc1, 1u);
           }
           GT_TRACE(3);
           tc_commit(&sm.empty[s]);
@@ -534,10 +537,11 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tc_mbar_wait(&sm.empty[s], ((it / P_STAGES) & 1) ^ 1);
           P3Stage& st = sm.stage[s];
           GT_TRACE(0);
-          tc_expect_tx(&sm.tma_full[s], (P_BM + (WLO ? 2 : 1) * P_BN) * P_BK * 4);
+          const bool wlo_tma = WLO && !(dbg & 16);
+          tc_expect_tx(&sm.tma_full[s], (P_BM + (wlo_tma ? 2 : 1) * P_BN) * P_BK * 4);
           tc_tma_2d(st.a_raw, &tmA, kc * P_BK, m0, &sm.tma_full[s]);
           tc_tma_2d(st.b_raw, &tmW, kc * P_BK, n0, &sm.tma_full[s]);
-          if (WLO) tc_tma_2d(st.b_lo, &tmWlo, kc * P_BK, n0, &sm.tma_full[s]);
+          if (wlo_tma) tc_tma_2d(st.b_lo, &tmWlo, kc * P_BK, n0, &sm.tma_full[s]);
         }
       }
     }
@@ -553,7 +557,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (warp == 10) GE_TRACE(0);
       const bool fast = m0 + P_BM <= M && n0 + P_BN <= N && vec_ok && !table && (reinterpret_cast<uintptr_t>(bias) & 7) == 0;
-      const bool nostore = g_gemm_debug == 2;  // timing experiment: no global stores
+      const bool nostore = (dbg & 2) != 0;  // timing experiment: no global stores
 #pragma unroll 1
       for (int jj = 0; jj < 2; ++jj) {
         const int j = 2 * ((warp - 10) >> 2) + jj;  // this warp's 64-column half of the tile

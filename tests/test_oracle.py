@@ -911,3 +911,85 @@ def test_one_agent_and_two_agent_selection_match_the_reference_functions(tmp_pat
     c.eval.eval_mode = "three_agent"
     with pytest.raises(ValueError):
         B200PolicyEvaluator(c, types.SimpleNamespace(model=types.SimpleNamespace(device="cpu")), scenes=scenes).select_scenes()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref")) or not os.path.isdir("/root/reference"),
+                    reason="needs the reference tree and its built simulator (build container only)")
+def test_reference_signature_adapter_runs_inside_the_stock_policy_evaluator(tmp_path, cfg):
+    """``B200AutoregressivePolicy`` has the reference's constructor and reset / update_state / predict / act
+    signatures, so the UNMODIFIED ``PolicyEvaluator.evaluate_policy()`` (its own Nocturne simulator and
+    vehicle_data_dict) drives it.  Here the device is replaced by a recording stand-in (no GPU in this container; the GPU
+    half is tests/test_gpu_parity.py::test_reference_signature_adapter_matches_the_batched_path): checks the call
+    shapes, that the one-scene batch built from the reference's dicts equals the one our own loader builds from the
+    scene JSON (ground truth, goals, sizes, evaluated set, focal order), the per-step state hand-over, and that what
+    predict() writes through key_dict is what the evaluator then applies."""
+    from ctrlsim_b200.batch import SceneBatch
+    from ctrlsim_b200.policy_adapter import B200AutoregressivePolicy
+    from ctrlsim_b200.scenario import parse_scenario
+    from ctrlsim_b200.synth import make_scene, write_dataset
+    from oracle import ref_harness, ref_shims
+    ref_shims.install()
+    from evaluators import PolicyEvaluator
+    scenes = [make_scene(11, n_vehicles=6, n_roads=1, n_chunks=4), make_scene(12, n_vehicles=9, n_roads=2, n_chunks=3, frac_short=0.4)]
+    paths = write_dataset(str(tmp_path), scenes)
+    rcfg = ref_harness.build_cfg(paths, 4, len(scenes))  # at most 4 evaluated vehicles: random.sample is exercised
+    steps = rcfg.nocturne.steps
+
+    class Backend:
+        def __init__(self):
+            self.batches, self.calls = [], []
+
+        def make_batch(self, cfg_, scene, scene_id, parsed, evaluated):
+            b = SceneBatch(cfg_, [scene], [scene_id], "cpu", eval_threshold=len(evaluated), parsed=[parsed], evaluated_sets=[evaluated])
+            self.batches.append((b, list(evaluated)))  # in the order random.sample drew them: it decides ties of the focal order
+            return b
+
+        def step(self, batch, t, states_t, actions_prev):
+            n = batch.N
+            assert states_t.shape == (n, 8) and np.isfinite(states_t).all()
+            assert (actions_prev is None) == (t == 0)
+            self.calls.append((len(self.batches) - 1, t, states_t.copy(), None if actions_prev is None else actions_prev.copy()))
+            ev = self.batches[-1][1]
+            nxt, rtg, act = np.zeros((n, 2)), -np.ones((n, 3), np.int64), -np.ones(n, np.int64)
+            for v in ev:
+                if states_t[v, 7]:
+                    nxt[v] = (0.25 * (v + 1), 0.01 * (t % 7))
+                    rtg[v], act[v] = (t, 35, 36), 524
+            return nxt, rtg, act
+
+    be = Backend()
+    kd = {"next_acceleration": "next_acceleration", "next_steering": "next_steering", "rtgs": "rtgs"}
+    td = {"tilt": True, "goal_tilt": 0, "veh_veh_tilt": 0, "veh_edge_tilt": 0}
+    policy = B200AutoregressivePolicy(rcfg, "synthetic", None, True, True, True, False, False, False, False, kd, td, "ctrl_sim",
+                                      1.0, False, 0.8, backend=be)
+    recs = []
+    ev = PolicyEvaluator(rcfg, policy)
+    orig = ev.update_running_statistics
+    ev.update_running_statistics = lambda d: (recs.append({k: {f: list(v[f]) if isinstance(v[f], list) else v[f] for f in ("acceleration", "steering", "rtgs", "existence")} for k, v in d.items()}), orig(d))[1]
+    metrics, lines = ev.evaluate_policy()
+    assert set(metrics) == {"goal", "collision_rate", "offroad_rate", "fde", "ade", "lin_speed_jsd", "ang_speed_jsd", "accel_jsd", "nearest_dist_jsd"}
+    assert len(be.batches) == len(scenes) and len(be.calls) == len(scenes) * steps and len(recs) == len(scenes)
+    assert [c[1] for c in be.calls] == list(range(steps)) * len(scenes)
+    for k, sc in enumerate(scenes):
+        b, evaluated = be.batches[k]
+        p = parse_scenario(sc["json"], steps)
+        assert b.t["scene_id"].tolist() == [k] and b.N == p["n"] and len(evaluated) == min(4, int(p["moving"].sum()))
+        assert np.array_equal(b.t["gt"][0].numpy(), p["gt"].astype(np.float64)) and np.array_equal(b.t["gt_valid"][0].numpy(), p["gt_valid"])
+        assert np.array_equal(b.t["goal"][0].numpy(), p["goal"])
+        assert np.array_equal(b.t["veh_len"][0].numpy(), p["size"][:, 0]) and np.array_equal(b.t["veh_wid"][0].numpy(), p["size"][:, 1])
+        ref_batch = SceneBatch(cfg, [sc], [k], "cpu", parsed=[p], evaluated_sets=[evaluated])
+        for f in ("evaluated", "eval_order", "road_xy", "road_valid", "road_type", "n_poly"):
+            assert np.array_equal(b.t[f].numpy(), ref_batch.t[f].numpy()), f
+        # what predict() wrote through key_dict is what the evaluator applied (from the first controlled step, t = 9, on)
+        d = recs[k]
+        for v in evaluated:
+            for t in range(rcfg.nocturne.history_steps - 1, steps):
+                if d[v]["existence"][t]:
+                    assert d[v]["acceleration"][t] == 0.25 * (v + 1) and d[v]["steering"][t] == 0.01 * (t % 7), (k, v, t)
+                    assert np.allclose(d[v]["rtgs"][t], [t / 349 * 10, 35 / 349 * 100 - 10, 36 / 349 * 100 - 10])
+        others = [v for v in range(p["n"]) if v not in evaluated]
+        assert all((np.asarray(d[v]["rtgs"][t]) == 0).all() for v in others for t in range(steps))
+        # the applied controls of step t-1 come back as the action history of step t
+        for (kk, t, st, ap) in be.calls:
+            if kk == k and t > 0:
+                assert np.array_equal(ap[:, 0], [d[v]["acceleration"][t - 1] for v in range(p["n"])])

@@ -8,6 +8,7 @@ dev = torch.device("cuda:0")
 shapes = [(256 * 2304, 768, 256), (256 * 2304, 256, 256), (256 * 2304, 1024, 256), (256 * 2304, 256, 1024)]
 if len(sys.argv) > 1:
     shapes = shapes[: int(sys.argv[1])]
+dbg = int(os.environ.get("GEMM_DEBUG", "0"))  # experiment bits of gemm_tc.cu (results are wrong when set)
 for M, N, K in shapes:
     A = torch.randn(M, K, device=dev)
     W = torch.randn(N, K, device=dev) / math.sqrt(K)
@@ -16,12 +17,14 @@ for M, N, K in shapes:
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(2):
         lib.ctrlsim_linear(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, 0, st)
+    lib.ctrlsim_debug_gemm(dbg)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
         lib.ctrlsim_linear(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, 0, st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
+    lib.ctrlsim_debug_gemm(0)
     ref = torch.nn.functional.linear(A[:512].double(), W.double(), b.double())
     err = (C[:512].double() - ref).abs().max().item()
-    print(f"M={M} N={N} K={K}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s  max|err|={err:.2e}  mode={os.environ.get('CTRLSIM_GEMM','default')}", flush=True)
+    print(f"M={M} N={N} K={K}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s  max|err|={err:.2e}  mode={os.environ.get('CTRLSIM_GEMM','default')} debug={dbg}", flush=True)
