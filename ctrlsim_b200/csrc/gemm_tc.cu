@@ -439,7 +439,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   P3Smem& sm = *reinterpret_cast<P3Smem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nk = K / P_BK;
-  const int dbg = g_gemm_debug;  // experiments (results are wrong): 4 = no A_lo derivation, 8 = no A_lo x B_hi MMAs, 16 = no W_lo TMA
+  const int dbg = g_gemm_debug;  // experiments (results are wrong): 4 = no A_lo derivation, 8 = no A_lo x B_hi MMAs, 16 = no W_lo TMA, 32 = no main MMAs
   const bool gtrace = (dbg == 1) && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
 
   if (tid == 0) {
@@ -515,7 +515,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (int ks = 0; ks < P_BK / 8; ++ks) {
             const uint64_t o = (uint64_t)(2 * ks);
-            tc_mma(d_main, dah + o, dbh + o, idesc2, (kc > 0 || ks > 0) ? 1u : 0u);
+            if (!(dbg & 32)) tc_mma(d_main, dah + o, dbh + o, idesc2, (kc > 0 || ks > 0) ? 1u : 0u);
             if (!(dbg & 8)) tc_mma(d_cross, dal + o, dbh + o, idesc1, 1u);
           }
           GT_TRACE(3);

@@ -135,6 +135,7 @@ class B200AutoregressivePolicy:
             self._evaluated = {self.veh_id_to_idx[v] for v in vehicles_to_evaluate}
         next_action, rtg_idx, act_idx = self.backend.step(self._batch, t, self.states[:, t],
                                                           self.actions[:, t - 1] if t > 0 else None)
+        self.last_rtg_idx, self.last_act_idx = rtg_idx, act_idx  # sampled bins of this step (-1: none), for parity dumps
         w, kd = self.cfg_rl_waymo, self.key_dict
         R = w.rtg_discretization - 1
         lo = (w.min_rtg_pos, w.min_rtg_veh, w.min_rtg_road)

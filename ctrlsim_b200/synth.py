@@ -105,6 +105,40 @@ def make_scene(scene_id: int, n_vehicles: int = 64, n_roads: int = 4, n_chunks: 
     return {"name": name, "json": scen, "preproc": preproc_from_json(scen)}
 
 
+def make_replay_scene(i: int):
+    """Scene i of the BASELINE config-4 workload ("Waymo val_interactive-shaped replay"): varied vehicle counts (4..64),
+    road layouts, parked and short-lived vehicles; in every fifth scene the first vehicle leaves its lane at 20 degrees,
+    runs into its neighbours and crosses a road edge, so that collisions, contact response and off-road events occur."""
+    sc = make_scene(5000 + i, n_vehicles=4 + (7 * i) % 61, n_roads=2 + i % 3, n_chunks=3 + i % 5, frac_short=0.25,
+                    frac_parked=0.2 if i % 2 else 0.0)
+    if i % 5 == 0:
+        o = sc["json"]["objects"][0]
+        th = math.radians(o["heading"][0]) + 0.35
+        sp = max(6.0, math.hypot(o["velocity"][0]["x"], o["velocity"][0]["y"]))
+        x0, y0 = o["position"][0]["x"], o["position"][0]["y"]
+        for t, ok in enumerate(o["valid"]):
+            if ok:
+                o["position"][t] = {"x": x0 + sp * 0.1 * t * math.cos(th), "y": y0 + sp * 0.1 * t * math.sin(th)}
+                o["heading"][t] = math.degrees(th)
+                o["velocity"][t] = {"x": sp * math.cos(th), "y": sp * math.sin(th)}
+        last = max(t for t, ok in enumerate(o["valid"]) if ok)
+        o["goalPosition"] = dict(o["position"][last])
+    return sc
+
+
+def replay_scene_summary(pos, heading, existence, reward, gt_pos):
+    """Per-scene figures of a log-replay episode (BASELINE config 4): vehicle-steps in a vehicle-vehicle collision,
+    off-road vehicle-steps, vehicles that ever collided / left the road, ADE against the logged positions, and an
+    order-independent checksum of the simulated positions.  Arrays [n, 91, ...] in the trace layout."""
+    ex = existence.astype(bool)
+    cv, ce = (reward[:, :, 6] > 0) & ex, (reward[:, :, 7] > 0) & ex
+    err = np.linalg.norm(pos.astype(np.float64) - gt_pos.astype(np.float64), axis=-1)
+    return {"n": int(pos.shape[0]), "veh_steps": int(ex.sum()), "coll_steps": int(cv.sum()), "off_steps": int(ce.sum()),
+            "coll_veh": int(cv.any(1).sum()), "off_veh": int(ce.any(1).sum()),
+            "ade": float(err[ex].mean()) if ex.any() else 0.0,
+            "pos_sum": float(np.abs(pos.astype(np.float64))[ex].sum()), "head_sum": float(np.abs(heading.astype(np.float64))[ex].sum())}
+
+
 def preproc_from_json(scen, n_pts: int = 100):
     """road_points [P,100,3] (x, y, exist) and road_types [P,8], chunked like datasets/rl_waymo/dataset.py:73-108."""
     pts, types = [], []

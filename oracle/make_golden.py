@@ -36,6 +36,10 @@ FIXTURES = {
     "sparse": dict(scene=dict(scene_id=3, n_vehicles=6, n_roads=6, n_chunks=4, lane_ids=[3], frac_short=0.34,
                               speed_range=(5.0, 12.0)),
                    weights=dict(seed=2, still_bias=12.0), tilts=(0, 0, 0), logit_steps=(9, 31, 32, 33, 89)),
+    # config2: ONE scene of BASELINE config 2's shape (64 vehicles x 256 polylines, every vehicle policy-controlled: ~12
+    # overlapping focal groups of 24 per step) for 44 steps - 12 of them in the sliding-window phase (t >= 32).
+    "config2": dict(scene=dict(scene_id=5, n_vehicles=64, n_roads=4, n_chunks=8), weights=dict(seed=0, still_bias=3.0),
+                    tilts=(0, 0, 0), logit_steps=(33,), steps=44),
 }
 
 
@@ -82,7 +86,7 @@ def main():
         sc = make_scene(**spec["scene"])
         weights = make_weights(default_config(), **spec["weights"])
         metrics, recs = run_reference([sc], weights=weights, seed=0, tilts=spec["tilts"],
-                                      logit_steps=spec["logit_steps"])
+                                      logit_steps=spec["logit_steps"], steps=spec.get("steps", 90))
         np.savez_compressed(os.path.join(GOLDEN, f"rollout_{name}.npz"), **pack(recs[0], metrics, spec))
         print(f"[golden] {name}: {time.time() - t0:.1f}s metrics={metrics}", flush=True)
 

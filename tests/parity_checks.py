@@ -23,16 +23,17 @@ def first_flip(tr, g, n, T):
 
 
 
-def check_rollout_vs_reference(tr, g, name, trig="glibc"):
+def check_rollout_vs_reference(tr, g, name, trig="glibc", steps=90, min_flip=None):
     """``tr``: trace arrays of ONE scene in SceneBatch.trace() layout; ``g``: the reference fixture.  Returns the first
     step with a marginal draw (90 if none).  ``trig``: "glibc" = the default simulator arithmetic (no difference to the
-    reference left: positions / headings compared bit for bit through contacts); "fp64" = CTRLSIM_TRIG=fp64."""
+    reference left: positions / headings compared bit for bit through contacts); "fp64" = CTRLSIM_TRIG=fp64.
+    ``steps``: episode length of the fixture; ``min_flip``: earliest step at which a marginal draw is tolerated."""
     n = g["pos"].shape[0]
     tc = first_contact(g)
-    t_r, t_a, bad_r, rtg = first_flip(tr, g, n, 90)
+    t_r, t_a, bad_r, rtg = first_flip(tr, g, n, steps)
     assert t_a >= t_r, (name, "an action draw differs before any RTG draw did", t_a, t_r)
-    if t_r < 90:
-        assert t_r >= min(tc + 8, 60), (name, "draws differ too early", t_r, tc, bad_r[:4].tolist())
+    if t_r < steps:
+        assert t_r >= (min(tc + 8, 60) if min_flip is None else min_flip), (name, "draws differ too early", t_r, tc, bad_r[:4].tolist())
         for t, v, c in bad_r[bad_r[:, 0] == t_r]:
             assert abs(int(rtg[t, v, c]) - int(g["rtg_idx"][t, v, c])) == 1, (name, t, v, c)
     T = t_r  # states up to and including step T depend on draws before T only
@@ -69,6 +70,6 @@ def check_rollout_vs_reference(tr, g, name, trig="glibc"):
         # oracle built with that trig reproduces the GPU numbers exactly (crowded: 0.73 mm, 2.3e-5 rad after 74 steps)
         assert dpos < POS_TOL and dhead < 2e-4 and dvel < 2e-3 and dacc < 5e-2 and drew < 1e-3 and dnd < 5e-3, \
             (name, "in contact", dpos, dhead, dvel, dacc, drew, dnd)
-    if tc <= 90:
+    if tc <= steps:
         assert T > tc, (name, "the comparison must cover the contact phase", T, tc)
     return t_r

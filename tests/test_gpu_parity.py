@@ -5,12 +5,13 @@ reference fixtures (tests/golden/, produced by the unmodified reference - oracle
 import ctypes as C
 import json
 import math
+import os
 
 import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden
+from conftest import ROOT, load_golden
 from parity_checks import check_rollout_vs_reference
 
 pytestmark = pytest.mark.gpu
@@ -53,6 +54,29 @@ def test_linear_matches_torch(lib, dev, M, N, K, relu):
     ref = torch.relu(ref) if relu else ref
     # tcgen05 accumulates with truncation: the error grows ~linearly with K/8 chained MMAs (gemm_tc.cu header)
     assert (Cc.double() - ref).abs().max().item() < 1e-5 * max(1.0, K / 256)
+
+
+@pytest.mark.parametrize("name,M,relu", [("self_attn.in_proj_weight", 90 * 2304, False), ("linear1.weight", 70001, True),
+                                         ("self_attn.out_proj.weight", 148 * 128 * 3 + 5, False), ("linear2.weight", 40000, False)])
+def test_linear_with_registered_weights_matches_torch(cfg, lib, dev, name, M, relu):
+    """Model weights are registered with the library (their lo tiles exist), which routes large K <= 256 layers to the
+    weight-stationary kernel (gemm_tc_ws_kernel) and the rest to the streaming one: both against fp64, full output."""
+    from ctrlsim_b200.model import DeviceModel
+    from ctrlsim_b200.weights import make_weights
+    model = DeviceModel(cfg, make_weights(cfg, seed=0), dev)
+    W = model.tensors["decoder.transformer_decoder.layers.1." + name]
+    N, K = W.shape
+    g = torch.Generator(device="cpu").manual_seed(M % 1000)
+    A = torch.randn(M, K, generator=g).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    C = torch.empty(M, N, device=dev)
+    _chk(model.lib.ctrlsim_linear(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, 1 if relu else 0, _stream()), model.lib)
+    idx = torch.cat([torch.arange(0, 300, device=dev), torch.randint(0, M, (2000,), generator=g).to(dev), torch.arange(M - 300, M, device=dev)])
+    ref = torch.nn.functional.linear(A[idx].double(), W.double(), b.double())
+    if relu:
+        ref = ref.relu()
+    assert (C[idx].double() - ref).abs().max().item() < (2e-5 if K <= 256 else 5e-5)
+    assert torch.isfinite(C).all()
 
 
 @pytest.mark.parametrize("M,res,relu", [(1, False, False), (1000, True, False), (257, True, True)])
@@ -332,6 +356,36 @@ def test_log_replay_batch_matches_oracle(cfg, dev):
     assert n_veh_steps > 30000 and n_off > 0 and n_coll_scenes >= 3 and n_coll_steps > 50, (n_veh_steps, n_off, n_coll_scenes, n_coll_steps)
 
 
+def test_replay_workload_matches_the_cpu_reference_table(cfg, dev):
+    """BASELINE config 4 (log replay of val_interactive-shaped scenes): the first 120 scenes of the workload of
+    tools/replay_eval.py as one GPU batch against tests/golden/replay_oracle.json - the same scenes through the C
+    restatement of the reference simulator (oracle/make_replay_table.py), 47 of them with vehicle-vehicle contacts.
+    Collision / off-road vehicle-steps and vehicles are identical, the position and heading checksums bit-identical."""
+    import json
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.model import DeviceModel
+    from ctrlsim_b200.synth import make_replay_scene, replay_scene_summary
+    from ctrlsim_b200.weights import make_weights
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "replay_oracle.json")))["rows"]
+    scenes = [make_replay_scene(i) for i in range(len(ref))]
+    pol = B200Policy(cfg, "synthetic", DeviceModel(cfg, make_weights(cfg, seed=0), dev), seed=0)
+    ev = B200PolicyEvaluator(cfg, pol, scenes=scenes)
+    b = ev.build_batch(eval_threshold=0, keep_replay_only=True)
+    ev.rollout(b)
+    tr = b.trace()
+    gt = b.t["gt"].cpu().numpy()
+    assert b.contact_overflow() == 0
+    n_contact = 0
+    for s, r in enumerate(ref):
+        n = int(tr["n_veh"][s])
+        got = replay_scene_summary(tr["tr_pos"][s, :n], tr["tr_heading"][s, :n], tr["tr_exist"][s, :n], tr["tr_reward"][s, :n], gt[s, :n, :, :2])
+        for k in ("n", "veh_steps", "coll_steps", "off_steps", "coll_veh", "off_veh", "pos_sum", "head_sum"):
+            assert got[k] == r[k], (s, k, got[k], r[k])
+        assert abs(got["ade"] - r["ade"]) < 1e-12
+        n_contact += r["coll_steps"] > 0
+    assert n_contact >= 40
+
+
 def test_geometry_known_answers(lib, dev):
     """Reference KATs: nocturne/cpp/tests/src/geometry/polygon_test.cc:60-86, intersection_test.cc:52-76."""
     eps = 1e-5
@@ -413,6 +467,25 @@ def test_rollout_matches_reference(cfg, dev, name):
     ev, b, tr = _rollout(cfg, spec, dev)
     t_r = check_rollout_vs_reference(tr, g, name)
     if t_r == 90:  # no marginal draw: the summary metrics must match the reference's compute_metrics
+        m = ev.metrics_from_summary(ev.summarize(b))
+        for k, v in ref_metrics.items():
+            assert abs(m[k] - v) < 1e-4 * max(1.0, abs(v)), (k, m[k], v)
+
+
+def test_config2_scene_rollout_matches_reference(cfg, dev):
+    """ONE scene of BASELINE config 2's shape - 64 vehicles, all policy-controlled (~12 overlapping focal groups of 24
+    per step), 256 polylines - against the unmodified reference evaluator for 44 steps: 12 of them in the sliding-window
+    phase (t >= 32), vehicle-vehicle contacts from step 14 on (149 vehicle-steps in collision).  Sampled bins bit for
+    bit (11,000 draws; a marginal draw, if any, must come after the window started sliding), states bit for bit."""
+    g, spec, ref_metrics = load_golden("config2")
+    c = cfg.copy()
+    c.nocturne = cfg.nocturne.copy()
+    c.nocturne.steps = spec["steps"]
+    ev, b, tr = _rollout(c, spec, dev)
+    n = g["pos"].shape[0]
+    assert n == 64 and b.Pm == 256 and len(g["evaluated"]) == 64
+    t_r = check_rollout_vs_reference(tr, g, "config2", steps=spec["steps"], min_flip=34)
+    if t_r == spec["steps"]:
         m = ev.metrics_from_summary(ev.summarize(b))
         for k, v in ref_metrics.items():
             assert abs(m[k] - v) < 1e-4 * max(1.0, abs(v)), (k, m[k], v)
@@ -658,3 +731,66 @@ def test_fp64_trig_mode_stays_within_tolerance_through_contacts(cfg, dev, monkey
     dpos = np.abs(tr["tr_pos"][0, :n].astype(np.float64) - g["pos"])[ex].max()
     dhead = np.abs(tr["tr_heading"][0, :n].astype(np.float64) - g["heading"])[ex].max()
     assert abs(dpos - 0.000732421875) < 1e-9 and abs(dhead - 2.3126602172851562e-05) < 1e-9, (dpos, dhead)
+
+
+def test_reference_signature_adapter_matches_the_batched_path(cfg, dev):
+    """SURVEY 8(b), GPU half: ``B200AutoregressivePolicy`` driven through the reference's own call sequence -
+    reset(vehicle_data_dict), then per step update_state(vdd, v2e, t) / predict(vdd, gt, preproc, dset, v2e, t) / act(veh,
+    t, vdd) with a dict-of-lists world state and a CPU simulator owned by the caller (here the oracle's simulator and
+    evaluator-loop restatement stand in for nocturne_cpp and PolicyEvaluator, which do not exist on the GPU box; the
+    stock PolicyEvaluator itself drives the same class in tests/test_oracle.py) - must draw the bins the unmodified
+    reference drew on the 'sparse' fixture, across the switch to the sliding window at t = 32."""
+    from ctrlsim_b200.policy_adapter import B200AutoregressivePolicy
+    from ctrlsim_b200.synth import make_scene
+    from oracle.policy_port import RolloutPort
+    g, spec, _ = load_golden("sparse")
+    sc = make_scene(**spec["scene"])
+    T = 36
+    kd = {"next_acceleration": "next_acceleration", "next_steering": "next_steering", "rtgs": "rtgs"}
+    tl = spec.get("tilts", [0, 0, 0])
+    td = {"tilt": True, "goal_tilt": tl[0], "veh_veh_tilt": tl[1], "veh_edge_tilt": tl[2]}
+    policy = B200AutoregressivePolicy(cfg, "synthetic", _model(cfg, spec, dev), True, True, True, False, False, False, False, kd,
+                                      td, "ctrl_sim", 1.0, False, 0.8, seed=0)
+    port = RolloutPort(cfg, None)
+    ctx = port.setup_scene(0, sc["json"])
+    n, sim, rec, gt = ctx["n"], ctx["sim"], ctx["rec"], ctx["gt"]
+    v2e = [int(v) for v in g["evaluated"]]
+    gt_data_dict = {v: {"traj": [list(gt[v, t]) for t in range(91)]} for v in range(n)}
+    vdd = {v: {"position": [], "velocity": [], "heading": [], "existence": [], "acceleration": [], "steering": [], "timestep": [],
+               "rtgs": [], "goal_position": {"x": ctx["goal"][v, 0], "y": ctx["goal"][v, 1]}, "goal_heading": ctx["goal"][v, 2],
+               "goal_speed": ctx["goal"][v, 3], "length": float(ctx["parsed"]["size"][v, 0]), "width": float(ctx["parsed"]["size"][v, 1]),
+               "type": "vehicle", "next_acceleration": 0.0, "next_steering": 0.0} for v in range(n)}
+
+    class Veh:  # the slice of the pybind Vehicle that act() touches
+        def __init__(self, v): self.v, self.acceleration, self.steering, self.braked, self.parked = v, None, None, None, False
+        def getID(self): return self.v
+        def brake(self, x): self.braked = x
+        def setPosition(self, x, y): self.parked = True
+
+    policy.scene_index = -1  # reset() advances it to 0 = the fixture's scene id
+    policy.reset(vdd)
+    next_act = np.zeros((n, 2))
+    for t in range(T):
+        port.observe(ctx, t)
+        for v in range(n):
+            d = vdd[v]
+            d["position"].append({"x": rec["pos"][v, t, 0], "y": rec["pos"][v, t, 1]})
+            d["velocity"].append({"x": rec["vel"][v, t, 0], "y": rec["vel"][v, t, 1]})
+            d["heading"].append(rec["heading"][v, t]); d["existence"].append(rec["existence"][v, t]); d["timestep"].append(t)
+        policy.update_state(vdd, v2e, t)
+        out = policy.predict(vdd, gt_data_dict, sc["preproc"], None, v2e, t)
+        assert out is vdd
+        assert (policy.last_rtg_idx == g["rtg_idx"][t]).all(), t
+        assert (policy.last_act_idx == g["act_idx"][t]).all(), t
+        for v in v2e:
+            if t >= cfg.nocturne.history_steps - 1:
+                veh, (a, s_) = policy.act(Veh(v), t, vdd)
+                assert veh.parked == (not rec["existence"][v, t]) and veh.steering == s_
+                assert (veh.acceleration == a) if a > 0 else (veh.braked == abs(a))
+                next_act[v] = (a, s_)
+        port.apply_controls(ctx, t, v2e, next_act)
+        for v in range(n):
+            vdd[v]["acceleration"].append(rec["accel"][v, t]); vdd[v]["steering"].append(rec["steer"][v, t])
+        sim.step(0.1)
+    assert np.abs(rec["pos"][:, :T] - g["pos"][:, :T]).max() == 0.0  # the caller's simulator saw the reference's controls
+    assert np.allclose(np.array([vdd[v]["rtgs"] for v in range(n)]), g["rtgs"][:, :T], atol=1e-12)

@@ -9,9 +9,17 @@ shapes = [(256 * 2304, 768, 256), (256 * 2304, 256, 256), (256 * 2304, 1024, 256
 if len(sys.argv) > 1:
     shapes = shapes[: int(sys.argv[1])]
 dbg = int(os.environ.get("GEMM_DEBUG", "0"))  # experiment bits of gemm_tc.cu (results are wrong when set)
+model = None
+if os.environ.get("GEMM_MODEL", "0") == "1":  # REGISTERED weights (lo tiles exist): the product path incl. the weight-stationary kernel
+    from ctrlsim_b200.config import default_config
+    from ctrlsim_b200.weights import make_weights
+    from ctrlsim_b200.model import DeviceModel
+    cfg = default_config(); model = DeviceModel(cfg, make_weights(cfg, seed=0), dev); lib = model.lib
+    pre = "decoder.transformer_decoder.layers.0."
+    names = {(768, 256): "self_attn.in_proj_weight", (256, 256): "self_attn.out_proj.weight", (1024, 256): "linear1.weight", (256, 1024): "linear2.weight"}
 for M, N, K in shapes:
     A = torch.randn(M, K, device=dev)
-    W = torch.randn(N, K, device=dev) / math.sqrt(K)
+    W = model.tensors[pre + names[(N, K)]] if model else torch.randn(N, K, device=dev) / math.sqrt(K)
     b = torch.randn(N, device=dev)
     C = torch.empty(M, N, device=dev)
     st = torch.cuda.current_stream().cuda_stream
@@ -27,4 +35,4 @@ for M, N, K in shapes:
     lib.ctrlsim_debug_gemm(0)
     ref = torch.nn.functional.linear(A[:512].double(), W.double(), b.double())
     err = (C[:512].double() - ref).abs().max().item()
-    print(f"M={M} N={N} K={K}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s  max|err|={err:.2e}  mode={os.environ.get('CTRLSIM_GEMM','default')} debug={dbg}", flush=True)
+    print(f"M={M} N={N} K={K}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s  max|err|={err:.2e}  mode={os.environ.get('CTRLSIM_GEMM','default')} debug={dbg} registered={model is not None} ws={os.environ.get('CTRLSIM_GEMM_WS','1')}", flush=True)
