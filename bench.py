@@ -44,10 +44,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 T_WIN = 32  # context length: steps t < 32 are the cached phase
+NPTS = 100  # points per polyline
 
 
 def workload_name(scenes, wide):
-    geom = "wide model caps A=64/P=256 (one focal group per scene)" if wide else "reference-default caps A=24/P=200 (~11.6 focal groups per scene)"
+    geom = "wide model caps A=64/P=256 (focal groups of up to 64 agents; the 60 m context radius still splits a scene into ~10 groups)" if wide else "reference-default caps A=24/P=200 (~11.6 focal groups per scene)"
     return (f"{scenes} synthetic 64-agent/256-polyline scenes per GPU, 90-step episodes, RTG-conditioned autoregressive "
             f"policy, {geom}")
 
@@ -399,14 +400,51 @@ def main():
     gemm_tf = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     pool_gbs = pool_by / (pool_ms * 1e-3) / 1e9 if pool_ms > 0 else 0.0
     n_full = phase_ms["full_window"][1]
-    enc = {"kernel": "map_pool_kernel (polyline pooling attention, TMA bulk + mbarrier ring)", "bound": "hbm",
-           "peak": pk["hbm"], "unit": "GB/s", "peak_source": pk["hbm_src"], "launches": int(pool_n),
-           "traffic": traffic.get("map_pool_kernel")}
+    # "encoder-attn" (BASELINE.json): SURVEY 8(d)(i) asks for both figures.  (1) the product's kernel, fused from the raw
+    # points (map_encoder.cu): 1.2 KB in + 8 KB out per polyline, FP32-pipe bound, timed live in the step;
+    enc_fused = {"kernel": "map_encode_pool_kernel (product path: point MLP layer 1 -> scores -> softmax -> pooled hidden vectors, "
+                           "fused from raw points; W3 / value / output projections folded into the next GEMM)",
+                 "bound": "fp32 pipe (not HBM: 0.44 MB per focal group where the unfused chain moved 82 MB)",
+                 "unit": "GB/s", "launches": int(pool_n)}
     if pool_n > 0:
-        enc.update({"achieved": pool_gbs, "frac": pool_gbs / pk["hbm"], "share_of_step": pool_ms / ms,
-                    "avg_launch_ms": pool_ms / pool_n, "algorithmic_bytes_per_launch": pool_by / pool_n})
+        enc_fused.update({"achieved": pool_gbs, "share_of_step": pool_ms / ms, "avg_launch_ms": pool_ms / pool_n,
+                          "algorithmic_bytes_per_launch": pool_by / pool_n,
+                          # per (point, channel): hidden layer twice (scores pass + pooling pass: 3 FMA + LN affine + ReLU each),
+                          # 8 score FMAs, 8 pooling FMAs ~ 54 flops
+                          "fp32_gflops_per_launch": pool_by / pool_n / (NPTS * 12 + 1 + 8192) * NPTS * 256 * 54 / 1e9})
+        enc_fused["fp32_tflops"] = enc_fused["fp32_gflops_per_launch"] / enc_fused["avg_launch_ms"]
     else:
-        enc.update({"achieved": None, "frac": None, "note": "not exercised: no full-window step in the timed region"})
+        enc_fused.update({"achieved": None, "note": "not exercised: no full-window step in the timed region"})
+    # (2) the HBM-streaming pooling attention over precomputed [points, 256] features (map_pool_kernel: one TMA bulk copy
+    # per 100 KB polyline tile, exported as ctrlsim_map_pool) - the kernel the roofline target is quoted on - timed here
+    # on one chunk's worth of polylines (5 GB of features, far beyond L2) with CUDA events on the launching stream
+    enc = {"kernel": "map_pool_kernel (HBM-streaming polyline pooling attention over precomputed features, TMA bulk + mbarrier "
+                     "ring; the unfused variant, not launched by the product path any more)", "bound": "hbm",
+           "peak": pk["hbm"], "unit": "GB/s", "peak_source": pk["hbm_src"], "traffic": traffic.get("map_pool_kernel"),
+           "timed": "in isolation inside this bench.py run, same polyline count as one chunk of the step"}
+    try:
+        n_poly = args.chunk * 200
+        feats = torch.randn(n_poly, 100, 256, device=dev)
+        pv = (torch.rand(n_poly, 100, device=dev) > 0.1).to(torch.uint8)
+        okp = torch.ones(n_poly, dtype=torch.uint8, device=dev)
+        U = torch.randn(8, 256, device=dev) * 0.1
+        outp = torch.empty(n_poly, 8, 256, device=dev)
+        st_ = torch.cuda.current_stream(dev).cuda_stream
+        for _ in range(3):
+            lib.ctrlsim_map_pool(feats.data_ptr(), pv.data_ptr(), okp.data_ptr(), U.data_ptr(), outp.data_ptr(), n_poly, st_)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(5):
+            lib.ctrlsim_map_pool(feats.data_ptr(), pv.data_ptr(), okp.data_ptr(), U.data_ptr(), outp.data_ptr(), n_poly, st_)
+        eb.record()
+        torch.cuda.synchronize()
+        t_ms = ea.elapsed_time(eb) / 5
+        by = n_poly * (100 * 256 * 4 + 100 + 8 * 256 * 4)
+        enc.update({"achieved": by / t_ms / 1e6, "frac": by / t_ms / 1e6 / pk["hbm"], "launches": 5, "avg_launch_ms": t_ms,
+                    "algorithmic_bytes_per_launch": by})
+        del feats, pv, okp, outp
+    except Exception as e:  # noqa: BLE001 - the headline must not die on this side measurement
+        enc.update({"achieved": None, "frac": None, "note": f"side measurement failed: {e}"})
     line = {
         "metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -430,6 +468,7 @@ def main():
                      "peak_source": pk["tf_src"], "share_of_step": gemm_ms / ms, "launches": int(gemm_n),
                      "avg_launch_ms": gemm_ms / max(gemm_n, 1), "algorithmic_flops_per_launch": gemm_fl / max(gemm_n, 1)},
         "encoder_attn": enc,
+        "encoder_attn_fused": enc_fused,
         "kernel_shares": {"gemm": gemm_ms / ms, "map_pool": pool_ms / ms, "decoder_self_attn": sa_ms / ms,
                           "decoder_cross_attn": ca_ms / ms,
                           "decoder_self_attn_tflops": sa_fl / (sa_ms * 1e-3) / 1e12 if sa_ms > 0 else 0.0,

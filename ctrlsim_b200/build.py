@@ -19,7 +19,7 @@ LIB_WIDE = os.path.join(OUT, "libctrlsim_b200_wide.so")  # same sources with -DC
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
           "--extended-lambda", "-I", os.path.join(os.path.dirname(HERE), "include")]
-UNITS = {"gemm.cu": [], "gemm_tc.cu": [], "attention.cu": [], "attention_mma.cu": [], "attention_tc.cu": [], "attention_step.cu": [], "tokens.cu": [], "sample.cu": [], "model.cu": [], "api.cu": [],
+UNITS = {"gemm.cu": [], "gemm_tc.cu": [], "attention.cu": [], "attention_mma.cu": [], "attention_tc.cu": [], "attention_step.cu": [], "map_encoder.cu": [], "tokens.cu": [], "sample.cu": [], "model.cu": [], "api.cu": [],
          "sim.cu": ["-fmad=false"]}
 
 

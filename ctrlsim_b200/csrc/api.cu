@@ -192,6 +192,9 @@ int ctrlsim_finalize_weights(CtrlSim* h) {
   NEED("derived.pool_U", NH * H, w.pool_U);
   NEED("derived.pool_W", (int64_t)H * NH * H, w.pool_W);
   NEED("derived.pool_b", H, w.pool_b);
+  NEED("derived.pool_U2", NH * H, w.pool_U2);
+  NEED("derived.pool_W2", (int64_t)H * NH * H, w.pool_W2);
+  NEED("derived.pool_b2", H, w.pool_b2);
   if ((rc = need_ln(h, me + ".norm1", w.map_n1))) return rc;
   if ((rc = need_ln(h, me + ".norm2", w.map_n2))) return rc;
   if ((rc = need_mlp(h, me + ".map_feats", H, H, w.map_feats))) return rc;
@@ -502,6 +505,11 @@ int ctrlsim_map_pool(const float* feats, const uint8_t* pt_valid, const uint8_t*
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   return launch_map_pool(feats, pt_valid, poly_valid, U, pooled, n_poly, n_sm, S(stream));
+}
+int ctrlsim_map_encode_pool(CtrlSim* h, const float* map_pts, const uint8_t* poly_valid, float* pooled, int32_t n_poly,
+                            void* stream) {
+  if (!h || !h->finalized) return set_error(-3, "ctrlsim_map_encode_pool: weights not finalized");
+  return launch_map_encode_pool(map_pts, h->w.road_pts, h->w.pool_U2, poly_valid, pooled, n_poly, h->n_sm, S(stream));
 }
 int ctrlsim_sample_rows(const float* x, int32_t rows, int32_t n, int32_t ld, int32_t stride, uint64_t seed,
                         const uint32_t* counters, int32_t* out_idx, void* stream) {

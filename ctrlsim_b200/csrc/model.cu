@@ -236,13 +236,12 @@ int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm
   // ---- M2 polyline encoder --------------------------------------------------------------------------------------
   if (Gm > 0) {
   CS_TRY(launch_map_flags(ws.tk.map_pts, ws.pt_valid, ws.poly_valid, Rp, st));
-  CS_TRY(launch_small_mlp1(3, ws.tk.map_pts, w.road_pts, ws.h1, (size_t)Rpt, st));
-  CS_TRY(gemm(ws.h1, w.road_pts.w3, w.road_pts.b3, ws.feats, Rpt, H, H, H, H, H, false, st));
-  // algorithmic bytes per polyline: the 100x256 fp32 feature tile + 100 validity bytes in, 8x256 fp32 pooled out
-  g_prof.begin(PROF_MAP_POOL, (double)Rp * (NP * H * 4.0 + NP + NH * H * 4.0), st);
-  CS_TRY(launch_map_pool(ws.feats, ws.pt_valid, ws.poly_valid, w.pool_U, ws.pooled, Rp, n_sm, st));
+  // "encoder-attn" of BASELINE.json, fused from the raw points (map_encoder.cu): point MLP layer 1 -> scores -> softmax
+  // -> pooled hidden vectors; algorithmic bytes per polyline: 100 x 3 fp32 points + validity in, 8 x 256 fp32 out
+  g_prof.begin(PROF_MAP_POOL, (double)Rp * (NP * 3 * 4.0 + 1.0 + NH * H * 4.0), st);
+  CS_TRY(launch_map_encode_pool(ws.tk.map_pts, w.road_pts, w.pool_U2, ws.poly_valid, ws.pooled, Rp, n_sm, st));
   g_prof.end(st);
-  CS_TRY(gemm(ws.pooled, w.pool_W, w.pool_b, ws.pe_a, Rp, H, NH * H, NH * H, NH * H, H, false, st));
+  CS_TRY(gemm(ws.pooled, w.pool_W2, w.pool_b2, ws.pe_a, Rp, H, NH * H, NH * H, NH * H, H, false, st));
   CS_TRY(ln(ws.pe_a, nullptr, w.map_n1, ws.pe_b, Rp, false, st));
   CS_TRY(gemm(ws.pe_b, w.map_feats.w0, w.map_feats.b0, ws.pe_a, Rp, H, H, H, H, H, false, st));
   CS_TRY(launch_layernorm(ws.pe_a, nullptr, w.map_feats.lnw, w.map_feats.lnb, ws.pe_a, Rp, H, H, H, true, st));

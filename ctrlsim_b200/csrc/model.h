@@ -32,9 +32,14 @@ struct EmbedW {  // what assemble_tokens needs
 struct ModelWeights {
   // map encoder (modules/map_encoder.py)
   MlpW road_pts;            // 3 -> 256 -> 256
-  const float* pool_U;      // derived [8,256]: W_k,h^T (q_h * d_h^-0.5)
+  const float* pool_U;      // derived [8,256]: W_k,h^T (q_h * d_h^-0.5)   (unfused chain, ctrlsim_map_pool)
   const float* pool_W;      // derived [256, 8*256]: out_proj . blockdiag(W_v)
   const float* pool_b;      // derived [256]: out_proj . b_v + out_proj.bias
+  // the same three with the second layer of road_pts_encoder (W3, b3) folded in (map_encoder.cu): the pooling runs on
+  // the hidden layer h = ReLU(LN(W0 x + b0)) and W3 is applied to the 8 pooled vectors instead of the 100 points
+  const float* pool_U2;     // derived [8,256]: W3^T U_h
+  const float* pool_W2;     // derived [256, 8*256]: block h = pool_W_h W3
+  const float* pool_b2;     // derived [256]: pool_b + sum_h pool_W_h b3
   LnW map_n1, map_n2;
   MlpW map_feats;           // 256 -> 256 -> 256
   const float* type_tab2;   // derived [9,256]: road_road_type_encoder.mlp.0 applied to the type half + its bias
@@ -69,6 +74,8 @@ int launch_convert_tokens(int G, int n_t, const float* agent_states, const float
                           const int* actions, const int* rtgs, const int* timesteps, const float* road_points,
                           const int* road_types, const TokenBufs& tk, cudaStream_t st);
 int launch_small_mlp1(int din, const float* X, const MlpW& w, float* Y, size_t M, cudaStream_t st);
+int launch_map_encode_pool(const float* map_pts, const MlpW& pts_mlp, const float* U2, const uint8_t* poly_valid,
+                           float* pooled, int n_poly, int n_sm, cudaStream_t st);  // map_encoder.cu
 int launch_map_flags(const float* map_pts, uint8_t* pt_valid, uint8_t* poly_valid, int n_poly, cudaStream_t st);
 int launch_assemble_tokens(int G, int n_t, const float* sg, const TokenBufs& tk, const EmbedW& ew, float* X, float* mem,
                            cudaStream_t st);

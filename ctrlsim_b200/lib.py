@@ -105,6 +105,7 @@ _SIGS = {
     "ctrlsim_attn_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_void_p]),
     "ctrlsim_map_pool": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
+    "ctrlsim_map_encode_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "ctrlsim_sample_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "ctrlsim_sample_rows_nucleus": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p,

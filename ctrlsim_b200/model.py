@@ -6,6 +6,9 @@ A few tensors are folded on the host in float64 once at load time (they are cons
 
   derived.pool_U     [8,256]   U_h = W_k,h^T (q_h d_h^-0.5), q = map_seeds W_q^T + b_q   (modules/map_encoder.py:16-19,41)
   derived.pool_W/b   [256,2048] out_proj . blockdiag_h(W_v,h) and out_proj . b_v + out_proj.bias
+  derived.pool_U2/W2/b2  the same three with road_pts_encoder.mlp.3 (W3, b3) folded in: U2_h = W3^T U_h, block h of W2 =
+                     pool_W_h W3, b2 = pool_b + sum_h pool_W_h b3 - the pooling then runs on the hidden layer of the
+                     point MLP and W3 is applied to 8 pooled vectors per polyline instead of 100 points (csrc/map_encoder.cu)
   derived.type_tab2  [9,256]   road_road_type_encoder.mlp.0[:, 256:] . road_type_encoder(one_hot_i) + bias; row 8 is
                                the all(-1) padding type (datasets/rl_waymo/dataset.py:425)
   derived.rtg_tab_*  [350,256] embed_rtg_{goal,veh,road}.weight folded through the matching block of embed_rtg
@@ -51,7 +54,13 @@ def derive_weights(state_dict, cfg) -> dict:
     tf = _mlp_f64(sd, f"{me}.road_type_encoder", types_in)
     Wrr, brr = sd[f"{me}.road_road_type_encoder.mlp.0.weight"], sd[f"{me}.road_road_type_encoder.mlp.0.bias"]
     tab2 = tf @ Wrr[:, H:].T + brr
-    out = {"derived.pool_U": U, "derived.pool_W": pool_W, "derived.pool_b": pool_b, "derived.type_tab2": tab2}
+    # second layer of road_pts_encoder folded through the (linear) pooling: csrc/map_encoder.cu
+    W3, b3 = sd[f"{me}.road_pts_encoder.mlp.3.weight"], sd[f"{me}.road_pts_encoder.mlp.3.bias"]
+    U2 = U @ W3
+    pool_W2 = np.concatenate([pool_W[:, h * H:(h + 1) * H] @ W3 for h in range(NH)], axis=1)
+    pool_b2 = pool_b + sum(pool_W[:, h * H:(h + 1) * H] @ b3 for h in range(NH))
+    out = {"derived.pool_U": U, "derived.pool_W": pool_W, "derived.pool_b": pool_b, "derived.type_tab2": tab2,
+           "derived.pool_U2": U2, "derived.pool_W2": pool_W2, "derived.pool_b2": pool_b2}
     Wr = sd["encoder.embed_rtg.weight"]
     for c, name in enumerate(("goal", "veh", "road")):
         out[f"derived.rtg_tab_{name}"] = sd[f"encoder.embed_rtg_{name}.weight"] @ Wr[:, c * H:(c + 1) * H].T

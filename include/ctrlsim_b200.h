@@ -186,6 +186,12 @@ int ctrlsim_attn_step(const float* KV, int32_t ld, int32_t k_off, int32_t v_off,
                       float* O, int32_t G, int32_t ti, int32_t own_row, void* stream);
 int ctrlsim_map_pool(const float* feats, const uint8_t* pt_valid, const uint8_t* poly_valid, const float* U,
                      float* pooled, int32_t n_poly, void* stream);
+/* the product's polyline front end, fused from the raw points (modules/map_encoder.py:34-45; csrc/map_encoder.cu): first
+ * layer of road_pts_encoder per point, scores against the folded seed-query matrix, masked softmax over the polyline's
+ * 100 points, attention-weighted sum of the HIDDEN vectors. map_pts [n_poly,100,3] (x, y, exists), poly_valid [n_poly]
+ * -> pooled [n_poly, 8, 256]; the remaining linear maps are folded into the next GEMM's weight (derived.pool_W2). */
+int ctrlsim_map_encode_pool(CtrlSim* h, const float* map_pts, const uint8_t* poly_valid, float* pooled, int32_t n_poly,
+                            void* stream);
 /* one categorical draw per row with the explicit sampler: x [rows, n] fp32 (already tilted / tempered) */
 int ctrlsim_sample_rows(const float* x, int32_t rows, int32_t n, int32_t ld, int32_t stride, uint64_t seed,
                         const uint32_t* counters /* [rows,4] */, int32_t* out_idx, void* stream);

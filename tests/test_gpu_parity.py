@@ -192,6 +192,48 @@ def test_map_pool_matches_torch(lib, dev):
     assert (pooled - ref).abs().max().item() < 2e-5
 
 
+def test_map_encode_pool_matches_the_unfused_chain(cfg, dev):
+    """The fused polyline front end (map_encoder.cu: point MLP layer 1 -> scores -> masked softmax -> pooled HIDDEN
+    vectors, W3 / value / output projections folded into derived.pool_W2) against the reference's chain in fp64:
+    road_pts_encoder (both layers) -> scores against the folded seed query -> softmax with key padding (all-masked
+    polylines un-mask point 0) -> weighted sum of the FEATURES -> value + output projection (modules/map_encoder.py:34-45)."""
+    from ctrlsim_b200.model import DeviceModel, derive_weights
+    from ctrlsim_b200.weights import make_weights
+    weights = make_weights(cfg, seed=6)
+    model = DeviceModel(cfg, weights, dev)
+    lib = model.lib
+    n_poly = 333
+    g = torch.Generator(device="cpu").manual_seed(9)
+    pts = torch.randn(n_poly, 100, 3, generator=g, dtype=torch.float64) * torch.tensor([40.0, 40.0, 0.0], dtype=torch.float64)
+    valid = torch.rand(n_poly, 100, generator=g) > 0.2
+    valid[5] = False                      # a padded polyline
+    valid[7] = False; valid[7, 0] = True  # a single point
+    pts[..., 2] = valid.double()
+    pts[~valid] = 0.0
+    poly_valid = valid.any(1)
+    d_pts = pts.float().to(dev).contiguous()
+    d_pv = poly_valid.to(torch.uint8).to(dev)
+    pooled = torch.full((n_poly, 8, 256), float("nan"), device=dev)
+    _chk(lib.ctrlsim_map_encode_pool(model.handle, d_pts.data_ptr(), d_pv.data_ptr(), pooled.data_ptr(), n_poly, _stream()), lib)
+    sd = {k: torch.from_numpy(np.asarray(v)).double() for k, v in weights.items()}
+    dv = {k: torch.from_numpy(v).double() for k, v in derive_weights(weights, cfg).items()}
+    me = "encoder.map_encoder.road_pts_encoder"
+    x = pts.float().double()
+    h = torch.relu(torch.nn.functional.layer_norm(x @ sd[f"{me}.mlp.0.weight"].T + sd[f"{me}.mlp.0.bias"], (256,),
+                                                  sd[f"{me}.mlp.1.weight"], sd[f"{me}.mlp.1.bias"], 1e-5))
+    feats = h @ sd[f"{me}.mlp.3.weight"].T + sd[f"{me}.mlp.3.bias"]
+    sc = feats @ dv["derived.pool_U"].T                                  # [n_poly, 100, 8]
+    mask = valid.clone()
+    mask[~poly_valid, 0] = True
+    prob = torch.softmax(sc.masked_fill(~mask[..., None], float("-inf")), dim=1)
+    pooled_feats = torch.einsum("nph,npd->nhd", prob, feats).reshape(n_poly, 8 * 256)
+    want = pooled_feats @ dv["derived.pool_W"].T + dv["derived.pool_b"]  # what the encoder adds norm1 to
+    got = pooled.double().cpu().reshape(n_poly, 8 * 256) @ dv["derived.pool_W2"].T + dv["derived.pool_b2"]
+    ok = poly_valid
+    assert torch.isfinite(pooled).all() and (pooled[~ok.to(dev)] == 0).all()
+    assert (got[ok] - want[ok]).abs().max().item() < 2e-5 * max(1.0, want[ok].abs().max().item())
+
+
 def test_sampler_bit_exact_vs_oracle(lib, dev):
     """Given identical fp32 inputs the device sampler returns exactly the oracle's index (integer CDF, explicit exp)."""
     from oracle import sampler

@@ -20,4 +20,7 @@ b = ev.build_batch(eval_threshold=64)
 ev.rollout(b, max_steps=steps)
 s = ev.summarize(b)
 torch.cuda.synchronize()
-print(f"sanitize target ok: {b.n_evaluated()} evaluated vehicles, {steps} steps, groups last step {pol.groups_last_step}")
+tr = b.trace()
+coll = int(((tr["tr_reward"][..., 6] > 0) & (tr["tr_exist"] > 0)).sum())
+print(f"sanitize target ok: {b.n_evaluated()} evaluated vehicles, {steps} steps, groups last step {pol.groups_last_step}, "
+      f"{coll} vehicle-steps in a vehicle-vehicle collision (Box2D contact response exercised), contact overflow {b.contact_overflow()}")

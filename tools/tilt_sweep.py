@@ -29,14 +29,21 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 cfg = default_config()
 model = DeviceModel(cfg, make_weights(cfg, seed=0), dev)
-scenes = [make_scene(i) for i in range(args.scenes)]  # every rank builds the list, build_batch keeps scene i on rank i % world
+# every rank generates only the scenes it owns (scene i -> rank i % world, the evaluator's own sharding rule; all 64
+# vehicles of every scene are evaluated, so no evaluated-set draw depends on the other ranks' scenes)
+mine = list(range(rank, args.scenes, world))
+scenes = [make_scene(i) for i in mine]
 points = [("none", (0.0, 0.0, 0.0))] + [(f"{n}={v:+g}", tuple(v if k == j else 0.0 for k in range(3)))
                                         for j, n in enumerate(("goal", "veh_veh", "veh_edge")) for v in args.values]
+batch = None
 for name, (tg, tv, te) in points:
     pol = B200Policy(cfg, "synthetic", model, tilt_dict={"tilt": True, "goal_tilt": tg, "veh_veh_tilt": tv, "veh_edge_tilt": te},
                      seed=0, chunk_groups=args.chunk)
-    ev = B200PolicyEvaluator(cfg, pol, scenes=scenes)
-    b = ev.build_batch(eval_threshold=64)
+    ev = B200PolicyEvaluator(cfg, pol, scenes=scenes, scene_ids=mine)
+    if batch is None:  # the scene batch is uploaded once; every sweep point resets its dynamic state (Policy.reset)
+        ev.rank, ev.world = 0, 1
+        batch = ev.build_batch(eval_threshold=64)
+    ev.rank, ev.world, ev.batch = rank, world, batch
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -44,12 +51,14 @@ for name, (tg, tv, te) in points:
     metrics, _ = ev.evaluate_policy()          # rollout + metrics kernel + the one all-reduce
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    n = torch.tensor([float(b.n_evaluated())], dtype=torch.float64, device=dev)
+    w = torch.tensor([wall], dtype=torch.float64, device=dev)
+    n = torch.tensor([float(batch.n_evaluated())], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(n)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({"point": name, "tilts": [tg, tv, te], "n_gpus": world, "scenes": args.scenes,
-                          "agent_steps_per_s": n.item() * cfg.nocturne.steps / wall, "wall_s": wall, "metrics": metrics}), flush=True)
-    del ev, b, pol
+                          "agent_steps_per_s": n.item() * cfg.nocturne.steps / w.item(), "wall_s": w.item(), "metrics": metrics}), flush=True)
+    del ev, pol
 if world > 1:
     dist.destroy_process_group()
