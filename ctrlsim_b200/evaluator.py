@@ -307,6 +307,64 @@ class B200PolicyEvaluator:
              "accel_jsd": _jsd(h[4][:accel_bins], h[5][:accel_bins]), "nearest_dist_jsd": _jsd(h[6], h[7])}
         return {k: float(v) for k, v in m.items()}
 
+    def scene_results(self, batch=None):
+        """The per-agent / per-sample lists the reference accumulates in update_running_statistics
+        (policy_evaluator.py:162-248) and saves per partition (``saved_scene_metrics``, :578-583), for THIS rank's scenes,
+        computed on the host from the device trace: goal_success, ade, fde (one entry per evaluated vehicle with at least
+        one existing future step), collision / off_road (one per scene), and the raw samples behind the four JSD metrics."""
+        b = batch or self.batch
+        tr = b.trace()
+        gt = b.t["gt"].cpu().numpy()
+        T1, hist, dt = self.steps + 1, self.history_steps, self.dt
+        out = {k: [] for k in ("goal_success", "ade", "fde", "accel_gt", "accel_sim", "ang_speed_gt", "ang_speed_sim",
+                               "lin_speed_gt", "lin_speed_sim", "nearest_dist_gt", "nearest_dist_sim", "collision", "off_road")}
+        for s in range(b.S):
+            colls, offs = [], []
+            for v in b.evaluated_ids[s]:
+                mask = tr["tr_exist"][s, v].astype(bool).copy()
+                mask[:hist] = False
+                if mask.sum() == 0:
+                    continue
+                rew = tr["tr_reward"][s, v].astype(np.float64)[mask]
+                out["goal_success"].append(float(np.any(rew[:, 0] == 1)))
+                colls.append(float(np.any(rew[:, 6] == 1)))
+                offs.append(float(np.any(rew[:, 7] == 1)))
+                pos, gpos = tr["tr_pos"][s, v].astype(np.float64), gt[s, v, :, :2]
+                out["ade"].append(float(np.linalg.norm(pos[mask] - gpos[mask], axis=1).mean()))
+                last = np.where(mask)[0][-1]
+                out["fde"].append(float(np.linalg.norm(pos[last] - gpos[last])))
+                out["lin_speed_sim"].append(np.linalg.norm(tr["tr_vel"][s, v].astype(np.float64)[mask], axis=1))
+                out["lin_speed_gt"].append(gt[s, v, :, 3][mask])
+                out["ang_speed_sim"].append(tr["tr_heading"][s, v].astype(np.float64)[mask] / dt)
+                out["ang_speed_gt"].append(gt[s, v, :, 2][mask] / dt)
+                gacc = np.zeros(T1)  # central difference of the logged speed, 0 at both ends (policy_evaluator.py:107-111)
+                gacc[1:self.steps - 1] = (gt[s, v, 2:self.steps, 3] - gt[s, v, 0:self.steps - 2, 3]) / (2 * dt)
+                am = np.ones(int(mask.sum()), bool)
+                am[0] = am[-1] = False
+                out["accel_gt"].append(gacc[mask][am])
+                out["accel_sim"].append(tr["tr_action"][s, v, :, 0][mask][am])
+                out["nearest_dist_sim"].append(tr["tr_nearest"][s, v, :, 0][mask])
+                out["nearest_dist_gt"].append(tr["tr_nearest"][s, v, :, 1][mask])
+            if colls:
+                out["collision"].append(float(np.mean(colls)))
+                out["off_road"].append(float(np.mean(offs)))
+        return out
+
+    def write_partition_metrics(self, path=None, batch=None):
+        """The per-partition JSON of the reference (policy_evaluator.py:578-593: ``<model dir>/scene_results/
+        partition_<k>.json`` with the lists of scene_results(); the reference writes it for its partitioned CTG++ runs,
+        ``eval=partitioned``) for this rank's scenes.  Returns the path."""
+        res = self.scene_results(batch)
+        ser = {k: [x.tolist() if isinstance(x, np.ndarray) else x for x in v] for k, v in res.items()}
+        if path is None:
+            part = self.cfg.eval.get("partition", self.rank) if hasattr(self.cfg.eval, "get") else self.rank
+            out_dir = os.path.join(os.path.dirname(str(self.policy.model_path)), "scene_results")
+            os.makedirs(out_dir, exist_ok=True)
+            path = os.path.join(out_dir, f"partition_{part}.json")
+        with open(path, "w") as f:
+            json.dump(ser, f)
+        return path
+
     def evaluate_policy(self):
         if self.batch is None:
             self.build_batch()

@@ -836,3 +836,45 @@ def test_reference_signature_adapter_matches_the_batched_path(cfg, dev):
         sim.step(0.1)
     assert np.abs(rec["pos"][:, :T] - g["pos"][:, :T]).max() == 0.0  # the caller's simulator saw the reference's controls
     assert np.allclose(np.array([vdd[v]["rtgs"] for v in range(n)]), g["rtgs"][:, :T], atol=1e-12)
+
+
+def test_evaluation_from_the_reference_file_layout(cfg, dev, tmp_path):
+    """N4 on the GPU: scenes written in the reference's on-disk formats (test_filenames.pkl, Nocturne scenario JSONs,
+    preprocess/test/*_physics.pkl; one scene without preprocessed data, which the reference skips without counting it)
+    and the weights as a Lightning checkpoint; ``B200PolicyEvaluator(cfg, policy)`` reads them like
+    ``PolicyEvaluator(cfg, policy)`` (policy_evaluator.py:33-41,436-464) and must give the metrics of the in-memory
+    evaluation of the same scenes, and the partition JSON of policy_evaluator.py:578-593."""
+    import json
+    from ctrlsim_b200.checkpoint import save_checkpoint
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.model import DeviceModel
+    from ctrlsim_b200.synth import make_scene, write_dataset
+    from ctrlsim_b200.weights import make_weights
+    scenes = [make_scene(60 + i, n_vehicles=5 + 2 * i, n_roads=1 + i % 2, n_chunks=3) for i in range(4)]
+    paths = write_dataset(str(tmp_path), scenes)
+    os.remove(os.path.join(paths["preprocess_dir"], "test", scenes[1]["name"] + "_physics.pkl"))
+    ckpt = str(tmp_path / "run" / "model.ckpt")
+    os.makedirs(os.path.dirname(ckpt))
+    weights = make_weights(cfg, seed=8, still_bias=6.0)
+    save_checkpoint(weights, ckpt, cfg)
+    c = cfg.copy()
+    c.eval = cfg.eval.copy()
+    c.dataset_root, c.nocturne_waymo_val_folder = paths["dataset_root"], paths["nocturne_waymo_val_folder"]
+    c.eval.num_files_to_evaluate, c.eval.multi_agent_eval_threshold = 3, 4
+    steps = 12
+    c.nocturne = cfg.nocturne.copy()
+    c.nocturne.steps = steps
+    pol = B200Policy(c, ckpt, DeviceModel.load_from_checkpoint(ckpt, c, dev), seed=2)
+    ev = B200PolicyEvaluator(c, pol)
+    m_files, lines = ev.evaluate_policy()
+    assert ev.scene_ids == [0, 2, 3] and len(lines) == 9      # scene 1 has no *_physics.pkl: skipped, not counted
+    kept = [scenes[0], scenes[2], scenes[3]]
+    pol2 = B200Policy(c, "synthetic", DeviceModel(c, weights, dev), seed=2)
+    ev2 = B200PolicyEvaluator(c, pol2, scenes=kept, scene_ids=[0, 2, 3])
+    m_mem, _ = ev2.evaluate_policy()
+    assert m_files == m_mem
+    path = ev.write_partition_metrics()
+    assert path == os.path.join(os.path.dirname(ckpt), "scene_results", "partition_0.json")
+    saved = json.load(open(path))
+    assert len(saved["collision"]) == 3 and len(saved["ade"]) == ev.batch.n_evaluated()
+    assert abs(float(np.mean(saved["ade"])) - m_files["ade"]) < 1e-9 and abs(float(np.mean(saved["goal_success"])) - m_files["goal"]) < 1e-12

@@ -993,3 +993,43 @@ def test_reference_signature_adapter_runs_inside_the_stock_policy_evaluator(tmp_
         for (kk, t, st, ap) in be.calls:
             if kk == k and t > 0:
                 assert np.array_equal(ap[:, 0], [d[v]["acceleration"][t - 1] for v in range(p["n"])])
+
+
+@pytest.mark.parametrize("name", ["plumbing", "sparse"])
+def test_partition_scene_results_match_the_metrics_port(tmp_path, cfg, name):
+    """N4: the per-partition ``scene_results`` JSON (policy_evaluator.py:578-593) - B200PolicyEvaluator.scene_results /
+    write_partition_metrics restate update_running_statistics (:162-248) on the host from the device trace.  Fed with a
+    reference fixture laid out as a trace, the lists equal the oracle's MetricsPort accumulators entry for entry."""
+    import json
+    import types
+    import torch
+    from ctrlsim_b200.evaluator import B200PolicyEvaluator
+    from oracle.policy_port import MetricsPort
+    g, spec, _ = load_golden(name)
+    n, ev_ids = g["pos"].shape[0], [int(v) for v in g["evaluated"]]
+    tr = {"tr_pos": g["pos"][None].astype(np.float32), "tr_vel": g["vel"][None].astype(np.float32),
+          "tr_heading": g["heading"][None].astype(np.float32), "tr_exist": g["existence"][None].astype(np.uint8),
+          "tr_action": np.stack([g["accel"], g["steer"]], -1)[None], "tr_reward": g["reward"][None].astype(np.float32),
+          "tr_nearest": np.stack([g["nearest_dist"], g["gt_nearest_dist"]], -1)[None]}
+    gt = np.concatenate([g["gt_pos"], g["gt_heading"][..., None], g["gt_speed"][..., None]], -1)[None]
+    batch = types.SimpleNamespace(S=1, evaluated_ids=[ev_ids], trace=lambda: tr, t={"gt": torch.from_numpy(gt)})
+    stub = types.SimpleNamespace(model=types.SimpleNamespace(device="cpu"), model_path=str(tmp_path / "model.ckpt"))
+    ev = B200PolicyEvaluator(cfg, stub, scenes=[])
+    res = ev.scene_results(batch)
+    mp_ = MetricsPort(cfg)
+    rec = {k: g[k] for k in ("existence", "reward", "pos", "gt_pos", "vel", "gt_speed", "heading", "gt_heading", "gt_accel", "accel",
+                             "gt_nearest_dist", "nearest_dist")}
+    mp_.add_scene(rec, ev_ids)
+    assert res["goal_success"] == mp_.goal and res["collision"] == [float(x) for x in mp_.coll] and res["off_road"] == [float(x) for x in mp_.off]
+    assert np.allclose(res["ade"], mp_.ade, rtol=0, atol=1e-6) and np.allclose(res["fde"], mp_.fde, rtol=0, atol=1e-6)  # fp32 trace positions
+    for a, b in (("lin_speed_sim", "lin_sim"), ("lin_speed_gt", "lin_gt"), ("ang_speed_sim", "ang_sim"), ("ang_speed_gt", "ang_gt"),
+                 ("accel_sim", "acc_sim"), ("accel_gt", "acc_gt"), ("nearest_dist_sim", "nd_sim"), ("nearest_dist_gt", "nd_gt")):
+        assert len(res[a]) == len(mp_.samples[b])
+        for x, y in zip(res[a], mp_.samples[b]):
+            assert x.shape == y.shape and np.allclose(x, y, rtol=0, atol=1e-5), (a, np.abs(x - y).max())
+    path = ev.write_partition_metrics(batch=batch)
+    assert path.endswith(os.path.join("scene_results", "partition_0.json"))
+    saved = json.load(open(path))
+    assert set(saved) == {"goal_success", "ade", "fde", "accel_gt", "accel_sim", "ang_speed_gt", "ang_speed_sim", "lin_speed_gt",
+                          "lin_speed_sim", "nearest_dist_gt", "nearest_dist_sim", "collision", "off_road"}  # the reference's keys
+    assert len(saved["lin_speed_sim"]) == len(res["ade"]) and saved["goal_success"] == res["goal_success"]
