@@ -23,7 +23,11 @@
 //               lazily updated INTEGER reference exponent (FlashAttention-4's conditional rescale): ref only moves when
 //               a score exceeds it by more than 2^16; moving it multiplies l, o and the part of P already written by an
 //               exact power of two.  P_hi overwrites S in place, P_lo has its own columns.  The tile's P V product is
-//               added to the register-resident running output with a rounded fp32 add.
+//               added to the register-resident running output with a rounded fp32 add - ONE TILE LATE: P V of tile j-1
+//               runs on the tensor pipe while tile j is swept and is collected right before p_ready(j) is signalled
+//               (scaled by the reference moves of that sweep), so a CTA's chain per tile is max(sweep, P V) instead of
+//               sweep + P V.  The single P_lo buffer is handed back early: P V issues its P_lo products first and
+//               commits them on plo_free.
 // TMEM (256 columns per CTA, two CTAs per SM): [0,64) S0 / P_hi, [64,128) S1 / P_hi, [128,192) P_lo, [192,224) O_a (main
 // products), [224,256) O_b (cross products).
 #include <cuda.h>
@@ -52,7 +56,7 @@ struct AtSmem {
   float q_lo[AT_QT * DH];
   AtKV kv[AT_STAGES];
   uint64_t q_full, q_lo_ready, k_full[AT_STAGES], k_ready[AT_STAGES], k_empty[AT_STAGES], v_ready[AT_STAGES],
-      v_empty[AT_STAGES], s_full[2], p_ready, o_full;
+      v_empty[AT_STAGES], s_full[2], p_ready, o_full, plo_free;
   uint32_t tmem_base;
   unsigned long long pad_mask[8];  // padded mode: bit c of word j = key 64 j + c is valid and inside Lk (Lk <= 512)
 };
@@ -215,7 +219,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       at_mbar_init(&sm.k_full[s], 1); at_mbar_init(&sm.k_ready[s], 2); at_mbar_init(&sm.k_empty[s], 1);
       at_mbar_init(&sm.v_ready[s], 2); at_mbar_init(&sm.v_empty[s], 1); at_mbar_init(&sm.s_full[s], 1);
     }
-    at_mbar_init(&sm.p_ready, 128); at_mbar_init(&sm.o_full, 1);
+    at_mbar_init(&sm.p_ready, 128); at_mbar_init(&sm.o_full, 1); at_mbar_init(&sm.plo_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (!CAUSAL) {  // key-padding bits: thread = key (Lk <= 512), one ballot per warp = one 32-bit half of a tile's mask
@@ -288,6 +292,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       AT_TRACE(0);
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      float fpend = 1.f;  // product of the reference moves of this sweep: the not yet collected O of tile j-1 needs it too
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32], rl[32];
@@ -308,6 +313,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const float dref = ref - nref;  // 0, a negative integer, or -inf (no reference before)
           const float f = dref == 0.f ? 1.f : (dref < -126.f ? 0.f : __int_as_float((127 + (int)dref) << 23));  // 2^dref, exact
           l *= f;
+          fpend *= f;
 #pragma unroll
           for (int i = 0; i < 4; ++i) s4[i] *= f;
 #pragma unroll
@@ -328,24 +334,36 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           rl[i] = __float_as_uint(p - __uint_as_float(hi));
         }
         at_st32(s_addr + 32 * c, r);
+        if (c == 0 && j > 0) {  // the single P_lo buffer is free once the P_lo products of tile j-1 (issued first) are done
+          at_wait(&sm.plo_free, (j - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
         at_st32(lane_addr + AT_PLO + 32 * c, rl);
       }
       l += (s4[0] + s4[1]) + (s4[2] + s4[3]);
       AT_TRACE(1);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      at_arrive(&sm.p_ready);
-      AT_TRACE(2);
-      at_wait(&sm.o_full, j & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      AT_TRACE(3);
-      {
+      if (j > 0) {  // collect P V of tile j-1 (it ran while this tile was swept); PV(j) may overwrite O only afterwards
+        at_wait(&sm.o_full, (j - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        AT_TRACE(3);
         uint32_t r[32], rb[32];
         at_ld32x2(lane_addr + AT_O, r, lane_addr + AT_O + DH, rb);
 #pragma unroll
-        for (int i = 0; i < DH; ++i) o[i] += __uint_as_float(r[i]) + __uint_as_float(rb[i]);
+        for (int i = 0; i < DH; ++i) o[i] = fmaf(__uint_as_float(r[i]) + __uint_as_float(rb[i]), fpend, o[i]);
+        AT_TRACE(4);
       }
-      AT_TRACE(4);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      at_arrive(&sm.p_ready);
+      AT_TRACE(2);
+    }
+    if (n_tiles > 0) {  // P V of the last tile
+      at_wait(&sm.o_full, (n_tiles - 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t r[32], rb[32];
+      at_ld32x2(lane_addr + AT_O, r, lane_addr + AT_O + DH, rb);
+#pragma unroll
+      for (int i = 0; i < DH; ++i) o[i] += __uint_as_float(r[i]) + __uint_as_float(rb[i]);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     if (row_ok) {
@@ -447,12 +465,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // V^T is K-major: 8 keys = 32 bytes inside a 128-byte atom row; key block cb (32 keys) = 8 KB [V_hi ; V_lo].
         // Per k-step two instructions: [O_a | O_b] += P_hi x [V_hi ; V_lo] (N = 64, P_hi read once) and O_b += P_lo x V_hi
         // (N = 32): O_a collects the 8 main products, O_b the 16 small cross products; they are added in registers.
+        // Order: the first N = 64 product zeroes both accumulators, then ALL P_lo products (committed on plo_free, so
+        // that the softmax warps can write the P_lo of tile j+1 while the remaining products still run), then the rest.
+        auto vt_off = [](int ks) { return (uint64_t)((ks >> 2) * ((2 * DH * 128) >> 4) + (ks & 3) * 2); };
+        at_mma_ts(tmem + AT_O, a_hi, dv + vt_off(0), id_pv2, 0u);
 #pragma unroll
-        for (int ks = 0; ks < AT_KT / 8; ++ks) {
-          const uint64_t ob = (uint64_t)((ks >> 2) * ((2 * DH * 128) >> 4) + (ks & 3) * 2);
-          at_mma_ts(tmem + AT_O, a_hi + 8 * ks, dv + ob, id_pv2, ks > 0 ? 1u : 0u);
-          at_mma_ts(tmem + AT_O + DH, a_lo + 8 * ks, dv + ob, id_pv, 1u);
-        }
+        for (int ks = 0; ks < AT_KT / 8; ++ks) at_mma_ts(tmem + AT_O + DH, a_lo + 8 * ks, dv + vt_off(ks), id_pv, 1u);
+        at_commit(&sm.plo_free);
+#pragma unroll
+        for (int ks = 1; ks < AT_KT / 8; ++ks) at_mma_ts(tmem + AT_O, a_hi + 8 * ks, dv + vt_off(ks), id_pv2, 1u);
         at_commit(&sm.v_empty[s]);
         at_commit(&sm.o_full);
       }

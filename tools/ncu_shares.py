@@ -17,6 +17,10 @@ def short(n):
 
 idx = [i for i, r in enumerate(rows) if short(r["Kernel Name"]).startswith("observe_kernel")]
 sel = rows[idx[-back]:idx[-back + 1]] if back > 1 else rows[idx[-1]:]
+# a simulator step ends with sim_step_kernel: drop what the bench launches after the last step (isolated micro-benchmarks)
+ends = [i for i, r in enumerate(sel) if short(r["Kernel Name"]).startswith("sim_step_kernel")]
+if ends:
+    sel = sel[:ends[-1] + 1]
 tot, cnt = collections.defaultdict(float), collections.Counter()
 for r in sel:
     v, u = float(r["Metric Value"]), r["Metric Unit"]

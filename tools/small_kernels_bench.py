@@ -40,3 +40,15 @@ out = torch.empty(n_poly, 8, 256, device=dev)
 ms = timeit(lambda: lib.ctrlsim_map_pool(feats.data_ptr(), pv.data_ptr(), ok.data_ptr(), U.data_ptr(), out.data_ptr(), n_poly, st))
 by = n_poly * (100 * 256 * 4 + 100 + 8 * 256 * 4)
 print(f"map_pool {n_poly} polylines: {ms*1e3:.1f} us, {by/ms/1e6:.0f} GB/s = {by/ms/1e6/peak:.3f} of measured HBM peak")
+# the product path's polyline encoder, fused from raw points (map_encoder.cu)
+from ctrlsim_b200.config import default_config
+from ctrlsim_b200.weights import make_weights
+from ctrlsim_b200.model import DeviceModel
+cfg = default_config(); model = DeviceModel(cfg, make_weights(cfg, seed=0), dev)
+pts = torch.randn(n_poly, 100, 3, device=dev)
+pts[..., 2] = (torch.rand(n_poly, 100, device=dev) > 0.1).float()
+pooled = torch.empty(n_poly, 8, 256, device=dev)
+ms = timeit(lambda: model.lib.ctrlsim_map_encode_pool(model.handle, pts.data_ptr(), ok.data_ptr(), pooled.data_ptr(), n_poly, st))
+by = n_poly * (100 * 3 * 4 + 1 + 8 * 256 * 4)
+fl = n_poly * 100 * (2 * 3 * 256 + 2 * 256 * 8 + 2 * 8 * 256)
+print(f"map_encode_pool {n_poly} polylines: {ms*1e3:.1f} us, {by/ms/1e6:.0f} GB/s algorithmic, {fl/ms/1e9:.1f} fp32 TFLOP/s")
