@@ -8,14 +8,15 @@ import numpy as np
 import torch
 
 from . import lib as _lib
-from .scenario import parse_scenario, road_arrays
+from .scenario import initial_rtgs, parse_scenario, road_arrays, road_edge_polylines
 
 # per-policy state: everything a Policy object owns in the reference (policies/policy.py:45-59: buffers, relevant agent
 # sets) plus the focal groups of the current step; a policy_view() gets its own copies, everything else is the shared world
 POLICY_FIELDS = ("evaluated", "eval_order", "hist_rtg", "relevant", "next_action", "tr_rtg_idx", "tr_act_idx", "n_groups",
-                 "group_off", "group_focal", "group_members", "group_served", "group_scene", "group_local")
+                 "group_off", "group_focal", "group_members", "group_served", "group_scene", "group_local", "rt_rtg")
 STATIC_FIELDS = {"scene_id", "n_veh", "veh_len", "veh_wid", "gt", "gt_valid", "goal", "goal_norm", "evaluated",
-                 "eval_order", "road_xy", "road_valid", "road_type", "n_poly", "segs", "n_seg"}
+                 "eval_order", "road_xy", "road_valid", "road_type", "n_poly", "segs", "n_seg",
+                 "edge_xy", "edge_off", "n_edge", "rtg_init"}
 
 _DT = {"int64": torch.int64, "int32": torch.int32, "int16": torch.int16, "int8": torch.int8, "uint8": torch.uint8,
        "float32": torch.float32, "float64": torch.float64}
@@ -44,6 +45,10 @@ class SceneBatch:
         if parsed is None:
             parsed = [parse_scenario(s["json"], steps, sc_cfg["moving_threshold"], sc_cfg["speed_threshold"]) for s in scenes]
         roads = [road_arrays(s["preproc"]) for s in scenes]
+        # real-time rewards: the road-edge polylines the signed distance is measured to, and the RTGs of
+        # the logged episode at t = 0 when the *_physics.pkl carries what they are derived from
+        # (a scene handed over pre-parsed, without its JSON, may carry them as 'edge_polylines'; else it has none)
+        edges = [road_edge_polylines(s["json"]) if "json" in s else list(s.get("edge_polylines", [])) for s in scenes]
         S = len(scenes)
         N = max(1, max((p["n"] for p in parsed), default=0))  # S == 0: a rank without scenes (more ranks than scenes)
         if N > MAX_VEH:
@@ -51,8 +56,11 @@ class SceneBatch:
         Pm = max(1, max((r[0].shape[0] for r in roads), default=0))
         E = max(1, max((p["segs"].shape[0] for p in parsed), default=0))
         T1 = steps + 1
-        dims = {"S": S, "N": N, "Pm": Pm, "E": E, "T": steps, "T1": T1, "A": cfg.dataset.waymo.max_num_agents}
-        self.S, self.N, self.Pm, self.E = S, N, Pm, E
+        Ep = max(1, max((sum(len(q) for q in e) for e in edges), default=0))
+        Pe = max(1, max((len(e) for e in edges), default=0))
+        dims = {"S": S, "N": N, "Pm": Pm, "E": E, "T": steps, "T1": T1, "A": cfg.dataset.waymo.max_num_agents,
+                "Ep": Ep, "Pe": Pe}
+        self.S, self.N, self.Pm, self.E, self.Ep, self.Pe = S, N, Pm, E, Ep, Pe
         host = {}
         for name, dt, shp in _lib.BATCH_FIELDS:
             shape = [eval(tok, {}, dims) for tok in shp.split(",")]
@@ -89,9 +97,20 @@ class SceneBatch:
             ns = p["segs"].shape[0]
             host["n_seg"][s] = ns
             host["segs"][s, :ns] = p["segs"]
+            host["n_edge"][s] = len(edges[s])
+            o = 0
+            for k, q in enumerate(edges[s]):
+                host["edge_off"][s, k] = o
+                host["edge_xy"][s, o:o + len(q)] = q
+                o += len(q)
+            host["edge_off"][s, len(edges[s]):] = o
+            pre = scenes[s]["preproc"]
+            if all(k in pre for k in ("ag_data", "ag_rewards", "veh_edge_dist_rewards", "veh_veh_dist_rewards")) \
+                    and len(pre["ag_data"]) == n:
+                host["rtg_init"][s, :n] = initial_rtgs(cfg, pre)
         self.t = {k: torch.from_numpy(v).to(self.device) for k, v in host.items()}
         self._init_dynamic = {k: host[k] for k in ("hist_rtg", "tr_rtg_idx", "tr_act_idx")}
-        self.struct = _lib.CtrlSimBatch(n_scenes=S, max_veh=N, max_poly=Pm, max_seg=E,
+        self.struct = _lib.CtrlSimBatch(n_scenes=S, max_veh=N, max_poly=Pm, max_seg=E, max_edge_pts=Ep, max_edge_poly=Pe,
                                         **{k: self.t[k].data_ptr() for k, _, _ in _lib.BATCH_FIELDS})
         self.n_total = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._owned = set(self.t)
@@ -103,7 +122,7 @@ class SceneBatch:
         with this batch and owns fresh per-policy state (POLICY_FIELDS) for its own set of controlled vehicles.
         ``gt``: optional replacement of the log-replay targets [S,N,T1,4] (a scripted trajectory for some vehicle)."""
         v = object.__new__(SceneBatch)
-        v.__dict__.update({k: getattr(self, k) for k in ("cfg", "device", "steps", "S", "N", "Pm", "E", "_gt_len")})
+        v.__dict__.update({k: getattr(self, k) for k in ("cfg", "device", "steps", "S", "N", "Pm", "E", "Ep", "Pe", "_gt_len")})
         v.t = dict(self.t)
         own = {}
         for k in POLICY_FIELDS:
@@ -132,6 +151,7 @@ class SceneBatch:
             assert v.t["gt"].shape == self.t["gt"].shape
             v._owned.add("gt")
         v.struct = _lib.CtrlSimBatch(n_scenes=self.S, max_veh=self.N, max_poly=self.Pm, max_seg=self.E,
+                                     max_edge_pts=self.Ep, max_edge_poly=self.Pe,
                                      **{k: v.t[k].data_ptr() for k, _, _ in _lib.BATCH_FIELDS})
         v.n_total = torch.zeros(1, dtype=torch.int32, device=self.device)
         return v
@@ -164,5 +184,5 @@ class SceneBatch:
     def trace(self) -> dict:
         """Device -> host copy of everything the reference keeps in vehicle_data_dict (for parity dumps)."""
         keys = ("tr_pos", "tr_vel", "tr_heading", "tr_exist", "tr_action", "tr_reward", "tr_nearest", "tr_rtg_idx",
-                "tr_act_idx", "n_veh")
+                "tr_act_idx", "n_veh", "tr_dense", "rt_rtg")
         return {k: self.t[k].cpu().numpy() for k in keys}

@@ -120,3 +120,16 @@ def default_config(wide: bool = False) -> AttrDict:
     cfg.nocturne["scenario"] = dict(nocturne["scenario"])
     cfg.nocturne["rew_cfg"] = AttrDict(nocturne["rew_cfg"])
     return cfg
+
+
+def dt_config(wide: bool = False) -> AttrDict:
+    """The decision-transformer baseline: cfgs/model/dt.yaml on top of cfgs/model/ctrl_sim.yaml
+    (continuous RTG inputs, (rtg, state, action) token order, no RTG head, no future-state head) and cfgs/policy/dt.yaml
+    (RTGs are not predicted but tracked in real time: they start at the maximum return and are decremented by the dense
+    reward of every step)."""
+    cfg = default_config(wide)
+    cfg.model.decision_transformer, cfg.model.predict_rtg, cfg.model.predict_future_states = True, False, False
+    cfg.eval.policy.update(run_name="dt", model="dt", use_rtg=True, predict_rtgs=False, discretize_rtgs=False,
+                           real_time_rewards=True, max_return=True)
+    return cfg
+

@@ -118,6 +118,11 @@ int ctrlsim_create(const CtrlSimConfig* c, CtrlSim** out) {
   h->mc.min_accel = c->min_accel; h->mc.max_accel = c->max_accel; h->mc.min_steer = c->min_steer; h->mc.max_steer = c->max_steer;
   h->mc.pos_tol = c->pos_tol; h->mc.heading_tol = c->heading_tol; h->mc.speed_tol = c->speed_tol;
   h->mc.goal_dist_scaling = c->goal_dist_scaling; h->mc.reward_scaling = c->reward_scaling;
+  h->mc.dt_model = c->decision_transformer ? 1 : 0;
+  for (int k = 0; k < 3; ++k) {
+    if (!(c->rtg_max[k] > c->rtg_min[k])) { delete h; return set_error(-2, "ctrlsim_create: rtg_min[%d] >= rtg_max[%d]", k, k); }
+    h->mc.rtg_min[k] = c->rtg_min[k]; h->mc.rtg_max[k] = c->rtg_max[k];
+  }
   { const char* e = getenv("CTRLSIM_CONTACTS"); h->mc.contacts = !(e && e[0] == '0'); }
   {  // process-wide (a __constant__ of the simulator kernels): sinf / cosf / tanf follow glibc's own algorithm
     // (glibc_trig.h) so that the simulator is bit-identical to the reference's through contacts; CTRLSIM_TRIG=fp64
@@ -207,10 +212,18 @@ int ctrlsim_finalize_weights(CtrlSim* h) {
   NEED("encoder.embed_timestep.weight", 90 * H, w.emb.ts);
   NEED("encoder.embed_agent_id.weight", A * H, w.emb.id);
   NEED("encoder.embed_action.weight", N_ACT * H, w.emb.act);
-  NEED("derived.rtg_tab_goal", N_RTG * H, w.emb.rtg_goal);
-  NEED("derived.rtg_tab_veh", N_RTG * H, w.emb.rtg_veh);
-  NEED("derived.rtg_tab_road", N_RTG * H, w.emb.rtg_road);
-  NEED("encoder.embed_rtg.bias", H, w.emb.rtg_bias);
+  w.dt = h->mc.dt_model != 0;
+  w.emb.dt = w.dt ? 1 : 0;
+  if (w.dt) {  // decision transformer: Linear(1, H) RTG embeddings folded through embed_rtg (ctrlsim_b200/model.py)
+    NEED("derived.rtg_lin", 3 * H, w.emb.rtg_lin);
+    NEED("derived.rtg_lin_bias", H, w.emb.rtg_bias);
+    w.emb.rtg_goal = w.emb.rtg_veh = w.emb.rtg_road = nullptr;
+  } else {
+    NEED("derived.rtg_tab_goal", N_RTG * H, w.emb.rtg_goal);
+    NEED("derived.rtg_tab_veh", N_RTG * H, w.emb.rtg_veh);
+    NEED("derived.rtg_tab_road", N_RTG * H, w.emb.rtg_road);
+    NEED("encoder.embed_rtg.bias", H, w.emb.rtg_bias);
+  }
   NEED("encoder.embed_ln.weight", H, w.emb.ln_w);
   NEED("encoder.embed_ln.bias", H, w.emb.ln_b);
   for (int l = 0; l < N_ENC; ++l) {
@@ -234,7 +247,8 @@ int ctrlsim_finalize_weights(CtrlSim* h) {
     if ((rc = need_ln(h, p + ".norm3", d.n3))) return rc;
   }
   if ((rc = need_mlp(h, "decoder.predict_action", H, N_ACT, w.head_action))) return rc;
-  if ((rc = need_mlp(h, "decoder.predict_rtg", H, N_RTG * 3, w.head_rtg))) return rc;
+  if (!w.dt) { if ((rc = need_mlp(h, "decoder.predict_rtg", H, N_RTG * 3, w.head_rtg))) return rc; }
+  else w.head_rtg = MlpW();
   // lo-part copies (x - trunc13(x)) of every registered tensor, in one allocation owned by the handle: the GEMM's TMA
   // fetches them as the W_lo operand of the 3xTF32 split. Call ctrlsim_finalize_weights again after changing weights.
   gemm_clear_weight_lo(h);
@@ -308,6 +322,11 @@ void ctrlsim_prefix_cache_stats(const CtrlSim* h, int64_t* incremental_chunks, i
 
 int ctrlsim_sim_reset(CtrlSim* h, CtrlSimBatch* b, void* stream) { return launch_sim_reset(*b, h->mc, S(stream)); }
 int ctrlsim_observe(CtrlSim* h, CtrlSimBatch* b, int32_t t, void* stream) { return launch_observe(*b, t, h->mc, S(stream)); }
+int ctrlsim_dense_reward(CtrlSim* h, CtrlSimBatch* b, const CtrlSimRewardParams* rp, int32_t t, void* stream) {
+  if (!h || !b || !rp) return set_error(-1, "ctrlsim_dense_reward: null argument");
+  if (rp->return_mode < 0 || rp->return_mode > 2) return set_error(-2, "ctrlsim_dense_reward: return_mode=%d", rp->return_mode);
+  return launch_dense_reward(*b, *rp, t, h->mc, S(stream));
+}
 int ctrlsim_plan_groups(CtrlSim* h, CtrlSimBatch* b, int32_t t, int32_t* n_groups_total, void* stream) {
   return launch_plan_groups(*b, t, h->mc, n_groups_total, S(stream));
 }
@@ -323,6 +342,9 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
                         void* workspace, int64_t workspace_bytes, int32_t chunk_groups, void* stream) {
   if (!h || !h->finalized) return set_error(-3, "ctrlsim_policy_step: weights not finalized");
   if (n_groups_total <= 0) return 0;
+  const int rtg_mode = p->rtg_mode;  // 0: RTGs predicted and sampled; 1: tracked in real time (b->rt_rtg)
+  if (rtg_mode != 0 && rtg_mode != 1) return set_error(-2, "ctrlsim_policy_step: rtg_mode=%d", rtg_mode);
+  if (h->w.dt && rtg_mode != 1) return set_error(-2, "ctrlsim_policy_step: the decision transformer has no RTG head; set rtg_mode = 1");
   NvtxRange nvtx_step("ctrlsim_policy_step");
   cudaStream_t st = S(stream);
   const int Sn = b->n_scenes;
@@ -414,7 +436,7 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
       NvtxRange r_tok("tokenize");
       if (pc && pc->incr) {
         // nothing upstream of the decoder is recomputed; tokenise the last two window steps only
-        if ((rc = launch_tokenize(*b, g0, ng, t, 2, ws.tk, h->mc, st, ws.map_sel, 0, t - 1))) return rc;
+        if ((rc = launch_tokenize(*b, g0, ng, t, 2, ws.tk, h->mc, st, ws.map_sel, 0, t - 1, rtg_mode))) return rc;
       } else if (use_mc) {
         int* slot_l = h->h_idx + 3 * (size_t)g0;  // [ng] slot | [ng] sel | [ng] dst, staged per chunk
         int* sel = slot_l + ng;
@@ -432,27 +454,30 @@ int ctrlsim_policy_step(CtrlSim* h, CtrlSimBatch* b, const CtrlSimPolicyParams* 
         if (ce == cudaSuccess && n_miss) ce = cudaMemcpyAsync(ws.map_dst, dst, sizeof(int) * n_miss, cudaMemcpyHostToDevice, st);
         if (ce != cudaSuccess) return set_error(-5, "policy_step: uploading map-cache lists: %s", cudaGetErrorString(ce));
         mp.n_map = n_miss; mp.slot = ws.map_slot; mp.dst = ws.map_dst; mp.cache_emb = h->mc_emb; mp.cache_valid = h->mc_valid;
-        if ((rc = launch_tokenize(*b, g0, ng, t, n_t, ws.tk, h->mc, st, ws.map_sel, n_miss))) return rc;
+        if ((rc = launch_tokenize(*b, g0, ng, t, n_t, ws.tk, h->mc, st, ws.map_sel, n_miss, 0, rtg_mode))) return rc;
       } else {
-        if ((rc = launch_tokenize(*b, g0, ng, t, n_t, ws.tk, h->mc, st))) return rc;
+        if ((rc = launch_tokenize(*b, g0, ng, t, n_t, ws.tk, h->mc, st, nullptr, 0, 0, rtg_mode))) return rc;
       }
       }
       {
         NvtxRange r("pass 1: encoders + decoder -> RTG logits");
         if ((rc = forward_pass1(h->w, ws, ng, n_t, h->n_sm, st, mp, pc))) return rc;
       }
-      {
+      if (rtg_mode == 0) {
         NvtxRange r("sample RTG");
         if ((rc = launch_resolve_rtg_range(*b, *p, t, s0, s1, g0, h->mc.steps, ws.rtg_logits, st))) return rc;
         if ((rc = launch_gather_rtg_steps(*b, g0, ng, t, h->mc.steps, ws.rtg_new, st))) return rc;
+      } else if (!h->w.dt) {  // tracked RTGs, CtRL-Sim network: the bins of the current step as the tokeniser made them
+        const bool incr = pc && pc->incr;
+        if ((rc = launch_gather_rtg_tokens(ng, incr ? 2 : n_t, incr ? 1 : n_t - 1, ws.tk, ws.rtg_new, st))) return rc;
       }
-      {
+      if (!h->w.dt) {  // the decision transformer's single pass already produced the action logits (state rows)
         NvtxRange r("pass 2: last-step rows -> action logits");
         if ((rc = forward_pass2(h->w, ws, ng, n_t, st, pc))) return rc;
       }
       NvtxRange r("sample actions");
       if ((rc = launch_sample_actions(*b, *p, g0, ng, t, ws.act_logits, h->mc, st))) return rc;
-    } else {
+    } else if (rtg_mode == 0) {
       int rc;  // scenes without any group still owe their vehicles the "(0,0,0) RTG appended" bookkeeping
       if ((rc = launch_resolve_rtg_range(*b, *p, t, s0, s1, g0, h->mc.steps, ws.rtg_logits, st))) return rc;
     }
@@ -493,11 +518,22 @@ int ctrlsim_attn_padded(const float* Q, int32_t ldq, const float* K, const float
 int ctrlsim_attn_causal(const float* QKV, float* O, int32_t G, int32_t n_t, void* stream) {
   return launch_attn_causal(QKV, O, G, n_t, S(stream));
 }
+int ctrlsim_attn_causal_order(const float* QKV, float* O, int32_t G, int32_t n_t, int32_t state_index, void* stream) {
+  if (state_index < 0 || state_index >= KT) return set_error(-2, "ctrlsim_attn_causal_order: state_index=%d", state_index);
+  return launch_attn_causal(QKV, O, G, n_t, S(stream), state_index);
+}
 int ctrlsim_attn_step(const float* KV, int32_t ld, int32_t k_off, int32_t v_off, int32_t group_rows, const float* qkv_rows,
                       float* O, int32_t G, int32_t ti, int32_t own_row, void* stream) {
   if (ti < 0 || ti >= T || (ti + 1) * TOK_T > group_rows) return set_error(-2, "ctrlsim_attn_step: need 0 <= ti < %d and (ti + 1) * %d <= group_rows", T, TOK_T);
   KvView v; v.base = KV; v.ld = ld; v.k_off = k_off; v.v_off = v_off; v.group_rows = group_rows;
-  return launch_attn_step(v, qkv_rows, O, G, ti, own_row != 0, S(stream));
+  return launch_attn_step(v, qkv_rows, O, G, ti, own_row != 0 ? 1 : 0, S(stream));
+}
+int ctrlsim_attn_step_order(const float* KV, int32_t ld, int32_t k_off, int32_t v_off, int32_t group_rows,
+                            const float* qkv_rows, float* O, int32_t G, int32_t ti, int32_t own_mode, int32_t state_index,
+                            void* stream) {
+  if (ti < 0 || ti >= T || (ti + 1) * TOK_T > group_rows) return set_error(-2, "ctrlsim_attn_step_order: need 0 <= ti < %d and (ti + 1) * %d <= group_rows", T, TOK_T);
+  KvView v; v.base = KV; v.ld = ld; v.k_off = k_off; v.v_off = v_off; v.group_rows = group_rows;
+  return launch_attn_step(v, qkv_rows, O, G, ti, own_mode, S(stream), state_index);
 }
 int ctrlsim_map_pool(const float* feats, const uint8_t* pt_valid, const uint8_t* poly_valid, const float* U,
                      float* pooled, int32_t n_poly, void* stream) {
@@ -521,6 +557,26 @@ int ctrlsim_sample_rows_nucleus(const float* x, int32_t rows, int32_t n, int32_t
   return launch_sample_rows(x, rows, n, ld, stride, seed, counters, out_idx, S(stream), true, top_p);
 }
 
+int ctrlsim_forward_tokens_dt(CtrlSim* h, int32_t G, int32_t n_t, int32_t ti, const float* agent_states,
+                              const float* agent_types, const float* goals, const int32_t* actions, const float* rtgs,
+                              const int32_t* timesteps, const float* road_points, const int32_t* road_types,
+                              float* action_logits, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!h || !h->finalized) return set_error(-3, "ctrlsim_forward_tokens_dt: weights not finalized");
+  if (!h->w.dt) return set_error(-2, "ctrlsim_forward_tokens_dt: the handle holds the CtRL-Sim network, not the decision transformer");
+  if (n_t < 1 || n_t > T || ti != n_t - 1) return set_error(-2, "forward_tokens_dt: need 1 <= n_t <= 32 and ti == n_t - 1");
+  cudaStream_t st = S(stream);
+  Workspace ws;
+  const size_t need_bytes = ws.carve(nullptr, 0, G);
+  if ((int64_t)need_bytes > workspace_bytes)
+    return set_error(-4, "forward_tokens_dt: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need_bytes);
+  ws.carve(workspace, need_bytes, G);
+  int rc;
+  if ((rc = launch_convert_tokens(G, n_t, agent_states, agent_types, goals, actions, rtgs, true, timesteps, road_points, road_types, ws.tk, st))) return rc;
+  if ((rc = forward_pass1(h->w, ws, G, n_t, h->n_sm, st))) return rc;
+  cudaMemcpyAsync(action_logits, ws.act_logits, sizeof(float) * (size_t)G * A * N_ACT, cudaMemcpyDeviceToDevice, st);
+  return 0;
+}
+
 int ctrlsim_forward_tokens(CtrlSim* h, int32_t G, int32_t n_t, int32_t ti, const float* agent_states,
                            const float* agent_types, const float* goals, const int32_t* actions, const int32_t* rtgs,
                            const int32_t* timesteps, const float* road_points, const int32_t* road_types,
@@ -535,7 +591,8 @@ int ctrlsim_forward_tokens(CtrlSim* h, int32_t G, int32_t n_t, int32_t ti, const
     return set_error(-4, "forward_tokens: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need_bytes);
   ws.carve(workspace, need_bytes, G);
   int rc;
-  if ((rc = launch_convert_tokens(G, n_t, agent_states, agent_types, goals, actions, rtgs, timesteps, road_points, road_types, ws.tk, st))) return rc;
+  if (h->w.dt) return set_error(-2, "ctrlsim_forward_tokens: the handle holds the decision transformer; use ctrlsim_forward_tokens_dt");
+  if ((rc = launch_convert_tokens(G, n_t, agent_states, agent_types, goals, actions, rtgs, false, timesteps, road_points, road_types, ws.tk, st))) return rc;
   if ((rc = forward_pass1(h->w, ws, G, n_t, h->n_sm, st))) return rc;
   cudaMemcpyAsync(rtg_logits, ws.rtg_logits, sizeof(float) * (size_t)G * A * N_RTG * 3, cudaMemcpyDeviceToDevice, st);
   cudaMemcpyAsync(ws.rtg_new, rtg_idx_pass2, sizeof(int) * (size_t)G * A * 3, cudaMemcpyDeviceToDevice, st);

@@ -149,21 +149,22 @@ int launch_attn_padded(const float* Q, int ldq, const float* Kp, const float* Vp
 
 // -------------------------------------------------------------------------------------------------------------
 // Rule M1: token index = (t*A + a)*3 + k. Query (tq, aq, kq) sees key (tk, ak, kk) iff
-//   tk < tq, or tk == tq and (kk == 0 or (ak == aq and kk <= kq)).
-__device__ __forceinline__ bool m1_allowed(int tq, int aq, int kq, int key) {
+//   tk < tq, or tk == tq and (kk == si or (ak == aq and kk <= kq)),  si = position of the state token (0; 1 for the
+//   decision transformer's (rtg, state, action) order).
+__device__ __forceinline__ bool m1_allowed(int tq, int aq, int kq, int key, int si) {
   const int tk = key / TOK_T;
   if (tk < tq) return true;
   if (tk > tq) return false;
   const int rem = key - tk * TOK_T;
   const int ak = rem / KT, kk = rem - ak * KT;
-  return kk == 0 || (ak == aq && kk <= kq);
+  return kk == si || (ak == aq && kk <= kq);
 }
 
 constexpr int CCH = 64;
 
 // QKV: [G * Lcur, 768] (q | k | v), Lcur = 72 * n_t rows per group. O: [G * Lcur, 256].
 __global__ void __launch_bounds__(128)
-attn_causal_kernel(const float* __restrict__ QKV, float* __restrict__ O, int Lcur) {
+attn_causal_kernel(const float* __restrict__ QKV, float* __restrict__ O, int Lcur, int si) {
   __shared__ __align__(16) KVTile<CCH> sm;
   const int g = blockIdx.z, h = blockIdx.y;
   const int r0 = blockIdx.x * 128;
@@ -197,7 +198,7 @@ attn_causal_kernel(const float* __restrict__ QKV, float* __restrict__ O, int Lcu
           for (int j = 0; j < 8; ++j) ok[j] = true;
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ok[j] = (b + j < lim) && m1_allowed(tq, aq, kq, k0 + b + j);
+          for (int j = 0; j < 8; ++j) ok[j] = (b + j < lim) && m1_allowed(tq, aq, kq, k0 + b + j, si);
         }
         online_block8(q, sm.k, sm.v, b, ok, m, l, acc);
       }
@@ -206,25 +207,27 @@ attn_causal_kernel(const float* __restrict__ QKV, float* __restrict__ O, int Lcu
   if (active) store_o(O + ((size_t)g * Lcur + row) * H + h * DH, acc, l);
 }
 
-int launch_attn_causal(const float* QKV, float* O, int G, int n_t, cudaStream_t st) {
+int launch_attn_causal(const float* QKV, float* O, int G, int n_t, cudaStream_t st, int si) {
   if (G <= 0 || n_t <= 0) return 0;
   if (attn_mode() == 2 && n_t * TOK_T >= 128 && (reinterpret_cast<uintptr_t>(QKV) & 15) == 0)
-    return launch_attn_tc(true, QKV, 3 * H, 3 * H, 0, QKV, 3 * H, 3 * H, H, 2 * H, nullptr, O, H, G, n_t * TOK_T, n_t * TOK_T, st);
-  if (use_mma_attn()) return launch_attn_causal_mma(QKV, O, G, n_t, st);
+    return launch_attn_tc(true, QKV, 3 * H, 3 * H, 0, QKV, 3 * H, 3 * H, H, 2 * H, nullptr, O, H, G, n_t * TOK_T, n_t * TOK_T, st,
+                          0, 0, si);
+  if (use_mma_attn()) return launch_attn_causal_mma(QKV, O, G, n_t, st, si);
   const int Lcur = n_t * TOK_T;
   dim3 grid((Lcur + 127) / 128, NH, G);
-  attn_causal_kernel<<<grid, 128, 0, st>>>(QKV, O, Lcur);
+  attn_causal_kernel<<<grid, 128, 0, st>>>(QKV, O, Lcur, si);
   CS_CHECK_LAUNCH("attn_causal");
   return 0;
 }
 
 // Incremental decode (prefix cache): the last n_q rows of every group attend to the group's first Lk cached keys.
-int launch_attn_causal_tail(const float* Q, int ldq, const KvView& kv, float* O, int G, int n_q, int Lk, cudaStream_t st) {
+int launch_attn_causal_tail(const float* Q, int ldq, const KvView& kv, float* O, int G, int n_q, int Lk, cudaStream_t st,
+                            int si) {
   if (G <= 0 || n_q <= 0) return 0;
   if (n_q < 128 || attn_mode() != 2 || ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(kv.base)) & 15))
     return set_error(-2, "attn_causal_tail: needs the tcgen05 kernel and at least 128 query rows (got %d)", n_q);
   return launch_attn_tc(true, Q, ldq, ldq, 0, kv.base, kv.ld, kv.ld, kv.k_off, kv.v_off, nullptr, O, H, G, n_q, Lk, st,
-                        Lk - n_q, kv.group_rows);
+                        Lk - n_q, kv.group_rows, si);
 }
 
 // attn_step (the A rows of the current window step against the first pass' K/V rows) lives in attention_step.cu

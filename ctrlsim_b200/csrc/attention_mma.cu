@@ -34,20 +34,20 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   hi = __float_as_uint(x) & 0xFFFFE000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
-__device__ __forceinline__ bool fa_m1_allowed(int tq, int aq, int kq, int key) {
+__device__ __forceinline__ bool fa_m1_allowed(int tq, int aq, int kq, int key, int si) {
   const int tk = key / TOK_T;
   if (tk < tq) return true;
   if (tk > tq) return false;
   const int rem = key - tk * TOK_T;
   const int ak = rem / KT, kk = rem - ak * KT;
-  return kk == 0 || (ak == aq && kk <= kq);
+  return kk == si || (ak == aq && kk <= kq);
 }
 
 // CAUSAL: Q/K/V are column blocks of QKV [G*L, 768]; PADDED: Q [G*Lq, ldq], K/V [G*Lk, ldkv] + key_pad [G*Lk].
 template <bool CAUSAL>
 __global__ void __launch_bounds__(128)
 attn_mma_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ Kp, const float* __restrict__ Vp, int ldkv,
-                const uint8_t* __restrict__ key_pad, float* __restrict__ O, int ldo, int Lq, int Lk) {
+                const uint8_t* __restrict__ key_pad, float* __restrict__ O, int ldo, int Lq, int Lk, int si) {
   __shared__ __align__(16) float sK[FA_KT][FA_LD];
   __shared__ __align__(16) float sV[FA_KT][FA_LD];
   __shared__ uint8_t sPad[FA_KT];
@@ -136,8 +136,8 @@ attn_mma_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
         const int key = k0 + kl;
         bool va, vb;
         if (CAUSAL) {
-          va = ok_a && kl < nk && (key < t_a * TOK_T || fa_m1_allowed(t_a, a_a, k_a, key));
-          vb = ok_b && kl < nk && (key < t_b * TOK_T || fa_m1_allowed(t_b, a_b, k_b, key));
+          va = ok_a && kl < nk && (key < t_a * TOK_T || fa_m1_allowed(t_a, a_a, k_a, key, si));
+          vb = ok_b && kl < nk && (key < t_b * TOK_T || fa_m1_allowed(t_b, a_b, k_b, key, si));
         } else {
           const bool kv = kl < nk && !sPad[kl];
           va = kv; vb = kv;
@@ -210,16 +210,16 @@ int launch_attn_padded_mma(const float* Q, int ldq, const float* Kp, const float
                            float* O, int ldo, int G, int Lq, int Lk, cudaStream_t st) {
   if (G <= 0 || Lq <= 0) return 0;
   dim3 grid((Lq + FA_ROWS - 1) / FA_ROWS, NH, G);
-  attn_mma_kernel<false><<<grid, 128, 0, st>>>(Q, ldq, Kp, Vp, ldkv, key_pad, O, ldo, Lq, Lk);
+  attn_mma_kernel<false><<<grid, 128, 0, st>>>(Q, ldq, Kp, Vp, ldkv, key_pad, O, ldo, Lq, Lk, 0);
   CS_CHECK_LAUNCH("attn_padded_mma");
   return 0;
 }
 
-int launch_attn_causal_mma(const float* QKV, float* O, int G, int n_t, cudaStream_t st) {
+int launch_attn_causal_mma(const float* QKV, float* O, int G, int n_t, cudaStream_t st, int si) {
   if (G <= 0 || n_t <= 0) return 0;
   const int Lcur = n_t * TOK_T;
   dim3 grid((Lcur + FA_ROWS - 1) / FA_ROWS, NH, G);
-  attn_mma_kernel<true><<<grid, 128, 0, st>>>(QKV, 3 * H, QKV + H, QKV + 2 * H, 3 * H, nullptr, O, H, Lcur, Lcur);
+  attn_mma_kernel<true><<<grid, 128, 0, st>>>(QKV, 3 * H, QKV + H, QKV + 2 * H, 3 * H, nullptr, O, H, Lcur, Lcur, si);
   CS_CHECK_LAUNCH("attn_causal_mma");
   return 0;
 }

@@ -2,7 +2,8 @@
 // step only - the state rows of the last first-pass layer (the rows the RTG head reads, modules/decoder.py:75) and the
 // rtg rows of the second pass (policies/autoregressive_policy.py:210) - against the keys / values the first pass left
 // in HBM.  Visible keys of row (ti, a, k): every token of window steps < ti, the A state tokens of step ti, and - second
-// pass - the row's own freshly computed rtg key.
+// pass - the row's own freshly computed rtg key.  Decision-transformer order (rtg, state, action): the state tokens sit at
+// position 1 of an agent's step and a state row also sees its own rtg token of step ti (own_mode 2, read from the K/V buffer).
 //
 // HBM-bound by construction: A query rows per (group, head) against up to 2304 K/V rows of 128 B each (4.7 MB per
 // group and layer), 2 x 32 flops per (query, key).  A CTA is one (group, head); warp w owns query rows 16 w .. 16 w + 15
@@ -46,7 +47,9 @@ __device__ __forceinline__ void st_wait() { asm volatile("cp.async.wait_group %0
 
 __global__ void __launch_bounds__(ST_WARPS * 32)
 attn_step_kernel(const float* __restrict__ KVbuf, int ld, int k_off, int v_off, int group_rows,
-                 const float* __restrict__ qkv_rows, float* __restrict__ O, int ti, int own_row) {
+                 const float* __restrict__ qkv_rows, float* __restrict__ O, int ti, int own_row, int si) {
+  // own_row: 0 none; 1 the row's own NEW key / value (qkv_rows); 2 the row's own first token of step ti (K/V buffer).
+  // si: position of the state token inside an agent's step (0, or 1 for the decision transformer)
   __shared__ __align__(16) StSmem sm;
   const int g = blockIdx.y, h = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -72,7 +75,8 @@ attn_step_kernel(const float* __restrict__ KVbuf, int ld, int k_off, int v_off, 
       if (in) {
         const int e = e0 + r;
         if (hist) { ks = base + (size_t)e * ld + k_off; vs = base + (size_t)e * ld + v_off; }
-        else if (e < A) { const size_t tok = (size_t)n_hist + (size_t)e * KT; ks = base + tok * ld + k_off; vs = base + tok * ld + v_off; }
+        else if (e < A) { const size_t tok = (size_t)n_hist + (size_t)e * KT + si; ks = base + tok * ld + k_off; vs = base + tok * ld + v_off; }
+        else if (own_row == 2) { const size_t tok = (size_t)n_hist + (size_t)(e - A) * KT; ks = base + tok * ld + k_off; vs = base + tok * ld + v_off; }
         else { ks = rows + (size_t)(e - A) * (3 * H) + H; vs = ks + H; }
       }
       st_cp16((uint32_t)__cvta_generic_to_shared(&sm.k[s][r][c * 4]), ks + c * 4, in ? 16 : 0);
@@ -213,11 +217,13 @@ attn_step_kernel(const float* __restrict__ KVbuf, int ld, int k_off, int v_off, 
   }
 }
 
-int launch_attn_step(const KvView& kv, const float* qkv_rows, float* O, int G, int ti, bool own_row, cudaStream_t st) {
+int launch_attn_step(const KvView& kv, const float* qkv_rows, float* O, int G, int ti, int own_mode, cudaStream_t st,
+                     int si) {
   if (G <= 0) return 0;
+  if (own_mode < 0 || own_mode > 2 || si < 0 || si >= KT) return set_error(-2, "attn_step: own_mode=%d state_index=%d", own_mode, si);
   dim3 grid(NH, G);
   attn_step_kernel<<<grid, ST_WARPS * 32, 0, st>>>(kv.base, kv.ld, kv.k_off, kv.v_off, kv.group_rows, qkv_rows, O, ti,
-                                                   own_row ? 1 : 0);
+                                                   own_mode, si);
   CS_CHECK_LAUNCH("attn_step");
   return 0;
 }

@@ -200,7 +200,8 @@ template <bool CAUSAL>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int q_col0, int k_col0,
                const float* __restrict__ Vbase, int ldkv, const uint8_t* __restrict__ key_pad, float* __restrict__ O,
-               int ldo, int Lq, int Lk, int q_pos0, int kv_group_rows) {
+               int ldo, int Lq, int Lk, int q_pos0, int kv_group_rows, int si) {
+  // si: position of the state token inside an agent's 3-token step (0 = CtRL-Sim order, 1 = decision transformer)
   // Lq query rows per group (tensor-map rows g * Lq + row); causal mode: row i sits at sequence position q_pos0 + i.
   // Lk keys are valid; the K / V rows of group g start at row g * kv_group_rows of their buffer.
   extern __shared__ unsigned char at_raw[];
@@ -247,8 +248,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int row = r0 + 32 * warp + lane;
     const bool row_ok = row < Lq;
     int tq = 0;
-    // rule M1 for the TOK_T keys of the row's own timestep: every state token (offsets 0, 3, 6, ...), plus the row's own
-    // rtg / action token if the row is at or past it (offsets 3 aq + 1 .. 3 aq + kq)
+    // rule M1 for the TOK_T keys of the row's own timestep: every state token (offsets si, si + 3, si + 6, ...), plus the
+    // row's own agent's tokens up to the row itself (offsets 3 aq .. 3 aq + kq)
     int aq = 0, kq = 0;
     if (CAUSAL) {
       tq = (q_pos0 + row) / TOK_T;
@@ -274,11 +275,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         else {
           const unsigned long long every3 = 0x9249249249249249ull;  // bits 0, 3, 6, ..., 63
           // keys of earlier timesteps (bits below base) are visible; state tokens of the own timestep sit at offsets
-          // = 0 (mod 3) from base
-          okm = base >= 0 ? (((1ull << base) - 1ull) | (every3 << base)) : (every3 >> ((-base) % 3));
+          // = si (mod 3) from base
+          const int p0 = base + si;                            // first state token of the own timestep, tile-relative
+          okm = (base > 0 ? ((1ull << base) - 1ull) : 0ull) |
+                (p0 >= AT_KT ? 0ull : (p0 >= 0 ? (every3 << p0) : (every3 >> ((-p0) % 3))));
           const int end = base + TOK_T;                        // first key of the next timestep (> 0 here)
           if (end < AT_KT) okm &= (1ull << end) - 1ull;
-          for (int kk = 1; kk <= kq; ++kk) {
+          for (int kk = 0; kk <= kq; ++kk) {
             const int c = base + 3 * aq + kk;
             if (c >= 0 && c < AT_KT) okm |= 1ull << c;
           }
@@ -522,7 +525,7 @@ static int at_make_map(AtEncodeFn enc, CUtensorMap* map, const float* base, long
 // Q rows: [G*Lq, q_cols] at Qbase (ldq), head h at columns q_col0 + 32h; K / V rows: [G*Lk, kv_cols] at KVbase (ldkv).
 int launch_attn_tc(bool causal, const float* Qbase, int ldq, int q_cols, int q_col0, const float* KVbase, int ldkv,
                    int kv_cols, int k_col0, int v_col0, const uint8_t* key_pad, float* O, int ldo, int G, int Lq, int Lk,
-                   cudaStream_t st, int q_pos0, int kv_group_rows) {
+                   cudaStream_t st, int q_pos0, int kv_group_rows, int si) {
   if (kv_group_rows <= 0) kv_group_rows = Lk;
   static AtEncodeFn enc = nullptr;
   const int smem = (int)sizeof(AtSmem) + 1024;
@@ -543,9 +546,9 @@ int launch_attn_tc(bool causal, const float* Qbase, int ldq, int q_cols, int q_c
   if ((rc = at_make_map(enc, &tmKV, KVbase, (long long)G * kv_group_rows, kv_cols, ldkv, AT_KT))) return rc;
   dim3 grid((Lq + AT_QT - 1) / AT_QT, NH, G);
   if (causal)
-    attn_tc_kernel<true><<<grid, AT_THREADS, smem, st>>>(tmQ, tmKV, q_col0, k_col0, KVbase + v_col0, ldkv, key_pad, O, ldo, Lq, Lk, q_pos0, kv_group_rows);
+    attn_tc_kernel<true><<<grid, AT_THREADS, smem, st>>>(tmQ, tmKV, q_col0, k_col0, KVbase + v_col0, ldkv, key_pad, O, ldo, Lq, Lk, q_pos0, kv_group_rows, si);
   else
-    attn_tc_kernel<false><<<grid, AT_THREADS, smem, st>>>(tmQ, tmKV, q_col0, k_col0, KVbase + v_col0, ldkv, key_pad, O, ldo, Lq, Lk, 0, kv_group_rows);
+    attn_tc_kernel<false><<<grid, AT_THREADS, smem, st>>>(tmQ, tmKV, q_col0, k_col0, KVbase + v_col0, ldkv, key_pad, O, ldo, Lq, Lk, 0, kv_group_rows, 0);
   CS_CHECK_LAUNCH("attn_tc");
   return 0;
 }

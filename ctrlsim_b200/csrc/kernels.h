@@ -32,19 +32,24 @@ int launch_layernorm(const float* X, const float* R, const float* gamma, const f
 // attention.cu
 int launch_attn_padded(const float* Q, int ldq, const float* Kp, const float* Vp, int ldkv, const uint8_t* key_pad,
                        float* O, int ldo, int G, int Lq, int Lk, cudaStream_t st);
-int launch_attn_causal(const float* QKV, float* O, int G, int n_t, cudaStream_t st);
+// si: position of the state token inside an agent's step (0 CtRL-Sim order, 1 decision-transformer order)
+int launch_attn_causal(const float* QKV, float* O, int G, int n_t, cudaStream_t st, int si = 0);
 int launch_attn_padded_mma(const float* Q, int ldq, const float* Kp, const float* Vp, int ldkv, const uint8_t* key_pad,
                            float* O, int ldo, int G, int Lq, int Lk, cudaStream_t st);  // attention_mma.cu
-int launch_attn_causal_mma(const float* QKV, float* O, int G, int n_t, cudaStream_t st);
+int launch_attn_causal_mma(const float* QKV, float* O, int G, int n_t, cudaStream_t st, int si = 0);
 int launch_attn_tc(bool causal, const float* Qbase, int ldq, int q_cols, int q_col0, const float* KVbase, int ldkv,
                    int kv_cols, int k_col0, int v_col0, const uint8_t* key_pad, float* O, int ldo, int G, int Lq, int Lk,
-                   cudaStream_t st, int q_pos0 = 0, int kv_group_rows = 0);  // attention_tc.cu
+                   cudaStream_t st, int q_pos0 = 0, int kv_group_rows = 0, int si = 0);  // attention_tc.cu
 // Where the decoder self-attention keys / values of a chunk live: the first-pass QKV buffer of the workspace
 // (ld 768, K at column 256, V at 512, Lcur rows per group) or the prefix cache (ld 512, K at 0, V at 256, 2304 rows).
 struct KvView { const float* base = nullptr; int ld = 0, k_off = 0, v_off = 0, group_rows = 0; };
 // causal attention of the LAST n_q rows of each group's Lk-row sequence (queries compact in Q: [G * n_q, ldq])
-int launch_attn_causal_tail(const float* Q, int ldq, const KvView& kv, float* O, int G, int n_q, int Lk, cudaStream_t st);
-int launch_attn_step(const KvView& kv, const float* qkv_rows, float* O, int G, int ti, bool own_row, cudaStream_t st);
+int launch_attn_causal_tail(const float* Q, int ldq, const KvView& kv, float* O, int G, int n_q, int Lk, cudaStream_t st,
+                            int si = 0);
+// own_mode 0: history + the step's state tokens; 1: + the row's own new key / value (columns [H, 3H) of qkv_rows);
+// 2: + the row's own first token of step ti from the K/V buffer (decision transformer: state rows see their rtg token)
+int launch_attn_step(const KvView& kv, const float* qkv_rows, float* O, int G, int ti, int own_mode, cudaStream_t st,
+                     int si = 0);
 int launch_map_pool(const float* feats, const uint8_t* pt_valid, const uint8_t* poly_valid, const float* U,
                     float* pooled, int n_poly, int n_sm, cudaStream_t st);
 

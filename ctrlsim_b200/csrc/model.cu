@@ -7,6 +7,9 @@
 //           memory tokens, and evaluates the RTG head on the 24 state rows of the current step only;
 //   pass 2  recomputes only the 24 rtg-token rows of the current step (the only rows whose inputs changed after the
 //           RTGs were sampled and that the action head reads), attending to the cached K/V.
+// Decision-transformer variant (ModelWeights::dt; cfgs/model/dt.yaml): tokens ordered (rtg, state, action) with continuous
+// RTG inputs, no RTG head; ONE pass - the action head reads the 24 state rows of the current step, which is exactly what
+// pass 1 computes for the last layer.
 #include <vector>
 
 #include "common.cuh"
@@ -81,6 +84,7 @@ size_t Workspace::carve(void* base, size_t bytes, int Gc) {
   tk.goal_feat = (float*)take(Ra * 5 * 4);
   tk.act_idx = (int*)take(Rta * 4);
   tk.rtg_idx = (int*)take(Rta * 3 * 4);
+  tk.rtg_val = (float*)take(Rta * 3 * 4);
   tk.ts = (int*)take(G * T * 4);
   tk.map_pts = (float*)take(Rpt * 3 * 4);
   tk.map_type = (int*)take(Rp * 4);
@@ -172,10 +176,13 @@ static int last_layer_state_rows(const ModelWeights& w, Workspace& ws, int G, in
                                  const KvView& kv, const float* kvc, const uint8_t* pad, cudaStream_t st) {
   const int Ra = G * A;
   const DecLayerW& d = w.dec[N_DEC - 1];
-  CS_TRY(launch_make_row_index(G, n_tok, ti_tok, 0, ws.row_idx, st));
+  // the state rows: position 0 of an agent's step, position 1 in the decision transformer's (rtg, state, action) order,
+  // where a state row additionally sees its own rtg token (rule M1: own tokens up to the row itself)
+  const int si = w.dt ? 1 : 0;
+  CS_TRY(launch_make_row_index(G, n_tok, ti_tok, si, ws.row_idx, st));
   CS_TRY(launch_gather_rows(Ra, ws.X, ws.row_idx, ws.xr, st));
   CS_TRY(gemm(ws.xr, d.sa.in_w, d.sa.in_b, ws.qkv_r, Ra, H, H, H, H, 3 * H, false, st));
-  CS_TRY(launch_attn_step(kv, ws.qkv_r, ws.att_r, G, ti_abs, false, st));
+  CS_TRY(launch_attn_step(kv, ws.qkv_r, ws.att_r, G, ti_abs, w.dt ? 2 : 0, st, si));
   CS_TRY(gemm(ws.att_r, d.sa.out_w, d.sa.out_b, ws.tmp_r, Ra, H, H, H, H, H, false, st));
   CS_TRY(ln(ws.xr, ws.tmp_r, d.n1, ws.xr, Ra, false, st));
   CS_TRY(gemm(ws.xr, d.ca.in_w, d.ca.in_b, ws.qc_r, Ra, H, H, H, H, H, false, st));
@@ -185,6 +192,12 @@ static int last_layer_state_rows(const ModelWeights& w, Workspace& ws, int G, in
   CS_TRY(gemm(ws.xr, d.l1w, d.l1b, ws.ff_r, Ra, FF, H, H, H, FF, true, st));
   CS_TRY(gemm(ws.ff_r, d.l2w, d.l2b, ws.tmp_r, Ra, H, FF, FF, FF, H, false, st));
   CS_TRY(ln(ws.xr, ws.tmp_r, d.n3, ws.xr, Ra, false, st));
+  if (w.dt) {  // decision transformer: the ACTION head reads the state rows (modules/decoder.py:55-57), no RTG head
+    CS_TRY(gemm(ws.xr, w.head_action.w0, w.head_action.b0, ws.hd1, Ra, H, H, H, H, H, false, st));
+    CS_TRY(launch_layernorm(ws.hd1, nullptr, w.head_action.lnw, w.head_action.lnb, ws.hd1, Ra, H, H, H, true, st));
+    CS_TRY(gemm(ws.hd1, w.head_action.w3, w.head_action.b3, ws.act_logits, Ra, N_ACT, H, H, H, N_ACT, false, st));
+    return 0;
+  }
   // ---- M8 RTG head ------------------------------------------------------------------------------------------------
   CS_TRY(gemm(ws.xr, w.head_rtg.w0, w.head_rtg.b0, ws.hd1, Ra, H, H, H, H, H, false, st));
   CS_TRY(launch_layernorm(ws.hd1, nullptr, w.head_rtg.lnw, w.head_rtg.lnb, ws.hd1, Ra, H, H, H, true, st));
@@ -216,7 +229,7 @@ static int forward_incr(const ModelWeights& w, Workspace& ws, int G, int t, cuda
       for (int tw = t - 1; tw <= t; ++tw) vis += (double)TOK_T * (TOK_T * tw + A) + 3.0 * A;
       g_prof.begin(PROF_ATTN_CAUSAL, (double)G * NH * vis * 4.0 * DH, st);
     }
-    CS_TRY(launch_attn_causal_tail(ws.QKV[l], 3 * H, cache_view(pc, l), ws.att, G, rows, Lk, st));
+    CS_TRY(launch_attn_causal_tail(ws.QKV[l], 3 * H, cache_view(pc, l), ws.att, G, rows, Lk, st, w.dt ? 1 : 0));
     g_prof.end(st);
     CS_TRY(decoder_layer_rest(d, ws, G, rows, pc.KVC[l], pc.PAD, st));
   }
@@ -291,7 +304,7 @@ int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm
       for (int tw = 0; tw < n_t; ++tw) vis += (double)TOK_T * (TOK_T * tw + A) + 3.0 * A;
       g_prof.begin(PROF_ATTN_CAUSAL, (double)G * NH * vis * 4.0 * DH, st);
     }
-    CS_TRY(launch_attn_causal(ws.QKV[l], ws.att, G, n_t, st));
+    CS_TRY(launch_attn_causal(ws.QKV[l], ws.att, G, n_t, st, w.dt ? 1 : 0));
     g_prof.end(st);
     CS_TRY(decoder_layer_rest(d, ws, G, Lcur, kvc, ws.pad, st));
   }
@@ -302,6 +315,7 @@ int forward_pass1(const ModelWeights& w, Workspace& ws, int G, int n_t, int n_sm
 // Second pass: the 24 rtg rows of the current step with the sampled RTGs, against the first pass' keys / values
 // (workspace or prefix-cache slot).
 int forward_pass2(const ModelWeights& w, Workspace& ws, int G, int n_t, cudaStream_t st, const PrefixSlot* pc) {
+  if (w.dt) return set_error(-2, "forward_pass2: the decision transformer has a single pass (its action head reads the state rows)");
   const bool incr = pc && pc->incr;
   const int Ra = G * A, ti = n_t - 1, n_tok = incr ? 2 : n_t, Lcur = n_t * TOK_T;
   CS_TRY(launch_assemble_rtg_rows(G, n_tok, n_tok - 1, ws.rtg_new, ws.tk, w.emb, ws.xr, st));
@@ -310,7 +324,7 @@ int forward_pass2(const ModelWeights& w, Workspace& ws, int G, int n_t, cudaStre
     const float* kvc = pc ? pc->KVC[l] : ws.kv_c[l];
     const uint8_t* pad = incr ? pc->PAD : ws.pad;
     CS_TRY(gemm(ws.xr, d.sa.in_w, d.sa.in_b, ws.qkv_r, Ra, 3 * H, H, H, H, 3 * H, false, st));
-    CS_TRY(launch_attn_step(incr ? cache_view(*pc, l) : ws_view(ws, l, Lcur), ws.qkv_r, ws.att_r, G, ti, true, st));
+    CS_TRY(launch_attn_step(incr ? cache_view(*pc, l) : ws_view(ws, l, Lcur), ws.qkv_r, ws.att_r, G, ti, 1, st));
     CS_TRY(gemm(ws.att_r, d.sa.out_w, d.sa.out_b, ws.tmp_r, Ra, H, H, H, H, H, false, st));
     CS_TRY(ln(ws.xr, ws.tmp_r, d.n1, ws.xr, Ra, false, st));
     CS_TRY(gemm(ws.xr, d.ca.in_w, d.ca.in_b, ws.qc_r, Ra, H, H, H, H, H, false, st));

@@ -15,6 +15,8 @@ struct ModelCfg {
   double min_accel = -10, max_accel = 10, min_steer = -0.7, max_steer = 0.7;
   double pos_tol = 1.0, heading_tol = 0.3, speed_tol = 1.0, goal_dist_scaling = 0.2, reward_scaling = 1.0;
   int contacts = 1;     // Box2D contact response between vehicles (sim_contacts.cuh); 0 = contact-free subset
+  int dt_model = 0;     // decision-transformer variant of the network (CtrlSimConfig.decision_transformer)
+  double rtg_min[3] = {0, -10, -10}, rtg_max[3] = {10, 90, 90};  // clip-normalisation of tracked RTGs (pos, veh, road)
 };
 
 struct MlpW {  // utils/layers.py MLPLayer: Linear - LayerNorm - ReLU - Linear
@@ -27,6 +29,11 @@ struct DecLayerW { MhaW sa, ca; const float *l1w, *l1b, *l2w, *l2b; LnW n1, n2, 
 
 struct EmbedW {  // what assemble_tokens needs
   const float *ts, *id, *act, *rtg_goal, *rtg_veh, *rtg_road, *rtg_bias, *ln_w, *ln_b;
+  // decision transformer (dt = 1): the three Linear(1, H) RTG embeddings folded through embed_rtg: rtg_lin [3, H] holds
+  // embed_rtg.weight[:, cH:(c+1)H] @ embed_rtg_c.weight[:, 0]; rtg_bias then also carries the folded Linear(1, H) biases;
+  // token order (rtg, state, action) instead of (state, rtg, action)
+  const float* rtg_lin = nullptr;
+  int dt = 0;
 };
 
 struct ModelWeights {
@@ -50,7 +57,8 @@ struct ModelWeights {
   EmbedW emb;
   EncLayerW enc[2];
   DecLayerW dec[4];
-  MlpW head_action, head_rtg;
+  MlpW head_action, head_rtg;  // head_rtg is absent (null) in the decision-transformer variant
+  bool dt = false;             // decision transformer: state token at position 1 of an agent's step, action head on state rows
 };
 
 struct TokenBufs {  // internal token representation of a chunk of groups (time-major)
@@ -59,6 +67,7 @@ struct TokenBufs {  // internal token representation of a chunk of groups (time-
   float* goal_feat;    // [G, A, 5]
   int* act_idx;        // [G, n_t, A]
   int* rtg_idx;        // [G, n_t, A, 3]
+  float* rtg_val;      // [G, n_t, A, 3] clip-normalised continuous RTGs (decision transformer)
   int* ts;             // [G, n_t]
   float* map_pts;      // [G, P, NP, 3]
   int* map_type;       // [G, P]
@@ -68,11 +77,15 @@ struct TokenBufs {  // internal token representation of a chunk of groups (time-
 // launchers (tokens.cu)
 // map_sel (optional, device): chunk-local groups whose polyline tokens are rebuilt (n_map of them, into map slots
 // 0..n_map-1); nullptr = every group.
+// rtg_mode 0: RTG tokens are the sampled bins of hist_rtg; 1: the tracked series rt_rtg, clip-normalised, then
+// discretised (CtRL-Sim network) or kept continuous (mc.dt_model)
 int launch_tokenize(const CtrlSimBatch& b, int g0, int ng, int t, int n_t, const TokenBufs& tk, const ModelCfg& mc,
-                    cudaStream_t st, const int* map_sel = nullptr, int n_map = 0, int tok_first = 0);
+                    cudaStream_t st, const int* map_sel = nullptr, int n_map = 0, int tok_first = 0, int rtg_mode = 0);
+// rtgs: int32 bins, or - rtgs_are_float - float32 continuous values (decision transformer)
 int launch_convert_tokens(int G, int n_t, const float* agent_states, const float* agent_types, const float* goals,
-                          const int* actions, const int* rtgs, const int* timesteps, const float* road_points,
-                          const int* road_types, const TokenBufs& tk, cudaStream_t st);
+                          const int* actions, const void* rtgs, bool rtgs_are_float, const int* timesteps,
+                          const float* road_points, const int* road_types, const TokenBufs& tk, cudaStream_t st);
+int launch_gather_rtg_tokens(int G, int n_t, int ti, const TokenBufs& tk, int* rtg_new, cudaStream_t st);
 int launch_small_mlp1(int din, const float* X, const MlpW& w, float* Y, size_t M, cudaStream_t st);
 int launch_map_encode_pool(const float* map_pts, const MlpW& pts_mlp, const float* U2, const uint8_t* poly_valid,
                            float* pooled, int n_poly, int n_sm, cudaStream_t st);  // map_encoder.cu
@@ -97,6 +110,7 @@ int launch_clamp_type_index(int n, const int* in, int* out, cudaStream_t st);
 int set_trig_mode(int glibc);  // sim.cu: 1 = sinf / cosf by glibc's algorithm (glibc_trig.h), 0 = fp64 and round once
 int launch_sim_reset(const CtrlSimBatch& b, const ModelCfg& mc, cudaStream_t st);
 int launch_observe(const CtrlSimBatch& b, int t, const ModelCfg& mc, cudaStream_t st);
+int launch_dense_reward(const CtrlSimBatch& b, const CtrlSimRewardParams& rp, int t, const ModelCfg& mc, cudaStream_t st);
 int launch_plan_groups(const CtrlSimBatch& b, int t, const ModelCfg& mc, int* n_total, cudaStream_t st);
 int launch_sim_step(const CtrlSimBatch& b, int t, const ModelCfg& mc, cudaStream_t st);
 int launch_metrics(const CtrlSimBatch& b, const ModelCfg& mc, double* out_scene, long long* out_hist, cudaStream_t st);

@@ -441,6 +441,132 @@ int launch_observe(const CtrlSimBatch& b, int t, const ModelCfg& mc, cudaStream_
   return 0;
 }
 
+// ---- S5': real-time dense reward + RTG bookkeeping (real_time_rewards policies) -------------------------------------
+// evaluators/evaluator.py:106-140 (compute_dense_reward), utils/data.py:152-290 (signed distance to the road-edge
+// polylines, a numpy port of the Waymo off-road metric), datasets/rl_waymo/dataset.py:239-275 (compute_rewards),
+// evaluators/policy_evaluator.py:123-149 (RTG series).  float64 in numpy's operation order (this file is built with
+// -fmad=false).  One block per scene, one thread per vehicle; every thread walks all road-edge points (a warp reads the
+// same point: broadcast loads).
+__device__ __forceinline__ double sgn_d(double x) { return (double)(x > 0.0) - (double)(x < 0.0); }
+
+// signed distance of (px, py) to one polyline of m + 1 points (utils/data.py:214-290)
+__device__ double signed_distance_polyline(double px, double py, const double* __restrict__ q, int m) {
+  const bool cyclic = ((q[0] - q[2 * m]) * (q[0] - q[2 * m]) + (q[1] - q[2 * m + 1]) * (q[1] - q[2 * m + 1])) < 1.0;
+  // pass 1: nearest segment (first minimum, like np.argmin)
+  int best = 0;
+  double best_d = 0.0;
+  for (int k = 0; k < m; ++k) {
+    const double sx = q[2 * k], sy = q[2 * k + 1];
+    const double ex = q[2 * k + 2] - sx, ey = q[2 * k + 3] - sy;      // start_to_end
+    const double ax = px - sx, ay = py - sy;                            // start_to_point
+    const double den = ex * ex + ey * ey;
+    double t = (ax * ex + ay * ey) / den;
+    if (t != t) t = 0.0;                                                // nan_to_num (0 / 0 of a degenerate segment)
+    else if (t > 1.7976931348623157e308) t = 1.7976931348623157e308;    // +-inf -> +-DBL_MAX
+    else if (t < -1.7976931348623157e308) t = -1.7976931348623157e308;
+    const double tc = fmin(fmax(t, 0.0), 1.0);
+    const double dx = ax - ex * tc, dy = ay - ey * tc;
+    const double d = sqrt(dx * dx + dy * dy);
+    if (k == 0 || d < best_d) { best_d = d; best = k; }
+  }
+  // pass 2: sign at the nearest segment from its own side value and, beyond its ends, the neighbour's and the convexity
+  auto seg = [&](int k, double& ex, double& ey) { ex = q[2 * k + 2] - q[2 * k]; ey = q[2 * k + 3] - q[2 * k + 1]; };
+  auto side = [&](int k) {
+    double ex, ey;
+    seg(k, ex, ey);
+    const double ax = px - q[2 * k], ay = py - q[2 * k + 1];
+    return sgn_d(ax * ey - ay * ex);
+  };
+  const int k = best;
+  double ex, ey;
+  seg(k, ex, ey);
+  const double ax = px - q[2 * k], ay = py - q[2 * k + 1];
+  double t = (ax * ex + ay * ey) / (ex * ex + ey * ey);
+  if (t != t) t = 0.0;
+  const double n = sgn_d(ax * ey - ay * ex);
+  double sign;
+  if (t < 0.0) {
+    // convexity at vertex k: cross(previous segment, this segment), the previous of the first one is the LAST segment
+    double pxe, pye;
+    seg(k == 0 ? m - 1 : k - 1, pxe, pye);
+    const bool convex = (pxe * ey - pye * ex) > 0.0;
+    const double n_prior = k == 0 ? (cyclic ? side(m - 1) : n) : side(k - 1);
+    sign = convex ? fmax(n, n_prior) : fmin(n, n_prior);
+  } else if (t < 1.0) {
+    sign = n;
+  } else {
+    double nxe, nye;
+    seg(k == m - 1 ? 0 : k + 1, nxe, nye);
+    const bool convex = (ex * nye - ey * nxe) > 0.0;
+    const double n_next = k == m - 1 ? (cyclic ? side(0) : n) : side(k + 1);
+    sign = convex ? fmax(n, n_next) : fmin(n, n_next);
+  }
+  return sign * best_d;
+}
+
+__global__ void __launch_bounds__(SIM_THREADS)
+dense_reward_kernel(CtrlSimBatch b, CtrlSimRewardParams rp, int t, ModelCfg mc) {
+  const int s = blockIdx.x, i = threadIdx.x, N = b.max_veh, T1 = mc.steps + 1;
+  if (i >= b.n_veh[s]) return;
+  const size_t vi = (size_t)s * N + i;
+  // RTG of step t: start value, or the previous one minus the dense reward of step t-1 (policy_evaluator.py:123-149)
+  if (t < mc.steps) {
+    double* rt = b.rt_rtg + (vi * mc.steps + t) * 3;
+    if (t == 0) {
+      if (rp.return_mode == 0) { rt[0] = b.rtg_init[vi * 3]; rt[1] = b.rtg_init[vi * 3 + 1]; rt[2] = b.rtg_init[vi * 3 + 2]; }
+      else if (rp.return_mode == 2 && b.evaluated[vi]) { rt[0] = 0.0; rt[1] = -10.0; rt[2] = -10.0; }
+      else { rt[0] = 10.0; rt[1] = 90.0; rt[2] = 90.0; }
+    } else {
+      const double* pr = b.rt_rtg + (vi * mc.steps + t - 1) * 3;
+      const double* pd = b.tr_dense + (vi * T1 + t - 1) * 3;
+      rt[0] = pr[0] - pd[0]; rt[1] = pr[1] - pd[1]; rt[2] = pr[2] - pd[2];
+    }
+  }
+  const double e = b.tr_exist[vi * T1 + t] ? 1.0 : 0.0;
+  const double px = b.tr_pos[(vi * T1 + t) * 2], py = b.tr_pos[(vi * T1 + t) * 2 + 1];
+  // nearest road-edge polyline by |signed distance| (utils/data.py:208-211; first minimum, degenerate polylines skipped)
+  const double* pts = b.edge_xy + (size_t)s * b.max_edge_pts * 2;
+  const int* off = b.edge_off + (size_t)s * (b.max_edge_poly + 1);
+  const int ne = b.n_edge[s];
+  double sd = 0.0;
+  bool have = false;
+  for (int p = 0; p < ne; ++p) {
+    const int m = off[p + 1] - off[p] - 1;
+    if (m < 1) continue;
+    const double d = signed_distance_polyline(px, py, pts + 2 * (size_t)off[p], m);
+    if (!have || fabs(d) < fabs(sd)) { sd = d; have = true; }
+  }
+  const double edge = (-sd / rp.dist_to_road_edge_scaling_factor) * e;
+  // nearest vehicle: tr_nearest[t] is the normalize=False distance x existence (observe_kernel)
+  double* nr = b.tr_nearest + (vi * T1 + t) * 2;
+  const double vv = fmin(fmax(nr[0], 0.0), rp.max_veh_veh_distance) / rp.max_veh_veh_distance;
+  nr[0] *= rp.max_veh_veh_distance;  // what this mode records as 'nearest_dist' / 'gt_nearest_dist' (evaluator.py:126-127)
+  nr[1] *= rp.max_veh_veh_distance;
+  // QUIRK: goal / collision terms of step 0 - compute_rewards gets the reward HISTORY and evaluator.py:138 reads index 0
+  const float* r0 = b.tr_reward + (vi * T1 + 0) * 8;
+  const double rg = (double)r0[0] * e, rs = (double)r0[3] * e, rv = (double)r0[6] * e, re = (double)r0[7] * e;
+  double goal = rg * rp.pos_target_achieved_rew_multiplier;
+  if (!rp.remove_shaped_goal)
+    goal = goal + (fmin(fmax(rs, rp.pos_goal_shaped_min), rp.pos_goal_shaped_max) - rp.pos_goal_shaped_max) * (1 / rp.pos_goal_shaped_max);
+  const double veh = rp.remove_shaped_veh_reward ? -1 * rv * rp.veh_veh_collision_rew_multiplier
+                                                 : vv - rv * rp.veh_veh_collision_rew_multiplier;
+  const double road = rp.remove_shaped_edge_reward
+                          ? -1 * re * rp.veh_edge_collision_rew_multiplier
+                          : fmin(fmax(fabs(edge) * rp.dist_to_road_edge_scaling_factor, 0.0), 5.0) / 5.0 - re * rp.veh_edge_collision_rew_multiplier;
+  double* d = b.tr_dense + (vi * T1 + t) * 3;
+  d[0] = goal * e; d[1] = veh * e; d[2] = road * e;
+}
+
+int launch_dense_reward(const CtrlSimBatch& b, const CtrlSimRewardParams& rp, int t, const ModelCfg& mc, cudaStream_t st) {
+  if (b.n_scenes <= 0) return 0;
+  if (!b.edge_xy || !b.edge_off || !b.n_edge || !b.rt_rtg || !b.tr_dense || (rp.return_mode == 0 && !b.rtg_init))
+    return set_error(-2, "dense_reward: the batch lacks the real-time-reward arrays (edge_xy / edge_off / n_edge / rt_rtg / tr_dense / rtg_init)");
+  if (t < 0 || t > mc.steps) return set_error(-2, "dense_reward: step %d outside 0..%d", t, mc.steps);
+  dense_reward_kernel<<<b.n_scenes, SIM_THREADS, 0, st>>>(b, rp, t, mc);
+  CS_CHECK_LAUNCH("dense_reward");
+  return 0;
+}
+
 // ---- T2: greedy focal grouping ------------------------------------------------------------------------------------
 // One warp per scene. Context sets are 64-bit masks over vehicle ids (lists in the reference are always ascending).
 __global__ void __launch_bounds__(32)

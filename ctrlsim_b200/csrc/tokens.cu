@@ -29,7 +29,8 @@ __device__ __forceinline__ double angle_sub_d(double cur, double tgt) {  // util
 // tokenize_agents: one block per compact group, one thread per (window step, slot).
 __global__ void __launch_bounds__(256)
 tokenize_agents_kernel(CtrlSimBatch b, int g0, int t, int n_t, int tok_first, int steps, TokenBufs tk, double min_accel,
-                       double max_accel, double min_steer, double max_steer, int n_steer) {
+                       double max_accel, double min_steer, double max_steer, int n_steer, int rtg_mode, int dt_model,
+                       double lo0, double lo1, double lo2, double hi0, double hi1, double hi2) {
   // n_t token steps starting at window index tok_first (0 = whole window; the incremental decode of the prefix cache
   // tokenises only the last two window steps); the normalisation frame is always the focal pose at window index 0.
   const int gl = blockIdx.x, g = g0 + gl;
@@ -58,6 +59,7 @@ tokenize_agents_kernel(CtrlSimBatch b, int g0, int t, int n_t, int tok_first, in
       tk.exist[row] = 0;
       tk.act_idx[row] = 0;
       tk.rtg_idx[row * 3 + 0] = tk.rtg_idx[row * 3 + 1] = tk.rtg_idx[row * 3 + 2] = 0;
+      if (dt_model) tk.rtg_val[row * 3 + 0] = tk.rtg_val[row * 3 + 1] = tk.rtg_val[row * 3 + 2] = 0.f;
     } else {
       const double* st = hs + ((size_t)v * steps + t0 + tok_first + tw) * 8;
       const double dx = st[0] - tx, dy = st[1] - ty;
@@ -74,8 +76,21 @@ tokenize_agents_kernel(CtrlSimBatch b, int g0, int t, int n_t, int tok_first, in
       const double a0 = (fmin(fmax(ac[0], min_accel), max_accel) - min_accel) / (max_accel - min_accel);
       const double a1 = (fmin(fmax(ac[1], min_steer), max_steer) - min_steer) / (max_steer - min_steer);
       tk.act_idx[row] = (int)(rint(a0 * (N_ACT / n_steer - 1)) * n_steer + rint(a1 * (n_steer - 1)));
-      const int16_t* rt = b.hist_rtg + ((size_t)s * N * steps + (size_t)v * steps + t0 + tok_first + tw) * 3;
-      tk.rtg_idx[row * 3 + 0] = rt[0]; tk.rtg_idx[row * 3 + 1] = rt[1]; tk.rtg_idx[row * 3 + 2] = rt[2];
+      if (rtg_mode == 0) {
+        const int16_t* rt = b.hist_rtg + ((size_t)s * N * steps + (size_t)v * steps + t0 + tok_first + tw) * 3;
+        tk.rtg_idx[row * 3 + 0] = rt[0]; tk.rtg_idx[row * 3 + 1] = rt[1]; tk.rtg_idx[row * 3 + 2] = rt[2];
+      } else {
+        // tracked (real-time) RTGs: clip-normalise in float64 (autoregressive_policy.py:73-78), then either discretise
+        // with np.round (dataset.py:382-387) or hand the value to the decision transformer as float32 (encoder.py:95)
+        const double* rr = b.rt_rtg + ((size_t)s * N * steps + (size_t)v * steps + t0 + tok_first + tw) * 3;
+        const double lo[3] = {lo0, lo1, lo2}, hi[3] = {hi0, hi1, hi2};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double x = (fmin(fmax(rr[c], lo[c]), hi[c]) - lo[c]) / (hi[c] - lo[c]);
+          if (dt_model) { tk.rtg_val[row * 3 + c] = (float)x; tk.rtg_idx[row * 3 + c] = 0; }
+          else tk.rtg_idx[row * 3 + c] = (int)rint(x * (N_RTG - 1));
+        }
+      }
     }
   }
   for (int tw = threadIdx.x; tw < n_t; tw += blockDim.x)
@@ -171,11 +186,15 @@ tokenize_map_kernel(CtrlSimBatch b, int g0, TokenBufs tk, const int* __restrict_
 }
 
 int launch_tokenize(const CtrlSimBatch& b, int g0, int ng, int t, int n_t, const TokenBufs& tk, const ModelCfg& mc,
-                    cudaStream_t st, const int* map_sel, int n_map, int tok_first) {
+                    cudaStream_t st, const int* map_sel, int n_map, int tok_first, int rtg_mode) {
   if (ng <= 0) return 0;
   if (b.max_poly > 1024) return set_error(-2, "tokenize: at most 1024 polylines per scene (got %d)", b.max_poly);
+  if (rtg_mode != 0 && !b.rt_rtg) return set_error(-2, "tokenize: tracked RTGs requested but the batch has no rt_rtg array");
+  if (mc.dt_model && rtg_mode == 0) return set_error(-2, "tokenize: the decision transformer needs tracked RTGs (rtg_mode 1)");
   tokenize_agents_kernel<<<ng, 256, 0, st>>>(b, g0, t, n_t, tok_first, mc.steps, tk, mc.min_accel, mc.max_accel,
-                                             mc.min_steer, mc.max_steer, mc.n_steer);
+                                             mc.min_steer, mc.max_steer, mc.n_steer, rtg_mode, mc.dt_model,
+                                             mc.rtg_min[0], mc.rtg_min[1], mc.rtg_min[2], mc.rtg_max[0], mc.rtg_max[1],
+                                             mc.rtg_max[2]);
   CS_CHECK_LAUNCH("tokenize_agents");
   const int nm = map_sel ? n_map : ng;
   if (nm > 0) {
@@ -188,9 +207,12 @@ int launch_tokenize(const CtrlSimBatch& b, int g0, int ng, int t, int n_t, const
 // Reference MotionData layout -> internal token buffers (parity-test entry ctrlsim_forward_tokens).
 __global__ void convert_tokens_kernel(int G, int n_t, const float* __restrict__ agent_states,
                                       const float* __restrict__ agent_types, const float* __restrict__ goals,
-                                      const int* __restrict__ actions, const int* __restrict__ rtgs,
-                                      const int* __restrict__ timesteps, const float* __restrict__ road_points,
-                                      const int* __restrict__ road_types, TokenBufs tk) {
+                                      const int* __restrict__ actions, const void* __restrict__ rtgs_any,
+                                      int rtgs_are_float, const int* __restrict__ timesteps,
+                                      const float* __restrict__ road_points, const int* __restrict__ road_types,
+                                      TokenBufs tk) {
+  const int* rtgs = reinterpret_cast<const int*>(rtgs_any);
+  const float* rtgs_f = reinterpret_cast<const float*>(rtgs_any);
   const int gl = blockIdx.x;
   for (int i = threadIdx.x; i < n_t * A; i += blockDim.x) {
     const int tw = i / A, a = i - tw * A;
@@ -201,7 +223,11 @@ __global__ void convert_tokens_kernel(int G, int n_t, const float* __restrict__ 
     for (int k = 0; k < 5; ++k) f[7 + k] = agent_types[((size_t)gl * A + a) * 5 + k];
     tk.exist[row] = st[7] != 0.f;
     tk.act_idx[row] = actions[((size_t)gl * A + a) * T + tw];
-    for (int c = 0; c < 3; ++c) tk.rtg_idx[row * 3 + c] = rtgs[(((size_t)gl * A + a) * T + tw) * 3 + c];
+    for (int c = 0; c < 3; ++c) {
+      const size_t src = (((size_t)gl * A + a) * T + tw) * 3 + c;
+      if (rtgs_are_float) { tk.rtg_val[row * 3 + c] = rtgs_f[src]; tk.rtg_idx[row * 3 + c] = 0; }
+      else tk.rtg_idx[row * 3 + c] = rtgs[src];
+    }
   }
   for (int tw = threadIdx.x; tw < n_t; tw += blockDim.x) tk.ts[gl * n_t + tw] = timesteps[gl * T + tw];
   for (int i = threadIdx.x; i < A * 5; i += blockDim.x) tk.goal_feat[(size_t)gl * A * 5 + i] = goals[(size_t)gl * A * 5 + i];
@@ -211,10 +237,10 @@ __global__ void convert_tokens_kernel(int G, int n_t, const float* __restrict__ 
 }
 
 int launch_convert_tokens(int G, int n_t, const float* agent_states, const float* agent_types, const float* goals,
-                          const int* actions, const int* rtgs, const int* timesteps, const float* road_points,
-                          const int* road_types, const TokenBufs& tk, cudaStream_t st) {
-  convert_tokens_kernel<<<G, 256, 0, st>>>(G, n_t, agent_states, agent_types, goals, actions, rtgs, timesteps,
-                                           road_points, road_types, tk);
+                          const int* actions, const void* rtgs, bool rtgs_are_float, const int* timesteps,
+                          const float* road_points, const int* road_types, const TokenBufs& tk, cudaStream_t st) {
+  convert_tokens_kernel<<<G, 256, 0, st>>>(G, n_t, agent_states, agent_types, goals, actions, rtgs, rtgs_are_float ? 1 : 0,
+                                           timesteps, road_points, road_types, tk);
   CS_CHECK_LAUNCH("convert_tokens");
   return 0;
 }
@@ -309,13 +335,16 @@ int launch_map_flags(const float* map_pts, uint8_t* pt_valid, uint8_t* poly_vali
 //   state:  sg[row] (= W_sg[:, :H] s_emb + W_sg[:, H:] g_emb + b_sg) + E_ts[ts] + E_id[a]
 //   rtg:    Rg[i0] + Rv[i1] + Rr[i2] + b_rtg + E_ts + E_id   (R* = embedding tables folded through embed_rtg)
 //   action: E_act[idx] + E_ts + E_id
+// Decision transformer (ew.dt): rows are ordered (rtg, state, action) (encoder.py:139-142) and the rtg embedding is
+//   r0 L[0] + r1 L[1] + r2 L[2] + b  with L = the three Linear(1, H) maps folded through embed_rtg (model.py).
 __global__ void __launch_bounds__(256)
 assemble_tokens_kernel(int n_rows, int n_t, const float* __restrict__ sg, TokenBufs tk, EmbedW ew,
                        float* __restrict__ X, float* __restrict__ mem /* [G, MEM, H] */) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= n_rows) return;
-  const int k = r % KT;
+  const int kpos = r % KT;
+  const int k = ew.dt ? (kpos == 0 ? 1 : (kpos == 1 ? 0 : 2)) : kpos;  // token kind: 0 state, 1 rtg, 2 action
   const int sa = r / KT;                 // (g, tw, a) flat
   const int a = sa % A;
   const int gtw = sa / A;
@@ -330,6 +359,12 @@ assemble_tokens_kernel(int n_rows, int n_t, const float* __restrict__ sg, TokenB
   if (k == 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = sg[(size_t)sa * H + CH(i)] + v[i];
+  } else if (k == 1 && ew.dt) {
+    const float r0 = tk.rtg_val[sa * 3], r1 = tk.rtg_val[sa * 3 + 1], r2 = tk.rtg_val[sa * 3 + 2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      v[i] = (((r0 * __ldg(ew.rtg_lin + CH(i)) + r1 * __ldg(ew.rtg_lin + H + CH(i))) +
+               r2 * __ldg(ew.rtg_lin + 2 * H + CH(i))) + __ldg(ew.rtg_bias + CH(i))) + v[i];
   } else if (k == 1) {
     const int i0 = tk.rtg_idx[sa * 3], i1 = tk.rtg_idx[sa * 3 + 1], i2 = tk.rtg_idx[sa * 3 + 2];
 #pragma unroll
@@ -415,6 +450,21 @@ int launch_assemble_rtg_rows(int G, int n_t, int ti, const int* rtg_new, const T
   if (n_rows <= 0) return 0;
   assemble_rtg_rows_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(n_rows, n_t, ti, rtg_new, tk, ew, Xr);
   CS_CHECK_LAUNCH("assemble_rtg_rows");
+  return 0;
+}
+
+// RTG bins of window step ti as the tokeniser produced them (tracked RTGs, CtRL-Sim network) -> rtg_new [G, A, 3]
+__global__ void gather_rtg_tokens_kernel(int n, int n_t, int ti, const int* __restrict__ rtg_idx, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = i % 3, ga = i / 3, a = ga % A, gl = ga / A;
+  out[i] = rtg_idx[(((size_t)gl * n_t + ti) * A + a) * 3 + c];
+}
+int launch_gather_rtg_tokens(int G, int n_t, int ti, const TokenBufs& tk, int* rtg_new, cudaStream_t st) {
+  const int n = G * A * 3;
+  if (n <= 0) return 0;
+  gather_rtg_tokens_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, n_t, ti, tk.rtg_idx, rtg_new);
+  CS_CHECK_LAUNCH("gather_rtg_tokens");
   return 0;
 }
 

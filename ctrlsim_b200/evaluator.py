@@ -36,9 +36,23 @@ class B200Policy:
                  nucleus_threshold=0.8, seed=0, chunk_groups=128):
         if not isinstance(model, DeviceModel):
             raise TypeError("B200Policy needs a ctrlsim_b200.model.DeviceModel (weights resident on the GPU)")
-        if not (use_rtg and predict_rtgs and discretize_rtgs) or real_time_rewards or max_return or min_return:
-            raise NotImplementedError("only the ctrl_sim policy mode (cfgs/policy/ctrl_sim.yaml) is implemented; "
-                                      "real_time_rewards / dt modes are SURVEY 8(f) N1")
+        # Supported switch combinations (cfgs/policy/*.yaml, policies/policy.py:9-39):
+        #   ctrl_sim  use_rtg, predict_rtgs, discretize_rtgs                      RTG head + sampling, two passes
+        #   dt        use_rtg, real_time_rewards, not predict_rtgs, not discretize_rtgs (+ max_return / min_return) with
+        #             the decision-transformer network (cfgs/model/dt.yaml): RTGs tracked from the dense reward
+        #   the same tracked RTGs, discretised, with the CtRL-Sim network (predict_rtgs=False, discretize_rtgs=True)
+        dt_model = bool(cfg.model.get("decision_transformer", False))
+        if not use_rtg:
+            raise NotImplementedError("use_rtg=False (the il / trajeglish baselines) is not implemented")
+        if predict_rtgs and (real_time_rewards or max_return or min_return or not discretize_rtgs or dt_model):
+            raise ValueError("predict_rtgs=True needs the CtRL-Sim network with discretize_rtgs=True and no real_time_rewards "
+                             "/ max_return / min_return (cfgs/policy/ctrl_sim.yaml)")
+        if not predict_rtgs and not real_time_rewards:
+            raise NotImplementedError("RTGs that are neither predicted nor tracked in real time: the reference then feeds "
+                                      "zeros (policies/policy.py:89-95); not implemented")
+        if real_time_rewards and discretize_rtgs == dt_model:
+            raise ValueError("discretize_rtgs must be False for the decision-transformer network (continuous RTG inputs, "
+                             "cfgs/policy/dt.yaml) and True for the CtRL-Sim network (RTG embedding tables)")
         self.cfg = cfg.copy()
         self.model_path, self.model, self.name = model_path, model, name
         self.model.eval()
@@ -73,7 +87,13 @@ class B200Policy:
         return _lib.CtrlSimPolicyParams(seed=self.seed, tilt=tilt, temperature=float(self.action_temperature),
                                         tilt_enabled=1 if td["tilt"] else 0,
                                         nucleus_sampling=1 if self.nucleus_sampling else 0,
-                                        nucleus_threshold=self.nucleus_threshold)
+                                        nucleus_threshold=self.nucleus_threshold,
+                                        rtg_mode=1 if self.real_time_rewards else 0)
+
+    def _reward_params(self):
+        # policy_evaluator.py:127-143: max_return wins over min_return
+        mode = "max_return" if self.max_return else ("min_return" if self.min_return else "data")
+        return _lib.make_reward_params(self.cfg, mode)
 
     def _stream(self):
         return torch.cuda.current_stream(self.model.device).cuda_stream
@@ -102,6 +122,10 @@ class B200Policy:
         if batch.S == 0:
             return
         _lib.check(self.lib.ctrlsim_observe(self.model.handle, batch.ptr, t, self._stream()), "ctrlsim_observe")
+        if self.real_time_rewards:  # compute_dense_reward + RTG bookkeeping (policy_evaluator.py:123-156)
+            rp = self._reward_params()
+            _lib.check(self.lib.ctrlsim_dense_reward(self.model.handle, batch.ptr, C.byref(rp), t, self._stream()),
+                       "ctrlsim_dense_reward")
 
     def predict(self, batch: SceneBatch, t: int):
         """Focal grouping, tokenisation, two-pass network, RTG + action sampling; leaves next_action on the device."""

@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libctrlsim_b200.so")
 LIB_PATH_WIDE = os.path.join(HERE, "lib", "libctrlsim_b200_wide.so")  # -DCTRLSIM_WIDE: 64 agents / 256 polylines per group
-ABI_VERSION = 5
+ABI_VERSION = 6
 GEOMETRY = {False: (24, 200), True: (64, 256)}  # (max_num_agents, max_num_road_polylines) of the two builds
 
 
@@ -30,6 +30,8 @@ class CtrlSimConfig(C.Structure):
         ("min_accel", C.c_double), ("max_accel", C.c_double), ("min_steer", C.c_double), ("max_steer", C.c_double),
         ("pos_tol", C.c_double), ("heading_tol", C.c_double), ("speed_tol", C.c_double),
         ("goal_dist_scaling", C.c_double), ("reward_scaling", C.c_double),
+        ("decision_transformer", C.c_int32), ("reserved0", C.c_int32),
+        ("rtg_min", C.c_double * 3), ("rtg_max", C.c_double * 3),
     ]
 
 
@@ -50,17 +52,31 @@ BATCH_FIELDS = [
     ("n_groups", "int32", "S"), ("group_off", "int32", "S+1"), ("group_focal", "int32", "S,N"),
     ("group_members", "int32", "S,N,A"), ("group_served", "int64", "S,N"), ("group_scene", "int32", "S*N"),
     ("group_local", "int32", "S*N"), ("cstate", "float32", "S,4+8*N+20*128"),
+    # ABI 6: real-time rewards (road-edge polylines for the signed distance, tracked RTG series, dense reward trace)
+    ("edge_xy", "float64", "S,Ep,2"), ("edge_off", "int32", "S,Pe+1"), ("n_edge", "int32", "S"),
+    ("rtg_init", "float64", "S,N,3"), ("rt_rtg", "float64", "S,N,T,3"), ("tr_dense", "float64", "S,N,T1,3"),
 ]
 
 
 class CtrlSimBatch(C.Structure):
     _fields_ = ([("n_scenes", C.c_int32), ("max_veh", C.c_int32), ("max_poly", C.c_int32), ("max_seg", C.c_int32)]
-                + [(name, C.c_void_p) for name, _, _ in BATCH_FIELDS])
+                + [(name, C.c_void_p) for name, _, _ in BATCH_FIELDS]
+                + [("max_edge_pts", C.c_int32), ("max_edge_poly", C.c_int32)])
 
 
 class CtrlSimPolicyParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("tilt", C.c_double * 3), ("temperature", C.c_float),
-                ("tilt_enabled", C.c_int32), ("nucleus_sampling", C.c_int32), ("nucleus_threshold", C.c_double)]
+                ("tilt_enabled", C.c_int32), ("nucleus_sampling", C.c_int32), ("nucleus_threshold", C.c_double),
+                ("rtg_mode", C.c_int32), ("reserved0", C.c_int32)]
+
+
+class CtrlSimRewardParams(C.Structure):
+    _fields_ = [("max_veh_veh_distance", C.c_double), ("dist_to_road_edge_scaling_factor", C.c_double),
+                ("veh_veh_collision_rew_multiplier", C.c_double), ("veh_edge_collision_rew_multiplier", C.c_double),
+                ("pos_goal_shaped_min", C.c_double), ("pos_goal_shaped_max", C.c_double),
+                ("pos_target_achieved_rew_multiplier", C.c_double),
+                ("remove_shaped_goal", C.c_int32), ("remove_shaped_veh_reward", C.c_int32),
+                ("remove_shaped_edge_reward", C.c_int32), ("return_mode", C.c_int32)]
 
 
 class CtrlSimError(RuntimeError):
@@ -85,6 +101,8 @@ _SIGS = {
     "ctrlsim_prefix_cache_stats": (None, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ctrlsim_sim_reset": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_void_p]),
     "ctrlsim_observe": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_int32, C.c_void_p]),
+    "ctrlsim_dense_reward": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.POINTER(CtrlSimRewardParams), C.c_int32,
+                                       C.c_void_p]),
     "ctrlsim_plan_groups": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.c_int32, C.c_void_p, C.c_void_p]),
     "ctrlsim_policy_step": (C.c_int, [C.c_void_p, C.POINTER(CtrlSimBatch), C.POINTER(CtrlSimPolicyParams), C.c_int32,
                                       C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
@@ -102,8 +120,11 @@ _SIGS = {
     "ctrlsim_attn_padded": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ctrlsim_attn_causal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "ctrlsim_attn_causal_order": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ctrlsim_attn_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_void_p]),
+    "ctrlsim_attn_step_order": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ctrlsim_map_pool": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
     "ctrlsim_map_encode_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "ctrlsim_sample_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p,
@@ -112,6 +133,8 @@ _SIGS = {
                                               C.c_double, C.c_void_p, C.c_void_p]),
     "ctrlsim_forward_tokens": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 11
                                + [C.c_void_p, C.c_int64, C.c_void_p]),
+    "ctrlsim_forward_tokens_dt": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 9
+                                  + [C.c_void_p, C.c_int64, C.c_void_p]),
     "ctrlsim_geom_poly_poly": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ctrlsim_geom_poly_seg": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
@@ -169,4 +192,24 @@ def make_config(cfg) -> CtrlSimConfig:
         agent_dist_threshold=w.agent_dist_threshold, min_accel=w.min_accel, max_accel=w.max_accel,
         min_steer=w.min_steer, max_steer=w.max_steer, pos_tol=rc["position_target_tolerance"],
         heading_tol=rc["heading_target_tolerance"], speed_tol=rc["speed_target_tolerance"],
-        goal_dist_scaling=rc.get("shaped_goal_distance_scaling", 1.0), reward_scaling=rc["reward_scaling"])
+        goal_dist_scaling=rc.get("shaped_goal_distance_scaling", 1.0), reward_scaling=rc["reward_scaling"],
+        decision_transformer=1 if m.get("decision_transformer", False) else 0,
+        rtg_min=(C.c_double * 3)(w.min_rtg_pos, w.min_rtg_veh, w.min_rtg_road),
+        rtg_max=(C.c_double * 3)(w.max_rtg_pos, w.max_rtg_veh, w.max_rtg_road))
+
+
+RETURN_MODES = {"data": 0, "max_return": 1, "min_return": 2}
+
+
+def make_reward_params(cfg, return_mode: str = "data") -> CtrlSimRewardParams:
+    """Constants of the real-time dense reward (cfgs/dataset/waymo/base.yaml:18-25,47-49) and how the RTG series starts
+    (policy_evaluator.py:124-143: from the data, at the maximum return, or at the minimum one for evaluated vehicles)."""
+    w = cfg.dataset.waymo
+    return CtrlSimRewardParams(
+        max_veh_veh_distance=w.max_veh_veh_distance, dist_to_road_edge_scaling_factor=w.dist_to_road_edge_scaling_factor,
+        veh_veh_collision_rew_multiplier=w.veh_veh_collision_rew_multiplier,
+        veh_edge_collision_rew_multiplier=w.veh_edge_collision_rew_multiplier,
+        pos_goal_shaped_min=w.pos_goal_shaped_min, pos_goal_shaped_max=w.pos_goal_shaped_max,
+        pos_target_achieved_rew_multiplier=w.pos_target_achieved_rew_multiplier,
+        remove_shaped_goal=int(bool(w.remove_shaped_goal)), remove_shaped_veh_reward=int(bool(w.remove_shaped_veh_reward)),
+        remove_shaped_edge_reward=int(bool(w.remove_shaped_edge_reward)), return_mode=RETURN_MODES[return_mode])

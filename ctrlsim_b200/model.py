@@ -12,6 +12,8 @@ A few tensors are folded on the host in float64 once at load time (they are cons
   derived.type_tab2  [9,256]   road_road_type_encoder.mlp.0[:, 256:] . road_type_encoder(one_hot_i) + bias; row 8 is
                                the all(-1) padding type (datasets/rl_waymo/dataset.py:425)
   derived.rtg_tab_*  [350,256] embed_rtg_{goal,veh,road}.weight folded through the matching block of embed_rtg
+  derived.rtg_lin / rtg_lin_bias  [3,256] / [256]  decision-transformer variant only (cfgs/model/dt.yaml): the three
+                     Linear(1, 256) RTG embeddings folded through embed_rtg (direction per component + one bias)
 """
 from __future__ import annotations
 
@@ -62,8 +64,17 @@ def derive_weights(state_dict, cfg) -> dict:
     out = {"derived.pool_U": U, "derived.pool_W": pool_W, "derived.pool_b": pool_b, "derived.type_tab2": tab2,
            "derived.pool_U2": U2, "derived.pool_W2": pool_W2, "derived.pool_b2": pool_b2}
     Wr = sd["encoder.embed_rtg.weight"]
-    for c, name in enumerate(("goal", "veh", "road")):
-        out[f"derived.rtg_tab_{name}"] = sd[f"encoder.embed_rtg_{name}.weight"] @ Wr[:, c * H:(c + 1) * H].T
+    if cfg.model.get("decision_transformer", False):
+        # continuous RTG inputs (modules/encoder.py:27-30,116-120): embed_rtg([w_g r_g + b_g; w_v r_v + b_v; w_r r_r + b_r])
+        # = r_g (Wr_g w_g) + r_v (Wr_v w_v) + r_r (Wr_r w_r) + (Wr_g b_g + Wr_v b_v + Wr_r b_r + b_rtg)
+        names = ("goal", "veh", "road")
+        out["derived.rtg_lin"] = np.stack([Wr[:, c * H:(c + 1) * H] @ sd[f"encoder.embed_rtg_{n}.weight"][:, 0]
+                                           for c, n in enumerate(names)])
+        out["derived.rtg_lin_bias"] = sd["encoder.embed_rtg.bias"] + sum(
+            Wr[:, c * H:(c + 1) * H] @ sd[f"encoder.embed_rtg_{n}.bias"] for c, n in enumerate(names))
+    else:
+        for c, name in enumerate(("goal", "veh", "road")):
+            out[f"derived.rtg_tab_{name}"] = sd[f"encoder.embed_rtg_{name}.weight"] @ Wr[:, c * H:(c + 1) * H].T
     return {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in out.items()}
 
 
@@ -143,6 +154,37 @@ class DeviceModel:
             ws.data_ptr(), ws.numel(), stream), "ctrlsim_forward_tokens")
         torch.cuda.synchronize(dev)
         return rtg_logits.cpu().numpy(), act_logits.cpu().numpy()
+
+    def forward_tokens_dt(self, data: dict, n_t: int):
+        """Parity entry of the decision-transformer variant: data in the reference MotionData layout with continuous
+        (clip-normalised) ``rtgs`` [G,A,32,3]. Returns action logits [G,A,1000] (state rows of window step n_t - 1)."""
+        dev = self.device
+        G = data["agent_states"].shape[0]
+
+        def f32(x):
+            return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32), device=dev)
+
+        def i32(x):
+            return torch.as_tensor(np.ascontiguousarray(x, dtype=np.int32), device=dev)
+        st, ty, go = f32(data["agent_states"]), f32(data["agent_types"]), f32(data["goals"])
+        ac, rt = i32(data["actions"]), f32(data["rtgs"])
+        ts = i32(np.asarray(data["timesteps"]).reshape(G, -1, 32)[:, 0] if np.asarray(data["timesteps"]).ndim > 2
+                 else data["timesteps"])
+        rp = f32(data["road_points"])
+        rtypes = np.asarray(data["road_types"])
+        if rtypes.ndim == 3:
+            rtypes = np.where(rtypes.sum(-1) > 0, rtypes.argmax(-1), -1)
+        rty = i32(rtypes)
+        A = self.cfg.dataset.waymo.max_num_agents
+        act_logits = torch.empty(G, A, 1000, dtype=torch.float32, device=dev)
+        ws = self.workspace(G)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self.lib.ctrlsim_forward_tokens_dt(
+            self.handle, G, n_t, n_t - 1, st.data_ptr(), ty.data_ptr(), go.data_ptr(), ac.data_ptr(), rt.data_ptr(),
+            ts.data_ptr(), rp.data_ptr(), rty.data_ptr(), act_logits.data_ptr(), ws.data_ptr(), ws.numel(), stream),
+            "ctrlsim_forward_tokens_dt")
+        torch.cuda.synchronize(dev)
+        return act_logits.cpu().numpy()
 
     def close(self):
         if self.handle:

@@ -61,6 +61,12 @@ class B200AutoregressivePolicy:
                  nucleus_sampling, nucleus_threshold, seed=0, backend=None):
         """Arguments as in the reference.  ``model``: a ``DeviceModel``.  ``seed``: key of the explicit sampler (DESIGN
         section 4).  ``backend`` (tests): object with ``make_batch`` / ``step`` standing in for the device."""
+        if real_time_rewards or not predict_rtgs:
+            # the stock evaluator would track the RTGs itself (policy_evaluator.py:123-149) and hand them over per
+            # vehicle; that hand-over is not wired - real_time_rewards policies (the DT baseline) run through the batched
+            # B200Policy / B200PolicyEvaluator pair, which computes the dense reward on the device
+            raise NotImplementedError("the per-scene adapter serves the ctrl_sim policy mode (cfgs/policy/ctrl_sim.yaml); "
+                                      "use B200PolicyEvaluator for real_time_rewards policies")
         if backend is None:
             self.inner = B200Policy(cfg, model_path, model, use_rtg, predict_rtgs, discretize_rtgs, real_time_rewards,
                                     privileged_return, max_return, min_return, key_dict, tilt_dict, name,

@@ -118,3 +118,46 @@ def road_arrays(preproc: dict):
         return np.zeros((0, 100, 2)), np.zeros((0, 100), np.uint8), np.zeros(0, np.int8)
     types = np.where(rt.sum(-1) > 0, rt.argmax(-1), -1).astype(np.int8)
     return rp[:, :, :2].copy(), (rp[:, :, 2] != 0).astype(np.uint8), types
+
+
+def road_edge_polylines(scen: dict):
+    """The point lists the reference measures the signed distance to (``Evaluator.extract_road_edge_polylines``,
+    evaluators/evaluator.py:143-158, on ``get_road_data``, utils/sim.py:67-73): every point of every ``road_edge`` road as
+    the simulator holds it - ``RoadLine::geometry_points()`` are float32 (nocturne/cpp/include/road.h:113), so the file's
+    doubles are rounded to float32 first.  Returns a list of [n_k, 2] float64 arrays."""
+    out = []
+    for road in scen["roads"]:
+        g = road["geometry"]
+        if isinstance(g, dict) or road["type"] != "road_edge":
+            continue
+        out.append(np.array([(q["x"], q["y"]) for q in g], np.float32).reshape(len(g), 2).astype(np.float64))
+    return out
+
+
+def initial_rtgs(cfg, preproc: dict):
+    """[n, 3] un-normalised returns-to-go (position goal, vehicle-vehicle, vehicle-edge) of the LOGGED episode at t = 0:
+    what a real_time_rewards policy without max_return / min_return starts from (``preproc_data['rtgs'][veh_idx, 0]``
+    components 0, 3, 4; policy_evaluator.py:125-126).  The reference derives them when it loads the ``*_physics.pkl``:
+    ``compute_rewards`` over the logged rewards and distances, then a reverse cumulative sum
+    (datasets/rl_waymo/dataset_ctrl_sim.py:38-92 eval branch, dataset.py:239-275)."""
+    w = cfg.dataset.waymo
+    ag = np.asarray(preproc["ag_data"], np.float64)
+    rew = np.asarray(preproc["ag_rewards"], np.float64)
+    edge = np.asarray(preproc["veh_edge_dist_rewards"], np.float64)
+    vv = np.asarray(preproc["veh_veh_dist_rewards"], np.float64)
+    ex = ag[:, :, -1]
+    goal = rew[:, :, 0] * w.pos_target_achieved_rew_multiplier
+    if not w.remove_shaped_goal:
+        goal = goal + (np.clip(rew[:, :, 3], w.pos_goal_shaped_min, w.pos_goal_shaped_max) - w.pos_goal_shaped_max) \
+            * (1 / w.pos_goal_shaped_max)
+    if w.remove_shaped_veh_reward:
+        veh = -1 * rew[:, :, 6] * w.veh_veh_collision_rew_multiplier
+    else:
+        veh = vv - rew[:, :, 6] * w.veh_veh_collision_rew_multiplier
+    if w.remove_shaped_edge_reward:
+        road = -1 * rew[:, :, 7] * w.veh_edge_collision_rew_multiplier
+    else:
+        road = np.clip(np.abs(edge) * w.dist_to_road_edge_scaling_factor, 0, 5) / 5. - rew[:, :, 7] * w.veh_edge_collision_rew_multiplier
+    allr = np.stack([goal * ex, veh * ex, road * ex], -1)
+    return np.cumsum(allr[:, ::-1], axis=1)[:, ::-1][:, 0].copy()
+

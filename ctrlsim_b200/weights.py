@@ -60,7 +60,10 @@ def param_spec(cfg):
     spec += _lin("encoder.embed_state_goal", 2 * H, H)
     spec += [("encoder.embed_action.weight", (n_act, H), "emb")]
     for c in ("goal", "veh", "road"):
-        spec += [(f"encoder.embed_rtg_{c}.weight", (w.rtg_discretization, H), "emb")]
+        if m.get("decision_transformer", False):  # continuous RTG inputs: nn.Linear(1, H) (modules/encoder.py:27-30)
+            spec += _lin(f"encoder.embed_rtg_{c}", 1, H)
+        else:
+            spec += [(f"encoder.embed_rtg_{c}.weight", (w.rtg_discretization, H), "emb")]
     spec += _lin("encoder.embed_rtg", H * m.num_reward_components, H)
     spec += [("encoder.embed_timestep.weight", (w.max_timestep, H), "emb"),
              ("encoder.embed_agent_id.weight", (w.max_num_agents, H), "emb")]
@@ -75,7 +78,8 @@ def param_spec(cfg):
         spec += _lin(f"{p}.linear1", H, FF) + _lin(f"{p}.linear2", FF, H)
         spec += _ln(f"{p}.norm1", H) + _ln(f"{p}.norm2", H) + _ln(f"{p}.norm3", H)
     spec += _mlp("decoder.predict_action", H, H, n_act)
-    spec += _mlp("decoder.predict_rtg", H, H, w.rtg_discretization * m.num_reward_components)
+    if m.predict_rtg:  # the DT baseline has no RTG head (cfgs/model/dt.yaml)
+        spec += _mlp("decoder.predict_rtg", H, H, w.rtg_discretization * m.num_reward_components)
     if m.predict_future_states:
         spec += _mlp("decoder.predict_future_states", H, H, w.train_context_length * 2)
     return spec
@@ -111,6 +115,8 @@ def make_weights(cfg, seed: int = 0, head_gain: float = 4.0, still_bias: float =
             raise ValueError(kind)
         out[key] = v.reshape(shape).astype(np.float32)
     for head in ("decoder.predict_action", "decoder.predict_rtg"):
+        if f"{head}.mlp.3.weight" not in out:
+            continue
         out[f"{head}.mlp.3.weight"] = (out[f"{head}.mlp.3.weight"] * np.float32(head_gain)).astype(np.float32)
     if still_bias:
         w = cfg.dataset.waymo

@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define CTRLSIM_ABI_VERSION 5
+#define CTRLSIM_ABI_VERSION 6
 #define CTRLSIM_MAX_VEH 64 /* vehicles per scene supported by the grouping kernel (bitmask width) */
 
 /* Model / episode geometry. The kernels are specialised at compile time: libctrlsim_b200.so to the reference defaults
@@ -34,6 +34,12 @@ typedef struct CtrlSimConfig {
   double agent_dist_threshold;                                                   /* 60.0 */
   double min_accel, max_accel, min_steer, max_steer;                             /* -10, 10, -0.7, 0.7 */
   double pos_tol, heading_tol, speed_tol, goal_dist_scaling, reward_scaling;     /* rew_cfg, cfgs/config.yaml:72-90 */
+  /* ABI 6: the decision-transformer variant of the network (cfgs/model/dt.yaml, modules/encoder.py:27-30,116-120,139-142,
+   * utils/train_utils.py:85-88): continuous RTG inputs through Linear(1, H), token order (rtg, state, action), the action
+   * head reads the STATE rows, no RTG head. 0 = the CtRL-Sim network. */
+  int32_t decision_transformer;
+  int32_t reserved0;
+  double rtg_min[3], rtg_max[3];  /* clip-normalisation of tracked RTGs: pos, veh, road (cfgs/dataset/waymo/base.yaml:27-36) */
 } CtrlSimConfig;
 
 /* A batch of S scenes resident in HBM (struct of arrays; N = max_veh, Pm = max_poly, E = max_seg, T1 = steps+1).
@@ -89,6 +95,15 @@ typedef struct CtrlSimBatch {
   /* ---- Box2D contact state of the vehicle bodies (simulator state, owned by the library) ------------------------ */
   float* cstate;              /* [S, 4 + 8*N + 20*128] per scene: header, proxy AABBs, mass data, contact manifolds with */
                               /* their warm-start impulses (ctrlsim_b200/csrc/sim_contacts.cuh); NULL = contact-free sim */
+  /* ---- ABI 6: real-time rewards (policies with real_time_rewards, e.g. the DT baseline of cfgs/policy/dt.yaml) ----- */
+  const double* edge_xy;      /* [S,Ep,2] points of the scene's road_edge polylines, concatenated; float32-valued like */
+                              /* RoadLine::geometry_points() (evaluators/evaluator.py:143-158, utils/sim.py:67-73)      */
+  const int32_t* edge_off;    /* [S,Pe+1] first point of polyline k; edge_off[s][n_edge[s]] = number of points          */
+  const int32_t* n_edge;      /* [S] road_edge polylines of the scene                                                   */
+  const double* rtg_init;     /* [S,N,3] un-normalised RTGs (pos, veh, road) at t = 0: preproc_data['rtgs'][:, 0, (0,3,4)] */
+  double* rt_rtg;             /* [S,N,steps,3] policy state: the tracked RTG series (policy_evaluator.py:123-149)        */
+  double* tr_dense;           /* [S,N,T1,3] trace: dense reward goal / veh-veh / veh-edge (evaluator.py:106-140)         */
+  int32_t max_edge_pts, max_edge_poly; /* Ep, Pe */
 } CtrlSimBatch;
 
 /* Sampling / control knobs of AutoregressivePolicy (cfgs/policy/ctrl_sim.yaml:6-11). */
@@ -99,7 +114,21 @@ typedef struct CtrlSimPolicyParams {
   int32_t tilt_enabled;
   int32_t nucleus_sampling;   /* 0 / 1: top-p filtering of the action distribution (autoregressive_policy.py:216-230) */
   double nucleus_threshold;   /* p, cfgs/policy/ctrl_sim.yaml:11 */
+  /* ABI 6: 0 = RTGs are predicted (RTG head + sampling, predict_rtgs); 1 = RTGs are given: the tracked series rt_rtg of
+   * a real_time_rewards policy (policies/policy.py:93-95) - no RTG head, no RTG sampling. The DT network needs 1. */
+  int32_t rtg_mode;
+  int32_t reserved0;
 } CtrlSimPolicyParams;
+
+/* Constants of the dense reward (cfgs/dataset/waymo/base.yaml:18-25,47-49) and how the RTG series starts
+ * (policy_evaluator.py:124-143). */
+typedef struct CtrlSimRewardParams {
+  double max_veh_veh_distance, dist_to_road_edge_scaling_factor;                 /* 15, 15 */
+  double veh_veh_collision_rew_multiplier, veh_edge_collision_rew_multiplier;    /* 10, 10 */
+  double pos_goal_shaped_min, pos_goal_shaped_max, pos_target_achieved_rew_multiplier; /* 0, 0.2, 10 */
+  int32_t remove_shaped_goal, remove_shaped_veh_reward, remove_shaped_edge_reward;     /* 1, 0, 0 */
+  int32_t return_mode;  /* 0: rtg_init; 1: max_return (10, 90, 90); 2: min_return (evaluated vehicles (0, -10, -10)) */
+} CtrlSimRewardParams;
 
 typedef struct CtrlSim CtrlSim;
 
@@ -144,6 +173,13 @@ void ctrlsim_prefix_cache_stats(const CtrlSim* h, int64_t* incremental_chunks, i
 int ctrlsim_sim_reset(CtrlSim* h, CtrlSimBatch* b, void* stream);
 /* S5 + T1: update_vehicle_data_dict + Policy.update_state at step t (policy_evaluator.py:99-159, policy.py:68-105) */
 int ctrlsim_observe(CtrlSim* h, CtrlSimBatch* b, int32_t t, void* stream);
+/* S5': compute_dense_reward + the RTG bookkeeping of update_vehicle_data_dict for step t of a real_time_rewards policy
+ * (evaluators/evaluator.py:106-140, policy_evaluator.py:123-156); call right after ctrlsim_observe(t). For every vehicle:
+ * signed distance to the nearest road_edge polyline (utils/data.py:152-290, float64 like numpy), nearest-vehicle distance
+ * (already in tr_nearest), dense reward -> tr_dense[t]; rt_rtg[t] = start value (t = 0) or rt_rtg[t-1] - tr_dense[t-1].
+ * Reference quirks kept: the goal / collision terms are those of STEP 0 (evaluator.py:112-113,136-138 index the reward
+ * history with 0), and tr_nearest[t] is rescaled by max_veh_veh_distance (evaluator.py:126-127). */
+int ctrlsim_dense_reward(CtrlSim* h, CtrlSimBatch* b, const CtrlSimRewardParams* rp, int32_t t, void* stream);
 /* T2: greedy focal grouping of AutoregressivePolicy.get_data; writes group tables and *n_groups_total (device int32) */
 int ctrlsim_plan_groups(CtrlSim* h, CtrlSimBatch* b, int32_t t, int32_t* n_groups_total, void* stream);
 /* T3 + M2-M9 for compact groups [g0, g0+ng): tokenise, encode map + scene, decode, sample RTGs, second pass, sample
@@ -178,12 +214,21 @@ int ctrlsim_layernorm(const float* X, const float* R, const float* gamma, const 
 int ctrlsim_attn_padded(const float* Q, int32_t ldq, const float* K, const float* V, int32_t ldkv,
                         const uint8_t* key_pad, float* O, int32_t G, int32_t Lq, int32_t Lk, void* stream);
 int ctrlsim_attn_causal(const float* QKV, float* O, int32_t G, int32_t n_t, void* stream);
+/* the same for a given position of the state token inside an agent's (3-token) step: 0 = (state, rtg, action), the
+ * CtRL-Sim order; 1 = (rtg, state, action), the decision-transformer order (utils/train_utils.py:85-88) */
+int ctrlsim_attn_causal_order(const float* QKV, float* O, int32_t G, int32_t n_t, int32_t state_index, void* stream);
 /* decoder self-attention of the max_agents rows of window step ti only (state rows of the last layer / rtg rows of the
  * second pass, policies/autoregressive_policy.py:190-210): queries = columns [0, 256) of qkv_rows [G * max_agents, 768];
  * keys / values = rows of KV [G * group_rows, ld] at column offsets k_off / v_off: every token of steps < ti, the state
  * tokens of step ti and - own_row - the row's own key / value (columns [256, 768) of qkv_rows). O [G * max_agents, 256]. */
 int ctrlsim_attn_step(const float* KV, int32_t ld, int32_t k_off, int32_t v_off, int32_t group_rows, const float* qkv_rows,
                       float* O, int32_t G, int32_t ti, int32_t own_row, void* stream);
+/* general form: own_mode 0 = nothing but history + the step's state tokens, 1 = + the row's own NEW key / value from
+ * qkv_rows (as above), 2 = + the row's own FIRST token of step ti taken from KV (the decision transformer's state rows
+ * see their own rtg token); state_index as in ctrlsim_attn_causal_order */
+int ctrlsim_attn_step_order(const float* KV, int32_t ld, int32_t k_off, int32_t v_off, int32_t group_rows,
+                            const float* qkv_rows, float* O, int32_t G, int32_t ti, int32_t own_mode, int32_t state_index,
+                            void* stream);
 int ctrlsim_map_pool(const float* feats, const uint8_t* pt_valid, const uint8_t* poly_valid, const float* U,
                      float* pooled, int32_t n_poly, void* stream);
 /* the product's polyline front end, fused from the raw points (modules/map_encoder.py:34-45; csrc/map_encoder.cu): first
@@ -201,6 +246,12 @@ int ctrlsim_sample_rows_nucleus(const float* x, int32_t rows, int32_t n, int32_t
 /* full first-pass forward on caller-provided tokens of G groups (parity tests against the reference modules):
  * writes rtg logits [G,24,1050] and, after overwriting the rtg tokens at `ti` with rtg_idx [G,24,3], action logits
  * [G,24,1000]. Token arrays follow the reference MotionData layout (float32 / int32). */
+/* decision-transformer handle: one forward on caller-provided tokens; rtgs are the clip-normalised continuous values
+ * [G,A,32,3] float32; writes action logits [G,A,1000] read from the state rows of step ti (modules/decoder.py:55-57) */
+int ctrlsim_forward_tokens_dt(CtrlSim* h, int32_t G, int32_t n_t, int32_t ti, const float* agent_states,
+                              const float* agent_types, const float* goals, const int32_t* actions, const float* rtgs,
+                              const int32_t* timesteps, const float* road_points, const int32_t* road_types,
+                              float* action_logits, void* workspace, int64_t workspace_bytes, void* stream);
 int ctrlsim_forward_tokens(CtrlSim* h, int32_t G, int32_t n_t, int32_t ti, const float* agent_states /*[G,24,32,8]*/,
                            const float* agent_types /*[G,24,5]*/, const float* goals /*[G,24,5]*/,
                            const int32_t* actions /*[G,24,32]*/, const int32_t* rtgs /*[G,24,32,3]*/,

@@ -133,3 +133,41 @@ class RtgTracker:
     def advance(self, dense_prev):
         self.rtg.append(self.rtg[-1] - np.asarray(dense_prev, np.float64))
         return self.rtg[-1]
+
+
+def road_edge_polylines(scen_json):
+    """evaluators/evaluator.py:143-158 on utils/sim.py:67-73: every point of every 'road_edge' road as the simulator
+    holds it - RoadLine::geometry_points() are float32 Vector2D (nocturne/cpp/include/road.h:113), so the file's doubles
+    are rounded to float32 before numpy sees them (2e-4 m at Waymo's coordinates of a few thousand metres)."""
+    out = []
+    for road in scen_json["roads"]:
+        geom = road["geometry"]
+        if isinstance(geom, dict):
+            continue
+        if road["type"] == "road_edge":
+            out.append(np.array([(np.float32(p["x"]), np.float32(p["y"])) for p in geom], np.float64))
+    return out
+
+
+def initial_rtgs(w, preproc, n):
+    """[n, 3] un-normalised RTGs at t = 0 (components 0, 3, 4 of the logged returns): the reverse cumulative sum of
+    compute_rewards over the logged episode stored in the *_physics.pkl (datasets/rl_waymo/dataset_ctrl_sim.py:88-92,
+    dataset.py:239-275; policy_evaluator.py:125-126)."""
+    ag = np.asarray(preproc["ag_data"], np.float64)
+    rew = np.asarray(preproc["ag_rewards"], np.float64)
+    edge = np.asarray(preproc["veh_edge_dist_rewards"], np.float64)
+    vv = np.asarray(preproc["veh_veh_dist_rewards"], np.float64)
+    ex = ag[:, :, -1]
+    if w.remove_shaped_goal:
+        goal = rew[:, :, 0] * w.pos_target_achieved_rew_multiplier
+    else:
+        goal = rew[:, :, 0] * w.pos_target_achieved_rew_multiplier + \
+            (np.clip(rew[:, :, 3], w.pos_goal_shaped_min, w.pos_goal_shaped_max) - w.pos_goal_shaped_max) * (1 / w.pos_goal_shaped_max)
+    veh = -1 * rew[:, :, 6] * w.veh_veh_collision_rew_multiplier if w.remove_shaped_veh_reward else \
+        vv - rew[:, :, 6] * w.veh_veh_collision_rew_multiplier
+    road = -1 * rew[:, :, 7] * w.veh_edge_collision_rew_multiplier if w.remove_shaped_edge_reward else \
+        np.clip(np.abs(edge) * w.dist_to_road_edge_scaling_factor, 0, 5) / 5. - rew[:, :, 7] * w.veh_edge_collision_rew_multiplier
+    allr = np.stack([goal * ex, veh * ex, road * ex], -1)
+    rtgs = np.cumsum(allr[:, ::-1], axis=1)[:, ::-1]
+    assert rtgs.shape[0] == n
+    return rtgs[:, 0].copy()

@@ -40,7 +40,22 @@ FIXTURES = {
     # overlapping focal groups of 24 per step) for 44 steps - 12 of them in the sliding-window phase (t >= 32).
     "config2": dict(scene=dict(scene_id=5, n_vehicles=64, n_roads=4, n_chunks=8), weights=dict(seed=0, still_bias=3.0),
                     tilts=(0, 0, 0), logit_steps=(33,), steps=44),
+    # dt: the decision-transformer baseline exactly as cfgs/policy/dt.yaml + cfgs/model/dt.yaml configure it (SURVEY 8(f)
+    # N1): continuous RTG inputs, (rtg, state, action) token order, no RTG head, ONE forward per focal group; the RTGs
+    # start at the maximum return (10, 90, 90) and are decremented by the real-time dense reward (signed distance to the
+    # road-edge polylines, nearest-vehicle distance, collision flags) every step.
+    "dt": dict(scene=dict(scene_id=11, n_vehicles=10, n_roads=2, n_chunks=4), weights=dict(seed=3), tilts=(0, 0, 0),
+               logit_steps=(0, 9, 31, 32, 60), policy="dt"),
 }
+
+DT_POLICY = dict(predict_rtgs=False, discretize_rtgs=False, real_time_rewards=True, max_return=True, name="dt",
+                 tilt_dict={"tilt": False, "goal_tilt": None, "veh_veh_tilt": None, "veh_edge_tilt": None})
+
+
+def dt_model_cfg(cfg):
+    """cfgs/model/dt.yaml on top of cfgs/model/ctrl_sim.yaml (same switches as ctrlsim_b200.config.dt_config)."""
+    cfg.model.decision_transformer, cfg.model.predict_rtg, cfg.model.predict_future_states = True, False, False
+    return cfg
 
 
 def pack(rec, metrics, spec):
@@ -57,7 +72,8 @@ def pack(rec, metrics, spec):
             served[t, g, : len(d["served"])] = d["served"]
     out.update(group_focal=focal, group_members=members, group_served=served)
     for (t, g), ent in rec["logits"].items():
-        out[f"rtg_logits_{t}_{g}"] = ent["rtg_logits"]
+        if "rtg_logits" in ent:
+            out[f"rtg_logits_{t}_{g}"] = ent["rtg_logits"]
         out[f"action_logits_{t}_{g}"] = ent["action_logits"]
         if "inputs" in ent and g == 0:
             for k, v in ent["inputs"].items():
@@ -84,9 +100,11 @@ def main():
             continue
         t0 = time.time()
         sc = make_scene(**spec["scene"])
-        weights = make_weights(default_config(), **spec["weights"])
+        dt = spec.get("policy") == "dt"
+        weights = make_weights(dt_model_cfg(default_config()) if dt else default_config(), **spec["weights"])
         metrics, recs = run_reference([sc], weights=weights, seed=0, tilts=spec["tilts"],
-                                      logit_steps=spec["logit_steps"], steps=spec.get("steps", 90))
+                                      logit_steps=spec["logit_steps"], steps=spec.get("steps", 90),
+                                      cfg_hook=dt_model_cfg if dt else None, policy_opts=DT_POLICY if dt else None)
         np.savez_compressed(os.path.join(GOLDEN, f"rollout_{name}.npz"), **pack(recs[0], metrics, spec))
         print(f"[golden] {name}: {time.time() - t0:.1f}s metrics={metrics}", flush=True)
 

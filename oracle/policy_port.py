@@ -19,7 +19,8 @@ tests/golden/ (oracle/make_golden.py).
 
 Deliberately preserved quirks: the served-vehicle loop removes from the list it iterates (so every other candidate is
 skipped, autoregressive_policy.py:123-127); np.round half-to-even; yaw sign convention of normalize_scene; angular
-speed histogram uses heading/dt; RTG (0,0,0) appended for vehicles in no context.
+speed histogram uses heading/dt; RTG (0,0,0) appended for vehicles in no context; with real_time_rewards the dense
+reward's goal / collision terms are those of step 0 (see run_scene).
 """
 from __future__ import annotations
 
@@ -148,8 +149,15 @@ class MetricsPort:
 
 class RolloutPort:
     def __init__(self, cfg, model, seed=0, tilts=(0, 0, 0), temperature=1.0, eval_threshold=None, nucleus=None,
-                 contacts=True, fp64_trig=False):
+                 contacts=True, fp64_trig=False, predict_rtgs=True, discretize_rtgs=True, real_time_rewards=False,
+                 max_return=False, min_return=False):
         self.cfg, self.model = cfg, model
+        # Policy constructor switches (policies/policy.py:9-39; cfgs/policy/dt.yaml sets predict_rtgs=False,
+        # discretize_rtgs=False, real_time_rewards=True, max_return=True): with real_time_rewards the RTG series is the
+        # un-normalised return still to collect, decremented by the dense reward of every step
+        # (policy_evaluator.py:123-149) instead of being sampled from the RTG head
+        self.predict_rtgs, self.discretize_rtgs, self.real_time = predict_rtgs, discretize_rtgs, real_time_rewards
+        self.max_return, self.min_return = max_return, min_return
         self.w, self.m = cfg.dataset.waymo, cfg.model
         self.seed, self.tilts, self.temperature = seed, tilts, float(temperature)
         self.nucleus = nucleus  # None, or the nucleus threshold p (autoregressive_policy.py:216-230)
@@ -228,7 +236,7 @@ class RolloutPort:
         a0 = (np.clip(ac[:, :, 0], w.min_accel, w.max_accel) - w.min_accel) / (w.max_accel - w.min_accel)
         a1 = (np.clip(ac[:, :, 1], w.min_steer, w.max_steer) - w.min_steer) / (w.max_steer - w.min_steer)
         act_idx = np.round(a0 * (w.accel_discretization - 1)) * w.steer_discretization + np.round(a1 * (w.steer_discretization - 1))
-        rtg_idx = np.round(rt * (w.rtg_discretization - 1))
+        rtg_idx = np.round(rt * (w.rtg_discretization - 1)) if self.discretize_rtgs else rt  # autoregressive_policy.py:141-142
         # normalize_scene
         yaw = st[origin, 0, 4]
         rot = (np.pi / 2) + np.sign(-yaw) * np.abs(yaw)
@@ -348,6 +356,8 @@ class RolloutPort:
         if t > 0:
             ep["actions"][:, t - 1, 0], ep["actions"][:, t - 1, 1] = rec["accel"][:, t - 1], rec["steer"][:, t - 1]
             ep["rtgs"][:, t - 1] = prec["rtgs"][:, t - 1]
+        if self.real_time:  # policies/policy.py:93-95: the RTG of the CURRENT step is known before the forward
+            ep["rtgs"][:, t] = prec["rtgs"][:, t]
         ep["goals"][:, t] = np.stack([goal[:, 0], goal[:, 1], goal[:, 3] * np.cos(goal[:, 2]),
                                       goal[:, 3] * np.sin(goal[:, 2]), goal[:, 2]], -1)[:, : w.goal_dim]
 
@@ -364,20 +374,23 @@ class RolloutPort:
             prec["groups"][t].append({"focal": focal, "members": members, "served": [int(v) for v in served]})
             slot = {int(a): k for k, a in enumerate(closest)}
             tok = self.tokenize(ep, t, focal, closest)
-            out = self._forward(tok)
-            rtg_logits = out["rtg_preds"][0, :, ti].numpy()
-            for a in rel:
-                if a not in done:
-                    tilted = a in served
-                    lg = rtg_logits[slot[a]].reshape(w.rtg_discretization, 3)
-                    done[a] = [sampler.sample_from_x(sampler.rtg_x(lg[:, c], self.tilts[c] if tilted else 0),
-                                                     self.seed, scene_idx, a, t, c) for c in range(3)]
-                    prec["rtg_idx"][t, a] = done[a]
-                tok["rtgs"][slot[a], ti] = done[a]
-            out2 = self._forward(tok)
+            if self.predict_rtgs:
+                out = self._forward(tok)
+                rtg_logits = out["rtg_preds"][0, :, ti].numpy()
+                for a in rel:
+                    if a not in done:
+                        tilted = a in served
+                        lg = rtg_logits[slot[a]].reshape(w.rtg_discretization, 3)
+                        done[a] = [sampler.sample_from_x(sampler.rtg_x(lg[:, c], self.tilts[c] if tilted else 0),
+                                                         self.seed, scene_idx, a, t, c) for c in range(3)]
+                        prec["rtg_idx"][t, a] = done[a]
+                    tok["rtgs"][slot[a], ti] = done[a]
+            out2 = self._forward(tok)  # the only forward when the RTGs are not predicted (autoregressive_policy.py:210)
             act_logits = out2["action_preds"][0, :, ti].numpy()
             if t in logit_steps:
-                prec["logits"][(t, g)] = {"rtg_logits": rtg_logits.copy(), "action_logits": act_logits.copy()}
+                prec["logits"][(t, g)] = {"action_logits": act_logits.copy()}
+                if self.predict_rtgs:
+                    prec["logits"][(t, g)]["rtg_logits"] = rtg_logits.copy()
             for v in served:
                 ax = sampler.action_x(act_logits[slot[v]], self.temperature)
                 if self.nucleus is None:
@@ -438,14 +451,34 @@ class RolloutPort:
         rec.update(self.policy_record(n))
         rec["evaluated"] = np.array(sorted(evaluated), np.int32)
         next_act = np.zeros((n, 2))
+        if self.real_time:
+            from . import dense_reward_port as drp
+            edges = drp.road_edge_polylines(scen_json)
+            rec["dense_reward"] = np.zeros((n, steps + 1, 3))
+            tracker = drp.RtgTracker(drp.initial_rtgs(self.w, preproc, n), evaluated, self.max_return, self.min_return)
         for t in range(run_steps):
             self.observe(ctx, t)
+            if self.real_time:  # policy_evaluator.py:123-156: RTG of step t from the dense reward of step t-1, then the
+                # dense reward of step t; 'nearest_dist' is recorded x max_veh_veh_distance in this mode (evaluator.py:126)
+                rec["rtgs"][:, t] = tracker.rtg[0] if t == 0 else tracker.advance(rec["dense_reward"][:, t - 1])
+                # QUIRK (evaluator.py:112-113,136-138): the whole reward HISTORY [n, t+1, 8] goes into compute_rewards and
+                # all_rewards[i, 0] picks time index 0 - the goal / collision terms of the dense reward are those of STEP 0
+                # at every step; only the two distance terms follow the current state
+                rec["dense_reward"][:, t], _ = drp.dense_reward_step(self.w, rec["pos"][:, t], rec["existence"][:, t],
+                                                                     rec["reward"][:, 0], edges)
+                rec["nearest_dist"][:, t] *= self.w.max_veh_veh_distance
+                rec["gt_nearest_dist"][:, t] *= self.w.max_veh_veh_distance
             self.update_state(ep, ctx, rec, t)
             self.predict_step(ep, rec, t, scene_idx, next_act, logit_steps)
             self.apply_controls(ctx, t, evaluated, next_act)
             sim.step(dt)
         if run_steps == steps:
             self.observe(ctx, steps)
+            if self.real_time:
+                rec["dense_reward"][:, steps], _ = drp.dense_reward_step(self.w, rec["pos"][:, steps], rec["existence"][:, steps],
+                                                                         rec["reward"][:, 0], edges)
+                rec["nearest_dist"][:, steps] *= self.w.max_veh_veh_distance
+                rec["gt_nearest_dist"][:, steps] *= self.w.max_veh_veh_distance
             if evaluated:
                 self.metrics.add_scene(rec, evaluated)
         return rec

@@ -84,8 +84,13 @@ def build_reference_model(cfg, weights):
 
 
 def run_reference(scenes, weights=None, seed=0, tilts=(0, 0, 0), temperature=1.0, eval_threshold=64,
-                  steps=90, logit_steps=(), workdir=None, cfg_hook=None):
-    """Returns (metrics_dict, [per-scene record dict])."""
+                  steps=90, logit_steps=(), workdir=None, cfg_hook=None, policy_opts=None):
+    """Returns (metrics_dict, [per-scene record dict]).
+
+    ``policy_opts`` overrides the AutoregressivePolicy constructor arguments (cfgs/policy/*.yaml), e.g. the DT baseline
+    of cfgs/policy/dt.yaml: dict(predict_rtgs=False, discretize_rtgs=False, real_time_rewards=True, max_return=True,
+    name="dt", tilt_dict={"tilt": False, ...}) together with a ``cfg_hook`` that selects cfgs/model/dt.yaml.  With
+    real_time_rewards the records also hold the dense reward series (evaluators/evaluator.py:106-140)."""
     ref_shims.install()
     import policies.policy as ref_policy_mod
     import policies.autoregressive_policy as ref_ar_mod
@@ -110,12 +115,15 @@ def run_reference(scenes, weights=None, seed=0, tilts=(0, 0, 0), temperature=1.0
     torch.multinomial = _multinomial_shim
     _Ctx.seed = seed
 
-    policy = AutoregressivePolicy(
+    pkw = dict(
         cfg=cfg, model_path="synthetic", model=model, use_rtg=True, predict_rtgs=True, discretize_rtgs=True,
         real_time_rewards=False, privileged_return=False, max_return=False, min_return=False,
         key_dict={"next_acceleration": "next_acceleration", "next_steering": "next_steering", "rtgs": "rtgs"},
         tilt_dict={"tilt": True, "goal_tilt": tilts[0], "veh_veh_tilt": tilts[1], "veh_edge_tilt": tilts[2]},
         name="ctrl_sim", action_temperature=temperature, nucleus_sampling=False, nucleus_threshold=0.8)
+    pkw.update(policy_opts or {})
+    policy = AutoregressivePolicy(**pkw)
+    passes = 2 if pkw["predict_rtgs"] else 1  # model calls per focal group (autoregressive_policy.py:190,210)
     evaluator = PolicyEvaluator(cfg, policy)
 
     records = []
@@ -173,12 +181,13 @@ def run_reference(scenes, weights=None, seed=0, tilts=(0, 0, 0), temperature=1.0
         if t in logit_steps:
             if call_no["step"] != t:
                 call_no["step"], call_no["n"] = t, 0
-            g, p = divmod(call_no["n"], 2)
+            g, p = divmod(call_no["n"], passes)
             call_no["n"] += 1
             ti = t if t < cfg.dataset.waymo.train_context_length else -1
             ent = _Ctx.rec["logits"].setdefault((t, g), {})
             if p == 0:
-                ent["rtg_logits"] = preds["rtg_preds"][0, :, ti].detach().numpy().astype(np.float32).copy()
+                if passes == 2:
+                    ent["rtg_logits"] = preds["rtg_preds"][0, :, ti].detach().numpy().astype(np.float32).copy()
                 ent["inputs"] = {
                     "agent_states": data["agent"].agent_states[0].numpy().copy(),
                     "agent_types": data["agent"].agent_types[0].numpy().copy(),
@@ -189,7 +198,7 @@ def run_reference(scenes, weights=None, seed=0, tilts=(0, 0, 0), temperature=1.0
                     "road_points": data["map"].road_points[0].numpy().astype(np.float32).copy(),
                     "road_types": data["map"].road_types[0].numpy().astype(np.float32).copy(),
                 }
-            else:
+            if p == passes - 1:
                 ent["action_logits"] = preds["action_preds"][0, :, ti].detach().numpy().astype(np.float32).copy()
                 ent["rtgs_pass2"] = data["agent"].rtgs[0].numpy().copy()
         return preds
@@ -217,6 +226,8 @@ def run_reference(scenes, weights=None, seed=0, tilts=(0, 0, 0), temperature=1.0
         rec["steer"] = arr("steering")
         rec["reward"] = np.array([[data_dict[v]["reward"][t] for t in range(T)] for v in ids], np.float64)
         rec["rtgs"] = np.array([[data_dict[v]["rtgs"][t] for t in range(steps)] for v in ids], np.float64)
+        if policy.real_time_rewards:
+            rec["dense_reward"] = np.array([[data_dict[v]["dense_reward"][t] for t in range(T)] for v in ids], np.float64)
         rec["nearest_dist"] = arr("nearest_dist")
         rec["gt_nearest_dist"] = arr("gt_nearest_dist")
         rec["gt_pos"] = arr("gt_position", ("x", "y"))

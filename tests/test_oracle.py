@@ -235,10 +235,90 @@ def test_rollout_port_matches_reference_prefix(cfg):
             assert d["served"] == [int(v) for v in g["group_served"][t, gi] if v >= 0]
 
 
+def test_rollout_port_dt_real_time_rewards_matches_reference_prefix():
+    """the decision-transformer baseline as cfgs/policy/dt.yaml runs it (RTGs tracked in real time from
+    the dense reward, one forward per focal group) - oracle port vs the unmodified reference evaluator
+    (tests/golden/rollout_dt.npz): sampled action bins, trajectories, the dense reward and the RTG series."""
+    from ctrlsim_b200.config import dt_config
+    from ctrlsim_b200.synth import make_scene
+    from ctrlsim_b200.weights import make_weights
+    from oracle.model_port import ModelPort
+    from oracle.policy_port import RolloutPort
+    g, spec, _ = load_golden("dt")
+    cfg = dt_config()
+    steps = 8
+    port = RolloutPort(cfg, ModelPort(cfg, make_weights(cfg, **spec["weights"])), seed=0, eval_threshold=64,
+                       predict_rtgs=False, discretize_rtgs=False, real_time_rewards=True, max_return=True)
+    sc = make_scene(**spec["scene"])
+    rec = port.run_scene(0, sc["json"], sc["preproc"], max_steps=steps, logit_steps=(0,))
+    assert (rec["act_idx"][:steps] == g["act_idx"][:steps]).all() and (rec["rtg_idx"][:steps] == -1).all()
+    for k in ("pos", "vel", "heading", "existence", "accel", "steer", "reward", "nearest_dist", "gt_nearest_dist",
+              "dense_reward", "rtgs"):
+        assert np.abs(rec[k][:, :steps] - g[k][:, :steps]).max() < 1e-9, k
+    assert (g["rtgs"][:, 0] == (10.0, 90.0, 90.0)).all() and np.abs(np.diff(g["rtgs"], axis=1)).max() > 0.1
+    for gi in range(len(rec["groups"][0])):
+        assert np.abs(rec["logits"][(0, gi)]["action_logits"] - g[f"action_logits_0_{gi}"]).max() < 5e-5
+
+
+def test_dense_reward_port_reproduces_the_reference_episode():
+    """The dense reward and the RTG bookkeeping of all 91 steps of the reference's DT episode, recomputed by the oracle
+    from the recorded states: bit-identical.  Pins two things no unit test of the functions shows: road-edge points are
+    the simulator's float32 copies, and the goal / collision terms are those of STEP 0 (evaluator.py:112-113,136-138
+    index the reward history with 0)."""
+    from ctrlsim_b200.config import dt_config
+    from ctrlsim_b200.synth import make_scene
+    from oracle import dense_reward_port as drp
+    g, spec, _ = load_golden("dt")
+    w = dt_config().dataset.waymo
+    sc = make_scene(**spec["scene"])
+    edges = drp.road_edge_polylines(sc["json"])
+    n = g["pos"].shape[0]
+    tr = drp.RtgTracker(drp.initial_rtgs(w, sc["preproc"], n), [int(v) for v in g["evaluated"]], max_return=True)
+    assert g["reward"][:, 1:, 7].max() == 1.0 and g["reward"][:, 0, 7].max() == 0.0  # an off-road flag appears later only
+    for t in range(91):
+        dense, _ = drp.dense_reward_step(w, g["pos"][:, t], g["existence"][:, t], g["reward"][:, 0], edges)
+        assert (dense == g["dense_reward"][:, t]).all(), t
+        if t < 90:
+            rtg = tr.rtg[0] if t == 0 else tr.advance(g["dense_reward"][:, t - 1])
+            assert (rtg == g["rtgs"][:, t]).all(), t
+
+
+@needs_reference
+def test_initial_rtgs_port_matches_the_reference_dataset(tmp_path, cfg):
+    """RTGs at t = 0 without max_return / min_return: reverse cumulative sum of compute_rewards over the logged episode of
+    the *_physics.pkl (datasets/rl_waymo/dataset_ctrl_sim.py:38-92 eval branch) - oracle restatement and the product's
+    loader (ctrlsim_b200.scenario.initial_rtgs) against the reference dataset object."""
+    import pickle
+    from oracle import ref_shims
+    from oracle.dense_reward_port import initial_rtgs
+    from ctrlsim_b200.scenario import initial_rtgs as product_initial_rtgs
+    ref_shims.install()
+    from datasets.rl_waymo import RLWaymoDatasetCtRLSim
+    rng = np.random.default_rng(3)
+    n = 9
+    pre = {"idx": 0, "num_agents": n, "road_points": np.zeros((4, 100, 3)), "road_types": np.zeros((4, 8)),
+           "ag_data": rng.normal(size=(n, 90, 8)), "ag_actions": np.zeros((n, 90, 2)), "ag_types": np.zeros((n, 5)),
+           "last_exist_timesteps": np.zeros(n), "ag_rewards": rng.uniform(0, 1, size=(n, 90, 8)),
+           "veh_edge_dist_rewards": rng.normal(size=(n, 90)) * 0.2, "veh_veh_dist_rewards": rng.uniform(0, 1, size=(n, 90)),
+           "filtered_ag_ids": list(range(n)), "ag_goals": np.zeros((n, 90, 5))}
+    pre["ag_data"][:, :, -1] = (rng.uniform(size=(n, 90)) > 0.2).astype(np.float64)
+    pre["ag_rewards"][:, :, [0, 6, 7]] = (pre["ag_rewards"][:, :, [0, 6, 7]] > 0.8).astype(np.float64)
+    dset = RLWaymoDatasetCtRLSim.__new__(RLWaymoDatasetCtRLSim)
+    dset.cfg_dataset, dset.preprocess, dset.mode = cfg.dataset.waymo, True, "eval"
+    for k, v in (("POS_TARGET_ACHIEVED_REW_IDX", 0), ("HEADING_TARGET_ACHIEVED_REW_IDX", 1), ("SPEED_TARGET_ACHIEVED_REW_IDX", 2),
+                 ("POS_GOAL_SHAPED_REW_IDX", 3), ("SPEED_GOAL_SHAPED_REW_IDX", 4), ("HEADING_GOAL_SHAPED_REW_IDX", 5),
+                 ("VEH_VEH_COLLISION_REW_IDX", 6), ("VEH_EDGE_COLLISION_REW_IDX", 7)):
+        assert getattr(dset, k) == v
+    rtgs, _, _ = dset.get_data(pre, 0)
+    want = np.concatenate([rtgs[:, 0, :1], rtgs[:, 0, 3:]], -1)
+    assert np.abs(initial_rtgs(cfg.dataset.waymo, pre, n) - want).max() < 1e-12
+    assert np.abs(product_initial_rtgs(cfg, pre) - want).max() < 1e-12
+
+
 def test_metrics_port_matches_reference_metrics(cfg):
     """S7: feeding the reference's own recorded trajectories through the oracle metrics reproduces its metrics dict."""
     from oracle.policy_port import MetricsPort
-    for name in ("plumbing", "crowded", "sparse"):
+    for name in ("plumbing", "crowded", "sparse", "dt"):
         g, spec, ref = load_golden(name)
         mp = MetricsPort(cfg)
         rec = {k: g[k] for k in ("existence", "reward", "pos", "gt_pos", "vel", "gt_speed", "heading", "gt_heading",
