@@ -580,6 +580,266 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// =====================================================================================================================
+// gemm_tc_ta_kernel: the same persistent TMA-fed 3xTF32 GEMM with the ACTIVATION operand in tensor memory.
+// In gemm_tc_tma_kernel every k-slab moves 160 KB through the SM's shared-memory port (TMA writes 48, A_lo derivation
+// 32, MMA operand reads 80) = 1250 cycles at 128 B/clk against 768 cycles of MMA issue time - the measured bound
+// (profiles/README.md).  Here the producer warps read the raw A tile from shared memory ONCE, split it into hi / lo in
+// registers and write both halves to TMEM (tcgen05.st), and the MMAs take A from TMEM (tcgen05.mma [d], [a], b-desc):
+// no A_lo store, no A operand reads - 112 KB per k-slab.  TMEM holds the A stages (4 x (32 hi + 32 lo) columns), so
+// there is room for only ONE accumulator pair (main | cross, 256 columns): the epilogue warps first drain it into
+// registers (adding main + cross), release it, and only then do bias / ReLU / stores; the ~500-cycle drain is hidden by
+// the 4-stage ring, which keeps filling while the MMA warp waits.  Needs the precomputed W_lo tile (registered weights).
+//   warps 0-7  A producers: warp w owns TMEM lanes 32 (w & 3) .. +31 (= tile rows, thread = row) and k columns
+//              16 (w >> 2) .. +15 of the slab;  warp 8 MMA issuer;  warp 9 TMA issuer;  warps 10-17 epilogue.
+constexpr int Q_STAGES = 4;
+constexpr uint32_t Q_TMEM_A = 256;  // first TMEM column of the A stages
+struct alignas(1024) QStage {
+  float a_raw[P_BM * P_BK];
+  float b_raw[P_BN * P_BK];
+  float b_lo[P_BN * P_BK];  // adjacent to b_raw: one N = 256 descriptor covers [B_hi ; B_lo]
+};
+struct QSmem {
+  QStage stage[Q_STAGES];
+  uint64_t tma_full[Q_STAGES];
+  uint64_t a_full[Q_STAGES];
+  uint64_t empty[Q_STAGES];
+  uint64_t acc_full;
+  uint64_t acc_empty;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
+// bias / table / ReLU / coalesced stores of 16 rows x 32 columns held in the 16x256b fragment layout (see
+// tc_epilogue_chunk_frag, whose second half this is): acc = main + cross, already summed.
+template <bool RELU, bool FAST>
+__device__ __forceinline__ void tc_epilogue_regs(const float (&acc)[16], int half, int m_base, int M, int nc0, int N,
+                                                 const float* __restrict__ bias, const float* __restrict__ table,
+                                                 const int* __restrict__ tidx, int ldt, float* __restrict__ C, int ldc,
+                                                 bool vec_ok, int lane, bool skip_store) {
+  const int t0 = lane & 3, t1 = lane >> 2, odd = t0 & 1;
+  float bz[4][2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = nc0 + 8 * k + 2 * t0;
+    if (FAST) {
+      if (bias) { const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + c)); bz[k][0] = b2.x; bz[k][1] = b2.y; }
+      else { bz[k][0] = 0.f; bz[k][1] = 0.f; }
+    } else {
+      bz[k][0] = (bias && c < N) ? __ldg(bias + c) : 0.f;
+      bz[k][1] = (bias && c + 1 < N) ? __ldg(bias + c + 1) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int h = 2 * half + hh;
+    const int m = m_base + t1 + 8 * h;
+    const float* trow = (!FAST && table && m < M) ? table + (size_t)tidx[m] * ldt : nullptr;
+    float v[4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float x = acc[4 * k + 2 * hh + e] + bz[k][e];
+        if (!FAST && trow) { const int c = nc0 + 8 * k + 2 * t0 + e; if (c < N) x += __ldg(trow + c); }
+        v[k][e] = RELU ? fmaxf(x, 0.f) : x;
+      }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const float k0 = odd ? v[2 * p + 1][0] : v[2 * p][0], k1 = odd ? v[2 * p + 1][1] : v[2 * p][1];
+      const float s0 = odd ? v[2 * p][0] : v[2 * p + 1][0], s1 = odd ? v[2 * p][1] : v[2 * p + 1][1];
+      const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+      const float4 out = odd ? make_float4(g0, g1, k0, k1) : make_float4(k0, k1, g0, g1);
+      const int c = nc0 + 8 * (2 * p + odd) + 2 * (t0 & 2);
+      if (FAST) {
+        if (!skip_store) *reinterpret_cast<float4*>(C + (size_t)m * ldc + c) = out;
+      } else if (m < M && !skip_store) {
+        float* dst = C + (size_t)m * ldc + c;
+        if (vec_ok && c + 3 < N) {
+          *reinterpret_cast<float4*>(dst) = out;
+        } else {
+          if (c < N) dst[0] = out.x;
+          if (c + 1 < N) dst[1] = out.y;
+          if (c + 2 < N) dst[2] = out.z;
+          if (c + 3 < N) dst[3] = out.w;
+        }
+      }
+    }
+  }
+}
+
+template <bool RELU>
+__global__ void __launch_bounds__(P3_THREADS, 1)
+gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* __restrict__ table,
+                  const int* __restrict__ tidx, float* __restrict__ C, int M, int N, int K, int ldc, int ldt, int n_tiles_n,
+                  int n_tiles) {
+  extern __shared__ unsigned char tc_raw[];
+  QSmem& sm = *reinterpret_cast<QSmem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk = K / P_BK;
+  const int dbg = g_gemm_debug;  // experiments (results are wrong): 2 = no global stores, 8 = no A_lo x B_hi MMAs, 32 = no main MMAs
+
+  if (tid == 0) {
+    for (int s = 0; s < Q_STAGES; ++s) {
+      tc_mbar_init(&sm.tma_full[s], 1); tc_mbar_init(&sm.a_full[s], 8); tc_mbar_init(&sm.empty[s], 1);
+    }
+    tc_mbar_init(&sm.acc_full, 1); tc_mbar_init(&sm.acc_empty, P3_EPI);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ A producers: smem raw tile -> hi / lo in TMEM
+    const int q = warp & 3, kh = warp >> 2;
+    const int row = 32 * q + lane;
+    const uint32_t row_off = (uint32_t)row * (P_BK * 4);
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16) + Q_TMEM_A + (uint32_t)(16 * kh);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int s = it % Q_STAGES;
+        // the TMA of this slab was issued only after the MMAs of slab it - Q_STAGES completed (empty[s]), so TMEM A
+        // stage s is free as soon as the data has landed
+        tc_mbar_wait(&sm.tma_full[s], (it / Q_STAGES) & 1);
+        const uint32_t a_raw = tc_smem_u32(sm.stage[s].a_raw) + row_off;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = lds128(a_raw + (uint32_t)(((4 * kh + i) ^ (row & 7)) << 4));
+          const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t h = __float_as_uint(x[e]) & 0xFFFFE000u;
+            hi[4 * i + e] = h;
+            lo[4 * i + e] = __float_as_uint(x[e] - __uint_as_float(h));
+          }
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tc_st16(t_lane + (uint32_t)(64 * s), hi);
+        tc_st16(t_lane + (uint32_t)(64 * s + 32), lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(&sm.a_full[s]);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    // per k-step: [main | cross] += A_hi x [B_hi ; B_lo] (N = 256), cross += A_lo x B_hi (N = 128); A from TMEM
+    const uint32_t idesc2 = tc_make_idesc(P_BM, 2 * P_BN), idesc1 = tc_make_idesc(P_BM, P_BN);
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      tc_mbar_wait(&sm.acc_empty, (ti & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int s = it % Q_STAGES;
+        tc_mbar_wait(&sm.tma_full[s], (it / Q_STAGES) & 1);
+        tc_mbar_wait(&sm.a_full[s], (it / Q_STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint64_t dbh = tc_make_desc(tc_smem_u32(sm.stage[s].b_raw));
+          const uint32_t a_hi = tmem + Q_TMEM_A + (uint32_t)(64 * s), a_lo = a_hi + 32;
+#pragma unroll
+          for (int ks = 0; ks < P_BK / 8; ++ks) {
+            const uint64_t o = (uint64_t)(2 * ks);
+            if (!(dbg & 32)) tc_mma_ts(tmem, a_hi + 8 * ks, dbh + o, idesc2, (kc > 0 || ks > 0) ? 1u : 0u);
+            if (!(dbg & 8)) tc_mma_ts(tmem + 128, a_lo + 8 * ks, dbh + o, idesc1, 1u);
+          }
+          tc_commit(&sm.empty[s]);
+          if (kc == nk - 1) tc_commit(&sm.acc_full);
+        }
+        __syncwarp();
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ TMA issuer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles_n) * P_BM, n0 = (tile % n_tiles_n) * P_BN;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % Q_STAGES;
+          tc_mbar_wait(&sm.empty[s], ((it / Q_STAGES) & 1) ^ 1);
+          QStage& st = sm.stage[s];
+          tc_expect_tx(&sm.tma_full[s], (P_BM + 2 * P_BN) * P_BK * 4);
+          tc_tma_2d(st.a_raw, &tmA, kc * P_BK, m0, &sm.tma_full[s]);
+          tc_tma_2d(st.b_raw, &tmW, kc * P_BK, n0, &sm.tma_full[s]);
+          tc_tma_2d(st.b_lo, &tmWlo, kc * P_BK, n0, &sm.tma_full[s]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 10..17)
+    const int lg = warp & 3;
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    const bool nostore = (dbg & 2) != 0;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int m0 = (tile / n_tiles_n) * P_BM, n0 = (tile % n_tiles_n) * P_BN;
+      tc_mbar_wait(&sm.acc_full, ti & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // drain this warp's 32 lanes x 64 columns (main + cross) into registers, then hand the accumulators back
+      float acc[2][2][16];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = 2 * ((warp - 10) >> 2) + jj;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t ta = tmem + ((uint32_t)(32 * lg + 16 * half) << 16) + (uint32_t)(32 * j);
+          uint32_t a0[16], x0[16];
+          tc_ld16x256_x4(ta, a0);
+          tc_ld16x256_x4(ta + 128, x0);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[jj][half][i] = __uint_as_float(a0[i]) + __uint_as_float(x0[i]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      tc_mbar_arrive(&sm.acc_empty);
+      const bool fast = m0 + P_BM <= M && n0 + P_BN <= N && vec_ok && !table && (reinterpret_cast<uintptr_t>(bias) & 7) == 0;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = 2 * ((warp - 10) >> 2) + jj;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (fast)
+            tc_epilogue_regs<RELU, true>(acc[jj][half], half, m0 + 32 * lg, M, n0 + 32 * j, N, bias, table, tidx, ldt, C, ldc, vec_ok, lane, nostore);
+          else
+            tc_epilogue_regs<RELU, false>(acc[jj][half], half, m0 + 32 * lg, M, n0 + 32 * j, N, bias, table, tidx, ldt, C, ldc, vec_ok, lane, nostore);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -657,6 +917,25 @@ static int launch_gemm_tc_tma(const GemmArgs& g, cudaStream_t st) {
   const int tn = (g.N + P_BN - 1) / P_BN, tm = (g.M + P_BM - 1) / P_BM;
   const long long tiles = (long long)tn * tm;
   const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+  {  // registered weights (W_lo tile exists): the kernel with the A operand in tensor memory; CTRLSIM_GEMM=tma keeps the older one
+    static int use_ta = -1;
+    static const int smem_q = (int)sizeof(QSmem) + 1024;
+    if (use_ta < 0) {
+      const char* e = getenv("CTRLSIM_GEMM");
+      use_ta = (e && std::string(e) == "tma") ? 0 : 1;
+      if (use_ta) {
+        cudaError_t ce = cudaFuncSetAttribute(gemm_tc_ta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tc_ta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q);
+        if (ce != cudaSuccess) { use_ta = -1; return set_error(-5, "gemm_tc_ta smem attr: %s", cudaGetErrorString(ce)); }
+      }
+    }
+    if (use_ta && wlo) {
+      if (g.relu) gemm_tc_ta_kernel<true><<<grid, P3_THREADS, smem_q, st>>>(tmA, tmW, tmWlo, g.bias, g.table, g.tidx, g.C, g.M, g.N, g.K, g.ldc, g.ldt, tn, (int)tiles);
+      else gemm_tc_ta_kernel<false><<<grid, P3_THREADS, smem_q, st>>>(tmA, tmW, tmWlo, g.bias, g.table, g.tidx, g.C, g.M, g.N, g.K, g.ldc, g.ldt, tn, (int)tiles);
+      CS_CHECK_LAUNCH("gemm_tc_ta");
+      return 0;
+    }
+  }
 #define CS_LAUNCH_TMA(R, L) gemm_tc_tma_kernel<R, L><<<grid, P3_THREADS, smem, st>>>(tmA, tmW, tmWlo, g.bias, g.table, g.tidx, g.C, g.M, g.N, g.K, g.ldc, g.ldt, tn, (int)tiles)
   if (g.relu) { if (wlo) CS_LAUNCH_TMA(true, true); else CS_LAUNCH_TMA(true, false); }
   else { if (wlo) CS_LAUNCH_TMA(false, true); else CS_LAUNCH_TMA(false, false); }

@@ -878,3 +878,113 @@ def test_evaluation_from_the_reference_file_layout(cfg, dev, tmp_path):
     saved = json.load(open(path))
     assert len(saved["collision"]) == 3 and len(saved["ade"]) == ev.batch.n_evaluated()
     assert abs(float(np.mean(saved["ade"])) - m_files["ade"]) < 1e-9 and abs(float(np.mean(saved["goal_success"])) - m_files["goal"]) < 1e-12
+
+
+# ------------------------------------------------------------------ real-time rewards / decision transformer
+def _dt_policy(cfg_dt, spec, dev):
+    from ctrlsim_b200.evaluator import B200Policy
+    p = cfg_dt.eval.policy
+    return B200Policy(cfg_dt, "synthetic", _model(cfg_dt, spec, dev), use_rtg=p.use_rtg, predict_rtgs=p.predict_rtgs,
+                      discretize_rtgs=p.discretize_rtgs, real_time_rewards=p.real_time_rewards,
+                      max_return=p.max_return, min_return=p.min_return, name="dt", seed=0)
+
+
+def test_dt_forward_matches_reference_logits(dev):
+    """Decision-transformer network (cfgs/model/dt.yaml: continuous RTG inputs through Linear(1, H), (rtg, state, action)
+    token order and its mask rule, no RTG head): the tokens the unmodified reference evaluator fed to its model at steps
+    0 / 9 / 31 / 32 / 60 of the DT episode -> its recorded action logits."""
+    from ctrlsim_b200.config import dt_config
+    g, spec, _ = load_golden("dt")
+    cfg_dt = dt_config()
+    model = _model(cfg_dt, spec, dev)
+    for t in spec["logit_steps"]:
+        n_t = min(t + 1, 32)
+        data = {k: g[f"in_{t}_{k}"][None] for k in ("agent_states", "agent_types", "goals", "actions", "road_points",
+                                                    "road_types")}
+        data["rtgs"] = g[f"in_{t}_rtgs_pass1"][None]
+        data["timesteps"] = g[f"in_{t}_timesteps"][None][:, 0, :, 0]
+        act_logits = model.forward_tokens_dt(data, n_t)
+        n_real = int((g[f"in_{t}_agent_types"].sum(-1) > 0).sum())
+        d_act = np.abs(act_logits[0, :n_real] - g[f"action_logits_{t}_0"][:n_real]).max()
+        assert d_act < LOGIT_TOL, (t, d_act)
+
+
+def test_dt_rollout_with_real_time_rewards_matches_reference(dev):
+    """cfgs/policy/dt.yaml end to end: RTGs start at the maximum return and are decremented every step
+    by the dense reward (signed distance to the road edges, nearest-vehicle distance, goal term; evaluator.py:106-140,
+    policy_evaluator.py:123-149), one forward per focal group, action sampling only.  Free-running GPU episode vs the
+    unmodified reference evaluator: sampled action bins bit for bit, states, the dense reward series and the tracked
+    RTG series of all 90 steps, and the final metrics."""
+    from ctrlsim_b200.config import dt_config
+    from ctrlsim_b200.evaluator import B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    g, spec, ref_metrics = load_golden("dt")
+    cfg_dt = dt_config()
+    pol = _dt_policy(cfg_dt, spec, dev)
+    ev = B200PolicyEvaluator(cfg_dt, pol, scenes=[make_scene(**spec["scene"])])
+    b = ev.build_batch(eval_threshold=64)
+    ev.rollout(b)
+    torch.cuda.synchronize()
+    tr = b.trace()
+    n = g["pos"].shape[0]
+    act = tr["tr_act_idx"][0, :n, :90].T.astype(np.int64)
+    bad = np.argwhere(act != g["act_idx"])
+    T = int(bad[:, 0].min()) if len(bad) else 90
+    assert T >= 60, ("an action draw differs early", T, bad[:4].tolist())
+    assert (tr["tr_rtg_idx"][0, :n] == -1).all()  # nothing is sampled for the RTGs
+    ex = g["existence"][:, :T + 1].astype(bool)
+    assert (tr["tr_exist"][0, :n, :T + 1] == g["existence"][:, :T + 1]).all()
+    dpos = np.abs(tr["tr_pos"][0, :n, :T + 1].astype(np.float64) - g["pos"][:, :T + 1])[ex].max()
+    dhead = np.abs(tr["tr_heading"][0, :n, :T + 1].astype(np.float64) - g["heading"][:, :T + 1])[ex].max()
+    assert dpos == 0.0 and dhead == 0.0, (dpos, dhead)
+    # dense reward of the states 0..T and the RTG series it drives (evaluated vehicles; others keep their start value)
+    dd = np.abs(tr["tr_dense"][0, :n, :T + 1] - g["dense_reward"][:, :T + 1])[ex].max()
+    assert dd < 1e-9, dd
+    Tr = min(T + 1, 90)
+    dr = np.abs(tr["rt_rtg"][0, :n, :Tr] - g["rtgs"][:, :Tr])[g["existence"][:, :Tr].astype(bool)].max()
+    assert dr < 1e-9, dr
+    if T == 90:
+        m = ev.metrics_from_summary(ev.summarize(b))
+        for k, v in ref_metrics.items():
+            assert abs(m[k] - v) < 1e-4 * max(1.0, abs(v)), (k, m[k], v)
+
+
+@pytest.mark.parametrize("mode", ["data", "min_return"])
+def test_ctrl_sim_network_with_tracked_rtgs_matches_oracle_port(cfg, dev, mode):
+    """real_time_rewards with the CtRL-Sim network (predict_rtgs=False, discretize_rtgs=True; policies/policy.py:89-118):
+    the tracked RTG series - started from the logged returns of the *_physics.pkl ('data') or from min_return - is
+    clip-normalised and discretised into the RTG embedding bins, one forward per group, actions sampled.  GPU == the
+    oracle port, scene by scene: action bins, positions, dense reward, RTG series."""
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    from ctrlsim_b200.weights import make_weights
+    from ctrlsim_b200.model import DeviceModel
+    from oracle.model_port import ModelPort
+    from oracle.policy_port import RolloutPort
+    weights = make_weights(cfg, seed=5, still_bias=2.0)
+    scenes = [make_scene(70 + i, n_vehicles=5 + 3 * i, n_roads=2, n_chunks=3) for i in range(2)]
+    rng = np.random.default_rng(12)
+    for sc in scenes:  # a logged episode with non-trivial returns, so that 'data' starts from different RTGs per vehicle
+        pre = sc["preproc"]
+        n_obj = pre["num_agents"]
+        pre["ag_data"][:, :, -1] = rng.random((n_obj, 90)) < 0.9
+        pre["ag_rewards"][:, :, 0] = rng.random((n_obj, 90)) < 0.05
+        pre["ag_rewards"][:, :, 6] = rng.random((n_obj, 90)) < 0.02
+        pre["ag_rewards"][:, :, 7] = rng.random((n_obj, 90)) < 0.02
+        pre["veh_edge_dist_rewards"][:] = rng.normal(size=(n_obj, 90)) * 0.2
+        pre["veh_veh_dist_rewards"][:] = rng.random((n_obj, 90))
+    steps = 5
+    kw = dict(predict_rtgs=False, discretize_rtgs=True, real_time_rewards=True, min_return=(mode == "min_return"))
+    pol = B200Policy(cfg, "synthetic", DeviceModel(cfg, weights, dev), seed=4, **kw)
+    ev = B200PolicyEvaluator(cfg, pol, scenes=scenes)
+    b = ev.build_batch(eval_threshold=64)
+    ev.rollout(b, max_steps=steps)
+    tr = b.trace()
+    port = RolloutPort(cfg, ModelPort(cfg, weights), seed=4, eval_threshold=64, **kw)
+    for s, sc in enumerate(scenes):
+        rec = port.run_scene(s, sc["json"], sc["preproc"], max_steps=steps)
+        n = rec["n"]
+        assert (tr["tr_act_idx"][s, :n, :steps].T == rec["act_idx"][:steps]).all()
+        assert np.abs(tr["tr_pos"][s, :n, :steps] - rec["pos"][:, :steps]).max() < POS_TOL
+        assert np.abs(tr["tr_dense"][s, :n, :steps] - rec["dense_reward"][:, :steps]).max() < 1e-9
+        assert np.abs(tr["rt_rtg"][s, :n, :steps] - rec["rtgs"][:, :steps]).max() < 1e-9
