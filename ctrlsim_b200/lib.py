@@ -179,9 +179,29 @@ def check(rc: int, what: str = ""):
         raise CtrlSimError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
 
 
+# switches of cfgs/config.yaml `nocturne:` whose reference default is compiled into observe_kernel / sim_step_kernel
+# (utils/sim.py compute_reward, policy_evaluator.py collision handling); any other value must fail loudly, not silently
+# evaluate something else
+_FIXED_SWITCHES = {"collision_fix": True}
+# (utils/sim.py:83-141 reads only these; shared_reward / collision_penalty / goal_distance_penalty belong to the RL env)
+_FIXED_REWARD_SWITCHES = {"shaped_goal_distance": True, "position_target": True, "speed_target": True,
+                          "heading_target": True}
+
+
+def check_fixed_switches(cfg):
+    n = cfg.nocturne
+    bad = [f"nocturne.{k}={n[k]!r} (supported: {v!r})" for k, v in _FIXED_SWITCHES.items() if k in n and n[k] != v]
+    rc = n["rew_cfg"]
+    bad += [f"nocturne.rew_cfg.{k}={rc[k]!r} (supported: {v!r})" for k, v in _FIXED_REWARD_SWITCHES.items()
+            if k in rc and rc[k] != v]
+    if bad:
+        raise NotImplementedError("the simulator / reward kernels implement the reference defaults only: " + "; ".join(bad))
+
+
 def make_config(cfg) -> CtrlSimConfig:
     w, m, n = cfg.dataset.waymo, cfg.model, cfg.nocturne
     rc = n["rew_cfg"]
+    check_fixed_switches(cfg)
     return CtrlSimConfig(
         abi_version=ABI_VERSION, hidden_dim=m.hidden_dim, num_heads=m.num_heads, dim_feedforward=m.dim_feedforward,
         enc_layers=m.num_transformer_encoder_layers, dec_layers=m.num_decoder_layers,

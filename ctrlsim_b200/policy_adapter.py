@@ -43,12 +43,14 @@ class _DeviceBackend:
         self.inner.attach_caches(b)
         return b
 
-    def step(self, batch, t, states_t, actions_prev):
+    def step(self, batch, t, states_t, actions_prev, rtgs_t=None):
         import torch
         dev = batch.device
         batch.t["hist_state"][0, :, t] = torch.from_numpy(states_t).to(dev)
         if actions_prev is not None:
             batch.t["hist_action"][0, :, t - 1] = torch.from_numpy(actions_prev).to(dev)
+        if rtgs_t is not None:  # real_time_rewards: the evaluator's tracked, un-normalised RTGs of step t
+            batch.t["rt_rtg"][0, :, t] = torch.from_numpy(np.ascontiguousarray(rtgs_t, np.float64)).to(dev)
         self.inner.predict(batch, t)
         torch.cuda.synchronize(dev)
         return (batch.t["next_action"][0].cpu().numpy(), batch.t["tr_rtg_idx"][0, :, t].cpu().numpy(),
@@ -61,19 +63,16 @@ class B200AutoregressivePolicy:
                  nucleus_sampling, nucleus_threshold, seed=0, backend=None):
         """Arguments as in the reference.  ``model``: a ``DeviceModel``.  ``seed``: key of the explicit sampler (DESIGN
         section 4).  ``backend`` (tests): object with ``make_batch`` / ``step`` standing in for the device."""
-        if real_time_rewards or not predict_rtgs:
-            # the stock evaluator would track the RTGs itself (policy_evaluator.py:123-149) and hand them over per
-            # vehicle; that hand-over is not wired - real_time_rewards policies (the DT baseline) run through the batched
-            # B200Policy / B200PolicyEvaluator pair, which computes the dense reward on the device
-            raise NotImplementedError("the per-scene adapter serves the ctrl_sim policy mode (cfgs/policy/ctrl_sim.yaml); "
-                                      "use B200PolicyEvaluator for real_time_rewards policies")
+        # real_time_rewards policies (cfgs/policy/dt.yaml): the stock evaluator computes the dense reward and tracks the
+        # RTGs itself (policy_evaluator.py:123-149, evaluator.py:106-140); update_state() picks the RTGs of step t up from
+        # vehicle_data_dict like policies/policy.py:91-93 and predict() hands them to the device (CtrlSimBatch.rt_rtg)
         if backend is None:
             self.inner = B200Policy(cfg, model_path, model, use_rtg, predict_rtgs, discretize_rtgs, real_time_rewards,
                                     privileged_return, max_return, min_return, key_dict, tilt_dict, name,
                                     action_temperature, nucleus_sampling, nucleus_threshold, seed=seed)
             backend = _DeviceBackend(self.inner)
-        elif not (use_rtg and predict_rtgs and discretize_rtgs) or real_time_rewards or max_return or min_return:
-            raise NotImplementedError("only the ctrl_sim policy mode (cfgs/policy/ctrl_sim.yaml) is implemented")
+        elif not use_rtg or (not predict_rtgs and not real_time_rewards):
+            raise NotImplementedError("use_rtg=False / RTGs that are neither predicted nor tracked are not implemented")
         self.backend = backend
         # what the reference's Policy.__init__ keeps and its evaluator reads (policy_evaluator.py:39-41,123-143,417-423)
         self.cfg = cfg.copy()
@@ -97,6 +96,7 @@ class B200AutoregressivePolicy:
         n = len(vehicle_data_dict.keys())
         self.states = np.zeros((n, self.steps, 8))
         self.actions = np.zeros((n, self.steps, 2))
+        self.rtgs = np.zeros((n, self.steps, 3))
         self.idx_to_veh_id, self.veh_id_to_idx = {}, {}
         for i, v in enumerate(vehicle_data_dict.keys()):
             self.idx_to_veh_id[i] = v
@@ -112,6 +112,8 @@ class B200AutoregressivePolicy:
                                  d["heading"][t], d["length"], d["width"], d["existence"][t])
             if t > 0:
                 self.actions[i, t - 1] = (d["acceleration"][t - 1], d["steering"][t - 1])
+            if self.real_time_rewards and self.use_rtg:  # policies/policy.py:91-93
+                self.rtgs[i, t] = np.asarray(d[self.key_dict["rtgs"]][t], np.float64)
 
     # ---- AutoregressivePolicy.predict -------------------------------------------------------------------------------
     def _make_batch(self, vehicle_data_dict, gt_data_dict, preproc_data, vehicles_to_evaluate):
@@ -139,8 +141,12 @@ class B200AutoregressivePolicy:
                 raise RuntimeError("predict() must be called for every step from t = 0 on after reset()")
             self._batch = self._make_batch(vehicle_data_dict, gt_data_dict, preproc_data, vehicles_to_evaluate)
             self._evaluated = {self.veh_id_to_idx[v] for v in vehicles_to_evaluate}
-        next_action, rtg_idx, act_idx = self.backend.step(self._batch, t, self.states[:, t],
-                                                          self.actions[:, t - 1] if t > 0 else None)
+        if self.real_time_rewards:
+            next_action, rtg_idx, act_idx = self.backend.step(self._batch, t, self.states[:, t],
+                                                              self.actions[:, t - 1] if t > 0 else None, self.rtgs[:, t])
+        else:
+            next_action, rtg_idx, act_idx = self.backend.step(self._batch, t, self.states[:, t],
+                                                              self.actions[:, t - 1] if t > 0 else None)
         self.last_rtg_idx, self.last_act_idx = rtg_idx, act_idx  # sampled bins of this step (-1: none), for parity dumps
         w, kd = self.cfg_rl_waymo, self.key_dict
         R = w.rtg_discretization - 1
@@ -148,7 +154,9 @@ class B200AutoregressivePolicy:
         hi = (w.max_rtg_pos, w.max_rtg_veh, w.max_rtg_road)
         for i, v in self.idx_to_veh_id.items():
             d = vehicle_data_dict[v]
-            if rtg_idx[i, 0] >= 0:  # an RTG was drawn for this vehicle this step (it is in some focal group's context)
+            if not self.predict_rtgs:  # the evaluator owns the RTG series (autoregressive_policy.py:243-248 is skipped)
+                pass
+            elif rtg_idx[i, 0] >= 0:  # an RTG was drawn for this vehicle this step (it is in some focal group's context)
                 rtg = np.array([rtg_idx[i, c] / R * (hi[c] - lo[c]) + lo[c] for c in range(3)])  # undiscretize_rtgs
                 d["next_rtg_goal"], d["next_rtg_veh"], d["next_rtg_road"] = rtg
                 d[kd["rtgs"]].append(rtg)

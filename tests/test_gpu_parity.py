@@ -988,3 +988,53 @@ def test_ctrl_sim_network_with_tracked_rtgs_matches_oracle_port(cfg, dev, mode):
         assert np.abs(tr["tr_pos"][s, :n, :steps] - rec["pos"][:, :steps]).max() < POS_TOL
         assert np.abs(tr["tr_dense"][s, :n, :steps] - rec["dense_reward"][:, :steps]).max() < 1e-9
         assert np.abs(tr["rt_rtg"][s, :n, :steps] - rec["rtgs"][:, :steps]).max() < 1e-9
+
+
+def test_reference_signature_adapter_with_real_time_rewards(dev):
+    """SURVEY 8(b) x 8(f) N1: the per-scene adapter in cfgs/policy/dt.yaml mode.  The stock evaluator tracks the RTGs
+    itself and hands them over in vehicle_data_dict['rtgs'][t] (policy_evaluator.py:123-149, policies/policy.py:91-93);
+    here the reference's recorded world of the DT fixture (states, applied controls, tracked RTGs) is replayed through
+    reset / update_state / predict / act, across the switch to the sliding window: every sampled action bin must be the
+    one the unmodified reference drew, and predict() must leave the RTG series alone."""
+    from ctrlsim_b200.config import dt_config
+    from ctrlsim_b200.policy_adapter import B200AutoregressivePolicy
+    from ctrlsim_b200.synth import make_scene
+    from oracle.policy_port import RolloutPort
+    g, spec, _ = load_golden("dt")
+    cfg_dt = dt_config()
+    sc = make_scene(**spec["scene"])
+    T = 36
+    kd = {"next_acceleration": "next_acceleration", "next_steering": "next_steering", "rtgs": "rtgs"}
+    td = {"tilt": True, "goal_tilt": 0, "veh_veh_tilt": 0, "veh_edge_tilt": 0}
+    p = cfg_dt.eval.policy
+    policy = B200AutoregressivePolicy(cfg_dt, "synthetic", _model(cfg_dt, spec, dev), p.use_rtg, p.predict_rtgs, p.discretize_rtgs,
+                                      p.real_time_rewards, p.privileged_return, p.max_return, p.min_return, kd, td, "dt", 1.0,
+                                      False, 0.8, seed=0)
+    ctx = RolloutPort(cfg_dt, None).setup_scene(0, sc["json"])
+    n, gt = ctx["n"], ctx["gt"]
+    v2e = [int(v) for v in g["evaluated"]]
+    gt_data_dict = {v: {"traj": [list(gt[v, t]) for t in range(91)]} for v in range(n)}
+    vdd = {v: {"position": [], "velocity": [], "heading": [], "existence": [], "acceleration": [], "steering": [], "timestep": [],
+               "rtgs": [], "goal_position": {"x": ctx["goal"][v, 0], "y": ctx["goal"][v, 1]}, "goal_heading": ctx["goal"][v, 2],
+               "goal_speed": ctx["goal"][v, 3], "length": float(ctx["parsed"]["size"][v, 0]), "width": float(ctx["parsed"]["size"][v, 1]),
+               "type": "vehicle", "next_acceleration": 0.0, "next_steering": 0.0} for v in range(n)}
+    policy.scene_index = -1
+    policy.reset(vdd)
+    undisc = lambda a: ((a // 50) * 2.0 * 10 / 19 - 10, (a % 50) * 2.0 * 0.7 / 49 - 0.7)  # dataset.py undiscretize_actions
+    for t in range(T):
+        for v in range(n):
+            d = vdd[v]
+            d["position"].append({"x": g["pos"][v, t, 0], "y": g["pos"][v, t, 1]})
+            d["velocity"].append({"x": g["vel"][v, t, 0], "y": g["vel"][v, t, 1]})
+            d["heading"].append(g["heading"][v, t]); d["existence"].append(g["existence"][v, t]); d["timestep"].append(t)
+            d["rtgs"].append(g["rtgs"][v, t].copy())
+        policy.update_state(vdd, v2e, t)
+        out = policy.predict(vdd, gt_data_dict, sc["preproc"], None, v2e, t)
+        assert out is vdd and all(len(vdd[v]["rtgs"]) == t + 1 for v in range(n))
+        assert (policy.last_act_idx == g["act_idx"][t]).all(), (t, policy.last_act_idx, g["act_idx"][t])
+        for v in v2e:
+            if g["act_idx"][t, v] >= 0:
+                a, s_ = undisc(int(g["act_idx"][t, v]))
+                assert abs(vdd[v]["next_acceleration"] - a) < 1e-5 and abs(vdd[v]["next_steering"] - s_) < 1e-6
+        for v in range(n):
+            vdd[v]["acceleration"].append(g["accel"][v, t]); vdd[v]["steering"].append(g["steer"][v, t])

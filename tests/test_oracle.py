@@ -1075,6 +1075,72 @@ def test_reference_signature_adapter_runs_inside_the_stock_policy_evaluator(tmp_
                 assert np.array_equal(ap[:, 0], [d[v]["acceleration"][t - 1] for v in range(p["n"])])
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref")) or not os.path.isdir("/root/reference"),
+                    reason="needs the reference tree and its built simulator (build container only)")
+def test_reference_signature_adapter_real_time_rewards_inside_the_stock_policy_evaluator(tmp_path):
+    """SURVEY 8(b) x 8(f) N1: the adapter built with the cfgs/policy/dt.yaml switches inside the UNMODIFIED
+    PolicyEvaluator.  The evaluator computes the dense reward and tracks the RTGs; the adapter must hand the device
+    exactly vehicle_data_dict['rtgs'][t] at step t (policies/policy.py:91-93) and must not append to the series itself
+    (autoregressive_policy.py:243-248 only runs with predict_rtgs).  Device replaced by a recording stand-in."""
+    from ctrlsim_b200.batch import SceneBatch
+    from ctrlsim_b200.policy_adapter import B200AutoregressivePolicy
+    from ctrlsim_b200.synth import make_scene, write_dataset
+    from oracle import ref_harness, ref_shims
+    ref_shims.install()
+    from evaluators import PolicyEvaluator
+    scenes = [make_scene(11, n_vehicles=6, n_roads=1, n_chunks=4)]
+    paths = write_dataset(str(tmp_path), scenes)
+    rcfg = ref_harness.build_cfg(paths, 4, len(scenes))
+    rcfg.model.decision_transformer, rcfg.model.predict_rtg, rcfg.model.predict_future_states = True, False, False
+    steps = rcfg.nocturne.steps
+
+    class Backend:
+        def __init__(self):
+            self.calls, self.evaluated = [], None
+
+        def make_batch(self, cfg_, scene, scene_id, parsed, evaluated):
+            self.evaluated = list(evaluated)
+            return SceneBatch(cfg_, [scene], [scene_id], "cpu", eval_threshold=len(evaluated), parsed=[parsed], evaluated_sets=[evaluated])
+
+        def step(self, batch, t, states_t, actions_prev, rtgs_t=None):
+            assert rtgs_t is not None and rtgs_t.shape == (batch.N, 3)
+            self.calls.append((t, rtgs_t.copy()))
+            n = batch.N
+            nxt, rtg, act = np.zeros((n, 2)), -np.ones((n, 3), np.int64), -np.ones(n, np.int64)
+            for v in self.evaluated:
+                if states_t[v, 7]:
+                    nxt[v], act[v] = (0.5, 0.02), 524
+            return nxt, rtg, act
+
+    be = Backend()
+    kd = {"next_acceleration": "next_acceleration", "next_steering": "next_steering", "rtgs": "rtgs"}
+    td = {"tilt": False, "goal_tilt": 0, "veh_veh_tilt": 0, "veh_edge_tilt": 0}
+    policy = B200AutoregressivePolicy(rcfg, "synthetic", None, True, False, False, True, False, True, False, kd, td, "dt",
+                                      1.0, False, 0.8, backend=be)
+    recs = []
+    ev = PolicyEvaluator(rcfg, policy)
+    orig = ev.update_running_statistics
+    ev.update_running_statistics = lambda d: (recs.append({k: {"rtgs": [np.array(r) for r in v["rtgs"]], "dense": [np.array(r) for r in v["dense_reward"]],
+                                                               "acceleration": list(v["acceleration"]), "existence": list(v["existence"])}
+                                                           for k, v in d.items()}), orig(d))[1]
+    metrics, _ = ev.evaluate_policy()
+    assert "goal" in metrics and len(recs) == 1 and [c[0] for c in be.calls] == list(range(steps))
+    d = recs[0]
+    ids = list(d.keys())
+    for t, rt in be.calls:
+        want = np.array([d[v]["rtgs"][t] for v in ids])
+        assert np.array_equal(rt, want), t
+    for v in ids:
+        assert len(d[v]["rtgs"]) == steps + 1  # one per update_vehicle_data_dict call; predict() appended nothing
+        assert np.array_equal(d[v]["rtgs"][0], [10, 90, 90])
+        for t in range(1, steps):
+            assert np.array_equal(d[v]["rtgs"][t], d[v]["rtgs"][t - 1] - d[v]["dense"][t - 1])
+    for v in be.evaluated:
+        for t in range(rcfg.nocturne.history_steps - 1, steps):
+            if d[v]["existence"][t]:
+                assert d[v]["acceleration"][t] == 0.5
+
+
 @pytest.mark.parametrize("name", ["plumbing", "sparse"])
 def test_partition_scene_results_match_the_metrics_port(tmp_path, cfg, name):
     """N4: the per-partition ``scene_results`` JSON (policy_evaluator.py:578-593) - B200PolicyEvaluator.scene_results /
@@ -1113,3 +1179,21 @@ def test_partition_scene_results_match_the_metrics_port(tmp_path, cfg, name):
     assert set(saved) == {"goal_success", "ade", "fde", "accel_gt", "accel_sim", "ang_speed_gt", "ang_speed_sim", "lin_speed_gt",
                           "lin_speed_sim", "nearest_dist_gt", "nearest_dist_sim", "collision", "off_road"}  # the reference's keys
     assert len(saved["lin_speed_sim"]) == len(res["ade"]) and saved["goal_success"] == res["goal_success"]
+
+
+def test_unsupported_simulator_switches_fail_loudly(cfg):
+    """`collision_fix` and the rew_cfg switches are compiled into the kernels at their reference defaults
+    (cfgs/config.yaml); any other value must raise instead of silently evaluating the default behaviour."""
+    from ctrlsim_b200 import lib as L
+    L.check_fixed_switches(cfg)
+    for path, key, val in (("nocturne", "collision_fix", False), ("rew", "position_target", False),
+                           ("rew", "shaped_goal_distance", False), ("rew", "heading_target", False)):
+        c = cfg.copy()
+        c.nocturne = cfg.nocturne.copy()
+        if path == "nocturne":
+            c.nocturne[key] = val
+        else:
+            c.nocturne["rew_cfg"] = dict(cfg.nocturne["rew_cfg"])
+            c.nocturne["rew_cfg"][key] = val
+        with pytest.raises(NotImplementedError):
+            L.check_fixed_switches(c)
