@@ -69,7 +69,7 @@ def _ncu_traffic():
 
 
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit"
 
     def __init__(self, index=0):
         self.rows, self.p, self.index = [], None, index
@@ -99,8 +99,15 @@ class ClockSampler:
         mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        def fl(r, i):
+            try:
+                return float(r[i])
+            except (IndexError, ValueError):
+                return None
+        pw = sorted(v for v in (fl(r, 6) for r in rows) if v is not None)
+        lim = [v for v in (fl(r, 7) for r in rows) if v is not None]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None, "power_limit_w": max(lim) if lim else None}
 
 
 def make_scenes(n, first_id, stride, **kw):
@@ -314,6 +321,12 @@ def main():
     segs = plan_segments(args.steps, args.warmup, n_ep)
     ms_total, groups, launches = 0.0, 0, 0
     phase_ms = {"cached": [0.0, 0], "full_window": [0.0, 0]}
+    pc_chunks = [0, 0]
+
+    def prefix_stats():
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        lib.ctrlsim_prefix_cache_stats(model.handle, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
     prof = [0.0] * 12
     spans = []
     for t_first, n in segs:
@@ -324,6 +337,7 @@ def main():
         fence()
         lib.ctrlsim_profile_enable(1)
         l0 = lib.ctrlsim_launch_count()
+        pc0 = prefix_stats()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
         r0 = clocks.mark()
         torch.cuda.synchronize()
@@ -336,6 +350,10 @@ def main():
         spans.append((r0, clocks.mark()))
         ms_total += evs[0].elapsed_time(evs[n])
         launches += lib.ctrlsim_launch_count() - l0
+        pc1 = prefix_stats()
+        if t_first % n_ep < T_WIN:  # chunks of the cached phase that ran incrementally / had to recompute their window
+            pc_chunks[0] += pc1[0] - pc0[0]
+            pc_chunks[1] += pc1[1] - pc0[1]
         for i in range(n):
             ph = phase_ms["cached" if (t_first + i) % n_ep < T_WIN else "full_window"]
             ph[0] += evs[i].elapsed_time(evs[i + 1])
@@ -458,13 +476,19 @@ def main():
                    "map_cache": "per-focal polyline-encoder cache for steps 0..31 (ctrlsim_attach_map_cache): " + ("on" if pol.use_map_cache else "off"),
                    "simulator": "FreeCar + Box2D vehicle-vehicle contact response: " + ("off" if os.environ.get("CTRLSIM_CONTACTS", "1") == "0" else "on")},
         "phases": {"cached_ms_per_step": phase_ms["cached"][0] / max(phase_ms["cached"][1], 1), "cached_steps": phase_ms["cached"][1],
+                   "cached_chunks_incremental": pc_chunks[0], "cached_chunks_recomputed": pc_chunks[1],
                    "full_window_ms_per_step": phase_ms["full_window"][0] / max(n_full, 1), "full_window_steps": n_full,
                    "episode_mix": "58 full-window : 32 cached steps per 90-step episode"},
         "gpu_launches": int(launches_all),
         "clocks": clk,
-        "roofline": {"kernel": "gemm_tc_tma_kernel (every nn.Linear: tcgen05 kind::tf32, 3-product hi/lo split = fp32-accurate, 3 tensor flops per counted flop)", "bound": "tensor", "achieved": gemm_tf,
+        "roofline": {"kernel": "gemm_tc_ta_kernel (every nn.Linear: tcgen05 kind::tf32 with the activation operand in TMEM, 3-product hi/lo split = fp32-accurate, 3 tensor flops per counted flop)", "bound": "tensor", "achieved": gemm_tf,
                      "peak": pk["tf"] / 1.0, "unit": "TFLOP/s", "frac": gemm_tf / pk["tf"],
-                     "traffic": traffic.get("gemm_tc_tma_kernel"),
+                     "traffic": traffic.get("gemm_tc_ta_kernel", traffic.get("gemm_tc_tma_kernel")),
+                     # the chip runs this kernel at its 1 kW cap (profiles/r02r_power_probe.txt): cuBLAS tf32 sustains
+                     # 596 TFLOP/s on the same box, so no 3-product tf32 GEMM can sustain more than 199 counted
+                     "power_limited": {"cublas_tf32_sustained_tflops": 596.3, "issued_tf32_tflops": 3.0 * gemm_tf,
+                                       "frac_of_tf32_x3_ceiling": 3.0 * gemm_tf / 596.3,
+                                       "source": "profiles/r02r_power_probe.txt (tools/power_probe.py, this pool's B200)"},
                      "peak_source": pk["tf_src"], "share_of_step": gemm_ms / ms, "launches": int(gemm_n),
                      "avg_launch_ms": gemm_ms / max(gemm_n, 1), "algorithmic_flops_per_launch": gemm_fl / max(gemm_n, 1)},
         "encoder_attn": enc,

@@ -6,7 +6,9 @@ from ctrlsim_b200 import lib as L
 lib = L.load()
 dev = torch.device("cuda:0")
 shapes = [(256 * 2304, 768, 256), (256 * 2304, 256, 256), (256 * 2304, 1024, 256), (256 * 2304, 256, 1024)]
-if len(sys.argv) > 1:
+if len(sys.argv) > 1 and sys.argv[1] == "ffn2":  # the launch profiles/ncu_traffic.json describes: FFN2 of 90 focal groups
+    shapes = [(90 * 2304, 256, 1024)]
+elif len(sys.argv) > 1:
     shapes = shapes[: int(sys.argv[1])]
 dbg = int(os.environ.get("GEMM_DEBUG", "0"))  # experiment bits of gemm_tc.cu (results are wrong when set)
 model = None

@@ -3,7 +3,9 @@ per launch of the two kernels bench.py reports a roofline for, next to the algor
 that bench.py can scale the figure to the launches it timed (the captures run 8 scenes = 90 focal groups per launch,
 the bench 256 groups per chunk).
 
-    python tools/ncu_traffic.py gpurun_out/r02a_gemm.ncu-rep gpurun_out/r02a_map_pool.ncu-rep
+    python tools/ncu_traffic.py gpurun_out/r02v_gemm_ffn2.ncu-rep gpurun_out/r02a_map_pool.ncu-rep
+(the GEMM capture: `ncu --set full -k regex:gemm_tc_ta -s 2 -c 1 ... python tools/gemm_bench.py ffn2`, which launches
+FFN2 at M = 90 x 2304 with registered weights)
 """
 import csv
 import io
@@ -40,13 +42,13 @@ def main(paths):
             if best is None or by > best[1]:
                 best = (name, by, r)
         name, by, r = best
-        key = "gemm_tc_tma_kernel" if "gemm_tc" in name else "map_pool_kernel" if "map_pool" in name else name.split("(")[0]
+        key = "gemm_tc_ta_kernel" if "gemm_tc" in name else "map_pool_kernel" if "map_pool" in name else name.split("(")[0]
         ent = {"kernel": name.split("(")[0], "dram_bytes_per_launch": by, "dram_read": val(r, "dram__bytes_read.sum"),
                "dram_write": val(r, "dram__bytes_write.sum"), "duration_us": float(r[ix["gpu__time_duration.sum"]])}
-        if key == "gemm_tc_tma_kernel":
+        if key == "gemm_tc_ta_kernel":
             # the launch with the most DRAM traffic is FFN2 (reads the 1024-wide hidden): M = 90 groups x 2304 rows,
             # N = 256, K = 1024; FFN1 (template <1, 1>, ReLU) moves the same bytes the other way round
-            M, N, K = (90 * 2304, 1024, 256) if "<1," in name else (90 * 2304, 256, 1024)
+            M, N, K = (90 * 2304, 1024, 256) if "kernel<1" in name.replace(" ", "") else (90 * 2304, 256, 1024)
             ent.update(shape=[M, N, K], algorithmic_flops=2.0 * M * N * K, algorithmic_bytes=4.0 * (M * K + N * K + M * N),
                        bytes_per_unit=by / (2.0 * M * N * K), unit="flop")
         elif key == "map_pool_kernel":
