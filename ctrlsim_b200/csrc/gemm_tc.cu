@@ -844,7 +844,26 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// Encoded tensor maps are pure functions of (base, rows, K, ld, box): the ~850 GEMM launches of a simulator step use a
+// few dozen distinct operands (weights, workspace activations), so the descriptors are kept in a small direct-mapped
+// cache instead of being re-encoded by the driver three times per launch.
+struct MapKey { const float* base; int rows, K, ld, box_rows; };
+struct MapSlot { MapKey key; CUtensorMap map; bool valid; };
+static thread_local MapSlot g_map_cache[256];  // per host thread: handles are used one thread each
+static int make_map_uncached(EncodeTiledFn enc, CUtensorMap* map, const float* base, int rows, int K, int ld, int box_rows);
 static int make_map(EncodeTiledFn enc, CUtensorMap* map, const float* base, int rows, int K, int ld, int box_rows) {
+  uint64_t h = reinterpret_cast<uintptr_t>(base) >> 4;
+  h = (h ^ (uint64_t)rows * 0x9E3779B97F4A7C15ull ^ (uint64_t)K * 0xC2B2AE3D27D4EB4Full ^ (uint64_t)ld * 0x165667B19E3779F9ull) + (uint64_t)box_rows;
+  MapSlot& sl = g_map_cache[(h ^ (h >> 29)) & 255];
+  if (sl.valid && sl.key.base == base && sl.key.rows == rows && sl.key.K == K && sl.key.ld == ld && sl.key.box_rows == box_rows) {
+    *map = sl.map;
+    return 0;
+  }
+  const int rc = make_map_uncached(enc, map, base, rows, K, ld, box_rows);
+  if (rc == 0) { sl.key = {base, rows, K, ld, box_rows}; sl.map = *map; sl.valid = true; }
+  return rc;
+}
+static int make_map_uncached(EncodeTiledFn enc, CUtensorMap* map, const float* base, int rows, int K, int ld, int box_rows) {
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)P_BK, (cuuint32_t)box_rows};
