@@ -139,18 +139,17 @@ __device__ __forceinline__ void tc_ld16x256_x4(uint32_t taddr, uint32_t (&r)[16]
       : "r"(taddr));
 }
 
-// Epilogue of one 32-row x 32-column chunk of a warp's accumulator rows, coalesced: the accumulators are read in the
-// 16x256b fragment layout (4 lanes share a row), lane pairs swap half of their values so that every lane owns four
-// consecutive columns, and each store instruction writes 8 rows x 64 contiguous bytes (instead of 32 rows x 16 bytes
-// with one row per thread).  m_base: first row of the warp's 32 rows; nc0: first column of the chunk.
-template <bool RELU, bool FAST /* tile fully inside C, vector stores, no table: no per-element checks */>
-__device__ __forceinline__ void tc_epilogue_chunk_frag(uint32_t tmem_main, uint32_t tmem_cross, int m_base, int M, int nc0,
-                                                       int N, const float* __restrict__ bias,
-                                                       const float* __restrict__ table, const int* __restrict__ tidx,
-                                                       int ldt, float* __restrict__ C, int ldc, bool vec_ok, int lane,
-                                                       bool skip_store) {
+// Epilogue of 16 rows x 32 columns of a warp's accumulator rows held in the 16x256b fragment layout (4 lanes share a
+// row; acc = main + cross, already summed): bias / table / ReLU, then lane pairs swap half of their values so that
+// every lane owns four consecutive columns and each store instruction writes 8 rows x 64 contiguous bytes (instead of
+// 32 rows x 16 bytes with one row per thread).  m_base: first row of the warp's 32 rows; half: lanes 0..15 or 16..31
+// of the warp's TMEM lane quadrant; nc0: first column of the chunk.
+template <bool RELU, bool FAST>
+__device__ __forceinline__ void tc_epilogue_regs(const float (&acc)[16], int half, int m_base, int M, int nc0, int N,
+                                                 const float* __restrict__ bias, const float* __restrict__ table,
+                                                 const int* __restrict__ tidx, int ldt, float* __restrict__ C, int ldc,
+                                                 bool vec_ok, int lane, bool skip_store) {
   const int t0 = lane & 3, t1 = lane >> 2, odd = t0 & 1;
-  // bias of the 8 columns this thread holds before the swap: columns nc0 + 8 k + 2 t0 + e
   float bz[4][2];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -164,13 +163,7 @@ __device__ __forceinline__ void tc_epilogue_chunk_frag(uint32_t tmem_main, uint3
     }
   }
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {  // lanes 0..15, then 16..31 of the warp's lane quadrant
-  uint32_t a0[16], x0[16];                // main / cross accumulators
-  tc_ld16x256_x4(tmem_main + ((uint32_t)(16 * half) << 16), a0);
-  tc_ld16x256_x4(tmem_cross + ((uint32_t)(16 * half) << 16), x0);
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {  // row t1 + 8 h of the warp's 32 rows
+  for (int hh = 0; hh < 2; ++hh) {
     const int h = 2 * half + hh;
     const int m = m_base + t1 + 8 * h;
     const float* trow = (!FAST && table && m < M) ? table + (size_t)tidx[m] * ldt : nullptr;
@@ -179,19 +172,17 @@ __device__ __forceinline__ void tc_epilogue_chunk_frag(uint32_t tmem_main, uint3
     for (int k = 0; k < 4; ++k)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int ri = 4 * k + 2 * hh + e;
-        const float acc = __uint_as_float(a0[ri]) + __uint_as_float(x0[ri]);
-        float x = acc + bz[k][e];
+        float x = acc[4 * k + 2 * hh + e] + bz[k][e];
         if (!FAST && trow) { const int c = nc0 + 8 * k + 2 * t0 + e; if (c < N) x += __ldg(trow + c); }
         v[k][e] = RELU ? fmaxf(x, 0.f) : x;
       }
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {  // column blocks 2p (kept by even t0) and 2p+1 (kept by odd t0)
+    for (int p = 0; p < 2; ++p) {
       const float k0 = odd ? v[2 * p + 1][0] : v[2 * p][0], k1 = odd ? v[2 * p + 1][1] : v[2 * p][1];
       const float s0 = odd ? v[2 * p][0] : v[2 * p + 1][0], s1 = odd ? v[2 * p][1] : v[2 * p + 1][1];
       const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
       const float4 out = odd ? make_float4(g0, g1, k0, k1) : make_float4(k0, k1, g0, g1);
-      const int c = nc0 + 8 * (2 * p + odd) + 2 * (t0 & 2);  // first of this lane's four consecutive columns
+      const int c = nc0 + 8 * (2 * p + odd) + 2 * (t0 & 2);
       if (FAST) {
         if (!skip_store) *reinterpret_cast<float4*>(C + (size_t)m * ldc + c) = out;
       } else if (m < M && !skip_store) {
@@ -207,6 +198,25 @@ __device__ __forceinline__ void tc_epilogue_chunk_frag(uint32_t tmem_main, uint3
       }
     }
   }
+}
+
+// The same for accumulators still in TMEM: both halves of one 32-row x 32-column chunk.
+template <bool RELU, bool FAST /* tile fully inside C, vector stores, no table: no per-element checks */>
+__device__ __forceinline__ void tc_epilogue_chunk_frag(uint32_t tmem_main, uint32_t tmem_cross, int m_base, int M, int nc0,
+                                                       int N, const float* __restrict__ bias,
+                                                       const float* __restrict__ table, const int* __restrict__ tidx,
+                                                       int ldt, float* __restrict__ C, int ldc, bool vec_ok, int lane,
+                                                       bool skip_store) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t a0[16], x0[16];  // main / cross accumulators
+    tc_ld16x256_x4(tmem_main + ((uint32_t)(16 * half) << 16), a0);
+    tc_ld16x256_x4(tmem_cross + ((uint32_t)(16 * half) << 16), x0);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(a0[i]) + __uint_as_float(x0[i]);
+    tc_epilogue_regs<RELU, FAST>(acc, half, m_base, M, nc0, N, bias, table, tidx, ldt, C, ldc, vec_ok, lane, skip_store);
   }
 }
 
@@ -622,64 +632,6 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
-}
-
-// bias / table / ReLU / coalesced stores of 16 rows x 32 columns held in the 16x256b fragment layout (see
-// tc_epilogue_chunk_frag, whose second half this is): acc = main + cross, already summed.
-template <bool RELU, bool FAST>
-__device__ __forceinline__ void tc_epilogue_regs(const float (&acc)[16], int half, int m_base, int M, int nc0, int N,
-                                                 const float* __restrict__ bias, const float* __restrict__ table,
-                                                 const int* __restrict__ tidx, int ldt, float* __restrict__ C, int ldc,
-                                                 bool vec_ok, int lane, bool skip_store) {
-  const int t0 = lane & 3, t1 = lane >> 2, odd = t0 & 1;
-  float bz[4][2];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = nc0 + 8 * k + 2 * t0;
-    if (FAST) {
-      if (bias) { const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + c)); bz[k][0] = b2.x; bz[k][1] = b2.y; }
-      else { bz[k][0] = 0.f; bz[k][1] = 0.f; }
-    } else {
-      bz[k][0] = (bias && c < N) ? __ldg(bias + c) : 0.f;
-      bz[k][1] = (bias && c + 1 < N) ? __ldg(bias + c + 1) : 0.f;
-    }
-  }
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    const int h = 2 * half + hh;
-    const int m = m_base + t1 + 8 * h;
-    const float* trow = (!FAST && table && m < M) ? table + (size_t)tidx[m] * ldt : nullptr;
-    float v[4][2];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float x = acc[4 * k + 2 * hh + e] + bz[k][e];
-        if (!FAST && trow) { const int c = nc0 + 8 * k + 2 * t0 + e; if (c < N) x += __ldg(trow + c); }
-        v[k][e] = RELU ? fmaxf(x, 0.f) : x;
-      }
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      const float k0 = odd ? v[2 * p + 1][0] : v[2 * p][0], k1 = odd ? v[2 * p + 1][1] : v[2 * p][1];
-      const float s0 = odd ? v[2 * p][0] : v[2 * p + 1][0], s1 = odd ? v[2 * p][1] : v[2 * p + 1][1];
-      const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-      const float4 out = odd ? make_float4(g0, g1, k0, k1) : make_float4(k0, k1, g0, g1);
-      const int c = nc0 + 8 * (2 * p + odd) + 2 * (t0 & 2);
-      if (FAST) {
-        if (!skip_store) *reinterpret_cast<float4*>(C + (size_t)m * ldc + c) = out;
-      } else if (m < M && !skip_store) {
-        float* dst = C + (size_t)m * ldc + c;
-        if (vec_ok && c + 3 < N) {
-          *reinterpret_cast<float4*>(dst) = out;
-        } else {
-          if (c < N) dst[0] = out.x;
-          if (c + 1 < N) dst[1] = out.y;
-          if (c + 2 < N) dst[2] = out.z;
-          if (c + 3 < N) dst[3] = out.w;
-        }
-      }
-    }
-  }
 }
 
 template <bool RELU>
