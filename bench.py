@@ -13,7 +13,10 @@ timed steps are drawn from both phases IN EPISODE PROPORTION (58 : 32): K = 90 q
 round(r 58/90) full-window steps (t >= 32) plus the remaining steps of the cached phase, ending at t = 31.  Each timed
 segment is bracketed by barrier + synchronize and timed with CUDA events; between segments the episode is
 fast-forwarded untimed.  W warm-up steps run untimed in front of each phase's segment.  So `value` is the whole-episode
-throughput for every K (the `phases` object gives the per-step time of either phase).  Scenes shard over ranks with
+throughput for every K (the `phases` object gives the per-step time of either phase).  For r > 0 it is slightly
+CONSERVATIVE: a cached step attends to t x 72 cached keys, so its cost grows linearly with t (13.6 ms at t = 1, 26.6 ms
+at t = 31 for 64 scenes, `tools/host_time_probe.py`), and the cached segment ends at t = 31 - the most expensive cached
+steps stand for the phase (whole-episode truth at 256 scenes: ~3 % above the K = 20 figure; K = 90 has no such bias).  Scenes shard over ranks with
 no data-path collective ("weak": per-GPU work fixed); the only collective is the summary all-reduce at the end of an
 evaluation, exercised in the e2e leg.
 
