@@ -1083,3 +1083,37 @@ def test_reference_signature_adapter_with_real_time_rewards(dev):
                 assert abs(vdd[v]["next_acceleration"] - a) < 1e-5 and abs(vdd[v]["next_steering"] - s_) < 1e-6
         for v in range(n):
             vdd[v]["acceleration"].append(g["accel"][v, t]); vdd[v]["steering"].append(g["steer"][v, t])
+
+
+def test_dt_multi_scene_rollout_matches_oracle_port(dev):
+    """Decision-transformer mode beyond the single fixture scene: a crowded scene (30 vehicles > the 24-agent cap, so
+    relevant-agent selection and several focal groups per step are exercised with the (rtg, state, action) order) and a
+    small one in ONE batch, min_return start (evaluated vehicles (0, -10, -10), the others (10, 90, 90)), against the
+    oracle port scene by scene: action bins, positions, dense reward, tracked RTGs."""
+    from ctrlsim_b200.config import dt_config
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    from ctrlsim_b200.weights import make_weights
+    from ctrlsim_b200.model import DeviceModel
+    from oracle.model_port import ModelPort
+    from oracle.policy_port import RolloutPort
+    cfg_dt = dt_config()
+    weights = make_weights(cfg_dt, seed=7, still_bias=2.0)
+    scenes = [make_scene(80, n_vehicles=30, n_roads=3, n_chunks=3), make_scene(81, n_vehicles=8, n_roads=2, n_chunks=3)]
+    steps = 3
+    kw = dict(predict_rtgs=False, discretize_rtgs=False, real_time_rewards=True, min_return=True)
+    pol = B200Policy(cfg_dt, "synthetic", DeviceModel(cfg_dt, weights, dev), seed=2, name="dt", **kw)
+    ev = B200PolicyEvaluator(cfg_dt, pol, scenes=scenes)
+    b = ev.build_batch(eval_threshold=8)
+    ev.rollout(b, max_steps=steps)
+    tr = b.trace()
+    port = RolloutPort(cfg_dt, ModelPort(cfg_dt, weights), seed=2, eval_threshold=8, **kw)
+    for s, sc in enumerate(scenes):
+        rec = port.run_scene(s, sc["json"], sc["preproc"], max_steps=steps)
+        n = rec["n"]
+        assert sorted(rec["evaluated"]) == b.evaluated_ids[s]
+        assert (tr["tr_act_idx"][s, :n, :steps].T == rec["act_idx"][:steps]).all()
+        assert np.abs(tr["tr_pos"][s, :n, :steps] - rec["pos"][:, :steps]).max() < POS_TOL
+        assert np.abs(tr["tr_dense"][s, :n, :steps] - rec["dense_reward"][:, :steps]).max() < 1e-9
+        assert np.abs(tr["rt_rtg"][s, :n, :steps] - rec["rtgs"][:, :steps]).max() < 1e-9
+    assert {tuple(v) for v in tr["rt_rtg"][0, :30, 0].tolist()} == {(0.0, -10.0, -10.0), (10.0, 90.0, 90.0)}
