@@ -122,14 +122,131 @@ def default_config(wide: bool = False) -> AttrDict:
     return cfg
 
 
-def dt_config(wide: bool = False) -> AttrDict:
+def dt_config(wide: bool = False, as_shipped: bool = False) -> AttrDict:
     """The decision-transformer baseline: cfgs/model/dt.yaml on top of cfgs/model/ctrl_sim.yaml
     (continuous RTG inputs, (rtg, state, action) token order, no RTG head, no future-state head) and cfgs/policy/dt.yaml
     (RTGs are not predicted but tracked in real time: they start at the maximum return and are decremented by the dense
     reward of every step)."""
     cfg = default_config(wide)
     cfg.model.decision_transformer, cfg.model.predict_rtg, cfg.model.predict_future_states = True, False, False
-    cfg.eval.policy.update(run_name="dt", model="dt", use_rtg=True, predict_rtgs=False, discretize_rtgs=False,
+    # NOTE: ``use_rtg=True`` is the evident intent of cfgs/policy/dt.yaml:11, which spells the key ``use_rtgs``; what Hydra
+    # composes from the reference's files AS SHIPPED is use_rtg=False (cfgs/policy/base.yaml:1; load_reference_config
+    # reproduces that), and then the network is fed RTG (0, 0, 0).  Both are implemented: dt_config(as_shipped=True).
+    cfg.eval.policy.update(run_name="dt", model="dt", use_rtg=not as_shipped, predict_rtgs=False, discretize_rtgs=False,
                            real_time_rewards=True, max_return=True)
+    for k in ("veh_veh_tilt", "veh_edge_tilt", "goal_tilt"):  # cfgs/policy/dt.yaml has no tilt keys
+        cfg.eval.policy.pop(k, None)
     return cfg
 
+
+
+# ---- reading the reference's own configuration tree --------------------------------------------------------------------
+def _load_group_file(cfgs_dir: str, group: str, option: str) -> dict:
+    """One file of a config group with its own ``defaults`` list composed first (Hydra semantics for the forms the
+    reference uses: ``- base`` = sibling option of the same group merged underneath; ``- /grp@key: opt`` = option
+    ``opt`` of the absolute group ``grp`` placed at ``key`` inside this file's package)."""
+    import os
+    import yaml
+    with open(os.path.join(cfgs_dir, group, option + ".yaml")) as f:
+        body = yaml.safe_load(f) or {}
+    out: dict = {}
+    for d in body.pop("defaults", None) or []:
+        if isinstance(d, str):
+            if d != "_self_":
+                _deep_merge(out, _load_group_file(cfgs_dir, group, d))
+        else:
+            (k, opt), = d.items()
+            if k.startswith("/"):
+                grp, _, at = k[1:].partition("@")
+                _deep_merge(out, {at or grp.replace("/", "."): _load_group_file(cfgs_dir, grp, opt)})
+            else:
+                sub, _, at = k.partition("@")
+                _deep_merge(out, {at or sub: _load_group_file(cfgs_dir, os.path.join(group, sub), opt)})
+    _deep_merge(out, body)
+    return out
+
+
+def _deep_merge(dst: dict, src: dict) -> dict:
+    for k, v in src.items():
+        if isinstance(v, dict) and isinstance(dst.get(k), dict):
+            _deep_merge(dst[k], v)
+        else:
+            dst[k] = copy.deepcopy(v)
+    return dst
+
+
+def _set_path(tree: dict, path: str, value):
+    keys = path.split(".")
+    for k in keys[:-1]:
+        tree = tree.setdefault(k, {})
+    if isinstance(value, dict) and isinstance(tree.get(keys[-1]), dict):
+        _deep_merge(tree[keys[-1]], value)
+    else:
+        tree[keys[-1]] = value
+
+
+def _resolve(tree: dict):
+    """``${a.b.c}`` interpolations against the root (OmegaConf); resolver calls such as ``${now:...}`` stay as they are."""
+    import re
+    pat = re.compile(r"\$\{([A-Za-z0-9_.]+)\}")
+
+    def get(path):
+        node = tree
+        for k in path.split("."):
+            node = node[k]
+        return node
+
+    def walk(node, depth=0):
+        for k, v in (node.items() if isinstance(node, dict) else enumerate(node)):
+            if isinstance(v, (dict, list)):
+                walk(v)
+            elif isinstance(v, str):
+                for _ in range(8):
+                    m = pat.fullmatch(v)
+                    if m:  # a whole-value reference keeps the referenced type
+                        v = get(m.group(1))
+                        if not isinstance(v, str):
+                            break
+                        continue
+                    new = pat.sub(lambda mm: str(get(mm.group(1))), v)
+                    if new == v:
+                        break
+                    v = new
+                node[k] = v
+    walk(tree)
+
+
+def load_reference_config(cfgs_dir: str, groups: dict | None = None, overrides: dict | None = None) -> AttrDict:
+    """Compose the reference's Hydra tree (``<cfgs_dir>/config.yaml`` + its config groups) into the attribute-dict the
+    rollout path reads - what ``@hydra.main(config_path=CONFIG_PATH, config_name="config")`` hands to ``eval_sim.py``
+    (cfgs/config.yaml:8-14, eval_sim.py:7-8), without Hydra.
+
+    ``groups``: group choices that replace the defaults list's, e.g. ``{"model": "dt", "eval.policy": "dt"}`` for
+    ``python eval_sim.py model=dt policy@eval.policy=dt`` (keys: the package the group lands in; the group directory of
+    ``eval.policy`` is ``policy``).  ``overrides``: dotted key -> value, applied last (``{"eval.eval_mode":
+    "multi_agent", "eval.policy.goal_tilt": 10}``)."""
+    import os
+    import yaml
+    with open(os.path.join(cfgs_dir, "config.yaml")) as f:
+        root = yaml.safe_load(f)
+    tree: dict = {}
+    chosen = dict(groups or {})
+    for d in root.pop("defaults", []):
+        (grp, opt), = d.items()
+        pkg = grp.replace("/", ".")
+        _set_path(tree, pkg, _load_group_file(cfgs_dir, grp, chosen.pop(pkg, opt)))
+    for pkg, opt in chosen.items():  # nested choices such as eval.policy / eval_planner_adversary.planner -> group "policy"
+        grp = {"policy": "policy", "planner": "policy", "adversary": "policy"}.get(pkg.split(".")[-1], pkg.replace(".", "/"))
+        node = tree
+        for k in pkg.split(".")[:-1]:
+            node = node.setdefault(k, {})
+        node[pkg.split(".")[-1]] = _load_group_file(cfgs_dir, grp, opt)  # a group choice REPLACES the default option
+    _deep_merge(tree, root)
+    tree.pop("hydra", None)
+    for k, v in (overrides or {}).items():
+        _set_path(tree, k, v)
+    _resolve(tree)
+    cfg = AttrDict.wrap(tree)
+    # the scenario dict is handed to pybind as-is by the reference: keep it a plain dict (cfgs/config.py:18-21)
+    cfg.nocturne["scenario"] = dict(tree["nocturne"]["scenario"])
+    return cfg

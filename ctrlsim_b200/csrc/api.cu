@@ -324,7 +324,7 @@ int ctrlsim_sim_reset(CtrlSim* h, CtrlSimBatch* b, void* stream) { return launch
 int ctrlsim_observe(CtrlSim* h, CtrlSimBatch* b, int32_t t, void* stream) { return launch_observe(*b, t, h->mc, S(stream)); }
 int ctrlsim_dense_reward(CtrlSim* h, CtrlSimBatch* b, const CtrlSimRewardParams* rp, int32_t t, void* stream) {
   if (!h || !b || !rp) return set_error(-1, "ctrlsim_dense_reward: null argument");
-  if (rp->return_mode < 0 || rp->return_mode > 2) return set_error(-2, "ctrlsim_dense_reward: return_mode=%d", rp->return_mode);
+  if (rp->return_mode < 0 || rp->return_mode > 3) return set_error(-2, "ctrlsim_dense_reward: return_mode=%d", rp->return_mode);
   return launch_dense_reward(*b, *rp, t, h->mc, S(stream));
 }
 int ctrlsim_plan_groups(CtrlSim* h, CtrlSimBatch* b, int32_t t, int32_t* n_groups_total, void* stream) {

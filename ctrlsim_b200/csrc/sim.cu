@@ -512,7 +512,9 @@ dense_reward_kernel(CtrlSimBatch b, CtrlSimRewardParams rp, int t, ModelCfg mc) 
   // RTG of step t: start value, or the previous one minus the dense reward of step t-1 (policy_evaluator.py:123-149)
   if (t < mc.steps) {
     double* rt = b.rt_rtg + (vi * mc.steps + t) * 3;
-    if (t == 0) {
+    if (rp.return_mode == 3) {  // use_rtg = False: the policy's RTG buffer is never written (policies/policy.py:89-95)
+      rt[0] = 0.0; rt[1] = 0.0; rt[2] = 0.0;
+    } else if (t == 0) {
       if (rp.return_mode == 0) { rt[0] = b.rtg_init[vi * 3]; rt[1] = b.rtg_init[vi * 3 + 1]; rt[2] = b.rtg_init[vi * 3 + 2]; }
       else if (rp.return_mode == 2 && b.evaluated[vi]) { rt[0] = 0.0; rt[1] = -10.0; rt[2] = -10.0; }
       else { rt[0] = 10.0; rt[1] = 90.0; rt[2] = 90.0; }

@@ -42,8 +42,12 @@ class B200Policy:
         #             the decision-transformer network (cfgs/model/dt.yaml): RTGs tracked from the dense reward
         #   the same tracked RTGs, discretised, with the CtRL-Sim network (predict_rtgs=False, discretize_rtgs=True)
         dt_model = bool(cfg.model.get("decision_transformer", False))
-        if not use_rtg:
-            raise NotImplementedError("use_rtg=False (the il / trajeglish baselines) is not implemented")
+        if not use_rtg and not (dt_model and real_time_rewards and not predict_rtgs):
+            # use_rtg=False with the decision-transformer network is what cfgs/policy/dt.yaml composes to AS SHIPPED (it
+            # spells the key `use_rtgs`, so cfgs/policy/base.yaml's use_rtg: False stays): the tracked RTGs never reach
+            # the policy's buffers (policies/policy.py:89-95) and the network is fed RTG (0, 0, 0) - supported
+            raise NotImplementedError("use_rtg=False is implemented for the decision-transformer baseline only (the il / "
+                                      "trajeglish baselines use other token layouts)")
         if predict_rtgs and (real_time_rewards or max_return or min_return or not discretize_rtgs or dt_model):
             raise ValueError("predict_rtgs=True needs the CtRL-Sim network with discretize_rtgs=True and no real_time_rewards "
                              "/ max_return / min_return (cfgs/policy/ctrl_sim.yaml)")
@@ -93,6 +97,8 @@ class B200Policy:
     def _reward_params(self):
         # policy_evaluator.py:127-143: max_return wins over min_return
         mode = "max_return" if self.max_return else ("min_return" if self.min_return else "data")
+        if not self.use_rtg:
+            mode = "unused"
         return _lib.make_reward_params(self.cfg, mode)
 
     def _stream(self):

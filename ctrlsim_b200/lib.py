@@ -218,7 +218,7 @@ def make_config(cfg) -> CtrlSimConfig:
         rtg_max=(C.c_double * 3)(w.max_rtg_pos, w.max_rtg_veh, w.max_rtg_road))
 
 
-RETURN_MODES = {"data": 0, "max_return": 1, "min_return": 2}
+RETURN_MODES = {"data": 0, "max_return": 1, "min_return": 2, "unused": 3}
 
 
 def make_reward_params(cfg, return_mode: str = "data") -> CtrlSimRewardParams:

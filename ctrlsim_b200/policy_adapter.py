@@ -71,8 +71,8 @@ class B200AutoregressivePolicy:
                                     privileged_return, max_return, min_return, key_dict, tilt_dict, name,
                                     action_temperature, nucleus_sampling, nucleus_threshold, seed=seed)
             backend = _DeviceBackend(self.inner)
-        elif not use_rtg or (not predict_rtgs and not real_time_rewards):
-            raise NotImplementedError("use_rtg=False / RTGs that are neither predicted nor tracked are not implemented")
+        elif not predict_rtgs and not real_time_rewards:
+            raise NotImplementedError("RTGs that are neither predicted nor tracked are not implemented")
         self.backend = backend
         # what the reference's Policy.__init__ keeps and its evaluator reads (policy_evaluator.py:39-41,123-143,417-423)
         self.cfg = cfg.copy()

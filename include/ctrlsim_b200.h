@@ -127,7 +127,8 @@ typedef struct CtrlSimRewardParams {
   double veh_veh_collision_rew_multiplier, veh_edge_collision_rew_multiplier;    /* 10, 10 */
   double pos_goal_shaped_min, pos_goal_shaped_max, pos_target_achieved_rew_multiplier; /* 0, 0.2, 10 */
   int32_t remove_shaped_goal, remove_shaped_veh_reward, remove_shaped_edge_reward;     /* 1, 0, 0 */
-  int32_t return_mode;  /* 0: rtg_init; 1: max_return (10, 90, 90); 2: min_return (evaluated vehicles (0, -10, -10)) */
+  int32_t return_mode;  /* 0: rtg_init; 1: max_return (10, 90, 90); 2: min_return (evaluated vehicles (0, -10, -10));
+                         * 3: use_rtg = False - rt_rtg stays (0, 0, 0), the dense reward is still traced */
 } CtrlSimRewardParams;
 
 typedef struct CtrlSim CtrlSim;

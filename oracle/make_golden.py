@@ -46,6 +46,12 @@ FIXTURES = {
     # road-edge polylines, nearest-vehicle distance, collision flags) every step.
     "dt": dict(scene=dict(scene_id=11, n_vehicles=10, n_roads=2, n_chunks=4), weights=dict(seed=3), tilts=(0, 0, 0),
                logit_steps=(0, 9, 31, 32, 60), policy="dt"),
+    # dt_as_shipped: the same baseline with the switches Hydra actually composes from the reference's files:
+    # cfgs/policy/dt.yaml:11 spells the key `use_rtgs`, so `eval.policy.use_rtg` keeps cfgs/policy/base.yaml's False and
+    # Policy.update_state never copies the tracked RTGs (policies/policy.py:89-95) - the network is fed RTG (0, 0, 0)
+    # at every step while the evaluator still tracks them.  34 steps (the reference needs steps >= its 32-step window).
+    "dt_as_shipped": dict(scene=dict(scene_id=11, n_vehicles=10, n_roads=2, n_chunks=4), weights=dict(seed=3),
+                          tilts=(0, 0, 0), logit_steps=(9, 33), policy="dt", use_rtg=False, steps=34),
 }
 
 DT_POLICY = dict(predict_rtgs=False, discretize_rtgs=False, real_time_rewards=True, max_return=True, name="dt",
@@ -104,7 +110,8 @@ def main():
         weights = make_weights(dt_model_cfg(default_config()) if dt else default_config(), **spec["weights"])
         metrics, recs = run_reference([sc], weights=weights, seed=0, tilts=spec["tilts"],
                                       logit_steps=spec["logit_steps"], steps=spec.get("steps", 90),
-                                      cfg_hook=dt_model_cfg if dt else None, policy_opts=DT_POLICY if dt else None)
+                                      cfg_hook=dt_model_cfg if dt else None,
+                                      policy_opts=dict(DT_POLICY, use_rtg=spec.get("use_rtg", True)) if dt else None)
         np.savez_compressed(os.path.join(GOLDEN, f"rollout_{name}.npz"), **pack(recs[0], metrics, spec))
         print(f"[golden] {name}: {time.time() - t0:.1f}s metrics={metrics}", flush=True)
 

@@ -150,7 +150,7 @@ class MetricsPort:
 class RolloutPort:
     def __init__(self, cfg, model, seed=0, tilts=(0, 0, 0), temperature=1.0, eval_threshold=None, nucleus=None,
                  contacts=True, fp64_trig=False, predict_rtgs=True, discretize_rtgs=True, real_time_rewards=False,
-                 max_return=False, min_return=False):
+                 max_return=False, min_return=False, use_rtg=True):
         self.cfg, self.model = cfg, model
         # Policy constructor switches (policies/policy.py:9-39; cfgs/policy/dt.yaml sets predict_rtgs=False,
         # discretize_rtgs=False, real_time_rewards=True, max_return=True): with real_time_rewards the RTG series is the
@@ -158,6 +158,9 @@ class RolloutPort:
         # (policy_evaluator.py:123-149) instead of being sampled from the RTG head
         self.predict_rtgs, self.discretize_rtgs, self.real_time = predict_rtgs, discretize_rtgs, real_time_rewards
         self.max_return, self.min_return = max_return, min_return
+        # use_rtg=False: Policy.update_state never copies RTGs into the policy's buffers (policies/policy.py:89-95), the
+        # network is fed RTG (0, 0, 0); this is what cfgs/policy/dt.yaml composes to as shipped (its key is `use_rtgs`)
+        self.use_rtg = use_rtg
         self.w, self.m = cfg.dataset.waymo, cfg.model
         self.seed, self.tilts, self.temperature = seed, tilts, float(temperature)
         self.nucleus = nucleus  # None, or the nucleus threshold p (autoregressive_policy.py:216-230)
@@ -355,8 +358,9 @@ class RolloutPort:
         ep["timesteps"][:, t, 0] = t
         if t > 0:
             ep["actions"][:, t - 1, 0], ep["actions"][:, t - 1, 1] = rec["accel"][:, t - 1], rec["steer"][:, t - 1]
-            ep["rtgs"][:, t - 1] = prec["rtgs"][:, t - 1]
-        if self.real_time:  # policies/policy.py:93-95: the RTG of the CURRENT step is known before the forward
+            if self.use_rtg:
+                ep["rtgs"][:, t - 1] = prec["rtgs"][:, t - 1]
+        if self.real_time and self.use_rtg:  # policies/policy.py:93-95: the RTG of the CURRENT step is known before the forward
             ep["rtgs"][:, t] = prec["rtgs"][:, t]
         ep["goals"][:, t] = np.stack([goal[:, 0], goal[:, 1], goal[:, 3] * np.cos(goal[:, 2]),
                                       goal[:, 3] * np.sin(goal[:, 2]), goal[:, 2]], -1)[:, : w.goal_dim]

@@ -1117,3 +1117,37 @@ def test_dt_multi_scene_rollout_matches_oracle_port(dev):
         assert np.abs(tr["tr_dense"][s, :n, :steps] - rec["dense_reward"][:, :steps]).max() < 1e-9
         assert np.abs(tr["rt_rtg"][s, :n, :steps] - rec["rtgs"][:, :steps]).max() < 1e-9
     assert {tuple(v) for v in tr["rt_rtg"][0, :30, 0].tolist()} == {(0.0, -10.0, -10.0), (10.0, 90.0, 90.0)}
+
+
+def test_dt_as_shipped_rollout_matches_reference(dev):
+    """The decision-transformer baseline with the switches Hydra composes from the reference's files AS SHIPPED:
+    cfgs/policy/dt.yaml:11 spells `use_rtgs`, so use_rtg stays False and the network is fed RTG (0, 0, 0) while the
+    evaluator keeps computing the dense reward.  34 free-running steps (two of them with the sliding window) vs the
+    unmodified reference evaluator: sampled action bins, states bit for bit, dense reward; the policy's RTG buffer is zero."""
+    from ctrlsim_b200.config import dt_config
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    g, spec, _ = load_golden("dt_as_shipped")
+    cfg_dt = dt_config(as_shipped=True)
+    cfg_dt.nocturne = cfg_dt.nocturne.copy()
+    cfg_dt.nocturne.steps = spec["steps"]
+    p = cfg_dt.eval.policy
+    assert p.use_rtg is False
+    pol = B200Policy(cfg_dt, "synthetic", _model(cfg_dt, spec, dev), use_rtg=p.use_rtg, predict_rtgs=p.predict_rtgs,
+                     discretize_rtgs=p.discretize_rtgs, real_time_rewards=p.real_time_rewards, max_return=p.max_return,
+                     min_return=p.min_return, name="dt", seed=0)
+    ev = B200PolicyEvaluator(cfg_dt, pol, scenes=[make_scene(**spec["scene"])])
+    b = ev.build_batch(eval_threshold=64)
+    ev.rollout(b)
+    tr = b.trace()
+    T, n = spec["steps"], g["pos"].shape[0]
+    assert (tr["tr_act_idx"][0, :n, :T].T == g["act_idx"][:T]).all()
+    ex = g["existence"][:, :T + 1].astype(bool)
+    assert (tr["tr_pos"][0, :n, :T + 1].astype(np.float64)[ex] == g["pos"][:, :T + 1][ex]).all()
+    assert (tr["tr_heading"][0, :n, :T + 1].astype(np.float64)[ex] == g["heading"][:, :T + 1][ex]).all()
+    assert np.abs(tr["tr_dense"][0, :n, :T + 1] - g["dense_reward"][:, :T + 1])[ex].max() < 1e-9
+    assert (tr["rt_rtg"][0] == 0).all()
+    d_act = np.abs(pol.model.forward_tokens_dt({**{k: g[f"in_33_{k}"][None] for k in ("agent_states", "agent_types", "goals", "actions", "road_points", "road_types")},
+                                                "rtgs": g["in_33_rtgs_pass1"][None], "timesteps": g["in_33_timesteps"][None][:, 0, :, 0]}, 32)[0, :n]
+                   - g["action_logits_33_0"][:n]).max()
+    assert d_act < LOGIT_TOL, d_act

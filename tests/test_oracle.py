@@ -1197,3 +1197,65 @@ def test_unsupported_simulator_switches_fail_loudly(cfg):
             c.nocturne["rew_cfg"][key] = val
         with pytest.raises(NotImplementedError):
             L.check_fixed_switches(c)
+
+
+@needs_reference
+def test_restated_config_equals_the_reference_yaml_tree(cfg):
+    """ctrlsim_b200.config restates the constants of the reference's Hydra tree; load_reference_config composes the tree
+    itself (cfgs/config.yaml + groups, without Hydra).  Every key default_config() defines must exist in the composed
+    tree with the same value, except paths and three deliberate defaults (eval_mode, the two verbose flags); the same for
+    dt_config(as_shipped=True) against `model=dt policy@eval.policy=dt` - which pins the `use_rtgs` typo of
+    cfgs/policy/dt.yaml:11: as shipped, the DT baseline runs with use_rtg=False."""
+    from ctrlsim_b200.config import dt_config, load_reference_config
+
+    def flat(x, pre=""):
+        out = {}
+        for k, v in x.items():
+            if isinstance(v, dict):
+                out.update(flat(v, pre + k + "."))
+            else:
+                out[pre + k] = v
+        return out
+
+    def compare(mine, ref, allowed):
+        fm, fr = flat(mine), flat(ref)
+        assert [k for k in fm if k not in fr] == []
+        diff = {k for k in fm if fm[k] != fr[k] and not (isinstance(fr[k], str) and not isinstance(fm[k], str) and float(fr[k]) == fm[k])}
+        paths = {k for k in diff if isinstance(fr[k], str) and ("/" in fr[k])}
+        assert diff - paths == allowed, (diff - paths, allowed)
+
+    ref = load_reference_config("/root/reference/cfgs")
+    compare(cfg, ref, {"eval.eval_mode", "eval.verbose", "eval_planner_adversary.verbose"})
+    assert ref.eval.eval_mode == "one_agent" and ref.eval.policy.model == "ctrl_sim" and ref.nocturne.steps == 90
+    assert ref.eval_planner_adversary.planner.goal_tilt == 10 and ref.eval_planner_adversary.adversary.veh_veh_tilt == -10
+    assert isinstance(ref.nocturne["scenario"], dict) and not hasattr(ref.nocturne["scenario"], "copy_") and "hydra" not in ref
+    ref_dt = load_reference_config("/root/reference/cfgs", groups={"model": "dt", "eval.policy": "dt"},
+                                   overrides={"eval.eval_mode": "multi_agent"})
+    assert ref_dt.eval.policy.use_rtg is False and ref_dt.eval.policy.use_rtgs is True  # the typo, as shipped
+    assert ref_dt.model.decision_transformer is True and ref_dt.eval.policy.real_time_rewards is True
+    compare(dt_config(as_shipped=True), ref_dt, {"eval.verbose", "eval_planner_adversary.verbose"})
+    assert dt_config().eval.policy.use_rtg is True  # the intended mode stays the default of dt_config()
+
+
+def test_rollout_port_dt_as_shipped_matches_reference_prefix():
+    """cfgs/policy/dt.yaml AS SHIPPED (use_rtg=False through the `use_rtgs` typo): the unmodified reference evaluator feeds
+    the DT network RTG (0, 0, 0) at every step while it keeps tracking the returns (tests/golden/rollout_dt_as_shipped.npz,
+    oracle/make_golden.py).  Oracle port with use_rtg=False: same sampled actions, trajectories, dense reward, and the
+    evaluator-side RTG series."""
+    from ctrlsim_b200.config import dt_config
+    from ctrlsim_b200.synth import make_scene
+    from ctrlsim_b200.weights import make_weights
+    from oracle.model_port import ModelPort
+    from oracle.policy_port import RolloutPort
+    g, spec, _ = load_golden("dt_as_shipped")
+    cfg = dt_config(as_shipped=True)
+    fed = np.unique(g["in_9_rtgs_pass1"].reshape(-1, 3), axis=0)  # normalised zeros; (0, 0, 0) = padding rows
+    assert len(fed) == 2 and np.allclose(fed, [[0.0, 0.0, 0.0], [0.0, 0.1, 0.1]])
+    steps = 6
+    port = RolloutPort(cfg, ModelPort(cfg, make_weights(cfg, **spec["weights"])), seed=0, eval_threshold=64,
+                       predict_rtgs=False, discretize_rtgs=False, real_time_rewards=True, max_return=True, use_rtg=False)
+    sc = make_scene(**spec["scene"])
+    rec = port.run_scene(0, sc["json"], sc["preproc"], max_steps=steps)
+    assert (rec["act_idx"][:steps] == g["act_idx"][:steps]).all()
+    for k in ("pos", "vel", "heading", "existence", "dense_reward", "rtgs"):
+        assert np.abs(rec[k][:, :steps] - g[k][:, :steps]).max() < 1e-9, k
