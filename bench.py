@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=256, help="focal groups per workspace chunk")
     ap.add_argument("--wide", action="store_true", help="wide model variant: A=64 agents / P=256 polylines per group")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-sub-batch", type=int, default=64, help="scenes per pipelined sub-batch of the e2e leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-torch-gpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=1)
@@ -385,27 +386,25 @@ def main():
         host_bytes = sum(v.numel() * v.element_size() for k, v in batch.t.items())
         t0 = time.perf_counter()
         ev2 = B200PolicyEvaluator(cfg, pol, scenes=scenes, scene_ids=ids)
-        ev2.rank, ev2.world = 0, 1
-        b2 = ev2.build_batch(eval_threshold=64)       # host parse + H2D of the scene batch
-        ev2.rank, ev2.world = rank, world
-        t_h2d = time.perf_counter()
-        ev2.batch = b2
-        ev2.rollout(b2)
-        summ = ev2.summarize(b2)                       # metrics kernel + the one all-reduce + D2H
-        tr = b2.trace()                                # D2H of the per-vehicle trace
+        ev2.scenes_presharded = True  # every rank owns all of ITS scenes (sharded above); the all-reduce still spans ranks
+        # the call a user makes: host parse + H2D (next sub-batch on a side stream while the current one rolls out) +
+        # 90 steps + metrics kernel + D2H of the per-vehicle traces, per sub-batch of 64 scenes; then the one all-reduce
+        m_e2e, _ = ev2.evaluate_policy(sub_batch_scenes=args.e2e_sub_batch, eval_threshold=64, keep_traces=True)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        d2h = sum(v.nbytes for v in tr.values()) + summ.nbytes
+        summ = ev2.last_summary
+        d2h = sum(v.nbytes for tr in ev2.traces for v in tr.values()) + summ.nbytes
         w = torch.tensor([wall], dtype=torch.float64, device=dev)
-        a = torch.tensor([float(b2.n_evaluated() * n_ep)], dtype=torch.float64, device=dev)
+        a = torch.tensor([float(ev2.n_evaluated * n_ep)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(w, op=dist.ReduceOp.MAX)
             dist.all_reduce(a, op=dist.ReduceOp.SUM)
         e2e = {"value": a.item() / w.item(), "unit": "agent-steps/s",
                "h2d_bytes_per_step": int(host_bytes / n_ep), "d2h_bytes_per_step": int(d2h / n_ep),
-               "episode_wall_s": w.item(), "host_parse_and_upload_s": t_h2d - t0,
-               "what": "B200PolicyEvaluator.evaluate_policy() pieces from host scene arrays: one whole 90-step episode",
-               "metrics": ev2.metrics_from_summary(summ) if rank == 0 else None}
+               "episode_wall_s": w.item(), "sub_batch_scenes": args.e2e_sub_batch,
+               "what": "B200PolicyEvaluator.evaluate_policy(sub_batch_scenes=...) from host scene dicts: whole 90-step "
+                       "episodes, the next sub-batch parsed + uploaded while the current one rolls out",
+               "metrics": m_e2e if rank == 0 else None}
 
     if rank != 0:
         if world > 1:

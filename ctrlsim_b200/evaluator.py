@@ -215,6 +215,7 @@ class B200PolicyEvaluator:
         self._from_files = scenes is None
         self.scenes = [] if scenes is None else scenes
         self.scene_ids = list(range(len(self.scenes))) if scene_ids is None else list(scene_ids)
+        self.scenes_presharded = False  # True: ``scenes`` already is this rank's share (no k mod world selection)
         self.batch = None
         self.last_summary = None
         self.contact_overflow = 0
@@ -232,10 +233,11 @@ class B200PolicyEvaluator:
                 pre = pickle.load(f)
             yield i, {"name": name, "json": js, "preproc": pre}
 
-    def select_scenes(self, eval_threshold=None, keep_replay_only=False):
-        """Host half of build_batch: walk the scenes in file order with the evaluation's seeded generator, draw the
-        evaluated vehicles of each (policy_evaluator.py:450-464) and keep this rank's share (scene k -> rank k mod
-        world, k counting accepted scenes). Returns (scenes, ids, parsed, evaluated_sets, threshold)."""
+    def iter_selected(self, eval_threshold=None, keep_replay_only=False):
+        """Walk the scenes in file order with the evaluation's seeded generator, draw the evaluated vehicles of each
+        (policy_evaluator.py:450-464) and yield this rank's share (scene k -> rank k mod world, k counting accepted
+        scenes) one at a time as (scene, id, parsed, evaluated_set) - so that a caller can overlap the host-side
+        parsing of later scenes with the device work on earlier ones (evaluate_policy(sub_batch_scenes=...))."""
         from .scenario import interesting_pairs, parse_scenario
         cfg = self.cfg
         mode = cfg.eval.eval_mode
@@ -251,7 +253,6 @@ class B200PolicyEvaluator:
         else:
             source = zip(self.scene_ids, self.scenes)
             limit = None
-        mine, mine_ids, mine_parsed, mine_ev = [], [], [], []
         accepted = 0
         for sid, s in source:
             if limit is not None and accepted == limit:
@@ -268,16 +269,24 @@ class B200PolicyEvaluator:
                 ev = [] if pick is None else ([pick[0]] if mode == "one_agent" else [pick[0], pick[1]])
             if not ev and not keep_replay_only:
                 continue  # no candidate agent: scene skipped (policy_evaluator.py:461-464)
-            own = accepted % self.world == self.rank
+            own = self.scenes_presharded or accepted % self.world == self.rank
             accepted += 1
             if self._from_files:
                 self.scenes.append(s if own else None)  # other ranks' scenes are not kept in memory
                 self.scene_ids.append(sid)
             if own:
-                mine.append(s)
-                mine_ids.append(sid)
-                mine_parsed.append(p)
-                mine_ev.append(ev)
+                yield s, sid, p, ev
+
+    def select_scenes(self, eval_threshold=None, keep_replay_only=False):
+        """Host half of build_batch: all of this rank's scenes at once. Returns (scenes, ids, parsed, evaluated_sets,
+        threshold)."""
+        thr = self.cfg.eval.multi_agent_eval_threshold if eval_threshold is None else eval_threshold
+        mine, mine_ids, mine_parsed, mine_ev = [], [], [], []
+        for s, sid, p, ev in self.iter_selected(eval_threshold, keep_replay_only):
+            mine.append(s)
+            mine_ids.append(sid)
+            mine_parsed.append(p)
+            mine_ev.append(ev)
         return mine, mine_ids, mine_parsed, mine_ev, thr
 
     def build_batch(self, eval_threshold=None, keep_replay_only=False):
@@ -304,7 +313,7 @@ class B200PolicyEvaluator:
             pol.update_state(b, self.steps)
         return b
 
-    def summarize(self, batch=None):
+    def summarize(self, batch=None, local_only=False):
         b = batch or self.batch
         dev = self.policy.model.device
         out_scene = torch.zeros(b.S, 8, dtype=torch.float64, device=dev)
@@ -320,6 +329,8 @@ class B200PolicyEvaluator:
                               "scenes no longer follow the reference's Box2D step")
         # flat summary: [goal_sum, n_agents, sum_scene_coll, sum_scene_off, n_scenes_with_agents, ade_sum, fde_sum, 0]
         summ = torch.cat([out_scene.sum(0), out_hist.to(torch.float64).flatten()])
+        if local_only:  # a sub-batch of a pipelined evaluation: the caller adds the summaries up and reduces once
+            return summ.cpu().numpy()
         if self.world > 1:
             torch.distributed.all_reduce(summ)  # the one collective of an evaluation
         self.last_summary = summ.cpu().numpy()
@@ -395,9 +406,77 @@ class B200PolicyEvaluator:
             json.dump(ser, f)
         return path
 
-    def evaluate_policy(self):
-        if self.batch is None:
-            self.build_batch()
-        self.rollout()
-        m = self.metrics_from_summary(self.summarize(), self.cfg_rl_waymo.accel_discretization)
+    def evaluate_policy(self, sub_batch_scenes=None, eval_threshold=None, keep_traces=False):
+        """PolicyEvaluator.evaluate_policy() -> (metrics_dict, [str]).
+
+        ``sub_batch_scenes``: evaluate this rank's scenes in sub-batches of that many scenes, with a host thread that
+        parses the next sub-batch's scenario JSONs and uploads its arrays WHILE the device rolls the current one out
+        (parsing is ~6 ms of Python per 64-vehicle scene; the device needs ~0.18 s per scene-episode, so everything but
+        the first sub-batch's parse is hidden).  Scene results do not depend on how scenes are batched
+        (test_full_size_batch_is_deterministic_and_shard_invariant) and the summary vectors add, so the metrics are
+        those of the one-batch evaluation.  ``keep_traces``: keep every sub-batch's trace() in ``self.traces``."""
+        if sub_batch_scenes is None:
+            if self.batch is None:
+                self.build_batch(eval_threshold)
+            self.rollout()
+            if keep_traces:
+                self.traces = [self.batch.trace()]
+            m = self.metrics_from_summary(self.summarize(), self.cfg_rl_waymo.accel_discretization)
+            return m, ["{}: {:.6f}".format(k, v) for k, v in m.items()]
+        import queue
+        import threading
+        thr = self.cfg.eval.multi_agent_eval_threshold if eval_threshold is None else eval_threshold
+        dev = self.policy.model.device
+        q: "queue.Queue" = queue.Queue(maxsize=2)
+
+        on_gpu = torch.device(dev).type == "cuda"
+        side = torch.cuda.Stream(device=dev) if on_gpu else None  # uploads must not queue behind the rollout's kernels
+
+        def upload(cur):
+            if side is None:
+                return SceneBatch(self.cfg, cur[0], cur[1], dev, thr, parsed=cur[2], evaluated_sets=cur[3])
+            with torch.cuda.stream(side):
+                b = SceneBatch(self.cfg, cur[0], cur[1], dev, thr, parsed=cur[2], evaluated_sets=cur[3])
+            side.synchronize()  # the consumer uses the arrays on its own stream
+            return b
+
+        def producer():
+            try:
+                cur = ([], [], [], [])
+                for item in self.iter_selected(eval_threshold):
+                    for lst, v in zip(cur, item):
+                        lst.append(v)
+                    if len(cur[0]) == sub_batch_scenes:
+                        q.put(upload(cur))
+                        cur = ([], [], [], [])
+                if cur[0]:
+                    q.put(upload(cur))
+                q.put(None)
+            except BaseException as e:  # noqa: BLE001 - handed to the consumer, which re-raises it
+                q.put(e)
+
+        th = threading.Thread(target=producer, daemon=True)
+        th.start()
+        total, self.traces, self.n_evaluated, overflow = None, [], 0, 0
+        while True:
+            b = q.get()
+            if b is None:
+                break
+            if isinstance(b, BaseException):
+                raise b
+            self.batch = b
+            self.rollout(b)
+            sm = self.summarize(b, local_only=True)
+            overflow += self.contact_overflow
+            total = sm if total is None else total + sm
+            self.n_evaluated += b.n_evaluated()
+            if keep_traces:
+                self.traces.append(b.trace())
+        th.join()
+        self.contact_overflow = overflow
+        summ = torch.as_tensor(total if total is not None else np.zeros(8 + 8 * 200), dtype=torch.float64, device=dev)
+        if self.world > 1:
+            torch.distributed.all_reduce(summ)  # the one collective of an evaluation (SURVEY 8(e))
+        self.last_summary = summ.cpu().numpy()
+        m = self.metrics_from_summary(self.last_summary, self.cfg_rl_waymo.accel_discretization)
         return m, ["{}: {:.6f}".format(k, v) for k, v in m.items()]

@@ -1151,3 +1151,31 @@ def test_dt_as_shipped_rollout_matches_reference(dev):
                                                 "rtgs": g["in_33_rtgs_pass1"][None], "timesteps": g["in_33_timesteps"][None][:, 0, :, 0]}, 32)[0, :n]
                    - g["action_logits_33_0"][:n]).max()
     assert d_act < LOGIT_TOL, d_act
+
+
+def test_pipelined_evaluation_equals_one_batch(cfg, dev):
+    """evaluate_policy(sub_batch_scenes=2) - next sub-batch parsed and uploaded on a side stream while the current one
+    rolls out - gives the metrics and, scene by scene, the traces of the one-batch evaluation (whole 90-step episodes)."""
+    from ctrlsim_b200.evaluator import B200Policy, B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    from ctrlsim_b200.weights import make_weights
+    from ctrlsim_b200.model import DeviceModel
+    scenes = [make_scene(500 + i, n_vehicles=6 + 3 * i, n_roads=2, n_chunks=3) for i in range(5)]
+    ids = [500 + i for i in range(5)]
+    model = DeviceModel(cfg, make_weights(cfg, seed=4, still_bias=3.0), dev)
+    one = B200PolicyEvaluator(cfg, B200Policy(cfg, "synthetic", model, seed=1), scenes=scenes, scene_ids=ids)
+    m1, _ = one.evaluate_policy(keep_traces=True)
+    pip = B200PolicyEvaluator(cfg, B200Policy(cfg, "synthetic", model, seed=1), scenes=scenes, scene_ids=ids)
+    m2, _ = pip.evaluate_policy(sub_batch_scenes=2, keep_traces=True)
+    assert len(pip.traces) == 3 and pip.n_evaluated == one.batch.n_evaluated()
+    for k in m1:
+        assert abs(m1[k] - m2[k]) <= 1e-12 * max(1.0, abs(m1[k])), (k, m1[k], m2[k])
+    assert np.array_equal(one.last_summary[8:], pip.last_summary[8:])  # histograms: integers, exact
+    s = 0
+    for tr in pip.traces:
+        for j in range(tr["tr_pos"].shape[0]):
+            n = int(tr["n_veh"][j])
+            for f in ("tr_act_idx", "tr_rtg_idx", "tr_pos", "tr_heading", "tr_exist"):
+                assert np.array_equal(tr[f][j, :n], one.traces[0][f][s, :n]), (s, f)
+            s += 1
+    assert s == 5

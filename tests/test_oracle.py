@@ -1259,3 +1259,49 @@ def test_rollout_port_dt_as_shipped_matches_reference_prefix():
     assert (rec["act_idx"][:steps] == g["act_idx"][:steps]).all()
     for k in ("pos", "vel", "heading", "existence", "dense_reward", "rtgs"):
         assert np.abs(rec[k][:, :steps] - g[k][:, :steps]).max() < 1e-9, k
+
+
+def test_pipelined_evaluation_plumbing_on_cpu(cfg):
+    """evaluate_policy(sub_batch_scenes=k): the producer thread hands over sub-batches in scene order whose scenes,
+    global ids and evaluated-vehicle draws are exactly those of the one-batch selection (the seeded generator is
+    walked once, in order), the per-sub-batch summaries are added, and an error in the producer reaches the caller."""
+    import types
+    from ctrlsim_b200.evaluator import B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    scenes = [make_scene(400 + i, n_vehicles=5 + 2 * i, n_roads=2, n_chunks=3) for i in range(7)]
+    ids = [400 + i for i in range(7)]
+    fake = types.SimpleNamespace(model=types.SimpleNamespace(device="cpu"))
+    c = cfg.copy()
+    c.eval = cfg.eval.copy()
+    c.eval.multi_agent_eval_threshold = 4  # random.sample is exercised
+
+    class Ev(B200PolicyEvaluator):
+        def rollout(self, batch=None, max_steps=None):
+            self.seen.append(batch)
+            return batch
+
+        def summarize(self, batch=None, local_only=False):
+            assert local_only
+            v = np.zeros(8 + 8 * 200)
+            v[1] = batch.n_evaluated()
+            v[4] = batch.S
+            return v
+
+        @staticmethod
+        def metrics_from_summary(s, accel_bins=20):
+            return {"n_agents": float(s[1]), "n_scenes": float(s[4])}
+
+    one = B200PolicyEvaluator(c, fake, scenes=scenes, scene_ids=ids)
+    _, want_ids, _, want_ev, _ = one.select_scenes()
+    ev = Ev(c, fake, scenes=scenes, scene_ids=ids)
+    ev.seen = []
+    m, lines = ev.evaluate_policy(sub_batch_scenes=3)
+    assert [b.S for b in ev.seen] == [3, 3, 1] and m == {"n_agents": float(sum(len(e) for e in want_ev)), "n_scenes": 7.0}
+    got_ids = [int(i) for b in ev.seen for i in b.t["scene_id"].tolist()]
+    got_ev = [e for b in ev.seen for e in b.evaluated_ids]
+    assert got_ids == want_ids and got_ev == [sorted(e) for e in want_ev]
+    assert ev.n_evaluated == sum(len(e) for e in want_ev) and len(lines) == 2
+    bad = Ev(c, fake, scenes=scenes[:2] + [{"json": {"objects": "broken"}, "preproc": {}}], scene_ids=[1, 2, 3])
+    bad.seen = []
+    with pytest.raises(Exception):
+        bad.evaluate_policy(sub_batch_scenes=2)
