@@ -48,7 +48,9 @@ class SceneBatch:
         # real-time rewards: the road-edge polylines the signed distance is measured to, and the RTGs of
         # the logged episode at t = 0 when the *_physics.pkl carries what they are derived from
         # (a scene handed over pre-parsed, without its JSON, may carry them as 'edge_polylines'; else it has none)
-        edges = [road_edge_polylines(s["json"]) if "json" in s else list(s.get("edge_polylines", [])) for s in scenes]
+        edges = [p["edge_polylines"] if "edge_polylines" in p else
+                 (road_edge_polylines(s["json"]) if "json" in s else list(s.get("edge_polylines", [])))
+                 for s, p in zip(scenes, parsed)]
         S = len(scenes)
         N = max(1, max((p["n"] for p in parsed), default=0))  # S == 0: a rank without scenes (more ranks than scenes)
         if N > MAX_VEH:

@@ -63,13 +63,15 @@ def parse_scenario(scen: dict, steps: int = 90, moving_threshold: float = 0.2, s
             dx, dy = pos[:, 0] - target[i, 0], pos[:, 1] - target[i, 1]
             dist = np.sqrt(dx * dx + dy * dy)
             moving[i] = bool(((sp > np.float32(speed_threshold)) | (dist > np.float32(moving_threshold)))[valid].any())
-    segs = []
+    segs, edge_polylines = [], []  # one pass over the roads: collision segments and road_edge_polylines() at once
     for road in scen["roads"]:
         g = road["geometry"]
-        if road["type"] != "road_edge" or isinstance(g, dict) or len(g) < 2:
+        if road["type"] != "road_edge" or isinstance(g, dict):
             continue
         pts = np.array([(q["x"], q["y"]) for q in g], np.float32).reshape(len(g), 2)
-        segs.append(np.concatenate([pts[:-1], pts[1:]], axis=1))
+        edge_polylines.append(pts.astype(np.float64))
+        if len(g) >= 2:
+            segs.append(np.concatenate([pts[:-1], pts[1:]], axis=1))
     segs = np.concatenate(segs, axis=0) if segs else np.zeros((0, 4), np.float32)
     # goals (evaluators/evaluator.py:60-76), float64 views of float32 values
     goal = np.zeros((n, 4), np.float64)
@@ -87,7 +89,7 @@ def parse_scenario(scen: dict, steps: int = 90, moving_threshold: float = 0.2, s
         goal[i] = (gp[0], gp[1], gh, gs)
     goal_norm = np.linalg.norm(gt[:, 0, :2].astype(np.float64) - goal[:, :2], axis=1)
     return dict(n=n, gt=gt, gt_valid=gt_valid, size=size, moving=moving, goal=goal, goal_norm=goal_norm,
-                segs=segs, goal_idx=goal_idx)
+                segs=segs, goal_idx=goal_idx, edge_polylines=edge_polylines)
 
 
 def interesting_pairs(parsed: dict, candidates, history_steps: int = 10, traj_len_threshold: int = 60,
