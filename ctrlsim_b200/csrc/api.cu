@@ -511,6 +511,16 @@ int ctrlsim_layernorm(const float* X, const float* R, const float* gamma, const 
                       int32_t relu, void* stream) {
   return launch_layernorm(X, R, gamma, beta, Y, M, H, H, H, relu != 0, S(stream));
 }
+int ctrlsim_linear_res_ln(const float* A, const float* W, const float* bias, float* X, const float* gamma,
+                          const float* beta, float* scratch, int32_t M, int32_t K, void* stream) {
+  const int rc = launch_gemm_res_ln(A, K, W, K, bias, X, H, gamma, beta, M, K, S(stream));
+  if (rc != 1) return rc;
+  if (!scratch) return set_error(-2, "ctrlsim_linear_res_ln: the fused kernel cannot serve this call and no scratch buffer was given");
+  GemmArgs g;
+  g.A = A; g.W = W; g.bias = bias; g.C = scratch; g.M = M; g.N = H; g.K = K; g.lda = K; g.ldw = K; g.ldc = H;
+  if (int r2 = launch_gemm(g, S(stream))) return r2;
+  return launch_layernorm(X, scratch, gamma, beta, X, M, H, H, H, false, S(stream));
+}
 int ctrlsim_attn_padded(const float* Q, int32_t ldq, const float* K, const float* V, int32_t ldkv,
                         const uint8_t* key_pad, float* O, int32_t G, int32_t Lq, int32_t Lk, void* stream) {
   return launch_attn_padded(Q, ldq, K, V, ldkv, key_pad, O, H, G, Lq, Lk, S(stream));

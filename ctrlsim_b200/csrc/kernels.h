@@ -20,6 +20,9 @@ struct GemmArgs {
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t st);     // dispatches to the tcgen05 kernel unless CTRLSIM_GEMM=simt
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);  // gemm_tc.cu
+// X = LayerNorm(X + A W^T + bias) * gamma + beta, N = H = 256, fused (gemm_tc.cu); 1 = not applicable, run the two steps
+int launch_gemm_res_ln(const float* A, int lda, const float* W, int ldw, const float* bias, float* X, int ldx,
+                       const float* gamma, const float* beta, int M, int K, cudaStream_t st);
 // gemm_tc.cu: lo-part copies of registered weights (fetched by TMA instead of being derived per tile)
 void gemm_register_weight_lo(const void* owner, const float* base, size_t count, const float* lo);
 void gemm_clear_weight_lo(const void* owner);

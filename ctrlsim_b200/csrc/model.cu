@@ -14,6 +14,9 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
+#include <string>
+
 #include "model.h"
 #include "model_ws.h"
 
@@ -41,6 +44,11 @@ void Prof::end(cudaStream_t st) {
   if (!on) return;
   cudaEventRecord(recs.back().b, st);
 }
+void Prof::cancel() {
+  if (!on || recs.empty()) return;
+  pool.push_back(recs.back().a); pool.push_back(recs.back().b);
+  recs.pop_back();
+}
 void Prof::flush(cudaStream_t st) {
   if (!on || recs.empty()) return;
   cudaStreamSynchronize(st);
@@ -66,6 +74,27 @@ static int gemm(const float* Ain, const float* W, const float* bias, float* C, i
 }
 static int ln(const float* X, const float* R, const LnW& w, float* Y, int M, bool relu, cudaStream_t st) {
   return launch_layernorm(X, R, w.w, w.b, Y, M, H, H, H, relu, st);
+}
+// X = LayerNorm(X + A W^T + b): the projection that closes a sub-block (post-LN).  One fused kernel when the GEMM can
+// take it (registered weights, M large enough to fill the SMs), else GEMM into tmp + the LayerNorm kernel.
+static int gemm_res_ln(const float* A, const float* W, const float* bias, float* X, const LnW& w, float* tmp, int M, int K,
+                       cudaStream_t st) {
+  // The fused kernel (gemm_tc_ta_ln_kernel) is correct and exported (ctrlsim_linear_res_ln) but OFF in the model path:
+  // measured at 64 scenes (profiles/r03k_ln_fusion_experiment.txt) the full-window step is 158.6 ms with all three
+  // sub-block projections fused and 156.4 ms with FFN2 only, against 155.8-156.1 ms with the separate LayerNorm kernel -
+  // with K = 256 the fused epilogue (residual read, pre-norm write, barrier, re-read, normalise, write) outlasts the
+  // tile's 8 k-slabs of MMAs, and the step runs at the power cap, where the saved HBM traffic buys no clock.
+  // CTRLSIM_LNFUSE=1 switches it on (CTRLSIM_LNFUSE_MINK: smallest K that takes it, default 1024).
+  static const bool fuse = getenv("CTRLSIM_LNFUSE") && std::string(getenv("CTRLSIM_LNFUSE")) == "1";
+  static const int min_k = getenv("CTRLSIM_LNFUSE_MINK") ? atoi(getenv("CTRLSIM_LNFUSE_MINK")) : 1024;
+  if (fuse && M >= 128 * 148 && K >= min_k) {
+    g_prof.begin(PROF_GEMM, 2.0 * M * (double)H * K, st);
+    const int rc = launch_gemm_res_ln(A, K, W, K, bias, X, H, w.w, w.b, M, K, st);
+    if (rc != 1) { g_prof.end(st); return rc; }
+    g_prof.cancel();
+  }
+  CS_TRY(gemm(A, W, bias, tmp, M, H, K, K, K, H, false, st));
+  return ln(X, tmp, w, X, M, false, st);
 }
 
 size_t Workspace::carve(void* base, size_t bytes, int Gc) {
@@ -156,17 +185,14 @@ static int embed_tokens(const ModelWeights& w, Workspace& ws, int G, int n_tok, 
 static int decoder_layer_rest(const DecLayerW& d, Workspace& ws, int G, int rows_per_group, const float* kvc,
                               const uint8_t* pad, cudaStream_t st) {
   const int R = G * rows_per_group;
-  CS_TRY(gemm(ws.att, d.sa.out_w, d.sa.out_b, ws.tmp, R, H, H, H, H, H, false, st));
-  CS_TRY(ln(ws.X, ws.tmp, d.n1, ws.X, R, false, st));
+  CS_TRY(gemm_res_ln(ws.att, d.sa.out_w, d.sa.out_b, ws.X, d.n1, ws.tmp, R, H, st));
   CS_TRY(gemm(ws.X, d.ca.in_w, d.ca.in_b, ws.q_c, R, H, H, H, H, H, false, st));
   g_prof.begin(PROF_ATTN_CROSS, (double)G * NH * rows_per_group * MEM * 4.0 * DH, st);
   CS_TRY(launch_attn_padded(ws.q_c, H, kvc, kvc + H, 2 * H, pad, ws.att, H, G, rows_per_group, MEM, st));
   g_prof.end(st);
-  CS_TRY(gemm(ws.att, d.ca.out_w, d.ca.out_b, ws.tmp, R, H, H, H, H, H, false, st));
-  CS_TRY(ln(ws.X, ws.tmp, d.n2, ws.X, R, false, st));
+  CS_TRY(gemm_res_ln(ws.att, d.ca.out_w, d.ca.out_b, ws.X, d.n2, ws.tmp, R, H, st));
   CS_TRY(gemm(ws.X, d.l1w, d.l1b, ws.ff, R, FF, H, H, H, FF, true, st));
-  CS_TRY(gemm(ws.ff, d.l2w, d.l2b, ws.tmp, R, H, FF, FF, FF, H, false, st));
-  CS_TRY(ln(ws.X, ws.tmp, d.n3, ws.X, R, false, st));
+  CS_TRY(gemm_res_ln(ws.ff, d.l2w, d.l2b, ws.X, d.n3, ws.tmp, R, FF, st));
   return 0;
 }
 

@@ -39,6 +39,7 @@ struct Prof {
   long long count[PROF_NCAT] = {0, 0, 0, 0};
   void begin(int cat, double work, cudaStream_t st);
   void end(cudaStream_t st);
+  void cancel();  // drop the record begin() just opened (the work was not launched)
   void flush(cudaStream_t st);
 };
 extern Prof g_prof;

@@ -117,6 +117,7 @@ _SIGS = {
     "ctrlsim_profile_read": (None, [C.POINTER(C.c_double)]),
     "ctrlsim_linear": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p]),
     "ctrlsim_layernorm": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 2 + [C.c_void_p]),
+    "ctrlsim_linear_res_ln": (C.c_int, [C.c_void_p] * 7 + [C.c_int32] * 2 + [C.c_void_p]),
     "ctrlsim_attn_padded": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ctrlsim_attn_causal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

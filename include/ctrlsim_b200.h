@@ -212,6 +212,12 @@ int ctrlsim_linear(const float* A, const float* W, const float* bias, float* C, 
                    int32_t relu, void* stream);
 int ctrlsim_layernorm(const float* X, const float* R, const float* gamma, const float* beta, float* Y, int32_t M,
                       int32_t relu, void* stream);
+/* X[M,256] = LayerNorm(X + A[M,K] W[256,K]^T + bias) * gamma + beta in place - the projection that closes a post-LN
+ * transformer sub-block (nn.TransformerDecoderLayer, modules/decoder.py:16-20) with residual add and LayerNorm in the
+ * GEMM epilogue when W is a registered weight (else the GEMM and the LayerNorm run one after the other, through
+ * `scratch` [M,256]).  Returns 0, or an error code. */
+int ctrlsim_linear_res_ln(const float* A, const float* W, const float* bias, float* X, const float* gamma,
+                          const float* beta, float* scratch, int32_t M, int32_t K, void* stream);
 int ctrlsim_attn_padded(const float* Q, int32_t ldq, const float* K, const float* V, int32_t ldkv,
                         const uint8_t* key_pad, float* O, int32_t G, int32_t Lq, int32_t Lk, void* stream);
 int ctrlsim_attn_causal(const float* QKV, float* O, int32_t G, int32_t n_t, void* stream);

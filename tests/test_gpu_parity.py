@@ -79,6 +79,43 @@ def test_linear_with_registered_weights_matches_torch(cfg, lib, dev, name, M, re
     assert torch.isfinite(C).all()
 
 
+@pytest.mark.parametrize("name,M", [("self_attn.out_proj.weight", 148 * 128 * 2 + 77), ("linear2.weight", 148 * 128 + 1),
+                                    ("multihead_attn.out_proj.weight", 90 * 2304), ("linear2.weight", 300)])
+def test_linear_res_ln_matches_torch(cfg, lib, dev, name, M):
+    """X = LayerNorm(X + A W^T + b) in ONE kernel (gemm_tc_ta_ln_kernel: residual add and LayerNorm in the GEMM epilogue,
+    a CTA owns whole rows) against torch in fp64, every row; K = 256 and K = 1024, a ragged last m-tile, and a small M
+    that the fused kernel still serves (the model only sends it M >= 148 tiles)."""
+    from ctrlsim_b200.model import DeviceModel
+    from ctrlsim_b200.weights import make_weights
+    model = DeviceModel(cfg, make_weights(cfg, seed=0), dev)
+    pre = "decoder.transformer_decoder.layers.2."
+    W = model.tensors[pre + name]
+    gamma, beta = model.tensors[pre + "norm2.weight"], model.tensors[pre + "norm2.bias"]
+    N, K = W.shape
+    assert N == 256
+    g = torch.Generator(device="cpu").manual_seed(M % 1000)
+    A = torch.randn(M, K, generator=g).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    X = (torch.randn(M, N, generator=g) * 2.0 + 0.5).to(dev)
+    gm = (gamma + 0.1 * torch.randn(N, generator=g).to(dev)).contiguous()
+    bt = (beta + 0.1 * torch.randn(N, generator=g).to(dev)).contiguous()
+    ref = torch.nn.functional.layer_norm(X.double() + torch.nn.functional.linear(A.double(), W.double(), b.double()), (N,),
+                                         gm.double(), bt.double(), 1e-5)
+    scratch = torch.empty(M, N, device=dev)
+    Xc = X.clone()
+    _chk(model.lib.ctrlsim_linear_res_ln(A.data_ptr(), W.data_ptr(), b.data_ptr(), Xc.data_ptr(), gm.data_ptr(), bt.data_ptr(),
+                                         scratch.data_ptr(), M, K, _stream()), model.lib)
+    err = (Xc.double() - ref).abs().max().item()
+    assert err < (2e-5 if K <= 256 else 5e-5), err
+    # the two-kernel path (what an unregistered W takes) gives the same to rounding
+    W2 = W.clone()
+    X2 = X.clone()
+    _chk(model.lib.ctrlsim_linear_res_ln(A.data_ptr(), W2.data_ptr(), b.data_ptr(), X2.data_ptr(), gm.data_ptr(), bt.data_ptr(),
+                                         scratch.data_ptr(), M, K, _stream()), model.lib)
+    assert (X2.double() - ref).abs().max().item() < (2e-5 if K <= 256 else 5e-5)
+    assert (X2 - Xc).abs().max().item() < 2e-5
+
+
 @pytest.mark.parametrize("M,res,relu", [(1, False, False), (1000, True, False), (257, True, True)])
 def test_layernorm_matches_torch(lib, dev, M, res, relu):
     g = torch.Generator(device="cpu").manual_seed(M)
