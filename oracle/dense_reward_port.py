@@ -1,7 +1,8 @@
-"""ORACLE (test infrastructure only): scalar restatement of the reference's real-time dense reward - groundwork for
-SURVEY 8(f) N1 (`real_time_rewards` policies: DT baseline, max/min-return modes).  No product code uses or mirrors
-this yet; it is pinned against the reference's own functions by tests/test_oracle.py so that the GPU kernel of the next
-round has a checker.
+"""ORACLE (test infrastructure only): scalar restatement of the reference's real-time dense reward (SURVEY 8(f) N1:
+`real_time_rewards` policies - DT baseline, max/min-return modes).  It is the checker of the product's
+`dense_reward_kernel` (ctrlsim_b200/csrc/sim.cu, ctrlsim_dense_reward): pinned against the reference's own functions
+and against the reference evaluator's DT episode by tests/test_oracle.py, compared with the GPU by
+tests/test_gpu_parity.py.  Never imported by the product path.
 
 Restated (reference file:line):
   signed distance to road-edge polylines   utils/data.py:152-290 (_compute_signed_distance_to_polyline(s))

@@ -849,7 +849,7 @@ def test_product_contact_code_equals_oracle_on_the_host(tmp_path, mode):
 def test_dense_reward_port_matches_the_reference_functions(cfg):
     """oracle/dense_reward_port.py (scalar loops) against the reference's own array code: signed distance to road-edge
     polylines (utils/data.py:152-290), nearest-vehicle distance and compute_rewards (datasets/rl_waymo/dataset.py:
-    202-275) as evaluators/evaluator.py:106-140 combines them.  No product counterpart yet (next round)."""
+    202-275) as evaluators/evaluator.py:106-140 combines them.  Product counterpart: dense_reward_kernel (GPU tests test_dt_*)."""
     from oracle import ref_shims
     from oracle.dense_reward_port import dense_reward_step, signed_distance_to_polylines
     ref_shims.install()
@@ -894,7 +894,8 @@ def test_dense_reward_port_matches_the_reference_functions(cfg):
 def test_model_port_dt_variant_matches_the_reference_modules(cfg):
     """Decision-transformer baseline (cfgs/model/dt.yaml: continuous RTG inputs, no RTG head): oracle/model_port.py against
     the reference Encoder / Decoder built with that configuration and its own random initialisation.  Oracle groundwork
-    for SURVEY 8(f) N1 - no product counterpart yet."""
+    for SURVEY 8(f) N1; product counterpart: the decision_transformer mode of the library (GPU test
+    test_dt_forward_matches_reference_logits)."""
     import copy
     import torch
     from oracle import ref_shims
