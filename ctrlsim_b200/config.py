@@ -196,7 +196,7 @@ def _resolve(tree: dict):
             node = node[k]
         return node
 
-    def walk(node, depth=0):
+    def walk(node):
         for k, v in (node.items() if isinstance(node, dict) else enumerate(node)):
             if isinstance(v, (dict, list)):
                 walk(v)

@@ -440,39 +440,56 @@ class B200PolicyEvaluator:
             side.synchronize()  # the consumer uses the arrays on its own stream
             return b
 
+        stop = threading.Event()  # set by the consumer when it gives up: the producer must not block on a full queue
+
+        def hand_over(x):
+            while not stop.is_set():
+                try:
+                    q.put(x, timeout=0.2)
+                    return True
+                except queue.Full:
+                    pass
+            return False
+
         def producer():
             try:
                 cur = ([], [], [], [])
                 for item in self.iter_selected(eval_threshold):
+                    if stop.is_set():
+                        return
                     for lst, v in zip(cur, item):
                         lst.append(v)
                     if len(cur[0]) == sub_batch_scenes:
-                        q.put(upload(cur))
+                        if not hand_over(upload(cur)):
+                            return
                         cur = ([], [], [], [])
-                if cur[0]:
-                    q.put(upload(cur))
-                q.put(None)
+                if cur[0] and not hand_over(upload(cur)):
+                    return
+                hand_over(None)
             except BaseException as e:  # noqa: BLE001 - handed to the consumer, which re-raises it
-                q.put(e)
+                hand_over(e)
 
         th = threading.Thread(target=producer, daemon=True)
         th.start()
         total, self.traces, self.n_evaluated, overflow = None, [], 0, 0
-        while True:
-            b = q.get()
-            if b is None:
-                break
-            if isinstance(b, BaseException):
-                raise b
-            self.batch = b
-            self.rollout(b)
-            sm = self.summarize(b, local_only=True)
-            overflow += self.contact_overflow
-            total = sm if total is None else total + sm
-            self.n_evaluated += b.n_evaluated()
-            if keep_traces:
-                self.traces.append(b.trace())
-        th.join()
+        try:
+            while True:
+                b = q.get()
+                if b is None:
+                    break
+                if isinstance(b, BaseException):
+                    raise b
+                self.batch = b
+                self.rollout(b)
+                sm = self.summarize(b, local_only=True)
+                overflow += self.contact_overflow
+                total = sm if total is None else total + sm
+                self.n_evaluated += b.n_evaluated()
+                if keep_traces:
+                    self.traces.append(b.trace())
+        finally:
+            stop.set()  # an error on this side (or the normal end) releases a producer waiting on the queue
+            th.join()
         self.contact_overflow = overflow
         summ = torch.as_tensor(total if total is not None else np.zeros(8 + 8 * 200), dtype=torch.float64, device=dev)
         if self.world > 1:

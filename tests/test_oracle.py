@@ -1306,3 +1306,22 @@ def test_pipelined_evaluation_plumbing_on_cpu(cfg):
     bad.seen = []
     with pytest.raises(Exception):
         bad.evaluate_policy(sub_batch_scenes=2)
+
+
+def test_pipelined_evaluation_releases_its_producer_when_the_consumer_fails(cfg):
+    """An error while a sub-batch is rolled out must not leave the producer thread blocked on the hand-over queue."""
+    import threading
+    import types
+    from ctrlsim_b200.evaluator import B200PolicyEvaluator
+    from ctrlsim_b200.synth import make_scene
+    scenes = [make_scene(420 + i, n_vehicles=4, n_roads=1, n_chunks=2) for i in range(8)]
+    fake = types.SimpleNamespace(model=types.SimpleNamespace(device="cpu"))
+
+    class Ev(B200PolicyEvaluator):
+        def rollout(self, batch=None, max_steps=None):
+            raise RuntimeError("device fault")
+
+    before = threading.active_count()
+    with pytest.raises(RuntimeError, match="device fault"):
+        Ev(cfg, fake, scenes=scenes).evaluate_policy(sub_batch_scenes=1)
+    assert threading.active_count() == before
