@@ -14,6 +14,8 @@ from __future__ import annotations
 
 import math
 
+from operator import itemgetter
+
 import numpy as np
 
 
@@ -29,6 +31,18 @@ def _normalize_angle_f32(deg: float) -> np.float32:
     return np.float32(r)
 
 
+_GET_X, _GET_Y = itemgetter("x"), itemgetter("y")
+
+
+def _xy_array(points) -> np.ndarray:
+    """[{'x': .., 'y': ..}, ...] -> [n, 2] float32.  Two flat lists convert about twice as fast as a list of pairs
+    (the parser is ~6 ms of Python per 64-vehicle scene, the only host work of an evaluation that scales with it)."""
+    out = np.empty((len(points), 2), np.float32)
+    out[:, 0] = list(map(_GET_X, points))
+    out[:, 1] = list(map(_GET_Y, points))
+    return out
+
+
 def parse_scenario(scen: dict, steps: int = 90, moving_threshold: float = 0.2, speed_threshold: float = 0.05):
     objs = [o for o in scen["objects"] if bool(o["valid"][0]) and o["type"] == "vehicle"]
     n, T1 = len(objs), steps + 1
@@ -38,7 +52,39 @@ def parse_scenario(scen: dict, steps: int = 90, moving_threshold: float = 0.2, s
     target = np.zeros((n, 4), np.float32)
     moving = np.zeros(n, bool)
     two_pi = 2.0 * math.pi
-    for i, o in enumerate(objs):
+    lengths = {len(o["position"]) for o in objs}
+    if len(lengths) == 1 and min(lengths) >= T1:
+        # every track has the same length (the Waymo-derived files: 91 states): all vehicles at once, the same
+        # element-wise float32 / float64 arithmetic as the per-vehicle loop below (bit-identical, ~3x faster)
+        L = lengths.pop()
+        pos, vel = np.empty((n, L, 2), np.float32), np.empty((n, L, 2), np.float32)
+        pos[:, :, 0] = [list(map(_GET_X, o["position"])) for o in objs]
+        pos[:, :, 1] = [list(map(_GET_Y, o["position"])) for o in objs]
+        vel[:, :, 0] = [list(map(_GET_X, o["velocity"])) for o in objs]
+        vel[:, :, 1] = [list(map(_GET_Y, o["velocity"])) for o in objs]
+        size[:] = [(o["length"], o["width"]) for o in objs]
+        gps = [o.get("goalPosition", {"x": 0.0, "y": 0.0}) for o in objs]
+        target[:, 0], target[:, 1] = list(map(_GET_X, gps)), list(map(_GET_Y, gps))
+        deg = np.asarray([o["heading"] for o in objs], np.float32).reshape(n, L)
+        rad = (deg.astype(np.float64) / 180.0 * math.pi).astype(np.float32)
+        r = np.fmod(rad.astype(np.float64), two_pi).astype(np.float32).astype(np.float64)
+        h = np.where(r > math.pi, r - two_pi, np.where(r < -math.pi, r + two_pi, r)).astype(np.float32)
+        sp = np.sqrt(vel[:, :, 0] * vel[:, :, 0] + vel[:, :, 1] * vel[:, :, 1])
+        gt[:, :, 0], gt[:, :, 1], gt[:, :, 2], gt[:, :, 3] = pos[:, :T1, 0], pos[:, :T1, 1], h[:, :T1], sp[:, :T1]
+        gt_valid[:] = pos[:, :T1, 0] != np.float32(-10000.0)  # utils/sim.py:28 existence rule
+        valid = np.asarray([o["valid"][:L] for o in objs], bool).reshape(n, L)
+        has = valid.any(axis=1)
+        last = L - 1 - np.argmax(valid[:, ::-1], axis=1)
+        rows = np.arange(n)
+        target[:, 2] = np.where(has, h[rows, last], np.float32(0))
+        target[:, 3] = np.where(has, sp[rows, last], np.float32(0))
+        dx, dy = pos[:, :, 0] - target[:, None, 0], pos[:, :, 1] - target[:, None, 1]
+        dist = np.sqrt(dx * dx + dy * dy)
+        moving[:] = (((sp > np.float32(speed_threshold)) | (dist > np.float32(moving_threshold))) & valid).any(axis=1)
+        objs_loop = []
+    else:
+        objs_loop = objs
+    for i, o in enumerate(objs_loop):
         L = len(o["position"])
         if L < T1:
             raise ValueError(f"object {i}: {L} states, the evaluator needs {T1}")
@@ -47,8 +93,7 @@ def parse_scenario(scen: dict, steps: int = 90, moving_threshold: float = 0.2, s
         target[i, :2] = (gp["x"], gp["y"])
         # whole track at once, in the arithmetic of the scalar rules above (float32 simulator values; the angle goes
         # float32 -> double -> float32 twice exactly like geometry_utils.h:41-58 with T = float)
-        pos = np.array([(q["x"], q["y"]) for q in o["position"]], np.float32).reshape(L, 2)
-        vel = np.array([(q["x"], q["y"]) for q in o["velocity"]], np.float32).reshape(L, 2)
+        pos, vel = _xy_array(o["position"]), _xy_array(o["velocity"])
         deg = np.asarray(o["heading"], np.float32)
         rad = (deg.astype(np.float64) / 180.0 * math.pi).astype(np.float32)
         r = np.fmod(rad.astype(np.float64), two_pi).astype(np.float32).astype(np.float64)
@@ -68,7 +113,7 @@ def parse_scenario(scen: dict, steps: int = 90, moving_threshold: float = 0.2, s
         g = road["geometry"]
         if road["type"] != "road_edge" or isinstance(g, dict):
             continue
-        pts = np.array([(q["x"], q["y"]) for q in g], np.float32).reshape(len(g), 2)
+        pts = _xy_array(g)
         edge_polylines.append(pts.astype(np.float64))
         if len(g) >= 2:
             segs.append(np.concatenate([pts[:-1], pts[1:]], axis=1))
