@@ -43,7 +43,10 @@ def _xy_array(points) -> np.ndarray:
     return out
 
 
-def parse_scenario(scen: dict, steps: int = 90, moving_threshold: float = 0.2, speed_threshold: float = 0.05):
+def parse_scenario(scen: dict, steps: int = 90, moving_threshold: float = 0.2, speed_threshold: float = 0.05,
+                   vectorize: bool = True):
+    """``vectorize=False`` forces the per-vehicle loop (what scenes with tracks of different lengths take); both paths
+    give bit-identical arrays (tests/test_oracle.py::test_parser_paths_are_bit_identical)."""
     objs = [o for o in scen["objects"] if bool(o["valid"][0]) and o["type"] == "vehicle"]
     n, T1 = len(objs), steps + 1
     gt = np.zeros((n, T1, 4), np.float32)
@@ -53,7 +56,7 @@ def parse_scenario(scen: dict, steps: int = 90, moving_threshold: float = 0.2, s
     moving = np.zeros(n, bool)
     two_pi = 2.0 * math.pi
     lengths = {len(o["position"]) for o in objs}
-    if len(lengths) == 1 and min(lengths) >= T1:
+    if vectorize and len(lengths) == 1 and min(lengths) >= T1:
         # every track has the same length (the Waymo-derived files: 91 states): all vehicles at once, the same
         # element-wise float32 / float64 arithmetic as the per-vehicle loop below (bit-identical, ~3x faster)
         L = lengths.pop()

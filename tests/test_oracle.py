@@ -1325,3 +1325,40 @@ def test_pipelined_evaluation_releases_its_producer_when_the_consumer_fails(cfg)
     with pytest.raises(RuntimeError, match="device fault"):
         Ev(cfg, fake, scenes=scenes).evaluate_policy(sub_batch_scenes=1)
     assert threading.active_count() == before
+
+
+def test_parser_paths_are_bit_identical():
+    """parse_scenario's all-vehicles-at-once path (tracks of one length) and its per-vehicle loop give the same arrays,
+    bit for bit and dtype for dtype - config-2 scenes, short / parked vehicles, replay scenes, the fixture scenes, and a
+    scene without any vehicle valid at t = 0; a scene with tracks of different lengths takes the loop by itself."""
+    import copy
+    from ctrlsim_b200.scenario import parse_scenario
+    from ctrlsim_b200.synth import make_replay_scene, make_scene
+    scenes = [make_scene(i)["json"] for i in range(2)]
+    scenes += [make_scene(100 + i, n_vehicles=3 + 5 * i, n_roads=1 + i % 3, n_chunks=2 + i % 4, frac_short=0.3, frac_parked=0.2)["json"] for i in range(6)]
+    scenes += [make_replay_scene(i)["json"] for i in range(6)]
+    scenes += [make_scene(**load_golden(name)[1]["scene"])["json"] for name in ("plumbing", "crowded", "sparse")]
+    empty = copy.deepcopy(scenes[3])
+    for o in empty["objects"]:
+        o["valid"][0] = False
+    scenes.append(empty)
+
+    def same(a, b):
+        assert a.keys() == b.keys()
+        for k in a:
+            if isinstance(a[k], list):
+                assert len(a[k]) == len(b[k]) and all(np.array_equal(x, y) and x.dtype == y.dtype for x, y in zip(a[k], b[k])), k
+            elif isinstance(a[k], np.ndarray):
+                assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+            else:
+                assert a[k] == b[k], k
+
+    for js in scenes:
+        for steps in (90, 44):
+            same(parse_scenario(js, steps), parse_scenario(js, steps, vectorize=False))
+    ragged = copy.deepcopy(scenes[4])
+    o = ragged["objects"][0]
+    for k in ("position", "velocity", "heading", "valid"):
+        o[k] = o[k] + [o[k][-1]] * 3
+    same(parse_scenario(ragged, 90), parse_scenario(ragged, 90, vectorize=False))
+    assert parse_scenario(ragged, 90)["n"] == parse_scenario(scenes[4], 90)["n"]
